@@ -1,0 +1,85 @@
+// Exact float32 binning against float64 edges (host + device).
+//
+// Replaces numpy.histogramdd's bin search (hop/density.py:129) and numpy.digitize in
+// HoppingTrajectory._coord2hop (hop/trajectory.py:428), both of which promote the float32
+// coordinate to float64 and do searchsorted(edges, x, side='right').
+//
+// Exactness argument.  For a float32 value x and a real edge e:  x >= e  <=>  x >= up32(e), where
+// up32(e) is the smallest float32 that is >= e (x is itself a float32, so no float32 lies in
+// [e, up32(e)) ).  up32 is monotone, hence
+//     searchsorted(edges, float64(x), 'right') = #{k : edges[k] <= x} = #{k : up32(edges[k]) <= x}
+// and the whole search runs on a float32 table with float32 compares -- bit-identical to the
+// float64 search, with no float64 arithmetic on the device.  A float32 multiply gives the starting
+// guess; two short loops walk to the exact answer, so the guess only affects speed.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define HOPB_HD __host__ __device__ __forceinline__
+#else
+#define HOPB_HD inline
+#endif
+
+#define HOPB_MAX_EDGES 4096  // per axis, n+1 edges (bench grids use <= ~600)
+
+// Per-axis constants that travel by value in kernel arguments.
+struct HopbAxis {
+  int32_t n;        // number of bins; edges 0..n
+  float lo;         // (float)edges[0]          -- starting guess only
+  float inv;        // (float)(n/(edges[n]-edges[0]))
+  float top_eq;     // (float)edges[n] if exactly representable, else NaN (histogramdd x == edges[-1])
+  float top_round;  // float32(np.around(edges[n], decimals))   (trajectory.py:437-439)
+  float p10;        // 10^|decimals|
+  int32_t dec_neg;  // 1 if decimals < 0 (np.around divides then multiplies)
+  int32_t off;      // offset of this axis' table in the packed float table
+};
+
+struct HopbGridTab {
+  HopbAxis ax[3];
+  int32_t table_len;  // total floats in the packed up32 table
+};
+
+// searchsorted(edges, x, 'right') in [0, n+1]; `eup` points at this axis' up32 table (n+1 floats).
+HOPB_HD int hopb_bin_right(float x, const HopbAxis& a, const float* eup) {
+  const int n = a.n;
+  float g = (x - a.lo) * a.inv;
+  int b;
+  if (!(g > -1.0f)) b = 0;                 // also catches NaN
+  else if (g >= (float)n) b = n + 1;
+  else b = (int)g + 1;
+  while (b <= n && x >= eup[b]) ++b;
+  while (b > 0 && !(x >= eup[b - 1])) --b;  // NaN: every compare false -> b = 0 (dropped / outlier)
+  return b;
+}
+
+// numpy.histogramdd: a point exactly on the last edge belongs to the last bin.
+HOPB_HD int hopb_bin_hist(float x, const HopbAxis& a, const float* eup) {
+  int b = hopb_bin_right(x, a, eup);
+  if (x == a.top_eq) b = a.n;
+  return b;  // counted iff 1 <= b <= n
+}
+
+#if defined(__CUDA_ARCH__)
+#define HOPB_FMUL(a, b) __fmul_rn((a), (b))
+#define HOPB_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define HOPB_FMUL(a, b) ((a) * (b))
+#define HOPB_FDIV(a, b) ((a) / (b))
+#endif
+
+// numpy.around(float32, decimals): multiply, rint, divide in float32 (divide, rint, multiply for
+// negative decimals).
+HOPB_HD float hopb_around32(float x, const HopbAxis& a) {
+  if (a.dec_neg) return HOPB_FMUL(rintf(HOPB_FDIV(x, a.p10)), a.p10);
+  return HOPB_FDIV(rintf(HOPB_FMUL(x, a.p10)), a.p10);
+}
+
+// _coord2hop index: digitize, then shift one bin left when the rounded coordinate equals the
+// rounded top edge (float32 comparison, numpy 1.x casting).  Result in [-1, n+1];
+// 1..n are map cells, everything else is an outlier.
+HOPB_HD int hopb_bin_hop(float x, const HopbAxis& a, const float* eup) {
+  int b = hopb_bin_right(x, a, eup);
+  if (hopb_around32(x, a) == a.top_round) b -= 1;
+  return b;
+}

@@ -1,0 +1,104 @@
+// CPU replay of the host/device headers used by the CUDA kernels -- TEST INFRASTRUCTURE ONLY.
+// Built by tests/emul/build.py with g++ and loaded by the `-m "not gpu"` tests; hop_b200 never
+// loads it.  It lets the chunk/slab stitching algebra (hopb_machine.h) and the float32 binning
+// (hopb_binning.h) be checked against the oracle without a GPU.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../hop_b200/csrc/hopb_binning.h"
+#include "../../hop_b200/csrc/hopb_gridtab_host.h"
+#include "../../hop_b200/csrc/hopb_machine.h"
+
+struct Ev { int32_t frame, iatom, s0, s, tau, tbar; };
+
+extern "C" {
+
+// labels [F][N] int32 (global frames frame0 .. frame0+F-1); slabs of `slab_len` frames are cut into
+// chunks of `chunk_len` frames, exactly like ranks x chunks on the GPUs.  Events are written
+// unsorted to ev_out (cap entries); returns the number of events, final state per atom in
+// state_out[N][4] and orbit column in orbit_out[F][N].
+int64_t emul_scan(const int32_t* labels, int64_t F, int64_t N, int64_t slab_len, int64_t chunk_len,
+                  Ev* ev_out, int64_t cap, int32_t* state_out, int32_t* orbit_out) {
+  std::vector<Ev> ev;
+  const int64_t nslabs = (F + slab_len - 1) / slab_len;
+  for (int64_t a = 0; a < N; ++a) {
+    auto emit = [&](int s0, int s, int frame, int tau, int tbar) {
+      ev.push_back(Ev{frame, (int32_t)a, s0, s, tau, tbar});
+    };
+    // pass 1: per chunk summaries (events of FULL phases emitted directly), per slab combine
+    std::vector<std::vector<HopbSummary>> chunks(nslabs);
+    std::vector<HopbSummary> slabs(nslabs);
+    for (int64_t r = 0; r < nslabs; ++r) {
+      const int64_t s_begin = r * slab_len, s_end = std::min(F, s_begin + slab_len);
+      HopbSummary slab = hopb_summary_empty();
+      int64_t done = 0;
+      for (int64_t c0 = s_begin; c0 < s_end; c0 += chunk_len) {
+        const int64_t c1 = std::min(s_end, c0 + chunk_len);
+        HopbSummary T = hopb_summary_empty();
+        int ypre = 0, y = 0; bool yknown = false;
+        for (int64_t f = c0; f < c1; ++f) {
+          const int lab = labels[f * N + a];
+          hopb_push_frame(T, lab, (int)f, emit);
+          if (lab > 0) { y = lab; yknown = true; }
+          if (!yknown) ++ypre;
+          orbit_out[f * N + a] = yknown ? y : 0;
+        }
+        T.ypre = ypre;
+        // round trip through the packed layout
+        int32_t packed[HOPB_SUMMARY_FIELDS];
+        hopb_summary_store(packed, 1, T);
+        T = hopb_summary_load(packed, 1);
+        chunks[r].push_back(T);
+        slab = hopb_combine(slab, T, (int)done);
+        done += c1 - c0;
+      }
+      slabs[r] = slab;
+    }
+    // pass 2: per slab, incoming state from the earlier slabs' summaries, then fix-up per chunk
+    for (int64_t r = 0; r < nslabs; ++r) {
+      HopbState S = hopb_state_virgin();
+      for (int64_t q = 0; q < r; ++q) hopb_apply(S, slabs[q], [](int, int, int, int, int) {});
+      const int64_t s_begin = r * slab_len;
+      for (size_t c = 0; c < chunks[r].size(); ++c) {
+        const HopbSummary& T = chunks[r][c];
+        const int yin = S.s0 > 0 ? S.s0 : 0;
+        const int64_t c0 = s_begin + (int64_t)c * chunk_len;
+        if (yin != 0) for (int k = 0; k < T.ypre; ++k) orbit_out[(c0 + k) * N + a] = yin;
+        hopb_apply(S, T, emit);
+      }
+      if (r == nslabs - 1) { state_out[a * 4 + 0] = S.s0; state_out[a * 4 + 1] = S.t0; state_out[a * 4 + 2] = S.t1; state_out[a * 4 + 3] = S.on; }
+    }
+    // cross-check: slab-level apply must reach the same final state as chunk-level apply
+    HopbState S2 = hopb_state_virgin();
+    for (int64_t q = 0; q < nslabs; ++q) hopb_apply(S2, slabs[q], [](int, int, int, int, int) {});
+    if (S2.s0 != state_out[a * 4 + 0] || S2.t0 != state_out[a * 4 + 1] || S2.on != state_out[a * 4 + 3] ||
+        (!S2.on && S2.t1 != state_out[a * 4 + 2]))
+      return -2;
+  }
+  if ((int64_t)ev.size() > cap) return -1;
+  std::memcpy(ev_out, ev.data(), ev.size() * sizeof(Ev));
+  return (int64_t)ev.size();
+}
+
+// Binning: mode 0 = histogram bin (1..n counted), mode 1 = hoptraj bin ([-1, n+1]).
+int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* ez, int nz,
+             const int* decimals, const float* xyz, int64_t npts, int mode, int32_t* out /*[npts][3]*/,
+             float* top_round_out /*[3]*/) {
+  const double* e[3] = {ex, ey, ez};
+  const int n[3] = {nx, ny, nz};
+  HopbGridTab tab;
+  std::vector<float> table;
+  if (hopb_build_gridtab(e, n, decimals, &tab, &table) != 0) return -1;
+  for (int d = 0; d < 3; ++d) top_round_out[d] = tab.ax[d].top_round;
+  for (int64_t i = 0; i < npts; ++i)
+    for (int d = 0; d < 3; ++d) {
+      const float x = xyz[i * 3 + d];
+      const float* eup = table.data() + tab.ax[d].off;
+      out[i * 3 + d] = mode == 0 ? hopb_bin_hist(x, tab.ax[d], eup) : hopb_bin_hop(x, tab.ax[d], eup);
+    }
+  return 0;
+}
+
+}  // extern "C"
