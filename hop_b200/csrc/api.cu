@@ -1,0 +1,130 @@
+// Handle, memory helpers and grid tables of libhopb200.so.
+#include "hopb_common.cuh"
+#include "hopb_gridtab_host.h"
+
+extern "C" {
+
+int hopb_version(void) { return 100; }
+
+int hopb_create(int device, hopb_handle** out) {
+  if (!out) return HOPB_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return HOPB_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return HOPB_E_CUDA;
+  hopb_handle* h = new hopb_handle();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return HOPB_E_CUDA; }
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return HOPB_OK;
+}
+
+void hopb_destroy(hopb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < HOPB_NUM_SCRATCH; ++i)
+    if (h->scratch[i]) cudaFree(h->scratch[i]);
+  delete h;
+}
+
+const char* hopb_last_error(const hopb_handle* h) { return h ? h->err : "null handle"; }
+
+int hopb_dev_alloc(hopb_handle* h, uint64_t bytes, void** out) {
+  HOPB_REQUIRE(h, out != nullptr, "null out");
+  HOPB_CUDA(h, cudaSetDevice(h->device));
+  HOPB_CUDA(h, cudaMalloc(out, bytes ? bytes : 1));
+  return HOPB_OK;
+}
+
+int hopb_dev_free(hopb_handle* h, void* p) {
+  HOPB_CUDA(h, cudaFree(p));
+  return HOPB_OK;
+}
+
+int hopb_memset(hopb_handle* h, void* stream, void* dev, int value, uint64_t bytes) {
+  HOPB_CUDA(h, cudaMemsetAsync(dev, value, bytes, (cudaStream_t)stream));
+  return HOPB_OK;
+}
+
+int hopb_h2d(hopb_handle* h, void* stream, void* dev, const void* host, uint64_t bytes) {
+  HOPB_CUDA(h, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return HOPB_OK;
+}
+
+int hopb_d2h(hopb_handle* h, void* stream, void* host, const void* dev, uint64_t bytes) {
+  HOPB_CUDA(h, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return HOPB_OK;
+}
+
+int hopb_stream_sync(hopb_handle* h, void* stream) {
+  HOPB_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return HOPB_OK;
+}
+
+int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey, int ny, const double* ez,
+                     int nz, const int* decimals, hopb_grid** out) {
+  HOPB_REQUIRE(h, h && out && ex && ey && ez, "null argument");
+  *out = nullptr;
+  const double* e[3] = {ex, ey, ez};
+  const int n[3] = {nx, ny, nz};
+  HOPB_REQUIRE(h, (int64_t)nx * ny * nz < ((int64_t)1 << 31), "grid has more than 2^31 cells");
+  HopbGridTab tab;
+  std::vector<float> table;
+  if (hopb_build_gridtab(e, n, decimals, &tab, &table) != 0)
+    return hopb_fail(h, HOPB_E_INVALID, "hopb_grid_create: edges must be strictly increasing, 1 <= n < %d", HOPB_MAX_EDGES);
+  HOPB_CUDA(h, cudaSetDevice(h->device));
+  hopb_grid* g = new hopb_grid();
+  memset(g, 0, sizeof(*g));
+  g->h = h;
+  g->tab = tab;
+  for (int d = 0; d < 3; ++d) g->n[d] = n[d];
+  cudaError_t err = cudaMalloc(&g->d_table, table.size() * sizeof(float));
+  if (err == cudaSuccess)
+    err = cudaMemcpy(g->d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice);
+  for (int d = 0; d < 3 && err == cudaSuccess; ++d) {
+    std::vector<double> w(n[d]), m(n[d]);
+    for (int k = 0; k < n[d]; ++k) {
+      w[k] = e[d][k + 1] - e[d][k];          // numpy.diff(edges)
+      m[k] = 0.5 * (e[d][k] + e[d][k + 1]);  // Grid._update midpoints (hop/sitemap.py:163)
+    }
+    err = cudaMalloc(&g->d_width[d], n[d] * sizeof(double));
+    if (err == cudaSuccess) err = cudaMalloc(&g->d_mid[d], n[d] * sizeof(double));
+    if (err == cudaSuccess) err = cudaMemcpy(g->d_width[d], w.data(), n[d] * sizeof(double), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(g->d_mid[d], m.data(), n[d] * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  if (err != cudaSuccess) {
+    hopb_grid_destroy(g);
+    return hopb_fail(h, HOPB_E_CUDA, "hopb_grid_create: %s", cudaGetErrorString(err));
+  }
+  *out = g;
+  return HOPB_OK;
+}
+
+void hopb_grid_destroy(hopb_grid* g) {
+  if (!g) return;
+  if (g->d_table) cudaFree(g->d_table);
+  for (int d = 0; d < 3; ++d) {
+    if (g->d_width[d]) cudaFree(g->d_width[d]);
+    if (g->d_mid[d]) cudaFree(g->d_mid[d]);
+  }
+  delete g;
+}
+
+}  // extern "C"
+
+int hopb_scratch(hopb_handle* h, int slot, size_t bytes, void** out) {
+  if (slot < 0 || slot >= HOPB_NUM_SCRATCH) return hopb_fail(h, HOPB_E_INVALID, "bad scratch slot");
+  if (h->scratch_bytes[slot] < bytes) {
+    if (h->scratch[slot]) HOPB_CUDA(h, cudaFree(h->scratch[slot]));
+    h->scratch[slot] = nullptr;
+    h->scratch_bytes[slot] = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    HOPB_CUDA(h, cudaMalloc(&h->scratch[slot], want));
+    h->scratch_bytes[slot] = want;
+  }
+  *out = h->scratch[slot];
+  return HOPB_OK;
+}

@@ -1,0 +1,83 @@
+// Internal definitions shared by the translation units of libhopb200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/hopb200.h"
+#include "hopb_binning.h"
+#include "hopb_machine.h"
+
+#define HOPB_NUM_SCRATCH 8
+
+struct hopb_handle {
+  int device;
+  int num_sms;
+  char err[512];
+  void* scratch[HOPB_NUM_SCRATCH];
+  size_t scratch_bytes[HOPB_NUM_SCRATCH];
+};
+
+struct hopb_grid {
+  hopb_handle* h;
+  HopbGridTab tab;
+  int n[3];
+  float* d_table;      // packed up32 tables (tab.table_len floats)
+  double* d_width[3];  // diff(edges[d]) in float64, n[d] entries
+  double* d_mid[3];    // 0.5*(e[:-1]+e[1:]), n[d] entries
+};
+
+static inline int hopb_fail(hopb_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define HOPB_CUDA(h, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return hopb_fail((h), HOPB_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call,             \
+                       cudaGetErrorString(_e));                                                  \
+  } while (0)
+
+#define HOPB_LAUNCH_CHECK(h) HOPB_CUDA(h, cudaGetLastError())
+
+#define HOPB_REQUIRE(h, cond, msg)                                                               \
+  do {                                                                                           \
+    if (!(cond)) return hopb_fail((h), HOPB_E_INVALID, "%s: %s", __func__, (msg));               \
+  } while (0)
+
+// Growable per-handle scratch slot.  Growing synchronises the device (cudaFree), so steady-state
+// calls with stable sizes never allocate.
+int hopb_scratch(hopb_handle* h, int slot, size_t bytes, void** out);
+
+// ---- device-wide primitives implemented in sort.cu --------------------------------------------
+// Exclusive prefix sum of n uint32 values (in -> out, may alias); total (device uint32*) optional.
+int hopb_exclusive_scan_u32(hopb_handle* h, cudaStream_t s, const uint32_t* in, uint32_t* out, int64_t n,
+                            uint32_t* total_dev);
+// Stable LSD radix sort of (key, value) pairs on key bits [begin_bit, end_bit).  Buffers ping-pong;
+// *in_alt tells whether the result ended in the *_alt buffers.
+int hopb_radix_sort_pairs(hopb_handle* h, cudaStream_t s, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals,
+                          uint32_t* vals_alt, int64_t n, int begin_bit, int end_bit, int* in_alt);
+
+static inline int hopb_bits_for(uint64_t v) {  // number of bits needed to represent values in [0, v]
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b < 1 ? 1 : b;
+}
+
+static inline unsigned hopb_grid_for(int64_t n, int block, int num_sms, int per_sm) {
+  int64_t need = (n + block - 1) / block;
+  int64_t cap = (int64_t)num_sms * per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}

@@ -1,0 +1,484 @@
+// Stage 2: thresholded hydration-site labelling (K2) -- Density.map_sites and friends.
+//
+// Replaces hop/sitemap.py:518-521 (mask), 1496-1541 (_make_graph/_shell: a networkx graph built
+// by a Python loop over cells x 7 forward offsets), 1543-1571 (_label_connected_graphs: connected
+// components ranked by size), 1574-1587 (_draw_map_from_sites), 877-918 (site_insert_bulk) and
+// 1589-1612 / 601-627 (_annotate_sites).
+//
+// Connectivity is the reference's 14-neighbourhood: offsets {0,1}^3 \ 0 and their negatives, no
+// periodic wrap.  Algorithm: lock-free union-find on the cell grid.
+//   1. rows: every z-run of above-threshold cells is pre-linked to its first cell (offset (0,0,1)
+//      costs nothing more);
+//   2. merge: the other six forward offsets, skipping every union that is implied by the z-runs
+//      and by the union one cell further down the run -- for a solid blob only run heads do work;
+//   3. flatten: parent = root = minimum C-order index of the component (links always point to the
+//      smaller index), which is exactly the tie-break key of the canonical numbering;
+//   4. component sizes (warp- and block-aggregated atomics), root list, 64-bit radix sort on
+//      (size desc, root desc), labels 1..S, relabel.
+// All per-cell passes are HBM streams over G cells (8 B density + 4 B parent).
+#include "hopb_common.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- 1. threshold + z-runs ----------------------------------------------------------------------
+// one warp per (x, y) row of nz cells
+__global__ void __launch_bounds__(256)
+ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_rows, int nz, int* __restrict__ parent) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int64_t base = row * nz;
+    int carry = -1;  // start (z) of the run that reaches the previous chunk's last cell, or -1
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      const bool m = z < nz && density[base + z] >= threshold;
+      const unsigned bits = __ballot_sync(kFull, m);
+      const unsigned below = ~bits & ((1u << lane) - 1);  // non-mask cells below this lane
+      int start;
+      if (below == 0) start = carry >= 0 ? carry : z0;
+      else start = z0 + (32 - __clz(below));
+      if (z < nz) parent[base + z] = m ? (int)(base + start) : -1;
+      const int s31 = __shfl_sync(kFull, start, 31);
+      carry = (bits >> 31) ? s31 : -1;
+    }
+  }
+}
+
+// ---- 2. merge -------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_parent(const int* parent, int i) {
+  return *reinterpret_cast<const volatile int*>(parent + i);
+}
+
+__device__ __forceinline__ int uf_find(const int* parent, int x) {
+  int p = ld_parent(parent, x);
+  while (p != x) { x = p; p = ld_parent(parent, x); }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }  // link the larger root under the smaller
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
+  const int64_t n_cells = (int64_t)nx * ny * nz;
+  const int64_t sy = nz, sx = (int64_t)ny * nz;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    if (parent[c] < 0) continue;
+    const int z = (int)(c % nz);
+    const int64_t r = c / nz;
+    const int y = (int)(r % ny);
+    const int x = (int)(r / ny);
+    const bool hx = x + 1 < nx, hy = y + 1 < ny, hz = z + 1 < nz, lz = z > 0;
+    // mask of the neighbours that matter (parent >= 0)
+    auto M = [&](int64_t idx) { return parent[idx] >= 0; };
+    const bool m_up = hz && M(c + 1);
+    const bool m_dn = lz && M(c - 1);
+    // the three in-plane offsets (0,1,0), (1,0,0), (1,1,0) and their +z partners
+    const int64_t offs[3] = {sy, sx, sx + sy};
+    const bool inb[3] = {hy, hx, hx && hy};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (!inb[k]) continue;
+      const int64_t nb = c + offs[k];
+      const bool m_nb = M(nb);
+      if (m_nb) {
+        // implied when both cells one step down the run are also connected the same way
+        const bool implied = m_dn && M(nb - 1);
+        if (!implied) uf_union(parent, (int)c, (int)nb);
+      }
+      if (hz && M(nb + 1)) {
+        // (c) ~ (nb+1): implied through nb (z-run of the neighbour row) or through c+1
+        if (!m_nb && !m_up) uf_union(parent, (int)c, (int)(nb + 1));
+      }
+    }
+  }
+}
+
+// ---- 3. flatten -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* parent, int64_t n_cells) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    if (parent[c] < 0) continue;
+    parent[c] = uf_find(parent, (int)c);
+  }
+}
+
+// ---- 4. sizes ---------------------------------------------------------------------------------------
+// size[root] += cells; aggregated per warp (neighbouring z cells share a root) and per block.
+__global__ void __launch_bounds__(256)
+ccl_size_kernel(const int* __restrict__ parent, int64_t n_cells, int* __restrict__ size) {
+  __shared__ int s_root[8];
+  __shared__ int s_cnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = ((n_cells + blockDim.x - 1) / blockDim.x) * blockDim.x;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += stride) {
+    const int r = c < n_cells ? parent[c] : -1;
+    // the dominant root of the warp (lane 0's peers) goes through shared memory; others go direct
+    const unsigned peers = __match_any_sync(kFull, r);
+    const bool leader = (peers & ((1u << lane) - 1)) == 0;
+    const int r0 = __shfl_sync(kFull, r, 0);
+    if (lane == 0) { s_root[warp] = r; s_cnt[warp] = __popc(peers); }
+    if (leader && r >= 0 && r != r0) atomicAdd(size + r, __popc(peers));
+    __syncthreads();
+    if (warp == 0) {
+      const int rr = lane < 8 ? s_root[lane] : -1;
+      const int cc = lane < 8 ? s_cnt[lane] : 0;
+      const unsigned p2 = __match_any_sync(kFull, rr);
+      int sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int rj = __shfl_sync(kFull, rr, j);
+        const int cj = __shfl_sync(kFull, cc, j);
+        if (rj == rr) sum += cj;
+      }
+      if (rr >= 0 && (p2 & ((1u << lane) - 1)) == 0) atomicAdd(size + rr, sum);
+    }
+    __syncthreads();
+  }
+}
+
+// roots with size >= minsite become sites; smaller components are dropped (label 0)
+__global__ void __launch_bounds__(256)
+ccl_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int64_t n_cells, int minsite,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ n_roots) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    if (parent[c] != (int)c) continue;
+    const int sz = size[c];
+    if (sz < minsite) { size[c] = 0; continue; }
+    const uint32_t slot = atomicAdd(n_roots, 1u);
+    if (slot < cap) {
+      // ascending sort on this key = size descending, then root index descending
+      keys[slot] = ((uint64_t)(uint32_t)(n_cells - sz) << 32) | (uint32_t)(n_cells - 1 - c);
+      vals[slot] = (uint32_t)c;
+    }
+  }
+}
+
+// label of rank i is i+1; size[root] is reused to hold the label
+__global__ void ccl_assign_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n_roots,
+                                  int64_t n_cells, int* __restrict__ size, int32_t* __restrict__ volumes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && volumes) volumes[0] = 0;
+  if (i >= n_roots) return;
+  const int sz = (int)(n_cells - (int64_t)(keys[i] >> 32));
+  size[vals[i]] = i + 1;
+  if (volumes) volumes[i + 1] = sz;
+}
+
+__global__ void __launch_bounds__(256)
+ccl_relabel_kernel(const int* __restrict__ parent, const int* __restrict__ rootlabel, int64_t n_cells, int32_t* __restrict__ labels) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    const int r = parent[c];
+    labels[c] = r >= 0 ? rootlabel[r] : 0;
+  }
+}
+
+// ---- bulk insertion / map painting ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+insert_bulk_kernel(int64_t n_cells, int32_t* __restrict__ own, const int32_t* __restrict__ bulk_labels, int32_t bulklabel,
+                   uint8_t* __restrict__ member, int16_t* __restrict__ map16) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t o = own[c] > 0 ? own[c] + 1 : 0;
+    const bool mb = bulk_labels && bulk_labels[c] == bulklabel;
+    own[c] = o;
+    member[c] = mb ? 1 : 0;
+    map16[c] = (int16_t)(o > 0 ? o : (mb ? 1 : 0));  // later (higher) labels overwrite the bulk site
+  }
+}
+
+__global__ void __launch_bounds__(256)
+to_map16_kernel(int64_t n_cells, const int32_t* __restrict__ labels, int16_t* __restrict__ map16) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x)
+    map16[c] = (int16_t)labels[c];
+}
+
+// ---- site properties ---------------------------------------------------------------------------------
+// acc[label] = {count, sum rho, sum mx, sum my, sum mz} (pass 0) or {sum (rho-mean)^2} (pass 1).
+// Large sites (the bulk site, a solid blob) hold most cells: every thread keeps a running partial
+// for the label it saw last and for the bulk membership, and blocks reduce those before touching
+// the global accumulators, so the number of same-address atomics stays ~#blocks, not #cells.
+__device__ __forceinline__ void prop_flush(double* acc, int label, const double* v, int nv) {
+  if (label <= 0) return;
+  for (int q = 0; q < nv; ++q)
+    if (v[q] != 0.0) atomicAdd(acc + (int64_t)label * 5 + q, v[q]);
+}
+
+__device__ __forceinline__ void prop_block_flush(double* acc, int label, double* v, int nv, double (*s_red)[5]) {
+  // all threads of the block hold partials for the same label
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < nv; ++q) {
+    double x = v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    if (lane == 0) s_red[warp][q] = x;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nv) {
+    double x = 0;
+    for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
+    if (x != 0.0 && label > 0) atomicAdd(acc + (int64_t)label * 5 + threadIdx.x, x);
+  }
+  __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+site_prop_kernel(const double* __restrict__ density, const int32_t* __restrict__ own, const uint8_t* __restrict__ member,
+                 int64_t n_cells, int ny, int nz, const double* __restrict__ mx, const double* __restrict__ my,
+                 const double* __restrict__ mz, const double* __restrict__ mean, double* __restrict__ acc /*[n_labels][5]*/) {
+  __shared__ double s_red[8][5];
+  constexpr int NV = PASS == 0 ? 5 : 1;
+  double b[5] = {0, 0, 0, 0, 0};  // partial of the bulk membership (label 1)
+  double a[5] = {0, 0, 0, 0, 0};  // partial of the run of `cur` labels
+  int cur = 0;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    const int o = own[c];
+    const bool mb = member && member[c];
+    if (o <= 0 && !mb) continue;
+    const double rho = density[c];
+    const int k = (int)(c % nz);
+    const int64_t r = c / nz;
+    const int j = (int)(r % ny);
+    const int i = (int)(r / ny);
+    if (o > 0) {
+      if (o != cur) {
+        prop_flush(acc, cur, a, NV);
+        for (int q = 0; q < 5; ++q) a[q] = 0;
+        cur = o;
+      }
+      if (PASS == 0) { a[0] += 1.0; a[1] += rho; a[2] += mx[i]; a[3] += my[j]; a[4] += mz[k]; }
+      else { const double d = rho - mean[o]; a[0] += d * d; }
+    }
+    if (mb) {
+      if (PASS == 0) { b[0] += 1.0; b[1] += rho; b[2] += mx[i]; b[3] += my[j]; b[4] += mz[k]; }
+      else { const double d = rho - mean[1]; b[0] += d * d; }
+    }
+  }
+  // own-label partials: one block-level flush when the whole block ended on the same label
+  const int first = __shfl_sync(kFull, cur, 0);
+  __shared__ int s_first;
+  if (threadIdx.x == 0) s_first = first;
+  __syncthreads();
+  const int uniform = __syncthreads_and(cur == s_first || cur == 0);
+  if (uniform) {
+    if (cur == 0) for (int q = 0; q < 5; ++q) a[q] = 0;
+    prop_block_flush(acc, s_first, a, NV, s_red);
+  } else {
+    prop_flush(acc, cur, a, NV);
+  }
+  if (member) prop_block_flush(acc, 1, b, NV, s_red);
+}
+
+__global__ void site_prop_mean_kernel(const double* __restrict__ acc, int n_labels, double* __restrict__ mean) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_labels) return;
+  const double n = acc[(int64_t)l * 5];
+  mean[l] = n > 0 ? acc[(int64_t)l * 5 + 1] / n : 0.0;
+}
+
+__global__ void site_prop_final_kernel(const double* __restrict__ acc0, const double* __restrict__ acc1, int n_labels,
+                                       int64_t* __restrict__ out_count, double* __restrict__ out_mean,
+                                       double* __restrict__ out_std, double* __restrict__ out_center) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_labels) return;
+  const double n = acc0[(int64_t)l * 5];
+  out_count[l] = (int64_t)n;
+  if (n > 0) {
+    out_mean[l] = acc0[(int64_t)l * 5 + 1] / n;
+    out_std[l] = sqrt(acc1[(int64_t)l * 5] / n);
+    for (int q = 0; q < 3; ++q) out_center[l * 3 + q] = acc0[(int64_t)l * 5 + 2 + q] / n;
+  } else {
+    out_mean[l] = 0; out_std[l] = 0;
+    for (int q = 0; q < 3; ++q) out_center[l * 3 + q] = 0;
+  }
+}
+
+// ---- cell lists ----------------------------------------------------------------------------------------
+// entry flags: cell c contributes (own[c] > 0) + (member[c] != 0) entries
+__global__ void __launch_bounds__(256)
+cells_count_kernel(int64_t n_cells, const int32_t* __restrict__ own, const uint8_t* __restrict__ member, uint32_t* __restrict__ cnt) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x)
+    cnt[c] = (own[c] > 0 ? 1u : 0u) + ((member && member[c]) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256)
+cells_emit_kernel(int64_t n_cells, const int32_t* __restrict__ own, const uint8_t* __restrict__ member,
+                  const uint32_t* __restrict__ pos, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t p = pos[c];
+    if (member && member[c]) { keys[p] = 1; vals[p] = (uint32_t)c; ++p; }
+    if (own[c] > 0) { keys[p] = (uint64_t)own[c]; vals[p] = (uint32_t)c; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cells_offsets_kernel(const uint64_t* __restrict__ keys, int64_t n, int n_labels, int64_t* __restrict__ offsets) {
+  // offsets[l] = first index with key >= l  (keys sorted ascending)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lo = i == 0 ? 0 : (int64_t)keys[i - 1] + 1;
+    const int64_t hi = i == n ? n_labels : (int64_t)keys[i];
+    for (int64_t l = lo; l <= hi; ++l) offsets[l] = i;
+  }
+}
+
+__global__ void __launch_bounds__(256) copy_u32_to_i32_kernel(const uint32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density, double threshold,
+                     int minsite, int32_t* labels, int32_t* n_sites, int32_t* volumes) {
+  HOPB_REQUIRE(h, density && labels && n_sites, "null argument");
+  HOPB_REQUIRE(h, nx > 0 && ny > 0 && nz > 0, "bad grid shape");
+  HOPB_REQUIRE(h, minsite == 1 || minsite == 2, "MINsite must be 1 or 2 (hop/sitemap.py:453-456)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_cells = (int64_t)nx * ny * nz;
+  HOPB_REQUIRE(h, n_cells < ((int64_t)1 << 31), "grid too large");
+  *n_sites = 0;
+  // scratch: parent[G], size[G] (slot 0); root keys/vals + counter (slot 1)
+  int* parent = nullptr;
+  int rc = hopb_scratch(h, 0, (size_t)n_cells * 2 * sizeof(int), (void**)&parent);
+  if (rc) return rc;
+  int* size = parent + n_cells;
+  const uint32_t cap = HOPB_MAX_SITES + 1;
+  unsigned char* rs = nullptr;
+  rc = hopb_scratch(h, 1, (size_t)cap * 2 * (sizeof(uint64_t) + sizeof(uint32_t)) + 64, (void**)&rs);
+  if (rc) return rc;
+  uint64_t* keys = (uint64_t*)rs;
+  uint64_t* keys_alt = keys + cap;
+  uint32_t* vals = (uint32_t*)(keys_alt + cap);
+  uint32_t* vals_alt = vals + cap;
+  uint32_t* n_roots_dev = vals_alt + cap;
+
+  HOPB_CUDA(h, cudaMemsetAsync(size, 0, (size_t)n_cells * sizeof(int), s));
+  HOPB_CUDA(h, cudaMemsetAsync(n_roots_dev, 0, sizeof(uint32_t), s));
+  const int64_t n_rows = (int64_t)nx * ny;
+  ccl_rows_kernel<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 8), 256, 0, s>>>(density, threshold, n_rows, nz, parent);
+  const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 8);
+  ccl_merge_kernel<<<gcells, 256, 0, s>>>(parent, nx, ny, nz);
+  ccl_flatten_kernel<<<gcells, 256, 0, s>>>(parent, n_cells);
+  ccl_size_kernel<<<gcells, 256, 0, s>>>(parent, n_cells, size);
+  ccl_roots_kernel<<<gcells, 256, 0, s>>>(parent, size, n_cells, minsite, keys, vals, cap, n_roots_dev);
+  HOPB_LAUNCH_CHECK(h);
+  uint32_t n_roots = 0;
+  HOPB_CUDA(h, cudaMemcpyAsync(&n_roots, n_roots_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  HOPB_CUDA(h, cudaStreamSynchronize(s));
+  if (n_roots > HOPB_MAX_SITES) {
+    *n_sites = (int32_t)n_roots;
+    return hopb_fail(h, HOPB_E_TOO_MANY_SITES,
+                     "map_sites: %u sites at this threshold; hop's int16 site map holds at most %d", n_roots, HOPB_MAX_SITES);
+  }
+  int in_alt = 0;
+  const int bits = hopb_bits_for((uint64_t)n_cells);
+  // low word uses `bits` bits, high word starts at bit 32
+  rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, n_roots, 0, bits, &in_alt);
+  if (rc) return rc;
+  uint64_t* k1 = in_alt ? keys_alt : keys; uint64_t* k1a = in_alt ? keys : keys_alt;
+  uint32_t* v1 = in_alt ? vals_alt : vals; uint32_t* v1a = in_alt ? vals : vals_alt;
+  int in_alt2 = 0;
+  rc = hopb_radix_sort_pairs(h, s, k1, k1a, v1, v1a, n_roots, 32, 32 + bits, &in_alt2);
+  if (rc) return rc;
+  const uint64_t* kf = in_alt2 ? k1a : k1;
+  const uint32_t* vf = in_alt2 ? v1a : v1;
+  ccl_assign_kernel<<<(n_roots + 256) / 256, 256, 0, s>>>(kf, vf, (int)n_roots, n_cells, size, volumes);
+  ccl_relabel_kernel<<<gcells, 256, 0, s>>>(parent, size, n_cells, labels);
+  HOPB_LAUNCH_CHECK(h);
+  *n_sites = (int32_t)n_roots;
+  return HOPB_OK;
+}
+
+int hopb_insert_bulk(hopb_handle* h, void* stream, int64_t n_cells, int32_t* own, const int32_t* bulk_labels,
+                     int32_t bulklabel, uint8_t* member, int16_t* map16) {
+  HOPB_REQUIRE(h, own && member && map16 && n_cells > 0, "null argument");
+  insert_bulk_kernel<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+      n_cells, own, bulk_labels, bulklabel, member, map16);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_labels_to_map16(hopb_handle* h, void* stream, int64_t n_cells, const int32_t* labels, int16_t* map16) {
+  HOPB_REQUIRE(h, labels && map16 && n_cells > 0, "null argument");
+  to_map16_kernel<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(n_cells, labels, map16);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_site_properties(hopb_handle* h, void* stream, const hopb_grid* g, const double* density, const int32_t* own,
+                         const uint8_t* member, int n_labels, int64_t* out_count, double* out_mean, double* out_std,
+                         double* out_center) {
+  HOPB_REQUIRE(h, g && density && own && out_count && out_mean && out_std && out_center, "null argument");
+  HOPB_REQUIRE(h, n_labels >= 1 && n_labels <= HOPB_MAX_SITES + 2, "bad n_labels");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_cells = (int64_t)g->n[0] * g->n[1] * g->n[2];
+  double* acc = nullptr;
+  int rc = hopb_scratch(h, 2, (size_t)n_labels * 11 * sizeof(double), (void**)&acc);
+  if (rc) return rc;
+  double* acc1 = acc + (size_t)n_labels * 5;
+  double* mean = acc1 + (size_t)n_labels * 5;
+  HOPB_CUDA(h, cudaMemsetAsync(acc, 0, (size_t)n_labels * 10 * sizeof(double), s));
+  const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 4);
+  site_prop_kernel<0><<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
+                                            g->d_mid[2], nullptr, acc);
+  site_prop_mean_kernel<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, n_labels, mean);
+  site_prop_kernel<1><<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
+                                            g->d_mid[2], mean, acc1);
+  site_prop_final_kernel<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, acc1, n_labels, out_count, out_mean, out_std, out_center);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const int32_t* own, const uint8_t* member,
+                    int n_labels, int32_t* cells, int64_t capacity, int64_t* offsets, int64_t* n_cells_out) {
+  HOPB_REQUIRE(h, own && offsets && n_cells_out && n_labels >= 1, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* pos = nullptr;
+  int rc = hopb_scratch(h, 3, ((size_t)n_grid_cells + 4) * sizeof(uint32_t), (void**)&pos);
+  if (rc) return rc;
+  uint32_t* total_dev = pos + n_grid_cells;
+  const unsigned gcells = hopb_grid_for(n_grid_cells, 256, h->num_sms, 8);
+  cells_count_kernel<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos);
+  rc = hopb_exclusive_scan_u32(h, s, pos, pos, n_grid_cells, total_dev);
+  if (rc) return rc;
+  uint32_t total = 0;
+  HOPB_CUDA(h, cudaMemcpyAsync(&total, total_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  HOPB_CUDA(h, cudaStreamSynchronize(s));
+  *n_cells_out = (int64_t)total;
+  if ((int64_t)total > capacity || (total > 0 && !cells))
+    return hopb_fail(h, HOPB_E_CAPACITY, "hopb_site_cells: need room for %u cells", total);
+  unsigned char* kv = nullptr;
+  rc = hopb_scratch(h, 4, ((size_t)total + 1) * 2 * (sizeof(uint64_t) + sizeof(uint32_t)), (void**)&kv);
+  if (rc) return rc;
+  uint64_t* keys = (uint64_t*)kv;
+  uint64_t* keys_alt = keys + total + 1;
+  uint32_t* vals = (uint32_t*)(keys_alt + total + 1);
+  uint32_t* vals_alt = vals + total + 1;
+  cells_emit_kernel<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos, keys, vals);
+  int in_alt = 0;
+  rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, total, 0, hopb_bits_for((uint64_t)n_labels), &in_alt);
+  if (rc) return rc;
+  const uint64_t* kf = in_alt ? keys_alt : keys;
+  const uint32_t* vf = in_alt ? vals_alt : vals;
+  cells_offsets_kernel<<<hopb_grid_for((int64_t)total + 1, 256, h->num_sms, 8), 256, 0, s>>>(kf, (int64_t)total, n_labels, offsets);
+  if (total > 0)
+    copy_u32_to_i32_kernel<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(vf, cells, (int64_t)total);
+  HOPB_LAUNCH_CHECK(h);
+  HOPB_CUDA(h, cudaStreamSynchronize(s));
+  return HOPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""Stage 4: transitions between sites -- drop-in for hop.graph.TransportNetwork.
+
+``TransportNetwork._analyze_hops`` (hop/graph.py:156-288) runs a per-atom state machine over the x
+column of the hopping trajectory with two nested Python loops; here the same machine runs on the
+GPU (csrc/hoptraj.cu, csrc/hopb_machine.h), the events are sorted on the device into the
+reference's emission order (csrc/events.cu) and come back as the ``graph_properties`` dictionary:
+edge tuple ``(i, j)`` or node ``i`` -> ``{'tau', 'tbarrier', 'frame', 'iatom'}`` arrays, times in ps.
+The transition-count matrix is ``len(tau)`` per edge.
+
+``HoppingGraph`` here is the container the network hands its results to (graph, properties,
+trjdata, site_properties); the rate fits of hop.graph.HoppingGraph (hop/graph.py:1677-1748) are a
+"next" row of the scope table.
+"""
+from __future__ import annotations
+
+import logging
+import pickle
+
+import numpy
+
+from . import sitemap, trajectory
+from .constants import SITELABEL
+
+logger = logging.getLogger("MDAnalysis.app.hop.graph")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class TransportNetwork(object):
+    """A framework for computing graphs from hopping trajectories; the unit of time is ps
+    (hop/graph.py:72-105)."""
+
+    def __init__(self, traj, density=None, sitelabels=None):
+        import networkx as NX
+
+        self._cache = dict()
+        if not isinstance(traj, trajectory.HoppingTrajectory):
+            errmsg = "'traj' must be a <hop.trajectory.HoppingTrajectory> instance."
+            logger.fatal(errmsg)
+            raise TypeError(errmsg)
+        self.traj = traj
+        if traj.hoptraj is not None:
+            self.n_atoms = traj.hoptraj.n_atoms
+            self.dt = traj.hoptraj.dt
+        else:
+            self.n_atoms = len(traj.tgroup)
+            self.dt = traj.traj.dt
+        self.totaltime = self.traj.totaltime
+        self.graph = NX.DiGraph(name='Transport network between sites')
+        if density is not None and not isinstance(density, sitemap.Density):
+            raise TypeError('density must be a <hop.sitemap.Density> instance.')
+        self.density = density
+        if sitelabels:
+            self._cache['sitelabels'] = sitelabels
+
+    # ---- labels on the device ---------------------------------------------------------------------------
+    def _hop_x_device(self):
+        """x column of the hoptraj as CUDA float32 [F][N]."""
+        t = _torch()
+        if self.traj.hoptraj is not None:
+            x = self.traj.hoptraj.plane_array(0)
+        else:
+            x, _ = self.traj.hop_arrays()
+        return t.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).cuda()
+
+    def _n_labels(self, hx):
+        try:
+            n = self.density._n_labels
+            if n is not None:
+                return int(n)
+        except AttributeError:
+            pass
+        return int(hx.max().item()) + 1
+
+    def graph_alltransitions(self):
+        """Graph with one edge for each (label[t-1] -> label[t]) pair observed, interstitial and
+        outliers included (hop/graph.py:107-135)."""
+        import networkx as NX
+
+        from . import kernels as K
+
+        self.graph = NX.DiGraph(name="Transitions between all sites, including interstitial and outliers")
+        hx = self._hop_x_device()
+        pairs = K.all_transitions(hx, self._n_labels(hx))
+        self.graph.add_edges_from((int(a), int(b)) for a, b in pairs)
+        self._cache['sitelabels'] = sorted(self.graph.nodes())
+
+    def HoppingGraph(self, verbosity=3):
+        """Compute the HoppingGraph from the data and return it."""
+        self.compute_residency_times(verbosity)
+        return self.hopgraph
+
+    def compute_residency_times(self, verbosity=3):
+        self._analyze_hops(verbosity=verbosity)
+        try:
+            site_properties = self.density.site_properties
+        except AttributeError:
+            site_properties = None
+        self.hopgraph = HoppingGraph(self.graph, self.graph_properties,
+                                     trjdata={'dt': self.dt, 'totaltime': self.totaltime, 'time_unit': 'ps'},
+                                     site_properties=site_properties)
+
+    def _analyze_hops(self, verbosity=0):
+        """Waiting times tau_ji for hops i->j (hop/graph.py:156-288).
+
+        self.graph: directed graph of all transitions; self.graph_properties: per edge (i,j) the
+        arrays tau, tbarrier (ps), frame and iatom in emission order, plus per node the residual
+        residency of atoms still assigned to it at the last frame (tbarrier None)."""
+        import networkx as NX
+
+        from . import kernels as K
+
+        try:
+            if len(self._cache['sitelabels']) < 3:
+                errmsg = 'TransportNetwork: Need at least 2 sites to analyze transitions: N=%d' % \
+                         len(self._cache['sitelabels'])
+                logger.error(errmsg)
+                raise ValueError(errmsg)
+        except KeyError:
+            pass
+        self.graph = NX.DiGraph()
+        self.graph.name = "Transitions between sites"
+        self.graph_properties = dict()
+
+        cached = getattr(self.traj, "_events_cache", None)
+        if cached is not None:
+            events, n_ev, state = cached       # produced by the fused hoptraj pass
+            F = self.traj.n_frames
+            n_labels = self._n_labels(None) if self.density is not None else None
+            if n_labels is None:
+                hx = self._hop_x_device()
+                n_labels = self._n_labels(hx)
+        else:
+            hx = self._hop_x_device()
+            F, N = int(hx.shape[0]), int(hx.shape[1])
+            n_labels = self._n_labels(hx)
+            n_chunks, chunk_len = K.plan_chunks(F, N)
+            events = K.EventBuffer(max(1 << 16, (F * N) // 8), hx.device)
+            for attempt in range(2):
+                s = K.hopscan_labels(hx, 0, n_chunks, chunk_len, events)
+                state = K.new_state(N, hx.device)
+                K.hop_advance(None, state, init=True)
+                K.hop_fixup(s, chunk_len, F, state, None, events)
+                n_ev = events.n()
+                if n_ev <= events.capacity:
+                    break
+                events = K.EventBuffer(n_ev, hx.device)
+        ev, e_s0, e_s, e_start, e_count = K.events_finalize(events, n_ev, self.n_atoms, F, n_labels)
+        ev = K.events_to_numpy(ev)
+        e_s0 = e_s0.cpu().numpy()
+        e_s = e_s.cpu().numpy()
+        e_start = e_start.cpu().numpy()
+        e_count = e_count.cpu().numpy()
+        # edges enter the graph in order of first occurrence, like the reference's add_edge calls
+        first = numpy.array([(ev['frame'][s], ev['iatom'][s]) for s in e_start], dtype=numpy.int64).reshape(-1, 2)
+        order = numpy.lexsort((first[:, 1], first[:, 0])) if len(first) else []
+        for k in order:
+            a, b, s, c = int(e_s0[k]), int(e_s[k]), int(e_start[k]), int(e_count[k])
+            seg = ev[s:s + c]
+            self.graph.add_edge(a, b)
+            self.graph_properties[(a, b)] = {
+                'tau': self.dt * seg['tau'].astype(numpy.int64),
+                'tbarrier': self.dt * seg['tbarrier'].astype(numpy.int64),
+                'frame': seg['frame'].astype(numpy.int64),
+                'iatom': seg['iatom'].astype(numpy.int64)}
+        # mop up: atoms still assigned to a site at the last frame (hop/graph.py:259-274)
+        st = state.cpu().numpy()
+        last = F - 1
+        ia = numpy.nonzero(st[0] != SITELABEL['interstitial'])[0]
+        for node in numpy.unique(st[0][ia]) if len(ia) else []:
+            sel = ia[st[0][ia] == node]
+            self.graph.add_node(int(node))
+            self.graph_properties[int(node)] = {
+                'tau': self.dt * (last - st[1][sel]).astype(numpy.int64),
+                'tbarrier': numpy.array([None] * len(sel)),
+                'frame': numpy.full(len(sel), last, dtype=numpy.int64),
+                'iatom': sel.astype(numpy.int64)}
+        if 'sitelabels' not in self._cache:
+            self._cache['sitelabels'] = sorted(self.graph.nodes())
+
+    def transition_counts(self):
+        """{(i, j): N_ij} -- the transition-count matrix in sparse form (len(tau) per edge)."""
+        return {k: len(v['tau']) for k, v in self.graph_properties.items() if isinstance(k, tuple)}
+
+
+class HoppingGraph(object):
+    """Container for the hopping graph that TransportNetwork produces (hop/graph.py:492-612):
+    ``graph`` (networkx.DiGraph), ``properties`` (per edge/node event arrays), ``trjdata`` and
+    ``site_properties``.  ``number_of_hops(i, j)`` is the transition count N_ij."""
+
+    def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None):
+        if graph is not None and properties is not None:
+            self.graph = graph
+            self.properties = properties
+            self.trjdata = trjdata
+            self.site_properties = site_properties
+        elif filename is not None:
+            self.load(filename)
+        else:
+            raise ValueError('Either a graph and properties or a filename is required.')
+
+    def number_of_hops(self, i, j):
+        return len(self.properties[(i, j)]['tau'])
+
+    def waitingtimes(self, i, j):
+        return self.properties[(i, j)]['tau']
+
+    def barriertimes(self, i, j):
+        return self.properties[(i, j)]['tbarrier']
+
+    def filename(self, filename=None, ext=None, set_default=False, use_my_ext=False):
+        from .utilities import filename_function
+
+        return filename_function(self, filename, ext, set_default, use_my_ext)
+
+    def save(self, filename=None):
+        """Save the graph, its properties, trjdata and site_properties as one pickle (hop/graph.py:760-767)."""
+        data = {'graph': self.graph, 'properties': self.properties, 'trjdata': self.trjdata,
+                'site_properties': self.site_properties}
+        with open(self.filename(filename, 'pickle', set_default=True), 'wb') as fh:
+            pickle.dump(data, fh, pickle.HIGHEST_PROTOCOL)
+
+    def load(self, filename=None):
+        with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
+            data = pickle.load(fh)
+        self.graph = data['graph']
+        self.properties = data['properties']
+        self.trjdata = data.get('trjdata')
+        self.site_properties = data.get('site_properties')

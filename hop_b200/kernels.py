@@ -1,0 +1,310 @@
+"""Thin functional layer over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function here enqueues hand-written sm_100a kernels from libhopb200.so on torch's current
+stream.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SUMMARY_INTS, STATE_INTS, HOPB_MAX_SITES
+
+EVENT_DTYPE = np.dtype([("frame", "<i4"), ("iatom", "<i4"), ("s0", "<i4"), ("s", "<i4"),
+                        ("tau", "<i4"), ("tbarrier", "<i4")])
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _h(t=None):
+    return _lib.handle(t.device.index if t is not None else None)
+
+
+def _cuda(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+class GridTables:
+    """Device-side binning tables for one set of bin edges (hopb_grid)."""
+
+    def __init__(self, edges, device=None):
+        self.edges = [np.ascontiguousarray(e, dtype=np.float64) for e in edges]
+        if len(self.edges) != 3:
+            raise ValueError("need three edge arrays")
+        self.shape = tuple(len(e) - 1 for e in self.edges)
+        self.n_cells = int(np.prod(self.shape))
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._handle = _lib.handle(self.device.index)
+        # `decimal` of hop/trajectory.py:435, computed with numpy exactly like the reference
+        decs = np.array([int(-np.log10(np.diff(e).min())) + 6 for e in self.edges], dtype=np.int32)
+        out = ctypes.c_void_p()
+        e = self.edges
+        rc = _lib.lib().hopb_grid_create(self._handle, e[0].ctypes.data, self.shape[0], e[1].ctypes.data, self.shape[1],
+                                         e[2].ctypes.data, self.shape[2], decs.ctypes.data, ctypes.byref(out))
+        _lib.check(self._handle, rc)
+        self._grid = out
+
+    @property
+    def ptr(self):
+        return self._grid
+
+    def __del__(self):
+        try:
+            if getattr(self, "_grid", None):
+                _lib.lib().hopb_grid_destroy(self._grid)
+                self._grid = None
+        except Exception:
+            pass
+
+
+def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor):
+    """counts[cell] += points per cell (hop/density.py:125-131).  xyz: float32 [..., 3]."""
+    _cuda(xyz, torch.float32, "xyz")
+    _cuda(counts, torch.int32, "counts")
+    if counts.numel() != grid.n_cells:
+        raise ValueError("counts has the wrong size")
+    n_points = xyz.numel() // 3
+    h = _h(xyz)
+    _lib.check(h, _lib.lib().hopb_hist_accumulate(h, _stream(), grid.ptr, _p(xyz), n_points, _p(counts)))
+    return counts
+
+
+def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
+    _cuda(counts, torch.int32, "counts")
+    if out is None:
+        out = torch.empty(grid.shape, dtype=torch.float64, device=counts.device)
+    h = _h(counts)
+    _lib.check(h, _lib.lib().hopb_density_from_counts(h, _stream(), grid.ptr, _p(counts), int(n_frames), float(factor), _p(out)))
+    return out
+
+
+def label_sites(density: torch.Tensor, threshold: float, minsite: int = 1):
+    """(labels int32 [nx,ny,nz], n_sites, volumes int32[n_sites+1]) -- Density.map_sites."""
+    _cuda(density, torch.float64, "density")
+    if density.dim() != 3:
+        raise ValueError("density must be 3-dimensional")
+    nx, ny, nz = density.shape
+    labels = torch.empty(density.shape, dtype=torch.int32, device=density.device)
+    volumes = torch.zeros(HOPB_MAX_SITES + 1, dtype=torch.int32, device=density.device)
+    n_sites = ctypes.c_int32(0)
+    h = _h(density)
+    rc = _lib.lib().hopb_label_sites(h, _stream(), nx, ny, nz, _p(density), float(threshold), int(minsite), _p(labels),
+                                     ctypes.byref(n_sites), _p(volumes))
+    _lib.check(h, rc)
+    return labels, int(n_sites.value), volumes[: n_sites.value + 1]
+
+
+def insert_bulk(own: torch.Tensor, bulk_labels, bulklabel: int = 1):
+    """In place on `own`; returns (member uint8, map16 int16)."""
+    _cuda(own, torch.int32, "own")
+    if bulk_labels is not None:
+        _cuda(bulk_labels, torch.int32, "bulk_labels")
+        if bulk_labels.shape != own.shape:
+            raise ValueError("The bulk density was defined on a different grid than this density.")
+    member = torch.empty(own.shape, dtype=torch.uint8, device=own.device)
+    map16 = torch.empty(own.shape, dtype=torch.int16, device=own.device)
+    h = _h(own)
+    _lib.check(h, _lib.lib().hopb_insert_bulk(h, _stream(), own.numel(), _p(own), _p(bulk_labels), int(bulklabel), _p(member), _p(map16)))
+    return member, map16
+
+
+def labels_to_map16(labels: torch.Tensor):
+    _cuda(labels, torch.int32, "labels")
+    map16 = torch.empty(labels.shape, dtype=torch.int16, device=labels.device)
+    h = _h(labels)
+    _lib.check(h, _lib.lib().hopb_labels_to_map16(h, _stream(), labels.numel(), _p(labels), _p(map16)))
+    return map16
+
+
+def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, member, n_labels: int):
+    """(count int64[n], mean f64[n], std f64[n], center f64[n,3]) per site label."""
+    _cuda(density, torch.float64, "density")
+    _cuda(own, torch.int32, "own")
+    dev = density.device
+    count = torch.empty(n_labels, dtype=torch.int64, device=dev)
+    mean = torch.empty(n_labels, dtype=torch.float64, device=dev)
+    std = torch.empty(n_labels, dtype=torch.float64, device=dev)
+    center = torch.empty((n_labels, 3), dtype=torch.float64, device=dev)
+    h = _h(density)
+    _lib.check(h, _lib.lib().hopb_site_properties(h, _stream(), grid.ptr, _p(density), _p(own), _p(member), int(n_labels),
+                                                  _p(count), _p(mean), _p(std), _p(center)))
+    return count, mean, std, center
+
+
+def site_cells(own: torch.Tensor, member, n_labels: int):
+    """CSR cell lists: (cells int32[M], offsets int64[n_labels+1])."""
+    _cuda(own, torch.int32, "own")
+    dev = own.device
+    offsets = torch.empty(n_labels + 1, dtype=torch.int64, device=dev)
+    n_cells = ctypes.c_int64(0)
+    h = _h(own)
+    capacity = 0
+    cells = None
+    for _ in range(2):
+        rc = _lib.lib().hopb_site_cells(h, _stream(), own.numel(), _p(own), _p(member), int(n_labels), _p(cells), capacity,
+                                        _p(offsets), ctypes.byref(n_cells))
+        if rc == _lib.HOPB_E_CAPACITY:
+            capacity = int(n_cells.value)
+            cells = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+            continue
+        _lib.check(h, rc)
+        break
+    if cells is None:
+        cells = torch.empty(0, dtype=torch.int32, device=dev)
+    return cells[: n_cells.value], offsets
+
+
+def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32):
+    """(n_chunks, chunk_len): enough (atom, chunk) threads to fill the GPU, chunks >= min_chunk frames."""
+    target_threads = num_sms * 2048
+    want = max(1, -(-target_threads // max(n_atoms, 1)))
+    max_chunks = max(1, n_frames // min_chunk)
+    n_chunks = max(1, min(want, max_chunks, 65535))
+    chunk_len = -(-n_frames // n_chunks)
+    n_chunks = -(-n_frames // chunk_len)
+    return int(n_chunks), int(chunk_len)
+
+
+class EventBuffer:
+    """Device buffer of hopb_event records plus the running device-side count."""
+
+    def __init__(self, capacity: int, device):
+        self.capacity = int(capacity)
+        self.data = torch.empty((max(self.capacity, 1), 6), dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def reset(self):
+        self.count.zero_()
+
+    def n(self):
+        return int(self.count.item())
+
+
+def hoptraj(grid: GridTables, xyz: torch.Tensor, map16: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
+            events: EventBuffer, hop_x=None, hop_y=None, summaries=None):
+    """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254)."""
+    _cuda(xyz, torch.float32, "xyz")
+    _cuda(map16, torch.int16, "map16")
+    F, N = xyz.shape[0], xyz.shape[1]
+    if map16.numel() != grid.n_cells:
+        raise ValueError("map does not match the grid")
+    dev = xyz.device
+    if summaries is None:
+        summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
+    h = _h(xyz)
+    rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(xyz), F, N, int(frame0), _p(map16), _p(hop_x), _p(hop_y),
+                                 int(n_chunks), int(chunk_len), _p(summaries), _p(events.data), _p(events.count),
+                                 events.capacity)
+    _lib.check(h, rc)
+    return summaries
+
+
+def hopscan_labels(hop_x: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int, events: EventBuffer, summaries=None):
+    _cuda(hop_x, torch.float32, "hop_x")
+    F, N = hop_x.shape
+    if summaries is None:
+        summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=hop_x.device)
+    h = _h(hop_x)
+    rc = _lib.lib().hopb_hopscan_labels(h, _stream(), _p(hop_x), F, N, int(frame0), int(n_chunks), int(chunk_len),
+                                        _p(summaries), _p(events.data), _p(events.count), events.capacity)
+    _lib.check(h, rc)
+    return summaries
+
+
+def hop_combine(summaries: torch.Tensor, chunk_len: int, n_frames: int):
+    n_chunks, _, N = summaries.shape
+    slab = torch.empty((SUMMARY_INTS, N), dtype=torch.int32, device=summaries.device)
+    h = _h(summaries)
+    _lib.check(h, _lib.lib().hopb_hop_combine(h, _stream(), N, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(slab)))
+    return slab
+
+
+def hop_advance(summaries, state: torch.Tensor, init: bool):
+    N = state.shape[1]
+    n = 0 if summaries is None else summaries.shape[0]
+    h = _h(state)
+    _lib.check(h, _lib.lib().hopb_hop_advance(h, _stream(), N, n, _p(summaries), 1 if init else 0, _p(state)))
+    return state
+
+
+def hop_fixup(summaries: torch.Tensor, chunk_len: int, n_frames: int, state: torch.Tensor, hop_y, events: EventBuffer):
+    n_chunks, _, N = summaries.shape
+    h = _h(summaries)
+    rc = _lib.lib().hopb_hop_fixup(h, _stream(), N, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(state),
+                                   _p(hop_y), _p(events.data), _p(events.count), events.capacity)
+    _lib.check(h, rc)
+    return state
+
+
+def new_state(n_atoms: int, device):
+    return torch.zeros((STATE_INTS, n_atoms), dtype=torch.int32, device=device)
+
+
+def events_finalize(events: EventBuffer, n_events: int, n_atoms: int, n_frames_total: int, n_labels: int):
+    """Sort events into reference order; returns (sorted [n,6] int32, edge_s0, edge_s, edge_start, edge_count)."""
+    dev = events.data.device
+    n = int(n_events)
+    sorted_ev = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
+    cap_edges = max(1, min(n, (n_labels + 1) ** 2))
+    e_s0 = torch.empty(cap_edges, dtype=torch.int32, device=dev)
+    e_s = torch.empty(cap_edges, dtype=torch.int32, device=dev)
+    e_start = torch.empty(cap_edges, dtype=torch.int64, device=dev)
+    e_count = torch.empty(cap_edges, dtype=torch.int64, device=dev)
+    n_edges = ctypes.c_int64(0)
+    h = _h(events.data)
+    rc = _lib.lib().hopb_events_finalize(h, _stream(), _p(events.data), n, int(n_atoms), int(n_frames_total), int(n_labels),
+                                         _p(sorted_ev), _p(e_s0), _p(e_s), _p(e_start), _p(e_count), ctypes.byref(n_edges))
+    _lib.check(h, rc)
+    k = int(n_edges.value)
+    return sorted_ev[:n], e_s0[:k], e_s[:k], e_start[:k], e_count[:k]
+
+
+def all_transitions(hop_x: torch.Tensor, n_labels: int):
+    """Sorted (K,2) int64 array of (label[t-1], label[t]) pairs (hop/graph.py:107-135)."""
+    _cuda(hop_x, torch.float32, "hop_x")
+    F, N = hop_x.shape
+    W = n_labels + 1
+    words = (W * W + 31) // 32
+    bitmap = torch.zeros(words, dtype=torch.int32, device=hop_x.device)
+    h = _h(hop_x)
+    _lib.check(h, _lib.lib().hopb_all_transitions(h, _stream(), _p(hop_x), F, N, int(n_labels), _p(bitmap)))
+    bits = np.unpackbits(bitmap.cpu().numpy().view(np.uint8), bitorder="little")[: W * W]
+    idx = np.nonzero(bits)[0]
+    return np.stack([idx // W - 1, idx % W - 1], axis=1).astype(np.int64)
+
+
+def synth_generate(params, frame_start=0, n_out=None, device=None, out=None):
+    """Device twin of hop_b200.synth.generate: float32 [n_out][N][3] in HBM."""
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    centres, half = params.lattice()
+    if n_out is None:
+        n_out = params.n_frames - frame_start
+    c = _lib.SynthParamsC(seed=params.seed, n_atoms=params.n_atoms, n_frames=params.n_frames,
+                          site_stride=params.site_stride, n_sites=len(centres), box=np.float32(params.box),
+                          cube_half=np.float32(half), sigma_site=np.float32(params.sigma_site),
+                          sigma_bulk=np.float32(params.sigma_bulk), p_hop=np.float32(params.p_hop),
+                          p_rebind=np.float32(params.p_rebind))
+    d_centres = torch.from_numpy(np.ascontiguousarray(centres)).to(dev)
+    if out is None:
+        out = torch.empty((n_out, params.n_atoms, 3), dtype=torch.float32, device=dev)
+    h = _lib.handle(dev.index)
+    rc = _lib.lib().hopb_synth_generate(h, _stream(), ctypes.byref(c), _p(d_centres), int(frame_start), int(n_out), _p(out))
+    _lib.check(h, rc)
+    torch.cuda.current_stream().synchronize()  # d_centres must outlive the kernel
+    return out
+
+
+def events_to_numpy(ev: torch.Tensor):
+    """[n,6] int32 device tensor -> structured numpy array (EVENT_DTYPE)."""
+    return np.ascontiguousarray(ev.cpu().numpy()).view(EVENT_DTYPE).reshape(-1)

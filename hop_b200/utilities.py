@@ -1,0 +1,177 @@
+"""Support code on the hot path: grid sizing, the pickle-based Saveable, small helpers.
+
+Mirrors the parts of hop/utilities.py that the four pipeline stages use
+(fixedwidth_bins 373-389, Saveable 119-261, filename_function 69-106, DefaultDict 754-760).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import warnings
+
+import numpy
+
+from .exceptions import MissingDataWarning
+
+
+def fixedwidth_bins(delta, xmin, xmax):
+    """Return bins of width delta that cover xmin,xmax (or a larger range).
+
+    dict = fixedwidth_bins(delta,xmin,xmax); keys 'Nbins', 'delta', 'min', 'max'
+    (hop/utilities.py:373-389).
+    """
+    if not numpy.all(xmin < xmax):
+        raise ValueError('Boundaries are not sane: should be xmin < xmax.')
+    _delta = numpy.asarray(delta, dtype=numpy.float64)
+    _xmin = numpy.asarray(xmin, dtype=numpy.float64)
+    _xmax = numpy.asarray(xmax, dtype=numpy.float64)
+    _length = _xmax - _xmin
+    N = numpy.ceil(_length / _delta).astype(numpy.int_)
+    dx = 0.5 * (N * _delta - _length)
+    return {'Nbins': N, 'delta': _delta, 'min': _xmin - dx, 'max': _xmax + dx}
+
+
+def filename_function(self, filename=None, ext=None, set_default=False, use_my_ext=False):
+    """Supply a file name for the object (hop/utilities.py:69-106)."""
+    if filename is None:
+        if not hasattr(self, '_filename'):
+            self._filename = None
+        if self._filename:
+            filename = self._filename
+        else:
+            raise ValueError("A file name is required because no default file name was defined.")
+        my_ext = None
+    else:
+        filename, my_ext = os.path.splitext(filename)
+        if set_default:
+            self._filename = filename
+    if my_ext and use_my_ext:
+        ext = my_ext
+    if ext is not None:
+        if ext.startswith('.'):
+            ext = ext[1:]
+        filename = filename + '.' + ext
+    return filename
+
+
+class DefaultDict(dict):
+    """Dictionary based on defaults and updated with keys/values from user."""
+
+    def __init__(self, defaultdict, userdict=None, **kwargs):
+        super(DefaultDict, self).__init__(**defaultdict)
+        if userdict is not None:
+            self.update(userdict)
+        self.update(kwargs)
+
+
+class Saveable(object):
+    """Baseclass that supports save()ing and load()ing of the attributes named in
+    ``_saved_attributes`` as one pickle (hop/utilities.py:119-261)."""
+
+    _saved_attributes = []
+    _merge_attributes = []
+    _excluded_attributes = []
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault('filename', None)
+        super(Saveable, self).__init__()
+        if kwargs['filename'] is not None:
+            self.load(kwargs['filename'], 'pickle')
+
+    def __getstate__(self):
+        if not self._saved_attributes:
+            warnings.warn("No data saved: the class declared empty '_saved_attributes'.")
+            return False
+        data = {}
+        if self._saved_attributes == 'all':
+            saved_attributes = [x for x in self.__dict__.keys() if x not in self._excluded_attributes]
+        else:
+            saved_attributes = self._saved_attributes
+        for attr in saved_attributes:
+            try:
+                data[attr] = self._get_saved_attribute(attr)
+            except (KeyError, AttributeError):
+                warnings.warn("Attribute '" + attr + "' has not been computed and will not be saved.",
+                              category=MissingDataWarning)
+        return data
+
+    def _get_saved_attribute(self, attr):
+        return self.__dict__[attr]
+
+    def __setstate__(self, data):
+        self.__dict__.update(data)
+
+    filename = filename_function
+
+    def save(self, filename=None):
+        """Save class to a pickled file."""
+        with open(self.filename(filename, 'pickle', set_default=True), 'wb') as fh:
+            pickle.dump(self, fh, pickle.HIGHEST_PROTOCOL)
+
+    def load(self, filename=None, merge=False):
+        """Reinstantiate class from a pickled file (produced with save())."""
+        with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
+            tmp = pickle.load(fh)
+        try:
+            data = tmp.__dict__
+        except AttributeError:
+            warnings.warn("Loading an old-style save file.", category=DeprecationWarning)
+            data = tmp
+            try:
+                data['P'] = data['parameters']
+            except KeyError:
+                pass
+        del tmp
+        if not self._saved_attributes:
+            warnings.warn("No data loaded: the object declared empty '_saved_attributes'.",
+                          category=MissingDataWarning)
+            return False
+        if self._saved_attributes == 'all':
+            saved_attributes = [x for x in data.keys() if x not in self._excluded_attributes]
+        else:
+            saved_attributes = self._saved_attributes
+        for attr in saved_attributes:
+            try:
+                if merge and attr in self._merge_attributes:
+                    self.__dict__[attr].update(data[attr])
+                else:
+                    self._set_loaded_attribute(attr, data[attr])
+            except KeyError:
+                warnings.warn("Expected attribute '" + attr + "' was not found in saved file '" + str(filename) + "'.",
+                              category=MissingDataWarning)
+        del data
+        return True
+
+    def _set_loaded_attribute(self, attr, value):
+        self.__dict__[attr] = value
+
+
+def iterable(obj):
+    """Returns True if obj can be iterated over and is NOT a string."""
+    if isinstance(obj, str):
+        return False
+    if hasattr(obj, 'next') or hasattr(obj, '__next__'):
+        return True
+    try:
+        len(obj)
+    except TypeError:
+        return False
+    return True
+
+
+def asiterable(obj):
+    """Return an object that is an iterable: object itself or wrapped in a list."""
+    if not iterable(obj):
+        obj = [obj]
+    return obj
+
+
+def flatten(l):
+    """Flatten nested lists/tuples into a flat list."""
+    out = []
+    for x in l:
+        if isinstance(x, (list, tuple)):
+            out.extend(flatten(x))
+        else:
+            out.append(x)
+    return out

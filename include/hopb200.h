@@ -1,0 +1,205 @@
+/* hopb200.h -- C ABI of libhopb200.so: the B200 (sm_100a) implementation of hop's trajectory hot path.
+ *
+ * Becksteinlab/hop is pure Python and has no FFI; the boundary this library replaces is the body
+ * of four Python methods.  Each entry point below names the reference code it stands in for
+ * (paths relative to the hop source tree).  INTEGRATION.md shows the ctypes binding a hop
+ * maintainer would add at those places.
+ *
+ * Conventions
+ *   - every pointer documented as "device" is a CUDA device pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr() or hopb_dev_alloc); "host" pointers are ordinary memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls only
+ *     enqueue work unless documented as synchronising;
+ *   - every function returns 0 on success or a negative HOPB_E_* code; the message for the last
+ *     error on a handle is hopb_last_error(h).  No C++ exception crosses this boundary;
+ *   - one handle per GPU and per host thread; handles own only scratch memory;
+ *   - grids are C-ordered [nx][ny][nz] (z fastest), coordinates are float32 [F][N][3] exactly as
+ *     MDAnalysis' `AtomGroup.positions` yields them frame by frame.
+ */
+#ifndef HOPB200_H
+#define HOPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOPB_OK 0
+#define HOPB_E_INVALID (-1)        /* bad argument */
+#define HOPB_E_CUDA (-2)           /* CUDA runtime error (see hopb_last_error) */
+#define HOPB_E_CAPACITY (-3)       /* event buffer too small; *n_events tells how many were produced */
+#define HOPB_E_TOO_MANY_SITES (-4) /* more than 32767 sites: not representable in hop's int16 map */
+#define HOPB_E_NOMEM (-5)
+
+#define HOPB_MAX_SITES 32767
+#define HOPB_SUMMARY_INTS 11 /* int32 per (chunk, atom) in a summary buffer [chunk][11][N] */
+#define HOPB_STATE_INTS 4    /* int32 per atom in a state buffer [4][N]: s0, t0, t1, on */
+
+typedef struct hopb_handle hopb_handle;
+typedef struct hopb_grid hopb_grid;
+
+/* One site-to-site transition; what TransportNetwork._analyze_hops appends to
+ * graph_properties[(s0, s)] (hop/graph.py:236-247).  Times are in frames. */
+typedef struct hopb_event {
+  int32_t frame;    /* frame at which site `s` was entered */
+  int32_t iatom;    /* index into the tracked atom group */
+  int32_t s0;       /* site left (may be -1: the reference's "(-1, N)" quirk, graph.py:217-221) */
+  int32_t s;        /* site entered */
+  int32_t tau;      /* t1 - t0: residence on s0 */
+  int32_t tbarrier; /* frame - t1: time spent in the interstitial */
+} hopb_event;
+
+/* ---- library / handle -------------------------------------------------------------------- */
+int hopb_version(void);
+int hopb_create(int device, hopb_handle** out);
+void hopb_destroy(hopb_handle* h);
+const char* hopb_last_error(const hopb_handle* h);
+
+/* Plain device-memory helpers so that a binding needs nothing but this library. */
+int hopb_dev_alloc(hopb_handle* h, uint64_t bytes, void** out);
+int hopb_dev_free(hopb_handle* h, void* p);
+int hopb_memset(hopb_handle* h, void* stream, void* dev, int value, uint64_t bytes);
+int hopb_h2d(hopb_handle* h, void* stream, void* dev, const void* host, uint64_t bytes);
+int hopb_d2h(hopb_handle* h, void* stream, void* host, const void* dev, uint64_t bytes);
+int hopb_stream_sync(hopb_handle* h, void* stream);
+
+/* ---- grid geometry ----------------------------------------------------------------------- */
+/* Bin edges as numpy.histogramdd returned them in DensityCollector.init_histogram
+ * (hop/density.py:99-117): three host float64 arrays with n+1 entries each.
+ * `decimals` (host int[3], may be NULL) are the rounding decimals of hop/trajectory.py:435
+ * computed by the caller; NULL lets the library compute int(-log10(min(diff(edges)))) + 6. */
+int hopb_grid_create(hopb_handle* h, const double* edges_x, int nx, const double* edges_y, int ny,
+                     const double* edges_z, int nz, const int* decimals, hopb_grid** out);
+void hopb_grid_destroy(hopb_grid* g);
+
+/* ---- stage 1: density ---------------------------------------------------------------------- */
+/* counts[cell] += number of points in the cell; replaces the per-frame
+ * `numpy.histogramdd(coord, bins, range)` + `grid += h` of DensityCollector.collect
+ * (hop/density.py:125-131).  xyz: device float32 [n_points][3] (any number of whole frames);
+ * counts: device uint32 [nx*ny*nz]. */
+int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
+                         int64_t n_points, uint32_t* counts);
+
+/* density = counts / n_frames / dx[i] / dy[j] / dz[k] * factor, in float64 and in exactly that
+ * order: DensityCollector.finish (hop/density.py:133-137), Grid.make_density
+ * (hop/sitemap.py:196-216), Grid.convert_density (hop/sitemap.py:236-264).  Pass factor = 1.0 for
+ * Angstrom^-3 (the multiplication is skipped, as in the reference).  density: device double [G]. */
+int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                             int64_t n_frames, double factor, double* density);
+
+/* ---- stage 2: site map --------------------------------------------------------------------- */
+/* Density.map_sites (hop/sitemap.py:480-521): mask = density >= threshold; connected components
+ * over the 7 forward offsets {0,1}^3 \ 0 and their negatives, no periodic wrap (_make_graph /
+ * _shell, sitemap.py:1496-1541); labels 1..S by volume descending, ties by larger minimum
+ * C-order cell index first (_label_connected_graphs, sitemap.py:1543-1571 with the canonical
+ * tie-break of SURVEY.md F4); minsite == 2 drops single-cell components.
+ *   labels   device int32 [G]  out: 0 = interstitial, 1..S
+ *   n_sites  host   int32      out: S
+ *   volumes  device int32 [HOPB_MAX_SITES+1] out (may be NULL): cells per label, volumes[0] = 0
+ * Synchronises the stream (S is needed on the host). */
+int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
+                     double threshold, int minsite, int32_t* labels, int32_t* n_sites, int32_t* volumes);
+
+/* Density.site_insert_bulk (hop/sitemap.py:877-918) on label grids: the cells with
+ * bulk_labels == bulklabel become site 1, every site of `labels` is shifted by +1 and overwrites
+ * the bulk where they overlap (_draw_map_from_sites, sitemap.py:1574-1587).
+ *   own      device int32 [G] in/out: hydration-site label of the cell after the shift, else 0
+ *   bulk_labels device int32 [G] (may be NULL = site_insert_nobulk, sitemap.py:933-943)
+ *   member   device uint8 [G] out: 1 where the cell belongs to the inserted bulk site
+ *   map16    device int16 [G] out: the painted map (what Density.map holds) */
+int hopb_insert_bulk(hopb_handle* h, void* stream, int64_t n_cells, int32_t* own,
+                     const int32_t* bulk_labels, int32_t bulklabel, uint8_t* member, int16_t* map16);
+
+/* int32 labels -> int16 map without a bulk site (plain map_sites result). */
+int hopb_labels_to_map16(hopb_handle* h, void* stream, int64_t n_cells, const int32_t* labels, int16_t* map16);
+
+/* Density._annotate_sites (hop/sitemap.py:1589-1612, 601-627): per site label the cell count,
+ * mean and population std of the density over the site's cells, and the mean cell midpoint.
+ * Membership: label own[c] (if > 0) and, where member[c] != 0, additionally label 1.
+ *   n_labels  number of labels including interstitial (len(sites))
+ *   out_count device int64 [n_labels]; out_mean, out_std device double [n_labels];
+ *   out_center device double [n_labels][3] (sum of midpoints / count; 0 for empty sites) */
+int hopb_site_properties(hopb_handle* h, void* stream, const hopb_grid* g, const double* density,
+                         const int32_t* own, const uint8_t* member, int n_labels, int64_t* out_count,
+                         double* out_mean, double* out_std, double* out_center);
+
+/* Cell lists (Density.sites) in CSR form, cells ascending within a site.
+ *   cells   device int32 [capacity]; offsets device int64 [n_labels+1]; n_cells host out.
+ * Returns HOPB_E_CAPACITY (with *n_cells set) if capacity is too small.  Synchronises. */
+int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const int32_t* own,
+                    const uint8_t* member, int n_labels, int32_t* cells, int64_t capacity,
+                    int64_t* offsets, int64_t* n_cells);
+
+/* ---- stage 3 + 4: hopping trajectory and transition scan ------------------------------------ */
+/* HoppingTrajectory._coord2hop (hop/trajectory.py:403-468) fused with the per-atom state machine
+ * of TransportNetwork._analyze_hops (hop/graph.py:212-254) over one slab of F frames.
+ * The slab is cut into n_chunks chunks of chunk_len frames (the last may be short); every
+ * (atom, chunk) runs independently and leaves a summary, hopb_hop_fixup stitches them.
+ *   xyz       device float32 [F][N][3]
+ *   map16     device int16 [G] (Density.map)
+ *   frame0    global frame number of the slab's first frame
+ *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
+ *             DCD, trajectory.py:456-463); either may be NULL
+ *   summaries device int32 [n_chunks][11][N] out
+ *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here) */
+int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t F, int64_t N,
+                 int64_t frame0, const int16_t* map16, float* hop_x, float* hop_y, int n_chunks,
+                 int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
+
+/* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
+ * hop/graph.py:190-254): labels = hop_x [F][N] float32. */
+int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N,
+                        int64_t frame0, int n_chunks, int64_t chunk_len, int32_t* summaries,
+                        hopb_event* events, uint64_t* n_events, uint64_t cap);
+
+/* Fold the chunk summaries of one slab into a single summary [11][N] (the message ranks exchange). */
+int hopb_hop_combine(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_t chunk_len, int64_t F,
+                     const int32_t* summaries, int32_t* slab_summary);
+
+/* state [4][N] (s0,t0,t1,on) <- apply n_summaries summaries [n][11][N] in order, no events.
+ * With init != 0 the state starts from the virgin state (start of the trajectory). */
+int hopb_hop_advance(hopb_handle* h, void* stream, int64_t N, int n_summaries, const int32_t* summaries,
+                     int init, int32_t* state);
+
+/* Stitch one slab: given the state at slab entry, emit the events the chunks left open, patch the
+ * inherited orbit prefix of every chunk in hop_y (may be NULL), and leave the state at slab exit in
+ * `state` (in/out, [4][N]). */
+int hopb_hop_fixup(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_t chunk_len, int64_t F,
+                   const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events,
+                   uint64_t* n_events, uint64_t cap);
+
+/* Sort events into the reference's emission order and count transitions.
+ * events_sorted is ordered by (s0, s) and within an edge by (frame, iatom) -- the order of the
+ * per-edge lists of hop/graph.py:236-247.  The COO transition-count matrix is
+ * (edge_s0[e], edge_s[e]) -> edge_count[e], with edge_start[e] the offset of the edge's first
+ * event.  All outputs device; edge arrays need capacity min(n, (n_labels+1)^2) entries.
+ * n_edges: host out.  Synchronises. */
+int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_event* events, uint64_t n, int64_t N,
+                         int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
+                         int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int64_t* n_edges);
+
+/* TransportNetwork.graph_alltransitions (hop/graph.py:107-135): bit (a+1)*(n_labels+1)+(b+1) of
+ * `bitmap` is set when some atom has label a in frame t-1 and b in frame t.
+ * bitmap: device uint32 [ceil((n_labels+1)^2 / 32)], OR-ed into (not cleared). */
+int hopb_all_transitions(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N,
+                         int n_labels, uint32_t* bitmap);
+
+/* ---- synthetic input (bench / tests) ------------------------------------------- */
+typedef struct hopb_synth_params {
+  uint64_t seed;
+  int64_t n_atoms, n_frames;
+  int32_t site_stride, n_sites;
+  float box, cube_half, sigma_site, sigma_bulk, p_hop, p_rebind;
+} hopb_synth_params;
+
+/* Writes frames [frame_start, frame_start+n_out) of the trajectory defined by `p` and the site
+ * centres (device float32 [n_sites][3]) into xyz (device float32 [n_out][N][3]).  Bit-identical to
+ * hop_b200/synth.py. */
+int hopb_synth_generate(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
+                        int64_t frame_start, int64_t n_out, float* xyz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPB200_H */

@@ -1,0 +1,322 @@
+"""Parity of every CUDA kernel (through the C ABI) against the CPU oracle.  Bit-exact unless stated."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import hop_oracle as O
+from hop_b200.synth import SynthParams, generate
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hop_b200 import kernels
+
+    return kernels
+
+
+@pytest.fixture(scope="module")
+def traj():
+    p = SynthParams(n_atoms=1000, n_frames=200)
+    return p, generate(p)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_synth_device_matches_host(K, traj):
+    p, xyz = traj
+    got = K.synth_generate(p).cpu().numpy()
+    assert got.shape == xyz.shape
+    assert np.array_equal(got.view(np.uint32), xyz.view(np.uint32))
+    tail = K.synth_generate(p, frame_start=150, n_out=20).cpu().numpy()
+    assert np.array_equal(tail, xyz[150:170])
+
+
+@pytest.mark.parametrize("delta", [1.0, 0.5])
+def test_histogram_counts(K, traj, delta):
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=delta)
+    ref = O.histogram_vectorised(xyz, edges)
+    g = K.GridTables(edges)
+    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    K.hist_accumulate(g, dev(xyz), counts)
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
+    # accumulate in two unaligned pieces (exercises the scalar lead/tail path)
+    counts.zero_()
+    flat = dev(xyz.reshape(-1, 3))
+    cut = 1000 * 77 + 3
+    K.hist_accumulate(g, flat[:cut], counts)
+    K.hist_accumulate(g, flat[cut:], counts)
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
+
+
+def test_histogram_edge_semantics(K):
+    rng = np.random.default_rng(3)
+    coords0 = (rng.random((300, 3)) * [17.3, 9.1, 23.7] - 1.9999).astype(np.float32)
+    _, _, edges = O.grid_geometry(coords0, delta=0.5)
+    from tests.test_machine_emul import adversarial_points
+
+    pts = adversarial_points(rng, edges, 50000)
+    pts = pts[~np.isnan(pts).any(axis=1)]
+    # include points exactly on the last edge when it is representable
+    ref = O.histogram_vectorised(pts[None], edges)
+    g = K.GridTables(edges)
+    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    K.hist_accumulate(g, dev(pts), counts)
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
+
+
+@pytest.mark.parametrize("unit", ["Angstrom^{-3}", "water", "TIP3P"])
+def test_density_normalisation_bit_exact(K, traj, unit):
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=1.0)
+    counts = O.histogram_vectorised(xyz, edges)
+    ref = O.make_density(counts, edges, xyz.shape[0], unit)
+    g = K.GridTables(edges)
+    factor = O.density_conversion_factor("Angstrom^{-3}", unit)
+    got = K.density_from_counts(g, dev(counts.astype(np.int32)), xyz.shape[0], factor).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def _check_labels(K, grid, thr, minsite=1):
+    sites, ref_map = O.map_sites(grid, thr, minsite)
+    labels, n_sites, volumes = K.label_sites(dev(grid), thr, minsite)
+    assert n_sites == len(sites) - 1
+    assert np.array_equal(labels.cpu().numpy(), ref_map.astype(np.int32))
+    assert np.array_equal(volumes.cpu().numpy(), np.array([len(s) for s in sites]))
+    return sites, labels
+
+
+@pytest.mark.parametrize("p_fill", [0.02, 0.1, 0.2, 0.35, 0.6, 0.95])
+@pytest.mark.parametrize("shape", [(24, 24, 24), (7, 33, 65), (40, 3, 70), (1, 1, 50), (5, 1, 1)])
+def test_label_sites_random_masks(K, p_fill, shape):
+    rng = np.random.default_rng(int(p_fill * 100) + shape[0])
+    grid = rng.random(shape)
+    thr = 1.0 - p_fill
+    if (grid >= thr).sum() > 20000:
+        pytest.skip("would exceed the site limit only through isolated cells")
+    try:
+        _check_labels(K, grid, thr)
+    except OverflowError:
+        assert len(O.label_sites_ndimage(grid, thr)) - 1 > 32767
+
+
+def test_label_sites_against_networkx_restatement(K):
+    rng = np.random.default_rng(9)
+    grid = rng.random((14, 15, 16))
+    sites_f = O.label_sites_faithful(grid, 0.75)
+    sites_n, labels = _check_labels(K, grid, 0.75)
+    assert sites_f == sites_n
+
+
+def test_label_sites_minsite2_and_ties(K):
+    rng = np.random.default_rng(4)
+    grid = rng.random((20, 20, 20))
+    _check_labels(K, grid, 0.85, minsite=2)
+    # many equal-volume sites: isolated pairs
+    g2 = np.zeros((16, 16, 16))
+    g2[::4, ::4, 2:4] = 1.0
+    g2[1, 1, 8:13] = 1.0
+    _check_labels(K, g2, 0.5)
+
+
+def test_label_sites_solid_blob_and_threshold_equality(K):
+    g = np.ones((33, 34, 35)) * 0.6
+    g[10:12, 10:12, 10:12] = 0.1
+    sites, labels = _check_labels(K, g, 0.6)  # >= threshold counts (sitemap.py:518)
+    assert len(sites) == 2
+    _check_labels(K, g, 0.6000001)
+
+
+def test_too_many_sites_raises(K):
+    g = np.zeros((80, 80, 80))
+    g[::2, ::2, ::2] = 1.0  # 64000 isolated cells
+    with pytest.raises(OverflowError):
+        K.label_sites(dev(g), 0.5, 1)
+
+
+def test_real_density_labels_bulk_insert_properties_cells(K, traj):
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=1.0)
+    counts = O.histogram_vectorised(xyz, edges)
+    grid = O.make_density(counts, edges, xyz.shape[0], "water")
+    sites = O.label_sites_ndimage(grid, math.e)
+    bulk = O.label_sites_ndimage(grid, math.exp(-0.5))
+    full = O.site_insert_bulk(sites, bulk)
+    ref_map = O.draw_map_from_sites(full, grid.shape)
+    ref_props = O.site_properties(full, grid, edges, "water")
+
+    g = K.GridTables(edges)
+    d = dev(grid)
+    own, n_sites, _ = K.label_sites(d, math.e)
+    bl, n_bulk, _ = K.label_sites(d, math.exp(-0.5))
+    member, map16 = K.insert_bulk(own, bl, 1)
+    assert np.array_equal(map16.cpu().numpy(), ref_map)
+    n_labels = n_sites + 2
+    assert n_labels == len(full)
+    count, mean, std, center = [t.cpu().numpy() for t in K.site_properties(g, d, own, member, n_labels)]
+    assert np.array_equal(count, np.array([len(s) for s in full]))
+    det = np.prod([(e[-1] - e[0]) / (len(e) - 1) for e in edges])
+    V = count * det * O.density_conversion_factor("water", "Angstrom^{-3}")
+    np.testing.assert_allclose(mean * V, ref_props["occupancy_avg"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(std * V, ref_props["occupancy_std"], rtol=1e-6, atol=1e-12)
+    nz = count > 0
+    np.testing.assert_allclose(center[nz], ref_props["center"][nz], rtol=1e-9)
+    cells, offsets = K.site_cells(own, member, n_labels)
+    cells, offsets = cells.cpu().numpy(), offsets.cpu().numpy()
+    for l, site in enumerate(full):
+        lin = np.ravel_multi_index(np.asarray(site).T, grid.shape) if len(site) else np.zeros(0, np.int64)
+        assert np.array_equal(cells[offsets[l]:offsets[l + 1]], lin)
+
+
+def _hop_reference(xyz, edges, site_map):
+    hop = O.coord2hop_vectorised(xyz, edges, site_map)
+    ev, nodes = O.analyze_hops_vectorised(hop[:, :, 0])
+    return hop, ev, nodes
+
+
+def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1):
+    """Single process, optionally emulating `slabs` ranks sequentially (same kernels, same exchange)."""
+    F, N = xyz.shape[:2]
+    g = K.GridTables(edges)
+    m16 = dev(site_map.astype(np.int16))
+    events = K.EventBuffer(F * N + 16, "cuda")
+    bounds = np.linspace(0, F, slabs + 1).astype(int)
+    X = torch.empty((F, N), dtype=torch.float32, device="cuda")
+    Y = torch.empty((F, N), dtype=torch.float32, device="cuda")
+    summaries, lens, slab_sums = [], [], []
+    for r in range(slabs):
+        a, b = bounds[r], bounds[r + 1]
+        chunk_len = -(-(b - a) // n_chunks)
+        nc = -(-(b - a) // chunk_len)
+        s = K.hoptraj(g, dev(xyz[a:b]), m16, int(a), nc, chunk_len, events, X[a:b], Y[a:b])
+        summaries.append(s)
+        lens.append(chunk_len)
+        slab_sums.append(K.hop_combine(s, chunk_len, b - a))
+    gathered = torch.stack(slab_sums)
+    state = None
+    for r in range(slabs):
+        a, b = bounds[r], bounds[r + 1]
+        state = K.new_state(N, "cuda")
+        K.hop_advance(gathered[:r] if r else None, state, init=True)
+        K.hop_fixup(summaries[r], lens[r], b - a, state, Y[a:b], events)
+    final = K.new_state(N, "cuda")
+    K.hop_advance(gathered, final, init=True)
+    assert np.array_equal(final.cpu().numpy()[:2], state.cpu().numpy()[:2])
+    n_ev = events.n()
+    return X.cpu().numpy(), Y.cpu().numpy(), events, n_ev, state.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_chunks,slabs", [(1, 1), (4, 1), (13, 1), (200, 1), (3, 2), (5, 8)])
+def test_hoptraj_and_transitions(K, traj, n_chunks, slabs):
+    p, xyz = traj
+    res = O.pipeline(xyz, delta=1.0)
+    hop, ev_ref, nodes_ref = res["hop"], res["events"], res["nodes"]
+    X, Y, events, n_ev, state = _run_hoptraj(K, xyz, res["edges"], res["map"], n_chunks, slabs)
+    assert np.array_equal(X, hop[:, :, 0])
+    assert np.array_equal(Y, hop[:, :, 1])
+    assert n_ev == len(ev_ref)
+    n_labels = len(res["sites"])
+    ev, e_s0, e_s, e_start, e_count = K.events_finalize(events, n_ev, xyz.shape[1], xyz.shape[0], n_labels)
+    ev = ev.cpu().numpy().astype(np.int64)
+    # reference order: by edge, then frame, then atom
+    order = np.lexsort((ev_ref[:, 1], ev_ref[:, 0], ev_ref[:, 3], ev_ref[:, 2]))
+    assert np.array_equal(ev, ev_ref[order])
+    pairs, cnts = O.events_to_counts(ev_ref)
+    assert np.array_equal(np.stack([e_s0.cpu().numpy(), e_s.cpu().numpy()], axis=1), pairs)
+    assert np.array_equal(e_count.cpu().numpy(), cnts)
+    assert np.array_equal(e_start.cpu().numpy(), np.concatenate([[0], np.cumsum(cnts)[:-1]]))
+    ia = np.nonzero(state[0] != 0)[0]
+    nodes = np.stack([ia, state[0][ia], (xyz.shape[0] - 1) - state[1][ia]], axis=1)
+    assert np.array_equal(nodes, nodes_ref)
+
+
+def test_hoptraj_outliers_and_top_edge(K, traj):
+    p, xyz = traj
+    xyz = xyz[:60].copy()
+    res0 = O.pipeline(xyz, delta=1.0)
+    edges, site_map = res0["edges"], res0["map"]
+    rng = np.random.default_rng(1)
+    # push atoms outside the grid (outliers), also in frame 0, and onto / next to the top edges
+    mask = rng.random(xyz.shape[:2]) < 0.05
+    xyz[mask] += np.float32(60.0)
+    xyz[0, :40] -= np.float32(80.0)
+    for d in range(3):
+        top = np.float32(edges[d][-1])
+        for k, v in enumerate([top, np.nextafter(top, np.float32(0)), np.nextafter(top, np.float32(1e9))]):
+            xyz[5 + k, 100 + 10 * d: 110 + 10 * d, d] = v
+    hop, ev_ref, nodes_ref = _hop_reference(xyz, edges, site_map)
+    assert (hop[:, :, 0] == -1).any() and (ev_ref[:, 2] == -1).any()
+    for n_chunks, slabs in [(1, 1), (7, 1), (2, 3)]:
+        X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs)
+        assert np.array_equal(X, hop[:, :, 0])
+        assert np.array_equal(Y, hop[:, :, 1])
+        ev = K.events_to_numpy(events.data[:n_ev])
+        order = np.lexsort((ev["iatom"], ev["frame"]))
+        got = np.stack([ev[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1)
+        assert np.array_equal(got, ev_ref)
+        ia = np.nonzero(state[0] != 0)[0]
+        assert np.array_equal(np.stack([ia, state[0][ia], 59 - state[1][ia]], axis=1), nodes_ref)
+
+
+def test_hopscan_from_labels_and_all_transitions(K):
+    from tests.test_machine_emul import random_labels
+
+    rng = np.random.default_rng(2)
+    lab = random_labels(rng, 300, 257, nsites=6, p_stay=0.9, p_out=0.05, p_zero=0.3)
+    ev_ref, nodes_ref = O.analyze_hops_vectorised(lab)
+    hx = dev(lab.astype(np.float32))
+    for n_chunks in (1, 6, 300):
+        events = K.EventBuffer(lab.size, "cuda")
+        chunk_len = -(-300 // n_chunks)
+        nc = -(-300 // chunk_len)
+        s = K.hopscan_labels(hx, 0, nc, chunk_len, events)
+        state = K.new_state(257, "cuda")
+        K.hop_advance(None, state, init=True)
+        K.hop_fixup(s, chunk_len, 300, state, None, events)
+        n_ev = events.n()
+        ev = K.events_to_numpy(events.data[:n_ev])
+        order = np.lexsort((ev["iatom"], ev["frame"]))
+        got = np.stack([ev[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1)
+        assert np.array_equal(got, ev_ref)
+    assert np.array_equal(K.all_transitions(hx, 8), O.graph_alltransitions(lab))
+
+
+def test_pipeline_config1_matches_faithful_oracle(K, traj):
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    ref = O.pipeline(xyz, delta=1.0, faithful=True)
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    for a, b in zip(edges, ref["edges"]):
+        assert np.array_equal(a, b)
+    pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig())
+    res = pipe.run(dev(xyz))
+    assert np.array_equal(res.counts.cpu().numpy(), ref["counts"].astype(np.int32))
+    assert np.array_equal(res.density.cpu().numpy(), ref["grid"])
+    assert np.array_equal(res.map16.cpu().numpy(), ref["map"])
+    assert np.array_equal(res.hop_x.cpu().numpy(), ref["hop"][:, :, 0])
+    assert np.array_equal(res.hop_y.cpu().numpy(), ref["hop"][:, :, 1])
+    ev = K.events_to_numpy(res.events)
+    e_s0, e_s = res.edge_s0.cpu().numpy(), res.edge_s.cpu().numpy()
+    e_start, e_count = res.edge_start.cpu().numpy(), res.edge_count.cpu().numpy()
+    props = ref["props"]
+    edge_keys = sorted(k for k in props if isinstance(k, tuple))
+    assert [tuple(x) for x in np.stack([e_s0, e_s], axis=1).tolist()] == edge_keys
+    for (a, b), st, c in zip(edge_keys, e_start, e_count):
+        seg = ev[st:st + c]
+        d = props[(a, b)]
+        assert np.array_equal(seg["frame"], d["frame"]) and np.array_equal(seg["iatom"], d["iatom"])
+        assert np.array_equal(seg["tau"], d["tau"]) and np.array_equal(seg["tbarrier"], d["tbarrier"])
+    M = res.count_matrix.cpu().numpy()
+    assert M.sum() == len(ev)
+    for (a, b), c in zip(edge_keys, e_count):
+        assert M[a + 1, b + 1] == c

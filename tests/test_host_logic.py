@@ -1,0 +1,167 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+the Universe stand-in, selections, DCD/PSF/DX formats, grid geometry, chunk planning."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import hop_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_header():
+    from hop_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "hopb200.h")).read()
+    declared = set(re.findall(r"^(?:int|void|const char\*)\s+(hopb_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations found in include/hopb200.h"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libhopb200.so does not export %s" % name
+    assert declared == set(_lib.exported_symbols())
+    assert _lib.lib().hopb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    from hop_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        _lib.handle()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hop_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "tests.emul" not in src, f
+
+
+def test_fixedwidth_bins_and_edges_match_histogramdd():
+    from hop_b200.pipeline import grid_edges_from_frame0
+    from hop_b200.utilities import fixedwidth_bins
+
+    rng = np.random.default_rng(0)
+    c0 = (rng.random((500, 3)) * [31.3, 17.9, 44.4] - 3.3).astype(np.float32)
+    for delta in (1.0, 0.5, 0.25, 0.7):
+        bins, arange, edges = O.grid_geometry(c0, delta=delta, padding=2.0)
+        got = grid_edges_from_frame0(c0, delta=delta, padding=2.0)
+        for a, b in zip(edges, got):
+            assert np.array_equal(a, b)
+        B = fixedwidth_bins(delta, c0.min(0) - 2.0, c0.max(0) + 2.0)
+        assert np.array_equal(B["Nbins"], bins)
+    with pytest.raises(ValueError):
+        fixedwidth_bins(1.0, np.array([1.0, 0, 0]), np.array([0.0, 1, 1]))
+
+
+def test_universe_selections_and_iteration():
+    from hop_b200.universe import Universe
+
+    xyz = np.arange(5 * 6 * 3, dtype=np.float32).reshape(5, 6, 3)
+    names = ["OH2", "H1", "H2", "OH2", "CA", "NA"]
+    resn = ["TIP3", "TIP3", "TIP3", "TIP3", "ALA", "ION"]
+    u = Universe(coordinates=xyz, names=names, resnames=resn, dt=2.0)
+    assert u.trajectory.n_frames == 5 and u.trajectory.totaltime == 8.0
+    w = u.select_atoms("name OH2")
+    assert list(w.indices) == [0, 3]
+    assert list(u.select_atoms("name H*").indices) == [1, 2]
+    assert list(u.select_atoms("protein and not name H*").indices) == [4]
+    assert list(u.select_atoms("resname TIP3 and not (name OH2 or name H1)").indices) == [2]
+    assert list(u.select_atoms("all").indices) == list(range(6))
+    assert list(u.select_atoms("index 1:2").indices) == [1, 2]
+    frames = [ts.frame for ts in u.trajectory]
+    assert frames == [0, 1, 2, 3, 4]
+    for ts in u.trajectory[1:4:2]:
+        assert np.array_equal(w.positions, xyz[ts.frame][[0, 3]])
+    u.trajectory.rewind()
+    assert u.trajectory.ts.frame == 0
+    assert u.trajectory.next().frame == 1
+    from hop_b200.exceptions import SelectionError
+
+    with pytest.raises(SelectionError):
+        u.select_atoms("name")
+
+
+def test_dcd_psf_roundtrip(tmp_path):
+    from hop_b200.dcd import DCDFile, DCDWriter, read_psf_atoms, write_dcd
+    from hop_b200.universe import Universe
+
+    rng = np.random.default_rng(1)
+    x = rng.integers(-1, 40, size=(7, 11)).astype(np.float32)
+    y = rng.integers(0, 40, size=(7, 11)).astype(np.float32)
+    fn = str(tmp_path / "hop.dcd")
+    with DCDWriter(fn, 11, dt=2.5, remarks="Hopping trajectory: x=site y=orbit_site z=0") as w:
+        for f in range(7):
+            w.write_planes(x[f], y[f], None, [41, 41, 1, 90, 90, 90])
+    d = DCDFile(fn)
+    assert d.n_frames == 7 and d.n_atoms == 11
+    assert abs(d.dt - 2.5) < 1e-5
+    assert d.remarks[0].startswith("Hopping trajectory")
+    assert np.array_equal(d.plane_array(0), x) and np.array_equal(d.plane_array(1), y)
+    assert np.all(d.plane_array(2) == 0)
+    assert np.allclose(d.dimensions(3), [41, 41, 1, 90, 90, 90])
+    # byte layout: 84-byte header record, CORD magic, per-frame records X,Y,Z of 4N bytes
+    raw = open(fn, "rb").read()
+    assert raw[:8] == b"T\x00\x00\x00CORD"
+    # full coordinates round trip through the Universe reader
+    xyz = rng.random((4, 5, 3)).astype(np.float32)
+    fn2 = str(tmp_path / "c.dcd")
+    write_dcd(fn2, xyz, dt=1.0)
+    psf = str(tmp_path / "c.psf")
+    with open(psf, "w") as f:
+        f.write("PSF EXT\n\n      1 !NTITLE\n* test\n\n         5 !NATOM\n")
+        for i in range(5):
+            f.write("%10d %8s %-8d %8s %-8s %4s %-14.6f%-14.4f%8d\n" % (i + 1, "W", i + 1, "TIP3", "OH2", "OT", -0.834, 15.9994, 0))
+    top = read_psf_atoms(psf)
+    assert list(top["name"]) == ["OH2"] * 5
+    u = Universe(psf, fn2)
+    got = np.stack([np.array(u.atoms.positions) for ts in u.trajectory])
+    assert np.array_equal(got, xyz)
+    assert np.array_equal(u.trajectory.coordinate_array(1, 3), xyz[1:3])
+
+
+def test_dx_roundtrip(tmp_path):
+    from hop_b200.dx import read_dx, write_dx
+
+    rng = np.random.default_rng(2)
+    g = rng.random((4, 5, 7))
+    fn = str(tmp_path / "d.dx")
+    write_dx(fn, g, [0.5, 1.0, 1.5], [1.0, 0.5, 0.25], ["hello"])
+    g2, edges = read_dx(fn)
+    np.testing.assert_allclose(g2, g, rtol=1e-8)
+    assert len(edges[2]) == 8 and abs(edges[2][1] - edges[2][0] - 0.25) < 1e-12
+
+
+def test_plan_chunks_tiles_exactly():
+    from hop_b200.kernels import plan_chunks
+
+    for F, N in [(200, 1000), (10000, 30000), (100000, 100000), (1, 5), (31, 7), (1000000, 300)]:
+        n, l = plan_chunks(F, N)
+        assert n >= 1 and l >= 1 and n * l >= F and (n - 1) * l < F and n <= 65535
+
+
+def test_unit_factors_and_labels():
+    from hop_b200 import constants as C
+
+    assert C.SITELABEL == dict(outlier=-1, interstitial=0, bulk=1)
+    assert C.get_conversion_factor("density", "Angstrom^{-3}", "water") == O.density_conversion_factor("Angstrom^{-3}", "water")
+    assert abs(C.get_conversion_factor("density", "Angstrom^{-3}", "water") * 0.0333679 - 1.0) < 2e-3
+
+
+def test_synth_generator_properties():
+    from hop_b200.synth import SynthParams, generate
+
+    p = SynthParams(n_atoms=600, n_frames=30)
+    xyz = generate(p)
+    assert xyz.dtype == np.float32 and xyz.shape == (30, 600, 3)
+    assert xyz.min() >= 0.0 and xyz.max() < p.box
+    assert np.array_equal(generate(p, 10, 20), xyz[10:20])
+    assert np.allclose(xyz[0, 1], 0.0) and xyz[0, 2].min() > p.box * 0.999
