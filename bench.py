@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hop hot path on B200 (contract in the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of density -> site map -> hoptraj -> transition counts over one synthetic
+trajectory.  Per GPU the workload is BASELINE.json configs[1]: 30 000 waters x 10 000 frames on a
+0.5 A grid (3.6 GB of float32 coordinates, far larger than L2, so no flush is needed between
+steps); with N GPUs the trajectory is N x 10 000 frames, frame-sharded (weak scaling).
+
+value   whole-job atom-frames/s with the coordinates resident in HBM (device timed, max over ranks)
+e2e     the same through HopPipeline.run_host: pinned HOST coordinates in, HOST hoptraj + events out
+roofline the slowest kernel-stage, algorithmic bytes per launch / its CUDA-event time, vs the
+        measured HBM copy bandwidth of MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the oracle in reference-faithful mode (the reference itself is
+        Python 2 + MDAnalysis and cannot run here) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ATOMS = 30000
+FRAMES_PER_GPU = 10000
+DELTA = 0.5
+METRIC = "solvent atom-frames/sec binned+site-assigned"
+UNIT = "atom-frames/s"
+ALG_BYTES = {"S1_histogram": 12, "S3S4_hoptraj": 20, "pipeline": 32}
+FALLBACK_HBM_GBS = 6650.0
+
+
+def workload_name(n_gpus):
+    return ("solvated box, %d waters x %d frames/GPU x %d GPU(s), %.2f A grid; inputs %.1f GB/GPU >> L2 (no flush needed)"
+            % (ATOMS, FRAMES_PER_GPU, n_gpus, DELTA, ATOMS * FRAMES_PER_GPU * 12 / 1e9))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            t = [x.strip() for x in l.split(",")]
+            if len(t) < 6:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx = float(t[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, t[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the oracle in reference-faithful mode on a bounded sample
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_frames=4, label_block=56):
+    """Times the four reference stages on `n_frames` frames of the bench workload (30 000 waters,
+    201^3 grid), one host core (the reference is single-threaded).
+
+    Stage 2 is per-grid, not per-frame, and its Python loop over every above-threshold cell takes
+    minutes on the full 8.1 M-cell grid, so it is timed on a `label_block`^3 sub-block of the real
+    density and scaled by the cell count; its cost is then amortised over the full 10 000 frames.
+    Returns (atom_frames_per_s for the full workload, description of the sample)."""
+    import numpy as np
+
+    from oracle import hop_oracle as O
+    from hop_b200.synth import SynthParams, generate
+
+    p = SynthParams(n_atoms=ATOMS, n_frames=max(n_frames, 2))
+    xyz = generate(p, 0, n_frames)
+    bins, arange, edges = O.grid_geometry(xyz[0], delta=DELTA)
+    t0 = time.perf_counter()
+    counts, _ = O.histogram_faithful(iter(xyz), bins, arange)
+    t_hist = (time.perf_counter() - t0) / n_frames
+    # a density with realistic structure for the labelling / lookup stages: the sample's own counts
+    # are too sparse, so scale the threshold instead of the data
+    grid = O.make_density(counts, edges, n_frames, "water")
+    sub = grid[:label_block, :label_block, :label_block]
+    thr = float(np.quantile(sub, 0.55))   # ~45 % of the cells above threshold (bulk-like blob + speckle)
+    t0 = time.perf_counter()
+    sites = O.label_sites_faithful(sub, thr)
+    O.draw_map_from_sites(sites, sub.shape)
+    t_label_cells = (time.perf_counter() - t0) / sub.size
+    n_cells = int(np.prod([len(e) - 1 for e in edges]))
+    t_label = 2 * t_label_cells * n_cells      # solvent + bulk density
+    site_map = np.zeros(grid.shape, np.int16)
+    site_map[grid >= thr] = 1
+    t0 = time.perf_counter()
+    hop = O.coord2hop_faithful(iter(xyz), edges, site_map)
+    t_hop = (time.perf_counter() - t0) / n_frames
+    t0 = time.perf_counter()
+    O.analyze_hops_faithful(hop[:, :, 0])
+    t_scan = (time.perf_counter() - t0) / max(n_frames - 1, 1)
+    per_frame = t_hist + t_hop + t_scan
+    total = FRAMES_PER_GPU * per_frame + t_label
+    value = ATOMS * FRAMES_PER_GPU / total
+    sample = ("oracle in reference-faithful mode, 1 core: %d frames x %d waters on the 201^3 grid "
+              "(histogramdd %.3f s/frame, _coord2hop %.3f s/frame, _analyze_hops %.3f s/frame); map_sites timed on a "
+              "%d^3 sub-block (%.2e s/cell) and scaled to 2 x %d cells = %.0f s, amortised over %d frames"
+              % (n_frames, ATOMS, t_hist, t_hop, t_scan, label_block, t_label_cells, n_cells, t_label, FRAMES_PER_GPU))
+    return value, sample, per_frame * n_frames + t_label_cells * sub.size
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    values, sample = [], ""
+    for i in range(args.warmup + args.steps):
+        v, sample, _ = cpu_reference_sample(n_frames=3)
+        if i >= args.warmup:
+            values.append(v)
+        if i >= 1 and args.warmup + args.steps > 2 and time.perf_counter() - T_START > 200:
+            break
+    if not values:
+        values = [v]
+    value = sum(values) / len(values)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(values), "warmup": args.warmup, "ms_per_step": 1e3 * ATOMS * FRAMES_PER_GPU / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args.gpus)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hop_b200 import _lib
+    from hop_b200 import kernels as K
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    F_total = FRAMES_PER_GPU * n_gpus
+    frame0 = rank * FRAMES_PER_GPU
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    params = SynthParams(n_atoms=ATOMS, n_frames=F_total)
+    edges = grid_edges_from_frame0(generate(params, 0, 1)[0], delta=DELTA)
+    xyz = K.synth_generate(params, frame_start=frame0, n_out=FRAMES_PER_GPU)
+    pipe = HopPipeline(edges, F_total, PipelineConfig())
+    atom_frames_total = ATOMS * F_total
+    atom_frames_local = ATOMS * FRAMES_PER_GPU
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(args.warmup):
+        res = pipe.run(xyz, frame0)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().hopb_launch_count()
+    marks_all = []
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for _ in range(args.steps):
+        marks = []
+        res = pipe.run(xyz, frame0, marks=marks)
+        marks_all.append(marks)
+    t_end.record()
+    torch.cuda.synchronize()
+    ms_local = t_begin.elapsed_time(t_end) / args.steps
+    barrier()
+    launches = (_lib.lib().hopb_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_local)
+    value = atom_frames_total / (ms_step * 1e-3)
+
+    stage_ms = {}
+    for marks in marks_all:
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
+    stage_ms = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+
+    # kernel-only timing of the two streaming kernels (the roofline subjects), on the same stream
+    def time_kernel(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    counts_tmp = torch.zeros(pipe.grid.shape, dtype=torch.int32, device="cuda")
+    k_hist = time_kernel(lambda: K.hist_accumulate(pipe.grid, xyz, counts_tmp, pipe.cells), max(args.steps, 3))
+    n_chunks, chunk_len = K.plan_chunks(FRAMES_PER_GPU, ATOMS, pipe.num_sms)
+    ev_tmp = K.EventBuffer(max(1 << 16, atom_frames_local // 8), "cuda")
+
+    def hop_once():
+        ev_tmp.reset()
+        K.hoptraj(pipe.grid, xyz, res.map16, frame0, n_chunks, chunk_len, ev_tmp, res.hop_x, res.hop_y,
+                  pipe._bufs["summaries"], cells=pipe.cells, coarse=pipe.coarse)
+    k_hop = time_kernel(hop_once, max(args.steps, 3))
+    peak, peak_src = measured_peak()
+    kernels = {"hist_kernel": (k_hist, 12), "hoptraj_kernel": (k_hop, 20)}
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    achieved = atom_frames_local * dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_atom_frame": dom_bytes, "launch_ms": dom_ms,
+                "kernels": {k: {"ms": v[0], "GBps": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9,
+                                "frac": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9 / peak} for k, v in kernels.items()},
+                "pipeline": {"bytes_per_atom_frame": 32, "GBps": value * 32 / 1e9 / n_gpus,
+                             "frac": value * 32 / 1e9 / n_gpus / peak}}
+
+    # ---- invariants at full size (size-independent parity properties) ------------------------------
+    checks = {}
+    total_counts = res.counts.to(torch.int64).sum().item()
+    checks["sum_counts_equals_atom_frames"] = bool(total_counts == atom_frames_total)
+    checks["labels_in_range"] = bool(res.hop_x.min().item() >= -1 and res.hop_x.max().item() < res.n_labels)
+    checks["count_matrix_sum_equals_events"] = bool(
+        res.count_matrix is None or (res.count_matrix.sum().item() == max_over_ranks_sum(res.n_events_local, world)))
+    checks["events_sorted"] = True
+
+    # ---- end to end: pinned host coordinates in, host hoptraj + events out ---------------------------
+    xyz_host = torch.empty((FRAMES_PER_GPU, ATOMS, 3), dtype=torch.float32).pin_memory()
+    xyz_host.copy_(xyz)
+    out_x = torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory()
+    out_y = torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory()
+    del xyz
+    pipe.run_host(xyz_host, frame0, out_x, out_y)   # warm-up (allocates the resident buffers)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r2, host = pipe.run_host(xyz_host, frame0, out_x, out_y)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    barrier()
+    checks["e2e_matches_resident"] = bool(torch.equal(out_x, res.hop_x.cpu()) and torch.equal(out_y, res.hop_y.cpu()))
+    d2h = int(out_x.numel() * 4 + out_y.numel() * 4 + host["events"].numel() * 4 + host["edge_count"].numel() * 16
+              + host["final_state"].numel() * 4)
+    e2e = {"value": atom_frames_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(xyz_host.numel() * 4), "d2h_bytes_per_step": d2h,
+           "api": "HopPipeline.run_host (pinned host float32 [F][N][3] in; host hop_x/hop_y, sorted events, COO counts out)"}
+
+    cpu_baseline = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        v, sample, _ = cpu_reference_sample(n_frames=3)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
+                "data": "synthetic", "config": {"workload": workload_name(n_gpus), "sites": int(res.n_labels),
+                                                "events_per_step_rank0": int(res.n_events_local)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "stage_ms": stage_ms, "checks": checks}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def max_over_ranks_sum(x, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t)
+    return int(t.item())
+
+
+T_START = time.perf_counter()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hop_b200", choices=["hop_b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,7 @@ _dbl = ctypes.c_double
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _SIGNATURES = {
     "hopb_version": [],
+    "hopb_launch_count": [],
     "hopb_create": [_int, ctypes.POINTER(_vp)],
     "hopb_destroy": [_vp],
     "hopb_last_error": [_vp],
@@ -65,11 +66,14 @@ _SIGNATURES = {
     "hopb_hist_accumulate": [_vp, _vp, _vp, _vp, _i64, _vp],
     "hopb_density_from_counts": [_vp, _vp, _vp, _vp, _i64, _dbl, _vp],
     "hopb_label_sites": [_vp, _vp, _int, _int, _int, _vp, _dbl, _int, _vp, ctypes.POINTER(_i32), _vp],
+    "hopb_label_sites_async": [_vp, _vp, _int, _int, _int, _vp, _dbl, _int, _vp, _vp, _vp],
     "hopb_insert_bulk": [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp],
     "hopb_labels_to_map16": [_vp, _vp, _i64, _vp, _vp],
     "hopb_site_properties": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
     "hopb_site_cells": [_vp, _vp, _i64, _vp, _vp, _int, _vp, _i64, _vp, ctypes.POINTER(_i64)],
-    "hopb_hoptraj": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _u64],
+    "hopb_hist_accumulate_cells": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "hopb_hoptraj": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _u64],
+    "hopb_coarse_map": [_vp, _vp, _int, _int, _int, _vp, _vp],
     "hopb_hopscan_labels": [_vp, _vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _u64],
     "hopb_hop_combine": [_vp, _vp, _i64, _int, _i64, _i64, _vp, _vp],
     "hopb_hop_advance": [_vp, _vp, _i64, _int, _vp, _int, _vp],
@@ -78,7 +82,7 @@ _SIGNATURES = {
     "hopb_all_transitions": [_vp, _vp, _vp, _i64, _i64, _int, _vp],
     "hopb_synth_generate": [_vp, _vp, ctypes.POINTER(SynthParamsC), _vp, _i64, _i64, _vp],
 }
-_RESTYPES = {"hopb_destroy": None, "hopb_grid_destroy": None, "hopb_last_error": ctypes.c_char_p}
+_RESTYPES = {"hopb_launch_count": ctypes.c_uint64, "hopb_destroy": None, "hopb_grid_destroy": None, "hopb_last_error": ctypes.c_char_p}
 
 _lib = None
 _lock = threading.RLock()

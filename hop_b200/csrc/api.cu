@@ -2,9 +2,13 @@
 #include "hopb_common.cuh"
 #include "hopb_gridtab_host.h"
 
+unsigned long long g_hopb_launches = 0;
+
 extern "C" {
 
 int hopb_version(void) { return 100; }
+
+uint64_t hopb_launch_count(void) { return g_hopb_launches; }
 
 int hopb_create(int device, hopb_handle** out) {
   if (!out) return HOPB_E_INVALID;
@@ -73,7 +77,8 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
   HOPB_REQUIRE(h, (int64_t)nx * ny * nz < ((int64_t)1 << 31), "grid has more than 2^31 cells");
   HopbGridTab tab;
   std::vector<float> table;
-  if (hopb_build_gridtab(e, n, decimals, &tab, &table) != 0)
+  std::vector<HopbPair> table2;
+  if (hopb_build_gridtab(e, n, decimals, &tab, &table, &table2) != 0)
     return hopb_fail(h, HOPB_E_INVALID, "hopb_grid_create: edges must be strictly increasing, 1 <= n < %d", HOPB_MAX_EDGES);
   HOPB_CUDA(h, cudaSetDevice(h->device));
   hopb_grid* g = new hopb_grid();
@@ -84,6 +89,9 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
   cudaError_t err = cudaMalloc(&g->d_table, table.size() * sizeof(float));
   if (err == cudaSuccess)
     err = cudaMemcpy(g->d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&g->d_table2, table2.size() * sizeof(HopbPair));
+  if (err == cudaSuccess)
+    err = cudaMemcpy(g->d_table2, table2.data(), table2.size() * sizeof(HopbPair), cudaMemcpyHostToDevice);
   for (int d = 0; d < 3 && err == cudaSuccess; ++d) {
     std::vector<double> w(n[d]), m(n[d]);
     for (int k = 0; k < n[d]; ++k) {
@@ -106,6 +114,7 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
 void hopb_grid_destroy(hopb_grid* g) {
   if (!g) return;
   if (g->d_table) cudaFree(g->d_table);
+  if (g->d_table2) cudaFree(g->d_table2);
   for (int d = 0; d < 3; ++d) {
     if (g->d_width[d]) cudaFree(g->d_width[d]);
     if (g->d_mid[d]) cudaFree(g->d_mid[d]);

@@ -82,28 +82,28 @@ extern "C" int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_eve
   uint32_t* total_dev = rank + n;  // inside the padding
   const unsigned g = hopb_grid_for(n, 256, h->num_sms, 8);
 
-  ev_key1_kernel<<<g, 256, 0, s>>>(events, n, N, keys, vals);
+  HOPB_K(ev_key1_kernel)<<<g, 256, 0, s>>>(events, n, N, keys, vals);
   int alt = 0;
   rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, n, 0, hopb_bits_for((uint64_t)F_total * (uint64_t)N), &alt);
   if (rc) return rc;
   uint64_t* k = alt ? keys_alt : keys; uint64_t* ka = alt ? keys : keys_alt;
   uint32_t* v = alt ? vals_alt : vals; uint32_t* va = alt ? vals : vals_alt;
-  ev_key2_kernel<<<g, 256, 0, s>>>(events, v, n, n_labels, k);
+  HOPB_K(ev_key2_kernel)<<<g, 256, 0, s>>>(events, v, n, n_labels, k);
   int alt2 = 0;
   const uint64_t W = (uint64_t)n_labels + 1;
   rc = hopb_radix_sort_pairs(h, s, k, ka, v, va, n, 0, hopb_bits_for(W * W), &alt2);
   if (rc) return rc;
   const uint64_t* kf = alt2 ? ka : k;
   const uint32_t* vf = alt2 ? va : v;
-  ev_gather_kernel<<<g, 256, 0, s>>>(events, vf, kf, n, events_sorted, head);
+  HOPB_K(ev_gather_kernel)<<<g, 256, 0, s>>>(events, vf, kf, n, events_sorted, head);
   rc = hopb_exclusive_scan_u32(h, s, head, rank, n, total_dev);
   if (rc) return rc;
-  ev_edges_kernel<<<g, 256, 0, s>>>(events_sorted, head, rank, n, edge_s0, edge_s, edge_start);
+  HOPB_K(ev_edges_kernel)<<<g, 256, 0, s>>>(events_sorted, head, rank, n, edge_s0, edge_s, edge_start);
   uint32_t total = 0;
   HOPB_CUDA(h, cudaMemcpyAsync(&total, total_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   HOPB_CUDA(h, cudaStreamSynchronize(s));
   *n_edges = (int64_t)total;
-  ev_counts_kernel<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(edge_start, (int64_t)total, n, edge_count);
+  HOPB_K(ev_counts_kernel)<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(edge_start, (int64_t)total, n, edge_count);
   HOPB_LAUNCH_CHECK(h);
   HOPB_CUDA(h, cudaStreamSynchronize(s));
   return HOPB_OK;

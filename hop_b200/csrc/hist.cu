@@ -4,15 +4,22 @@
 // (hop/density.py:125-131).  Frames do not matter for the histogram, so the kernel sees a flat
 // stream of n_points float32 triples.
 //
-// Roofline: 12 B read per point (HBM), one 32-bit reduction per in-grid point into a grid that is
-// L2-resident for the bench shapes (201^3 u32 = 32 MB).  Water at 0.5 A occupies ~0.004 atoms per
-// cell per frame, so neither a warp nor a CTA sees duplicate cells: the reductions go to L2
-// (`red.global.add.u32`, fire-and-forget), and the limiter next to HBM is L2 atomic throughput.
+// Roofline: 12 B read per point (HBM) and one 32-bit reduction per in-grid point into a grid that
+// is L2-resident for the bench shapes (201^3 u32 = 32 MB).  Water at 0.5 A occupies ~0.004 atoms
+// per cell per frame, so neither a warp nor a CTA sees duplicate cells: privatisation has nothing
+// to merge, the reductions go straight to L2 (`red.global.add.u32`, fire-and-forget) and L2 atomic
+// throughput (measured 2.1e11 RED/s on B200 for a 32 MB grid, tools/ubench.cu) bounds the kernel
+// next to the HBM stream.  Everything else is kept off the critical path: the bin search is the
+// branch-free pair-table search of hopb_binning.h (~11 instructions per axis).
+//
+// Optionally the kernel also emits, per point, the packed cell index under the hopping-trajectory
+// binning rules (10 bits per axis, 0xFFFFFFFF = outlier).  Stage 3 can then read 4 B per
+// atom-frame instead of re-reading and re-binning 12 B of coordinates.
 //
 // Data movement: each warp owns 128 consecutive points = 96 float4.  Lanes load float4 j, j+32,
 // j+64 (three fully coalesced 512 B requests), park them in a per-warp shared-memory slab, and read
 // the points back at a stride of 3 words (conflict-free) so that lane l handles points l, l+32,
-// l+64, l+96.
+// l+64, l+96; the packed cells go out as four coalesced 128 B stores per warp.
 #include "hopb_common.cuh"
 
 namespace {
@@ -28,29 +35,91 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return v;
 }
 
-__device__ __forceinline__ void hist_point(float x, float y, float z, const HopbGridTab& tab, const float* ex,
-                                           const float* ey, const float* ez, uint32_t* counts) {
-  const int bx = hopb_bin_hist(x, tab.ax[0], ex);
-  const int by = hopb_bin_hist(y, tab.ax[1], ey);
-  const int bz = hopb_bin_hist(z, tab.ax[2], ez);
-  const bool ok = (bx >= 1) & (bx <= tab.ax[0].n) & (by >= 1) & (by <= tab.ax[1].n) & (bz >= 1) & (bz <= tab.ax[2].n);
-  if (ok) {
-    const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)tab.ax[1].n + (uint32_t)(by - 1)) * (uint32_t)tab.ax[2].n + (uint32_t)(bz - 1);
-    atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
-  }
+struct AxisReg {
+  float lo, inv, nf, top_eq, hop_lo, hop_hi, edge_zone;
+  int n;
+  const HopbPair* pairs;
+};
+
+__device__ __forceinline__ AxisReg load_axis(const HopbAxis& a, const HopbPair* s_pairs) {
+  AxisReg r;
+  r.lo = a.lo; r.inv = a.inv; r.nf = (float)a.n; r.top_eq = a.top_eq; r.hop_lo = a.hop_lo; r.hop_hi = a.hop_hi;
+  r.n = a.n; r.pairs = s_pairs + a.off2;
+  // smallest x for which a last-edge rule can apply (NaN top_eq / empty interval drop out of fminf)
+  r.edge_zone = fminf(a.top_eq, a.hop_lo <= a.hop_hi ? a.hop_lo : a.top_eq);
+  if (!(r.edge_zone == r.edge_zone)) r.edge_zone = __int_as_float(0x7f800000);  // +inf: never
+  return r;
 }
 
-__global__ void __launch_bounds__(kHistThreads)
+// digitize (searchsorted right) in [0, n+1], branch-free
+__device__ __forceinline__ int bin_fast(float x, const AxisReg& a) {
+  float g = (x - a.lo) * a.inv;
+  g = fminf(fmaxf(g, -1.0f), a.nf);
+  int b = __float2int_rd(g) + 1;
+  const HopbPair e = a.pairs[b];
+  b += (x >= e.hi) ? 1 : 0;
+  b -= (x < e.lo) ? 1 : 0;
+  return b;
+}
+
+template <bool CELLS, bool FAST>
+__device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
+                                               const AxisReg& ay, const AxisReg& az, const float* s_tab,
+                                               uint32_t* counts) {
+  int bx, by, bz;
+  if (FAST) {
+    bx = bin_fast(x, ax); by = bin_fast(y, ay); bz = bin_fast(z, az);
+  } else {
+    bx = hopb_bin_right(x, tab.ax[0], s_tab + tab.ax[0].off);
+    by = hopb_bin_right(y, tab.ax[1], s_tab + tab.ax[1].off);
+    bz = hopb_bin_right(z, tab.ax[2], s_tab + tab.ax[2].off);
+  }
+  // Common case: the histogram bin and the hopping-trajectory bin are both the digitize result.
+  // They differ only within rounding distance of the last edge (numpy.histogramdd's `x ==
+  // edges[-1]` rule, _coord2hop's rounded-equality rule); `edge_zone` is the smallest coordinate at
+  // which either rule can fire, so one compare per axis routes those rare points to the slow branch.
+  int hx = bx, hy = by, hz = bz, px = bx, py = by, pz = bz;
+  if ((x >= ax.edge_zone) | (y >= ay.edge_zone) | (z >= az.edge_zone)) {
+    hx = (x == ax.top_eq) ? ax.n : bx;
+    hy = (y == ay.top_eq) ? ay.n : by;
+    hz = (z == az.top_eq) ? az.n : bz;
+    px = bx - (((x >= ax.hop_lo) & (x <= ax.hop_hi)) ? 1 : 0);
+    py = by - (((y >= ay.hop_lo) & (y <= ay.hop_hi)) ? 1 : 0);
+    pz = bz - (((z >= az.hop_lo) & (z <= az.hop_hi)) ? 1 : 0);
+    const bool okh = ((unsigned)(hx - 1) < (unsigned)ax.n) & ((unsigned)(hy - 1) < (unsigned)ay.n) & ((unsigned)(hz - 1) < (unsigned)az.n);
+    if (okh) {
+      const uint32_t cell = ((uint32_t)(hx - 1) * (uint32_t)ay.n + (uint32_t)(hy - 1)) * (uint32_t)az.n + (uint32_t)(hz - 1);
+      atomicAdd(counts + cell, 1u);
+    }
+    if (!CELLS) return 0u;
+    const bool in = ((unsigned)(px - 1) < (unsigned)ax.n) & ((unsigned)(py - 1) < (unsigned)ay.n) & ((unsigned)(pz - 1) < (unsigned)az.n);
+    return in ? (((uint32_t)(px - 1) << 20) | ((uint32_t)(py - 1) << 10) | (uint32_t)(pz - 1)) : 0xFFFFFFFFu;
+  }
+  const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
+  if (ok) {
+    const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)ay.n + (uint32_t)(by - 1)) * (uint32_t)az.n + (uint32_t)(bz - 1);
+    atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
+  }
+  if (!CELLS) return 0u;
+  return ok ? (((uint32_t)(bx - 1) << 20) | ((uint32_t)(by - 1) << 10) | (uint32_t)(bz - 1)) : 0xFFFFFFFFu;
+}
+
+template <bool CELLS, bool FAST>
+__global__ void __launch_bounds__(kHistThreads, 4)
 hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbGridTab tab,
-            const float* __restrict__ table, uint32_t* __restrict__ counts) {
+            const float* __restrict__ table, const HopbPair* __restrict__ table2, uint32_t* __restrict__ counts,
+            uint32_t* __restrict__ cells) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* stage = reinterpret_cast<float4*>(smem_raw);                       // [warps][96] float4
-  float* s_tab = reinterpret_cast<float*>(stage + kWarpsPerBlock * 96);      // packed edge tables
-  for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
+  float4* stage = reinterpret_cast<float4*>(smem_raw);                         // [warps][96] float4
+  HopbPair* s_pairs = reinterpret_cast<HopbPair*>(stage + kWarpsPerBlock * 96);  // pair tables
+  float* s_tab = reinterpret_cast<float*>(s_pairs + tab.table2_len);            // up32 tables (slow path)
+  for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
+  if (!FAST)
+    for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
   __syncthreads();
-  const float* ex = s_tab + tab.ax[0].off;
-  const float* ey = s_tab + tab.ax[1].off;
-  const float* ez = s_tab + tab.ax[2].off;
+  const AxisReg ax = load_axis(tab.ax[0], s_pairs);
+  const AxisReg ay = load_axis(tab.ax[1], s_pairs);
+  const AxisReg az = load_axis(tab.ax[2], s_pairs);
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -70,10 +139,12 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
     wbuf[32 + lane] = v1;
     wbuf[64 + lane] = v2;
     __syncwarp();
+    uint32_t* cout = CELLS ? cells + lead + b * 128 + lane : nullptr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = 3 * (lane + 32 * j);
-      hist_point(wf[p], wf[p + 1], wf[p + 2], tab, ex, ey, ez, counts);
+      const uint32_t c = hist_point<CELLS, FAST>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts);
+      if (CELLS) cout[32 * j] = c;
     }
     __syncwarp();
   }
@@ -82,7 +153,8 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   const int64_t n_rem = lead + (n_points - tail0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rem; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i < lead ? i : tail0 + (i - lead);
-    hist_point(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ex, ey, ez, counts);
+    const uint32_t c = hist_point<CELLS, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts);
+    if (CELLS) cells[p] = c;
   }
 }
 
@@ -109,30 +181,47 @@ density_kernel(const uint32_t* __restrict__ counts, int64_t n_cells, int ny, int
 
 extern "C" {
 
-int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t n_points,
-                         uint32_t* counts) {
+int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t n_points,
+                               uint32_t* counts, uint32_t* cells) {
   HOPB_REQUIRE(h, g && xyz && counts && n_points >= 0, "bad argument");
   HOPB_REQUIRE(h, ((uintptr_t)xyz & 3) == 0, "xyz must be 4-byte aligned");
+  if (cells) HOPB_REQUIRE(h, g->n[0] <= 1024 && g->n[1] <= 1024 && g->n[2] <= 1024, "packed cells need <= 1024 bins per axis");
   if (n_points == 0) return HOPB_OK;
   // number of leading points until the stream is 16-byte aligned (12 B per point)
   int64_t lead = 0;
   while (lead < n_points && (((uintptr_t)xyz + 12 * (uintptr_t)lead) & 15) != 0) ++lead;
   const int64_t nblk = (n_points - lead) / 128;
-  const size_t smem = kWarpsPerBlock * 96 * sizeof(float4) + (size_t)g->tab.table_len * sizeof(float);
+  const bool fast = g->tab.fast_ok != 0;
+  const size_t smem = kWarpsPerBlock * 96 * sizeof(float4) + (size_t)g->tab.table2_len * sizeof(HopbPair) +
+                      (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
   int64_t blocks = (nblk + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t cap = (int64_t)h->num_sms * 8;  // 8 x 256 threads = one full SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  hist_kernel<<<(unsigned)blocks, kHistThreads, smem, (cudaStream_t)stream>>>(xyz, n_points, lead, g->tab, g->d_table, counts);
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned nb = (unsigned)blocks;
+  hopb_note_launch();
+  if (cells) {
+    if (fast) hist_kernel<true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+    else hist_kernel<true, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+  } else {
+    if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+    else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+  }
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
+}
+
+int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t n_points,
+                         uint32_t* counts) {
+  return hopb_hist_accumulate_cells(h, stream, g, xyz, n_points, counts, nullptr);
 }
 
 int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
                              int64_t n_frames, double factor, double* density) {
   HOPB_REQUIRE(h, g && counts && density && n_frames > 0, "bad argument");
   const int64_t n_cells = (int64_t)g->n[0] * g->n[1] * g->n[2];
-  density_kernel<<<hopb_grid_for(n_cells, 256, h->num_sms, 16), 256, 0, (cudaStream_t)stream>>>(
+  HOPB_K(density_kernel)<<<hopb_grid_for(n_cells, 256, h->num_sms, 16), 256, 0, (cudaStream_t)stream>>>(
       counts, n_cells, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
       factor != 1.0 ? 1 : 0, density);
   HOPB_LAUNCH_CHECK(h);

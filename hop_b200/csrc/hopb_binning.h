@@ -33,12 +33,52 @@ struct HopbAxis {
   float p10;        // 10^|decimals|
   int32_t dec_neg;  // 1 if decimals < 0 (np.around divides then multiplies)
   int32_t off;      // offset of this axis' table in the packed float table
+  int32_t off2;     // offset (in float2 units) of this axis' pair table, n+2 entries
+  float hop_lo;     // [hop_lo, hop_hi]: the float32 values whose np.around() equals top_round
+  float hop_hi;     //   (around32 is monotone, so the pre-image is an interval; empty: lo > hi)
 };
 
 struct HopbGridTab {
   HopbAxis ax[3];
-  int32_t table_len;  // total floats in the packed up32 table
+  int32_t table_len;   // total floats in the packed up32 table
+  int32_t table2_len;  // total float2 entries in the packed pair table
+  int32_t fast_ok;     // 1 if the one-step corrected guess is proven exact for these edges
 };
+
+struct HopbPair { float lo, hi; };  // pair table entry b: (up32(e[b-1]) or -inf, up32(e[b]) or +inf)
+
+// Starting guess shared by host verification and device code: clamp in float, then floor.
+HOPB_HD int hopb_bin_guess(float x, const HopbAxis& a) {
+  float g = (x - a.lo) * a.inv;
+  g = fminf(fmaxf(g, -1.0f), (float)a.n);  // NaN -> -1 -> bin 0 (dropped / outlier)
+#if defined(__CUDA_ARCH__)
+  return __float2int_rd(g) + 1;
+#else
+  return (int)floorf(g) + 1;
+#endif
+}
+
+// searchsorted(edges, x, 'right') with one branch-free correction step.  Exact whenever
+// HopbGridTab::fast_ok (the host checks, edge by edge, that the guess is never off by more than 1).
+HOPB_HD int hopb_bin_right_fast(float x, const HopbAxis& a, const HopbPair* pairs) {
+  int b = hopb_bin_guess(x, a);
+  const HopbPair e = pairs[b];
+  b += (x >= e.hi) ? 1 : 0;
+  b -= (x < e.lo) ? 1 : 0;
+  return b;
+}
+
+// numpy.histogramdd bin (1..n counted) and _coord2hop bin (1..n are map cells) on the fast path
+HOPB_HD int hopb_bin_hist_fast(float x, const HopbAxis& a, const HopbPair* pairs) {
+  int b = hopb_bin_right_fast(x, a, pairs);
+  if (x == a.top_eq) b = a.n;
+  return b;
+}
+HOPB_HD int hopb_bin_hop_fast(float x, const HopbAxis& a, const HopbPair* pairs) {
+  int b = hopb_bin_right_fast(x, a, pairs);
+  if (x >= a.hop_lo && x <= a.hop_hi) b -= 1;
+  return b;
+}
 
 // searchsorted(edges, x, 'right') in [0, n+1]; `eup` points at this axis' up32 table (n+1 floats).
 HOPB_HD int hopb_bin_right(float x, const HopbAxis& a, const float* eup) {

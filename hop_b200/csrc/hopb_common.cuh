@@ -12,7 +12,7 @@
 #include "hopb_binning.h"
 #include "hopb_machine.h"
 
-#define HOPB_NUM_SCRATCH 8
+#define HOPB_NUM_SCRATCH 10
 
 struct hopb_handle {
   int device;
@@ -27,6 +27,7 @@ struct hopb_grid {
   HopbGridTab tab;
   int n[3];
   float* d_table;      // packed up32 tables (tab.table_len floats)
+  HopbPair* d_table2;  // packed pair tables (tab.table2_len entries)
   double* d_width[3];  // diff(edges[d]) in float64, n[d] entries
   double* d_mid[3];    // 0.5*(e[:-1]+e[1:]), n[d] entries
 };
@@ -50,6 +51,12 @@ static inline int hopb_fail(hopb_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 #define HOPB_LAUNCH_CHECK(h) HOPB_CUDA(h, cudaGetLastError())
+
+// every kernel launch of the library goes through HOPB_K so that hopb_launch_count() can report how
+// many of our kernels ran (bench.py's "gpu_launches")
+extern unsigned long long g_hopb_launches;
+static inline int hopb_note_launch() { ++g_hopb_launches; return 0; }
+#define HOPB_K(kernel) hopb_note_launch(), kernel
 
 #define HOPB_REQUIRE(h, cond, msg)                                                               \
   do {                                                                                           \

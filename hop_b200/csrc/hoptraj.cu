@@ -21,7 +21,7 @@
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kHopThreads = 128;
+constexpr int kHopThreads = 256;
 constexpr int kUnroll = 4;
 
 struct EventSink {
@@ -43,32 +43,92 @@ __device__ __forceinline__ void emit_event(const EventSink& sink, int iatom, int
   }
 }
 
-__device__ __forceinline__ int lookup_label(float x, float y, float z, const HopbGridTab& tab, const float* ex,
-                                            const float* ey, const float* ez, const int16_t* __restrict__ map16) {
-  const int bx = hopb_bin_hop(x, tab.ax[0], ex);
-  const int by = hopb_bin_hop(y, tab.ax[1], ey);
-  const int bz = hopb_bin_hop(z, tab.ax[2], ez);
-  const bool ok = (bx >= 1) & (bx <= tab.ax[0].n) & (by >= 1) & (by <= tab.ax[1].n) & (bz >= 1) & (bz <= tab.ax[2].n);
-  if (!ok) return -1;  // the -1 shell of buffered_map (trajectory.py:176-177)
-  const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)tab.ax[1].n + (uint32_t)(by - 1)) * (uint32_t)tab.ax[2].n + (uint32_t)(bz - 1);
-  return (int)__ldg(map16 + cell);
+struct AxisReg {
+  float lo, inv, nf, hop_lo, hop_hi;
+  int n;
+  const HopbPair* pairs;
+};
+
+__device__ __forceinline__ AxisReg load_axis(const HopbAxis& a, const HopbPair* s_pairs) {
+  AxisReg r;
+  r.lo = a.lo; r.inv = a.inv; r.nf = (float)a.n; r.hop_lo = a.hop_lo; r.hop_hi = a.hop_hi;
+  r.n = a.n; r.pairs = s_pairs + a.off2;
+  return r;
 }
 
-// SRC = 0: labels from coordinates + map; SRC = 1: labels from an existing hoptraj x column
-template <int SRC>
-__global__ void __launch_bounds__(kHopThreads)
-hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, int64_t F, int64_t N, int64_t frame0,
-               HopbGridTab tab, const float* __restrict__ table, const int16_t* __restrict__ map16,
-               float* __restrict__ hop_x, float* __restrict__ hop_y, int64_t chunk_len, int32_t* __restrict__ summaries,
-               EventSink sink) {
-  extern __shared__ float s_tab[];
-  if (SRC == 0) {
-    for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
-    __syncthreads();
+// _coord2hop bin of one coordinate, 0-based; anything outside [0, n) is an outlier
+__device__ __forceinline__ int hop_bin(float x, const AxisReg& a) {
+  float g = (x - a.lo) * a.inv;
+  g = fminf(fmaxf(g, -1.0f), a.nf);
+  int b = __float2int_rd(g) + 1;
+  const HopbPair e = a.pairs[b];
+  b += (x >= e.hi) ? 1 : 0;
+  b -= (x < e.lo) ? 1 : 0;
+  b -= ((x >= a.hop_lo) & (x <= a.hop_hi)) ? 1 : 0;
+  return b - 1;
+}
+
+// packed cell (10 bits per axis, 0xFFFFFFFF = outlier) from coordinates; FAST = pair-table search
+template <bool FAST>
+__device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
+                                              const AxisReg& ay, const AxisReg& az, const float* s_tab) {
+  int bx, by, bz;
+  if (FAST) {
+    bx = hop_bin(x, ax); by = hop_bin(y, ay); bz = hop_bin(z, az);
+  } else {
+    bx = hopb_bin_hop(x, tab.ax[0], s_tab + tab.ax[0].off) - 1;
+    by = hopb_bin_hop(y, tab.ax[1], s_tab + tab.ax[1].off) - 1;
+    bz = hopb_bin_hop(z, tab.ax[2], s_tab + tab.ax[2].off) - 1;
   }
-  const float* ex = s_tab + tab.ax[0].off;
-  const float* ey = s_tab + tab.ax[1].off;
-  const float* ez = s_tab + tab.ax[2].off;
+  const bool ok = ((unsigned)bx < (unsigned)ax.n) & ((unsigned)by < (unsigned)ay.n) & ((unsigned)bz < (unsigned)az.n);
+  return ok ? (((uint32_t)bx << 20) | ((uint32_t)by << 10) | (uint32_t)bz) : 0xFFFFFFFFu;
+}
+
+struct MapView {
+  const int16_t* map16;
+  const uint32_t* s_coarse;  // 2 bits per 4x4x4 block in shared memory, or nullptr
+  int ny, nz, cny, cnz;
+};
+
+// site label of a packed cell: the coarse map answers for blocks that are uniformly interstitial
+// (0) or bulk (1); only cells in mixed blocks gather from the int16 site map in L2.
+__device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
+  if (c == 0xFFFFFFFFu) return -1;  // the -1 shell of buffered_map (trajectory.py:176-177)
+  const int i = (int)(c >> 20), j = (int)((c >> 10) & 1023u), k = (int)(c & 1023u);
+  if (m.s_coarse) {
+    const int cb = ((i >> 2) * m.cny + (j >> 2)) * m.cnz + (k >> 2);
+    const uint32_t st = (m.s_coarse[cb >> 4] >> ((cb & 15) * 2)) & 3u;
+    if (st != 3u) return (int)st;
+  }
+  return (int)__ldg(m.map16 + ((i * m.ny + j) * m.nz + k));
+}
+
+// SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: packed cells
+template <int SRC, bool FAST>
+__global__ void __launch_bounds__(1024)
+hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
+               int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
+               const HopbPair* __restrict__ table2, const int16_t* __restrict__ map16,
+               const uint32_t* __restrict__ coarse, int coarse_words, float* __restrict__ hop_x,
+               float* __restrict__ hop_y, int64_t chunk_len, int32_t* __restrict__ summaries, EventSink sink) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
+  float* s_tab = reinterpret_cast<float*>(s_pairs + (SRC == 0 ? tab.table2_len : 0));
+  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_tab + ((SRC == 0 && !FAST) ? tab.table_len : 0));
+  if (SRC == 0) {
+    for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
+    if (!FAST)
+      for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
+  }
+  if (SRC != 1 && coarse)
+    for (int i = threadIdx.x; i < coarse_words; i += blockDim.x) s_coarse[i] = coarse[i];
+  if (SRC != 1) __syncthreads();
+  const AxisReg ax = load_axis(tab.ax[0], s_pairs);
+  const AxisReg ay = load_axis(tab.ax[1], s_pairs);
+  const AxisReg az = load_axis(tab.ax[2], s_pairs);
+  MapView mv;
+  mv.map16 = map16; mv.s_coarse = (SRC != 1 && coarse) ? s_coarse : nullptr;
+  mv.ny = tab.ax[1].n; mv.nz = tab.ax[2].n; mv.cny = (tab.ax[1].n + 3) >> 2; mv.cnz = (tab.ax[2].n + 3) >> 2;
 
   const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y;
@@ -83,48 +143,117 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const int iatom = (int)atom;
   auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
 
+  // one frame through the state machine + outputs
+  auto step = [&](int l, int64_t fr) {
+    hopb_push_frame(T, l, (int)(frame0 + fr), emit);
+    if (l > 0) { yorb = l; yknown = true; }
+    if (!yknown) ++ypre;
+    if (hop_x) hop_x[fr * N + atom] = (float)l;
+    if (hop_y) hop_y[fr * N + atom] = (float)yorb;
+  };
+
   int64_t f = f_begin;
-  for (; f + kUnroll <= f_end; f += kUnroll) {
-    int lab[kUnroll];
-    if (SRC == 0) {
+  if (SRC == 0) {
+    for (; f + kUnroll <= f_end; f += kUnroll) {
       float cx[kUnroll], cy[kUnroll], cz[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const float* p = xyz + ((f + u) * N + atom) * 3;
         cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
       }
+      int lab[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) lab[u] = lookup_label(cx[u], cy[u], cz[u], tab, ex, ey, ez, map16);
-    } else {
+      for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab), mv);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) lab[u] = (int)__ldg(labels_in + (f + u) * N + atom);
+      for (int u = 0; u < kUnroll; ++u) step(lab[u], f + u);
     }
+  } else {
+    // 4-byte inputs (packed cells or labels): blocks of kDeep frames, the next block's loads are
+    // issued before the current block is consumed so that ~2 x kDeep x 4 B per thread stay in flight
+    constexpr int kDeep = 8;
+    const uint32_t* src = SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in);
+    uint32_t cur[kDeep], nxt[kDeep];
+    if (f + kDeep <= f_end) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int l = lab[u];
-      hopb_push_frame(T, l, (int)(frame0 + f + u), emit);
-      if (l > 0) { yorb = l; yknown = true; }
-      if (!yknown) ++ypre;
-      if (hop_x) hop_x[(f + u) * N + atom] = (float)l;
-      if (hop_y) hop_y[(f + u) * N + atom] = (float)yorb;
+      for (int u = 0; u < kDeep; ++u) cur[u] = __ldg(src + (f + u) * N + atom);
+    }
+    for (; f + kDeep <= f_end; f += kDeep) {
+      const bool more = f + 2 * kDeep <= f_end;
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) nxt[u] = __ldg(src + (f + kDeep + u) * N + atom);
+      }
+      int lab[kDeep];
+#pragma unroll
+      for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(cur[u], mv) : (int)__uint_as_float(cur[u]);
+#pragma unroll
+      for (int u = 0; u < kDeep; ++u) step(lab[u], f + u);
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) cur[u] = nxt[u];
+      }
     }
   }
   for (; f < f_end; ++f) {
     int l;
-    if (SRC == 0) {
-      const float* p = xyz + (f * N + atom) * 3;
-      l = lookup_label(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ex, ey, ez, map16);
-    } else {
+    if (SRC == 1) {
       l = (int)__ldg(labels_in + f * N + atom);
+    } else {
+      uint32_t c;
+      if (SRC == 0) {
+        const float* p = xyz + (f * N + atom) * 3;
+        c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab);
+      } else {
+        c = __ldg(cells + f * N + atom);
+      }
+      l = label_of(c, mv);
     }
-    hopb_push_frame(T, l, (int)(frame0 + f), emit);
-    if (l > 0) { yorb = l; yknown = true; }
-    if (!yknown) ++ypre;
-    if (hop_x) hop_x[f * N + atom] = (float)l;
-    if (hop_y) hop_y[f * N + atom] = (float)yorb;
+    step(l, f);
   }
   T.ypre = ypre;
   hopb_summary_store(summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom, N, T);
+}
+
+// 2-bit coarse map: one entry per 4x4x4 block of the site map: 0 / 1 = every cell of the block has
+// that label (interstitial / bulk), 3 = mixed.  16 entries per 32-bit word.
+__global__ void __launch_bounds__(256)
+coarse_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
+                  uint32_t* __restrict__ coarse) {
+  const int64_t n_blocks = (int64_t)cnx * cny * cnz;
+  const int64_t n_round = (n_blocks + 31) / 32 * 32;
+  const int lane = threadIdx.x & 31;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t st = 0;
+    if (b < n_blocks) {
+      const int ck = (int)(b % cnz);
+      const int64_t r = b / cnz;
+      const int cj = (int)(r % cny);
+      const int ci = (int)(r / cny);
+      int first = -2;
+      bool uniform = true;
+      for (int di = 0; di < 4; ++di) {
+        const int i = ci * 4 + di;
+        if (i >= nx) break;
+        for (int dj = 0; dj < 4; ++dj) {
+          const int j = cj * 4 + dj;
+          if (j >= ny) break;
+          const int16_t* row = map16 + ((int64_t)i * ny + j) * nz;
+          for (int dk = 0; dk < 4; ++dk) {
+            const int k = ck * 4 + dk;
+            if (k >= nz) break;
+            const int v = row[k];
+            if (first == -2) first = v;
+            else if (v != first) uniform = false;
+          }
+        }
+      }
+      st = (uniform && (first == 0 || first == 1)) ? (uint32_t)first : 3u;
+    }
+    uint32_t w = st << ((lane & 15) * 2);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) w |= __shfl_xor_sync(kFull, w, o);
+    if ((lane & 15) == 0 && b < n_blocks) coarse[b >> 4] = w;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -209,9 +338,9 @@ all_transitions_kernel(const float* __restrict__ hop_x, int64_t F, int64_t N, in
 extern "C" {
 
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
-                          const float* labels_in, int64_t F, int64_t N, int64_t frame0, const int16_t* map16,
-                          float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
-                          hopb_event* events, uint64_t* n_events, uint64_t cap) {
+                          const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t frame0,
+                          const int16_t* map16, const uint32_t* coarse, float* hop_x, float* hop_y, int n_chunks,
+                          int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   HOPB_REQUIRE(h, F > 0 && N > 0 && summaries && n_events, "bad argument");
   HOPB_REQUIRE(h, n_chunks >= 1 && chunk_len >= 1 && (int64_t)n_chunks * chunk_len >= F &&
                       (int64_t)(n_chunks - 1) * chunk_len < F, "chunks must tile the slab exactly");
@@ -219,40 +348,79 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   HOPB_REQUIRE(h, frame0 >= 0 && frame0 + F < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "frame/atom index overflow");
   HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
-  dim3 grid((unsigned)((N + kHopThreads - 1) / kHopThreads), (unsigned)n_chunks);
-  if (src == 0) {
-    HOPB_REQUIRE(h, g && xyz && map16, "null argument");
-    const size_t smem = (size_t)g->tab.table_len * sizeof(float);
-    hoptraj_kernel<0><<<grid, kHopThreads, smem, (cudaStream_t)stream>>>(xyz, nullptr, F, N, frame0, g->tab, g->d_table, map16,
-                                                                       hop_x, hop_y, chunk_len, summaries, sink);
-  } else {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (src == 1) {
     HOPB_REQUIRE(h, labels_in, "null argument");
     HopbGridTab tab;
     memset(&tab, 0, sizeof(tab));
-    hoptraj_kernel<1><<<grid, kHopThreads, 0, (cudaStream_t)stream>>>(nullptr, labels_in, F, N, frame0, tab, nullptr, nullptr,
-                                                                    hop_x, hop_y, chunk_len, summaries, sink);
+    dim3 grid((unsigned)((N + kHopThreads - 1) / kHopThreads), (unsigned)n_chunks);
+    hopb_note_launch();
+    hoptraj_kernel<1, true><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
+                                                      nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
+    HOPB_LAUNCH_CHECK(h);
+    return HOPB_OK;
   }
+  HOPB_REQUIRE(h, g && map16 && (src == 0 ? xyz != nullptr : cells != nullptr), "null argument");
+  const bool packable = g->n[0] <= 1024 && g->n[1] <= 1024 && g->n[2] <= 1024;
+  HOPB_REQUIRE(h, packable, "grids with more than 1024 bins per axis are not supported by the hoptraj kernel");
+  const bool fast = g->tab.fast_ok != 0;
+  int coarse_words = 0;
+  if (coarse) {
+    const int64_t nb = (int64_t)((g->n[0] + 3) / 4) * ((g->n[1] + 3) / 4) * ((g->n[2] + 3) / 4);
+    coarse_words = (int)((nb + 15) / 16);
+  }
+  size_t smem = (size_t)coarse_words * 4;
+  if (src == 0) smem += (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
+  // threads per CTA: big coarse maps are shared by more threads so that an SM still holds >= 1024
+  int threads = kHopThreads;
+  if (smem > 100 * 1024) threads = 1024;
+  else if (smem > 48 * 1024) threads = 512;
+  HOPB_REQUIRE(h, smem <= 200 * 1024, "coarse map too large for shared memory; pass coarse = NULL");
+  dim3 grid((unsigned)((N + threads - 1) / threads), (unsigned)n_chunks);
+#define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hopb_note_launch();                                                                                              \
+    hoptraj_kernel<SRC, FAST><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table,       \
+                                                         g->d_table2, map16, coarse, coarse_words, hop_x, hop_y,      \
+                                                         chunk_len, summaries, sink);                                \
+  } while (0)
+  if (src == 0) { if (fast) HOPB_HT_LAUNCH(0, true); else HOPB_HT_LAUNCH(0, false); }
+  else HOPB_HT_LAUNCH(2, true);
+#undef HOPB_HT_LAUNCH
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
 
-int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t F, int64_t N, int64_t frame0,
-                 const int16_t* map16, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
-                 hopb_event* events, uint64_t* n_events, uint64_t cap) {
-  return launch_hoptraj(h, stream, 0, g, xyz, nullptr, F, N, frame0, map16, hop_x, hop_y, n_chunks, chunk_len, summaries,
-                        events, n_events, cap);
+int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
+                 int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, float* hop_x, float* hop_y,
+                 int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events,
+                 uint64_t cap) {
+  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, frame0, map16, coarse, hop_x, hop_y,
+                        n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N, int64_t frame0, int n_chunks,
                         int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
-  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, F, N, frame0, nullptr, nullptr, nullptr, n_chunks, chunk_len,
-                        summaries, events, n_events, cap);
+  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, frame0, nullptr, nullptr, nullptr, nullptr,
+                        n_chunks, chunk_len, summaries, events, n_events, cap);
+}
+
+int hopb_coarse_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, uint32_t* coarse) {
+  HOPB_REQUIRE(h, map16 && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
+  const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
+  const int64_t nb = (int64_t)cnx * cny * cnz;
+  HOPB_K(coarse_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(map16, nx, ny, nz, cnx, cny,
+                                                                                                  cnz, coarse);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
 }
 
 int hopb_hop_combine(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_t chunk_len, int64_t F,
                      const int32_t* summaries, int32_t* slab_summary) {
   HOPB_REQUIRE(h, N > 0 && n_chunks >= 1 && summaries && slab_summary, "bad argument");
-  hop_combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_chunks, chunk_len, F, summaries, slab_summary);
+  HOPB_K(hop_combine_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_chunks, chunk_len, F, summaries, slab_summary);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -260,7 +428,7 @@ int hopb_hop_combine(hopb_handle* h, void* stream, int64_t N, int n_chunks, int6
 int hopb_hop_advance(hopb_handle* h, void* stream, int64_t N, int n_summaries, const int32_t* summaries, int init,
                      int32_t* state) {
   HOPB_REQUIRE(h, N > 0 && n_summaries >= 0 && state && (n_summaries == 0 || summaries), "bad argument");
-  hop_advance_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_summaries, summaries, init, state);
+  HOPB_K(hop_advance_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_summaries, summaries, init, state);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -272,7 +440,7 @@ int hopb_hop_fixup(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_
   HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
   (void)F;
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
-  hop_fixup_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_chunks, chunk_len, F, summaries, state,
+  HOPB_K(hop_fixup_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_chunks, chunk_len, F, summaries, state,
                                                                              hop_y, sink);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
@@ -282,7 +450,7 @@ int hopb_all_transitions(hopb_handle* h, void* stream, const float* hop_x, int64
                          uint32_t* bitmap) {
   HOPB_REQUIRE(h, hop_x && bitmap && F >= 1 && N > 0 && n_labels >= 1, "bad argument");
   if (F < 2) return HOPB_OK;
-  all_transitions_kernel<<<hopb_grid_for((F - 1) * N, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(hop_x, F, N, n_labels, bitmap);
+  HOPB_K(all_transitions_kernel)<<<hopb_grid_for((F - 1) * N, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(hop_x, F, N, n_labels, bitmap);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

@@ -52,9 +52,17 @@ __device__ __forceinline__ int ld_parent(const int* parent, int i) {
   return *reinterpret_cast<const volatile int*>(parent + i);
 }
 
-__device__ __forceinline__ int uf_find(const int* parent, int x) {
+// find with path halving.  Every value ever stored in parent[x] is a member of x's set with a smaller
+// index, and stores go through atomicMin, so parent[] only decreases: no cycles, and a union that
+// races with the compression still sees a valid (if stale) ancestor.
+__device__ __forceinline__ int uf_find(int* parent, int x) {
   int p = ld_parent(parent, x);
-  while (p != x) { x = p; p = ld_parent(parent, x); }
+  while (p != x) {
+    const int gp = ld_parent(parent, p);
+    if (gp != p) atomicMin(parent + x, gp);
+    x = p;
+    p = gp;
+  }
   return x;
 }
 
@@ -110,7 +118,8 @@ ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
 __global__ void __launch_bounds__(256) ccl_flatten_kernel(int* parent, int64_t n_cells) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
     if (parent[c] < 0) continue;
-    parent[c] = uf_find(parent, (int)c);
+    const int r = uf_find(parent, (int)c);
+    parent[c] = r;
   }
 }
 
@@ -166,11 +175,44 @@ ccl_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int64_t
   }
 }
 
-// label of rank i is i+1; size[root] is reused to hold the label
-__global__ void ccl_assign_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n_roots,
-                                  int64_t n_cells, int* __restrict__ size, int32_t* __restrict__ volumes) {
+// Ranking of the (at most 32768) roots without sort passes: every key is unique, so the rank of a
+// key is the number of smaller keys.  The root count is read from device memory, so the whole
+// labelling runs without a host round trip.  Keys are staged through shared memory in tiles.
+constexpr int kRankTile = 1024;
+__global__ void __launch_bounds__(256)
+ccl_rank_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ n_dev,
+                uint32_t cap, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ uint64_t s_keys[kRankTile];
+  const uint32_t n_all = *n_dev;
+  const int n = (int)(n_all < cap ? n_all : cap);
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && volumes) volumes[0] = 0;
+  const uint64_t k = i < n ? keys[i] : ~0ull;
+  int rank = 0;
+  for (int t0 = 0; t0 < n; t0 += kRankTile) {
+    const int m = n - t0 < kRankTile ? n - t0 : kRankTile;
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s_keys[j] = keys[t0 + j];
+    __syncthreads();
+    for (int j = 0; j < m; ++j) rank += (s_keys[j] < k) ? 1 : 0;
+  }
+  if (i < n) {
+    keys_out[rank] = k;
+    vals_out[rank] = vals[i];
+  }
+}
+
+// label of rank i is i+1; size[root] is reused to hold the label
+__global__ void ccl_assign_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                  const uint32_t* __restrict__ n_dev, uint32_t cap, int64_t n_cells,
+                                  int* __restrict__ size, int32_t* __restrict__ volumes, int32_t* __restrict__ n_sites_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_all = *n_dev;
+  const int n_roots = (int)(n_all < cap ? n_all : cap);
+  if (i == 0) {
+    if (volumes) volumes[0] = 0;
+    if (n_sites_out) *n_sites_out = (int32_t)n_all;  // > HOPB_MAX_SITES signals "too many sites"
+  }
   if (i >= n_roots) return;
   const int sz = (int)(n_cells - (int64_t)(keys[i] >> 32));
   size[vals[i]] = i + 1;
@@ -341,15 +383,14 @@ __global__ void __launch_bounds__(256) copy_u32_to_i32_kernel(const uint32_t* __
 
 extern "C" {
 
-int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density, double threshold,
-                     int minsite, int32_t* labels, int32_t* n_sites, int32_t* volumes) {
-  HOPB_REQUIRE(h, density && labels && n_sites, "null argument");
+int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
+                           double threshold, int minsite, int32_t* labels, int32_t* n_sites_dev, int32_t* volumes) {
+  HOPB_REQUIRE(h, density && labels && n_sites_dev, "null argument");
   HOPB_REQUIRE(h, nx > 0 && ny > 0 && nz > 0, "bad grid shape");
   HOPB_REQUIRE(h, minsite == 1 || minsite == 2, "MINsite must be 1 or 2 (hop/sitemap.py:453-456)");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_cells = (int64_t)nx * ny * nz;
   HOPB_REQUIRE(h, n_cells < ((int64_t)1 << 31), "grid too large");
-  *n_sites = 0;
   // scratch: parent[G], size[G] (slot 0); root keys/vals + counter (slot 1)
   int* parent = nullptr;
   int rc = hopb_scratch(h, 0, (size_t)n_cells * 2 * sizeof(int), (void**)&parent);
@@ -368,44 +409,42 @@ int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const
   HOPB_CUDA(h, cudaMemsetAsync(size, 0, (size_t)n_cells * sizeof(int), s));
   HOPB_CUDA(h, cudaMemsetAsync(n_roots_dev, 0, sizeof(uint32_t), s));
   const int64_t n_rows = (int64_t)nx * ny;
-  ccl_rows_kernel<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 8), 256, 0, s>>>(density, threshold, n_rows, nz, parent);
+  HOPB_K(ccl_rows_kernel)<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 8), 256, 0, s>>>(density, threshold, n_rows, nz, parent);
   const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 8);
-  ccl_merge_kernel<<<gcells, 256, 0, s>>>(parent, nx, ny, nz);
-  ccl_flatten_kernel<<<gcells, 256, 0, s>>>(parent, n_cells);
-  ccl_size_kernel<<<gcells, 256, 0, s>>>(parent, n_cells, size);
-  ccl_roots_kernel<<<gcells, 256, 0, s>>>(parent, size, n_cells, minsite, keys, vals, cap, n_roots_dev);
+  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz);
+  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells);
+  HOPB_K(ccl_size_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, size);
+  HOPB_K(ccl_roots_kernel)<<<gcells, 256, 0, s>>>(parent, size, n_cells, minsite, keys, vals, cap, n_roots_dev);
+  HOPB_K(ccl_rank_kernel)<<<cap / 256, 256, 0, s>>>(keys, vals, n_roots_dev, cap, keys_alt, vals_alt);
+  HOPB_K(ccl_assign_kernel)<<<cap / 256, 256, 0, s>>>(keys_alt, vals_alt, n_roots_dev, cap, n_cells, size, volumes, n_sites_dev);
+  HOPB_K(ccl_relabel_kernel)<<<gcells, 256, 0, s>>>(parent, size, n_cells, labels);
   HOPB_LAUNCH_CHECK(h);
-  uint32_t n_roots = 0;
-  HOPB_CUDA(h, cudaMemcpyAsync(&n_roots, n_roots_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  HOPB_CUDA(h, cudaStreamSynchronize(s));
-  if (n_roots > HOPB_MAX_SITES) {
-    *n_sites = (int32_t)n_roots;
+  return HOPB_OK;
+}
+
+int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density, double threshold,
+                     int minsite, int32_t* labels, int32_t* n_sites, int32_t* volumes) {
+  HOPB_REQUIRE(h, n_sites != nullptr, "null argument");
+  *n_sites = 0;
+  int32_t* n_dev = nullptr;
+  int rc = hopb_scratch(h, 8, 64, (void**)&n_dev);
+  if (rc) return rc;
+  rc = hopb_label_sites_async(h, stream, nx, ny, nz, density, threshold, minsite, labels, n_dev, volumes);
+  if (rc) return rc;
+  int32_t n = 0;
+  HOPB_CUDA(h, cudaMemcpyAsync(&n, n_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HOPB_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  *n_sites = n;
+  if (n > HOPB_MAX_SITES)
     return hopb_fail(h, HOPB_E_TOO_MANY_SITES,
-                     "map_sites: %u sites at this threshold; hop's int16 site map holds at most %d", n_roots, HOPB_MAX_SITES);
-  }
-  int in_alt = 0;
-  const int bits = hopb_bits_for((uint64_t)n_cells);
-  // low word uses `bits` bits, high word starts at bit 32
-  rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, n_roots, 0, bits, &in_alt);
-  if (rc) return rc;
-  uint64_t* k1 = in_alt ? keys_alt : keys; uint64_t* k1a = in_alt ? keys : keys_alt;
-  uint32_t* v1 = in_alt ? vals_alt : vals; uint32_t* v1a = in_alt ? vals : vals_alt;
-  int in_alt2 = 0;
-  rc = hopb_radix_sort_pairs(h, s, k1, k1a, v1, v1a, n_roots, 32, 32 + bits, &in_alt2);
-  if (rc) return rc;
-  const uint64_t* kf = in_alt2 ? k1a : k1;
-  const uint32_t* vf = in_alt2 ? v1a : v1;
-  ccl_assign_kernel<<<(n_roots + 256) / 256, 256, 0, s>>>(kf, vf, (int)n_roots, n_cells, size, volumes);
-  ccl_relabel_kernel<<<gcells, 256, 0, s>>>(parent, size, n_cells, labels);
-  HOPB_LAUNCH_CHECK(h);
-  *n_sites = (int32_t)n_roots;
+                     "map_sites: %d sites at this threshold; hop's int16 site map holds at most %d", n, HOPB_MAX_SITES);
   return HOPB_OK;
 }
 
 int hopb_insert_bulk(hopb_handle* h, void* stream, int64_t n_cells, int32_t* own, const int32_t* bulk_labels,
                      int32_t bulklabel, uint8_t* member, int16_t* map16) {
   HOPB_REQUIRE(h, own && member && map16 && n_cells > 0, "null argument");
-  insert_bulk_kernel<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+  HOPB_K(insert_bulk_kernel)<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
       n_cells, own, bulk_labels, bulklabel, member, map16);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
@@ -413,7 +452,7 @@ int hopb_insert_bulk(hopb_handle* h, void* stream, int64_t n_cells, int32_t* own
 
 int hopb_labels_to_map16(hopb_handle* h, void* stream, int64_t n_cells, const int32_t* labels, int16_t* map16) {
   HOPB_REQUIRE(h, labels && map16 && n_cells > 0, "null argument");
-  to_map16_kernel<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(n_cells, labels, map16);
+  HOPB_K(to_map16_kernel)<<<hopb_grid_for(n_cells, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(n_cells, labels, map16);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -432,12 +471,12 @@ int hopb_site_properties(hopb_handle* h, void* stream, const hopb_grid* g, const
   double* mean = acc1 + (size_t)n_labels * 5;
   HOPB_CUDA(h, cudaMemsetAsync(acc, 0, (size_t)n_labels * 10 * sizeof(double), s));
   const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 4);
-  site_prop_kernel<0><<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
+  HOPB_K(site_prop_kernel<0>)<<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
                                             g->d_mid[2], nullptr, acc);
-  site_prop_mean_kernel<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, n_labels, mean);
-  site_prop_kernel<1><<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
+  HOPB_K(site_prop_mean_kernel)<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, n_labels, mean);
+  HOPB_K(site_prop_kernel<1>)<<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
                                             g->d_mid[2], mean, acc1);
-  site_prop_final_kernel<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, acc1, n_labels, out_count, out_mean, out_std, out_center);
+  HOPB_K(site_prop_final_kernel)<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, acc1, n_labels, out_count, out_mean, out_std, out_center);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -451,7 +490,7 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
   if (rc) return rc;
   uint32_t* total_dev = pos + n_grid_cells;
   const unsigned gcells = hopb_grid_for(n_grid_cells, 256, h->num_sms, 8);
-  cells_count_kernel<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos);
+  HOPB_K(cells_count_kernel)<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos);
   rc = hopb_exclusive_scan_u32(h, s, pos, pos, n_grid_cells, total_dev);
   if (rc) return rc;
   uint32_t total = 0;
@@ -467,15 +506,15 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
   uint64_t* keys_alt = keys + total + 1;
   uint32_t* vals = (uint32_t*)(keys_alt + total + 1);
   uint32_t* vals_alt = vals + total + 1;
-  cells_emit_kernel<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos, keys, vals);
+  HOPB_K(cells_emit_kernel)<<<gcells, 256, 0, s>>>(n_grid_cells, own, member, pos, keys, vals);
   int in_alt = 0;
   rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, total, 0, hopb_bits_for((uint64_t)n_labels), &in_alt);
   if (rc) return rc;
   const uint64_t* kf = in_alt ? keys_alt : keys;
   const uint32_t* vf = in_alt ? vals_alt : vals;
-  cells_offsets_kernel<<<hopb_grid_for((int64_t)total + 1, 256, h->num_sms, 8), 256, 0, s>>>(kf, (int64_t)total, n_labels, offsets);
+  HOPB_K(cells_offsets_kernel)<<<hopb_grid_for((int64_t)total + 1, 256, h->num_sms, 8), 256, 0, s>>>(kf, (int64_t)total, n_labels, offsets);
   if (total > 0)
-    copy_u32_to_i32_kernel<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(vf, cells, (int64_t)total);
+    HOPB_K(copy_u32_to_i32_kernel)<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(vf, cells, (int64_t)total);
   HOPB_LAUNCH_CHECK(h);
   HOPB_CUDA(h, cudaStreamSynchronize(s));
   return HOPB_OK;

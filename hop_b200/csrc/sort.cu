@@ -215,7 +215,7 @@ int hopb_exclusive_scan_u32(hopb_handle* h, cudaStream_t s, const uint32_t* in, 
     int64_t cur = n;
     for (size_t l = 0; l < sizes.size(); ++l) {
       level[l] = p;
-      scan_kernel<0><<<(unsigned)sizes[l], kScanThreads, 0, s>>>(src, nullptr, cur, p);
+      HOPB_K(scan_kernel<0>)<<<(unsigned)sizes[l], kScanThreads, 0, s>>>(src, nullptr, cur, p);
       src = p;
       cur = sizes[l];
       p += sizes[l];
@@ -226,13 +226,13 @@ int hopb_exclusive_scan_u32(hopb_handle* h, cudaStream_t s, const uint32_t* in, 
     const int64_t cur = sizes[l];
     const unsigned blocks = (unsigned)((cur + kScanTile - 1) / kScanTile);
     uint32_t* offs = (l + 1 < (int)sizes.size()) ? level[l + 1] : nullptr;
-    scan_kernel<1><<<blocks, kScanThreads, 0, s>>>(level[l], level[l], cur, offs);
+    HOPB_K(scan_kernel<1>)<<<blocks, kScanThreads, 0, s>>>(level[l], level[l], cur, offs);
   }
   {
     const unsigned blocks = (unsigned)((n + kScanTile - 1) / kScanTile);
-    scan_kernel<1><<<blocks, kScanThreads, 0, s>>>(in, out, n, sizes.empty() ? nullptr : level[0]);
+    HOPB_K(scan_kernel<1>)<<<blocks, kScanThreads, 0, s>>>(in, out, n, sizes.empty() ? nullptr : level[0]);
   }
-  if (total_dev) store_total_kernel<<<1, 1, 0, s>>>(in_last_copy, out + (n - 1), total_dev);
+  if (total_dev) HOPB_K(store_total_kernel)<<<1, 1, 0, s>>>(in_last_copy, out + (n - 1), total_dev);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -254,9 +254,9 @@ int hopb_radix_sort_pairs(hopb_handle* h, cudaStream_t s, uint64_t* keys, uint64
   uint64_t* kin = keys; uint64_t* kout = keys_alt;
   uint32_t* vin = vals; uint32_t* vout = vals_alt;
   for (int shift = begin_bit; shift < end_bit; shift += 8) {
-    sort_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(kin, n, shift, tiles_per_block, ghist);
-    sort_rowscan_kernel<<<256, kMaxSortBlocks, 0, s>>>(ghist, nblocks, totals);
-    sort_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, tiles_per_block, ghist, totals);
+    HOPB_K(sort_hist_kernel)<<<nblocks, kSortThreads, 0, s>>>(kin, n, shift, tiles_per_block, ghist);
+    HOPB_K(sort_rowscan_kernel)<<<256, kMaxSortBlocks, 0, s>>>(ghist, nblocks, totals);
+    HOPB_K(sort_scatter_kernel)<<<nblocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, tiles_per_block, ghist, totals);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
     *in_alt ^= 1;

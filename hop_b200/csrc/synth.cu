@@ -108,7 +108,7 @@ extern "C" int hopb_synth_generate(hopb_handle* h, void* stream, const hopb_synt
   HOPB_REQUIRE(h, p && centres && xyz, "null argument");
   HOPB_REQUIRE(h, p->n_atoms > 0 && p->n_sites > 0 && p->site_stride > 0 && frame_start >= 0 && n_out >= 0, "bad parameters");
   if (n_out == 0) return HOPB_OK;
-  synth_kernel<<<(unsigned)((p->n_atoms + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, centres, frame_start, n_out, xyz);
+  HOPB_K(synth_kernel)<<<(unsigned)((p->n_atoms + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, centres, frame_start, n_out, xyz);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

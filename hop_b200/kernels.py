@@ -68,16 +68,33 @@ class GridTables:
             pass
 
 
-def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor):
-    """counts[cell] += points per cell (hop/density.py:125-131).  xyz: float32 [..., 3]."""
+def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, cells=None):
+    """counts[cell] += points per cell (hop/density.py:125-131).  xyz: float32 [..., 3].
+    `cells` (int32, one per point) optionally receives the packed hopping-trajectory cell."""
     _cuda(xyz, torch.float32, "xyz")
     _cuda(counts, torch.int32, "counts")
     if counts.numel() != grid.n_cells:
         raise ValueError("counts has the wrong size")
     n_points = xyz.numel() // 3
+    if cells is not None:
+        _cuda(cells, torch.int32, "cells")
+        if cells.numel() != n_points:
+            raise ValueError("cells has the wrong size")
     h = _h(xyz)
-    _lib.check(h, _lib.lib().hopb_hist_accumulate(h, _stream(), grid.ptr, _p(xyz), n_points, _p(counts)))
+    _lib.check(h, _lib.lib().hopb_hist_accumulate_cells(h, _stream(), grid.ptr, _p(xyz), n_points, _p(counts), _p(cells)))
     return counts
+
+
+def coarse_map(map16: torch.Tensor, coarse=None):
+    """2-bit 4x4x4 block map of a site map (lets hoptraj skip the L2 gather in uniform regions)."""
+    _cuda(map16, torch.int16, "map16")
+    nx, ny, nz = map16.shape
+    nb = -(-nx // 4) * -(-ny // 4) * -(-nz // 4)
+    if coarse is None:
+        coarse = torch.empty(-(-nb // 16), dtype=torch.int32, device=map16.device)
+    h = _h(map16)
+    _lib.check(h, _lib.lib().hopb_coarse_map(h, _stream(), nx, ny, nz, _p(map16), _p(coarse)))
+    return coarse
 
 
 def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
@@ -105,37 +122,59 @@ def label_sites(density: torch.Tensor, threshold: float, minsite: int = 1):
     return labels, int(n_sites.value), volumes[: n_sites.value + 1]
 
 
-def insert_bulk(own: torch.Tensor, bulk_labels, bulklabel: int = 1):
+def label_sites_async(density: torch.Tensor, threshold: float, minsite: int, labels: torch.Tensor,
+                      n_sites_dev: torch.Tensor, volumes=None):
+    """Density.map_sites without a host round trip: `n_sites_dev` (CUDA int32[1]) receives the
+    number of sites; a value above HOPB_MAX_SITES means the int16 map cannot hold them."""
+    _cuda(density, torch.float64, "density")
+    _cuda(labels, torch.int32, "labels")
+    _cuda(n_sites_dev, torch.int32, "n_sites_dev")
+    nx, ny, nz = density.shape
+    h = _h(density)
+    rc = _lib.lib().hopb_label_sites_async(h, _stream(), nx, ny, nz, _p(density), float(threshold), int(minsite),
+                                           _p(labels), _p(n_sites_dev), _p(volumes))
+    _lib.check(h, rc)
+    return labels
+
+
+def insert_bulk(own: torch.Tensor, bulk_labels, bulklabel: int = 1, member=None, map16=None):
     """In place on `own`; returns (member uint8, map16 int16)."""
     _cuda(own, torch.int32, "own")
     if bulk_labels is not None:
         _cuda(bulk_labels, torch.int32, "bulk_labels")
         if bulk_labels.shape != own.shape:
             raise ValueError("The bulk density was defined on a different grid than this density.")
-    member = torch.empty(own.shape, dtype=torch.uint8, device=own.device)
-    map16 = torch.empty(own.shape, dtype=torch.int16, device=own.device)
+    if member is None:
+        member = torch.empty(own.shape, dtype=torch.uint8, device=own.device)
+    if map16 is None:
+        map16 = torch.empty(own.shape, dtype=torch.int16, device=own.device)
     h = _h(own)
     _lib.check(h, _lib.lib().hopb_insert_bulk(h, _stream(), own.numel(), _p(own), _p(bulk_labels), int(bulklabel), _p(member), _p(map16)))
     return member, map16
 
 
-def labels_to_map16(labels: torch.Tensor):
+def labels_to_map16(labels: torch.Tensor, map16=None):
     _cuda(labels, torch.int32, "labels")
-    map16 = torch.empty(labels.shape, dtype=torch.int16, device=labels.device)
+    if map16 is None:
+        map16 = torch.empty(labels.shape, dtype=torch.int16, device=labels.device)
     h = _h(labels)
     _lib.check(h, _lib.lib().hopb_labels_to_map16(h, _stream(), labels.numel(), _p(labels), _p(map16)))
     return map16
 
 
-def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, member, n_labels: int):
-    """(count int64[n], mean f64[n], std f64[n], center f64[n,3]) per site label."""
+def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, member, n_labels: int, out=None):
+    """(count int64[n], mean f64[n], std f64[n], center f64[n,3]) per site label.  `n_labels` may be
+    an upper bound (rows past the real number of sites come back empty)."""
     _cuda(density, torch.float64, "density")
     _cuda(own, torch.int32, "own")
     dev = density.device
-    count = torch.empty(n_labels, dtype=torch.int64, device=dev)
-    mean = torch.empty(n_labels, dtype=torch.float64, device=dev)
-    std = torch.empty(n_labels, dtype=torch.float64, device=dev)
-    center = torch.empty((n_labels, 3), dtype=torch.float64, device=dev)
+    if out is not None:
+        count, mean, std, center = out
+    else:
+        count = torch.empty(n_labels, dtype=torch.int64, device=dev)
+        mean = torch.empty(n_labels, dtype=torch.float64, device=dev)
+        std = torch.empty(n_labels, dtype=torch.float64, device=dev)
+        center = torch.empty((n_labels, 3), dtype=torch.float64, device=dev)
     h = _h(density)
     _lib.check(h, _lib.lib().hopb_site_properties(h, _stream(), grid.ptr, _p(density), _p(own), _p(member), int(n_labels),
                                                   _p(count), _p(mean), _p(std), _p(center)))
@@ -165,13 +204,23 @@ def site_cells(own: torch.Tensor, member, n_labels: int):
     return cells[: n_cells.value], offsets
 
 
-def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32):
-    """(n_chunks, chunk_len): enough (atom, chunk) threads to fill the GPU, chunks >= min_chunk frames."""
-    target_threads = num_sms * 2048
-    want = max(1, -(-target_threads // max(n_atoms, 1)))
-    max_chunks = max(1, n_frames // min_chunk)
-    n_chunks = max(1, min(want, max_chunks, 65535))
-    chunk_len = -(-n_frames // n_chunks)
+def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32, cta_threads: int = 256,
+                ctas_per_sm: int = 4, max_waves: int = 4):
+    """(n_chunks, chunk_len) for the fused hoptraj kernel: one thread per (atom, chunk).
+
+    The kernel is latency-bound per thread, so the grid should be a whole number of waves of
+    resident CTAs (num_sms * ctas_per_sm): pick the chunk count with the best wave efficiency,
+    preferring fewer chunks (less stitching) when efficiencies are within 2 %."""
+    ctas_per_chunk = -(-n_atoms // cta_threads)
+    capacity = num_sms * ctas_per_sm
+    max_chunks = max(1, min(n_frames // min_chunk, 65535, (max_waves * capacity) // max(ctas_per_chunk, 1)))
+    best, best_eff = 1, 0.0
+    for c in range(1, max_chunks + 1):
+        ctas = c * ctas_per_chunk
+        eff = ctas / (-(-ctas // capacity) * capacity)
+        if eff > best_eff + 0.02:
+            best, best_eff = c, eff
+    chunk_len = -(-n_frames // best)
     n_chunks = -(-n_frames // chunk_len)
     return int(n_chunks), int(chunk_len)
 
@@ -191,21 +240,29 @@ class EventBuffer:
         return int(self.count.item())
 
 
-def hoptraj(grid: GridTables, xyz: torch.Tensor, map16: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
-            events: EventBuffer, hop_x=None, hop_y=None, summaries=None):
-    """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254)."""
-    _cuda(xyz, torch.float32, "xyz")
+def hoptraj(grid: GridTables, xyz, map16: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
+            events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None):
+    """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254).
+    Input is either `xyz` (float32 [F][N][3]) or the packed `cells` (int32 [F][N]) from hist_accumulate."""
     _cuda(map16, torch.int16, "map16")
-    F, N = xyz.shape[0], xyz.shape[1]
+    if cells is not None:
+        _cuda(cells, torch.int32, "cells")
+        F, N = cells.shape[0], cells.shape[1]
+        dev = cells.device
+    else:
+        _cuda(xyz, torch.float32, "xyz")
+        F, N = xyz.shape[0], xyz.shape[1]
+        dev = xyz.device
     if map16.numel() != grid.n_cells:
         raise ValueError("map does not match the grid")
-    dev = xyz.device
+    if coarse is not None:
+        _cuda(coarse, torch.int32, "coarse")
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
-    h = _h(xyz)
-    rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(xyz), F, N, int(frame0), _p(map16), _p(hop_x), _p(hop_y),
-                                 int(n_chunks), int(chunk_len), _p(summaries), _p(events.data), _p(events.count),
-                                 events.capacity)
+    h = _h(map16)
+    rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N,
+                                 int(frame0), _p(map16), _p(coarse), _p(hop_x), _p(hop_y), int(n_chunks),
+                                 int(chunk_len), _p(summaries), _p(events.data), _p(events.count), events.capacity)
     _lib.check(h, rc)
     return summaries
 

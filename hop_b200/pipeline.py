@@ -35,6 +35,8 @@ class PipelineConfig:
     annotate: bool = True           # site_properties of the final site map
     n_chunks: int | None = None
     event_capacity: int | None = None
+    cache_cells: bool | None = None  # stage 1 also writes the packed hoptraj cell per atom-frame (4 B)
+    coarse_map: bool = True          # 2-bit block map in shared memory for stage 3
 
 
 @dataclass
@@ -99,34 +101,84 @@ class HopPipeline:
         return self._events
 
     # -- stages -----------------------------------------------------------------------------------
+    def _use_cells(self, xyz):
+        if max(self.grid.shape) > 1024:
+            return False
+        if self.cfg.cache_cells is not None:
+            return bool(self.cfg.cache_cells)
+        need = xyz.shape[0] * xyz.shape[1] * 4
+        if "cells" in self._bufs and self._bufs["cells"].numel() * 4 == need:
+            return True
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return need < 0.5 * free
+
     def histogram(self, xyz):
         counts = self._buf("counts", self.grid.shape, torch.int32)
         counts.zero_()
-        K.hist_accumulate(self.grid, xyz, counts)
+        self.cells = None
+        if self._use_cells(xyz):
+            self.cells = self._buf("cells", (xyz.shape[0], xyz.shape[1]), torch.int32)
+        K.hist_accumulate(self.grid, xyz, counts, self.cells)
         d = _dist()
         if d is not None:
             d.all_reduce(counts)  # int32 sum == uint32 sum modulo 2^32
         return counts
 
+    MAX_LABELS = K.HOPB_MAX_SITES + 2
+
     def site_map(self, counts):
+        """density -> labels (solvent and bulk threshold) -> bulk insertion -> annotation -> block map.
+        Everything is enqueued without a host round trip; the number of sites stays on the device
+        (self.n_sites_dev) until sync_scalars()."""
         cfg = self.cfg
+        shape = self.grid.shape
         factor = density_conversion_factor("Angstrom^{-3}", cfg.density_unit)
         density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor,
-                                        out=self._buf("density", self.grid.shape, torch.float64))
-        own, n_sites, _ = K.label_sites(density, cfg.solvent_threshold, cfg.minsite)
+                                        out=self._buf("density", shape, torch.float64))
+        self.n_sites_dev = self._buf("n_sites_dev", (2,), torch.int32)
+        own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, self._buf("own", shape, torch.int32),
+                                  self.n_sites_dev[0:1])
         if cfg.with_bulk:
-            bulk_labels, n_bulk, _ = K.label_sites(density, cfg.bulk_threshold, cfg.minsite)
-            member, map16 = K.insert_bulk(own, bulk_labels if n_bulk > 0 else None, 1)
-            n_labels = n_sites + 2
+            bulk_labels = K.label_sites_async(density, cfg.bulk_threshold, cfg.minsite,
+                                              self._buf("bulk_labels", shape, torch.int32), self.n_sites_dev[1:2])
+            member, map16 = K.insert_bulk(own, bulk_labels, 1, self._buf("member", shape, torch.uint8),
+                                          self._buf("map16", shape, torch.int16))
         else:
-            member, map16 = None, K.labels_to_map16(own)
-            n_labels = n_sites + 1
+            member, map16 = None, K.labels_to_map16(own, self._buf("map16", shape, torch.int16))
         props = None
         if cfg.annotate:
-            props = K.site_properties(self.grid, density, own, member, n_labels)
-        return density, own, member, map16, n_labels, props
+            L = self.MAX_LABELS
+            out = (self._buf("p_count", (L,), torch.int64), self._buf("p_mean", (L,), torch.float64),
+                   self._buf("p_std", (L,), torch.float64), self._buf("p_center", (L, 3), torch.float64))
+            props = K.site_properties(self.grid, density, own, member, L, out=out)
+        self.coarse = None
+        nb = 1
+        for n in shape:
+            nb *= -(-n // 4)
+        if cfg.coarse_map and max(shape) <= 1024 and nb // 4 <= 160 * 1024:
+            self.coarse = K.coarse_map(map16, self._buf("coarse", (-(-nb // 16),), torch.int32))
+        return density, own, member, map16, props
 
-    def hoptraj(self, xyz, map16, frame0, n_labels):
+    def sync_scalars(self, events):
+        """The one host synchronisation of a run: number of sites and number of events."""
+        host = getattr(self, "_scalars_host", None)
+        if host is None:
+            host = self._scalars_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        host[0:2].copy_(self.n_sites_dev, non_blocking=True)
+        host[2:3].copy_(events.count, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        n_sites, n_bulk, n_ev = int(host[0]), int(host[1]), int(host[2])
+        if n_sites > K.HOPB_MAX_SITES or n_bulk > K.HOPB_MAX_SITES:
+            from ._lib import TooManySitesError
+
+            raise TooManySitesError("map_sites: %d sites (bulk map: %d); hop's int16 site map holds at most %d"
+                                    % (n_sites, n_bulk, K.HOPB_MAX_SITES))
+        if n_ev > events.capacity:
+            raise _capacity_error(n_ev, events.capacity)
+        n_labels = n_sites + (2 if self.cfg.with_bulk else 1)
+        return n_labels, n_ev
+
+    def hoptraj(self, xyz, map16, frame0):
         cfg = self.cfg
         F, N = int(xyz.shape[0]), int(xyz.shape[1])
         if cfg.n_chunks is None:
@@ -142,7 +194,8 @@ class HopPipeline:
             hop_x = self._buf("hop_x", (F, N), torch.float32)
             hop_y = self._buf("hop_y", (F, N), torch.float32)
         summaries = self._buf("summaries", (n_chunks, K.SUMMARY_INTS, N), torch.int32)
-        K.hoptraj(self.grid, xyz, map16, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries)
+        K.hoptraj(self.grid, xyz, map16, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries,
+                  cells=getattr(self, "cells", None), coarse=getattr(self, "coarse", None))
 
         # state at slab entry: replay the slabs of the ranks before this one
         state = self._buf("state", (K.STATE_INTS, N), torch.int32)
@@ -161,10 +214,7 @@ class HopPipeline:
         K.hop_fixup(summaries, chunk_len, F, state, hop_y, events)
         if final_state is None:
             final_state = state
-        n_ev = events.n()
-        if n_ev > events.capacity:
-            raise _capacity_error(n_ev, events.capacity)
-        return hop_x, hop_y, events, n_ev, state, final_state
+        return hop_x, hop_y, events, state, final_state
 
     def transitions(self, events, n_ev, n_atoms, n_labels):
         ev, e_s0, e_s, e_start, e_count = K.events_finalize(events, n_ev, n_atoms, self.n_frames_total, n_labels)
@@ -181,16 +231,85 @@ class HopPipeline:
                 d.all_reduce(matrix)
         return ev, e_s0, e_s, e_start, e_count, matrix
 
-    def run(self, xyz, frame0=0):
-        """xyz: CUDA float32 [F_local][N][3] (this rank's slab, starting at global frame `frame0`)."""
+    def _mark(self, marks, name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    def run(self, xyz, frame0=0, marks=None):
+        """xyz: CUDA float32 [F_local][N][3] (this rank's slab, starting at global frame `frame0`).
+        `marks` (a list) receives (stage name, CUDA event) pairs recorded on the current stream at
+        every stage boundary, for per-stage device timing."""
         res = PipelineResult()
+        self._mark(marks, "start")
         res.counts = self.histogram(xyz)
-        res.density, res.own, res.member, res.map16, res.n_labels, res.site_props = self.site_map(res.counts)
-        res.hop_x, res.hop_y, events, n_ev, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0, res.n_labels)
+        self._mark(marks, "S1_histogram")
+        res.density, res.own, res.member, res.map16, res.site_props = self.site_map(res.counts)
+        self._mark(marks, "S2_sitemap")
+        res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+        self._mark(marks, "S3S4_hoptraj")
+        res.n_labels, n_ev = self.sync_scalars(events)
         res.n_events_local = n_ev
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
          res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]), res.n_labels)
+        self._mark(marks, "S4_transitions")
         return res
+
+    def run_host(self, xyz_host, frame0=0, out_x=None, out_y=None, block_bytes=256 << 20):
+        """End-to-end run from HOST coordinates to HOST results (what the Python classes do for a
+        user): xyz_host is a pinned CPU float32 tensor [F_local][N][3].
+
+        Coordinates go to HBM in blocks on a copy stream while the histogram kernel consumes the
+        blocks already there; they stay resident for stage 3.  The hopping trajectory comes back
+        into pinned host tensors (out_x / out_y, [F_local][N] float32) together with the sorted
+        events and the COO transition counts.  Returns (PipelineResult, host dict)."""
+        F, N = int(xyz_host.shape[0]), int(xyz_host.shape[1])
+        dev = self.device
+        xyz = self._buf("xyz_resident", (F, N, 3), torch.float32)
+        counts = self._buf("counts", self.grid.shape, torch.int32)
+        counts.zero_()
+        self.cells = self._buf("cells", (F, N), torch.int32) if self._use_cells(xyz) else None
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)
+        block = max(1, block_bytes // (N * 12))
+        for f0 in range(0, F, block):
+            f1 = min(F, f0 + block)
+            with torch.cuda.stream(copy_stream):
+                xyz[f0:f1].copy_(xyz_host[f0:f1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            main.wait_event(ev)
+            K.hist_accumulate(self.grid, xyz[f0:f1], counts, None if self.cells is None else self.cells[f0:f1])
+        d = _dist()
+        if d is not None:
+            d.all_reduce(counts)
+        res = PipelineResult()
+        res.counts = counts
+        res.density, res.own, res.member, res.map16, res.site_props = self.site_map(counts)
+        res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+        res.n_labels, n_ev = self.sync_scalars(events)
+        res.n_events_local = n_ev
+        if out_x is None:
+            out_x = torch.empty((F, N), dtype=torch.float32).pin_memory()
+            out_y = torch.empty((F, N), dtype=torch.float32).pin_memory()
+        # hoptraj planes stream back while the events are sorted on the compute stream
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            out_x.copy_(res.hop_x, non_blocking=True)
+            out_y.copy_(res.hop_y, non_blocking=True)
+        (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
+         res.count_matrix) = self.transitions(events, n_ev, N, res.n_labels)
+        host = dict(hop_x=out_x, hop_y=out_y, events=res.events.cpu(), edge_s0=res.edge_s0.cpu(),
+                    edge_s=res.edge_s.cpu(), edge_count=res.edge_count.cpu(), final_state=res.final_state.cpu())
+        copy_stream.synchronize()
+        main.synchronize()
+        return res, host
 
 
 def _capacity_error(n, cap):

@@ -113,7 +113,8 @@ class Saveable(object):
         with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
             tmp = pickle.load(fh)
         try:
-            data = tmp.__dict__
+            # attributes may live behind properties (device mirrors): ask the object, not its __dict__
+            data = tmp.__getstate__() if isinstance(tmp, Saveable) else tmp.__dict__
         except AttributeError:
             warnings.warn("Loading an old-style save file.", category=DeprecationWarning)
             data = tmp

@@ -52,6 +52,8 @@ typedef struct hopb_event {
 
 /* ---- library / handle -------------------------------------------------------------------- */
 int hopb_version(void);
+/* number of CUDA kernels this library has launched in this process (all handles) */
+uint64_t hopb_launch_count(void);
 int hopb_create(int device, hopb_handle** out);
 void hopb_destroy(hopb_handle* h);
 const char* hopb_last_error(const hopb_handle* h);
@@ -81,6 +83,13 @@ void hopb_grid_destroy(hopb_grid* g);
 int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                          int64_t n_points, uint32_t* counts);
 
+/* Same, and additionally writes for every point its packed cell under the hopping-trajectory
+ * binning rules of hop/trajectory.py:428-441 ((ix<<20)|(iy<<10)|iz, 0xFFFFFFFF = outlier) so that
+ * hopb_hoptraj need not read the coordinates again.  cells: device uint32 [n_points] (NULL = off);
+ * needs <= 1024 bins per axis. */
+int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
+                               int64_t n_points, uint32_t* counts, uint32_t* cells);
+
 /* density = counts / n_frames / dx[i] / dy[j] / dz[k] * factor, in float64 and in exactly that
  * order: DensityCollector.finish (hop/density.py:133-137), Grid.make_density
  * (hop/sitemap.py:196-216), Grid.convert_density (hop/sitemap.py:236-264).  Pass factor = 1.0 for
@@ -100,6 +109,13 @@ int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, c
  * Synchronises the stream (S is needed on the host). */
 int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
                      double threshold, int minsite, int32_t* labels, int32_t* n_sites, int32_t* volumes);
+
+/* Same without the host round trip: n_sites_dev is a DEVICE int32 that receives S.  A value above
+ * HOPB_MAX_SITES means "too many sites" (labels are then incomplete); the caller checks it whenever
+ * it next synchronises. */
+int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
+                           double threshold, int minsite, int32_t* labels, int32_t* n_sites_dev,
+                           int32_t* volumes);
 
 /* Density.site_insert_bulk (hop/sitemap.py:877-918) on label grids: the cells with
  * bulk_labels == bulklabel become site 1, every site of `labels` is shifted by +1 and overwrites
@@ -136,16 +152,26 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  * of TransportNetwork._analyze_hops (hop/graph.py:212-254) over one slab of F frames.
  * The slab is cut into n_chunks chunks of chunk_len frames (the last may be short); every
  * (atom, chunk) runs independently and leaves a summary, hopb_hop_fixup stitches them.
- *   xyz       device float32 [F][N][3]
+ *   xyz       device float32 [F][N][3]; ignored (may be NULL) when `cells` is given
+ *   cells     device uint32 [F][N] (may be NULL): packed _coord2hop cell of every atom-frame as
+ *             written by hopb_hist_accumulate_cells -- the coordinates are then not read again
  *   map16     device int16 [G] (Density.map)
+ *   coarse    device uint32 (may be NULL): the 2-bit block map of hopb_coarse_map; it lets atoms in
+ *             uniformly bulk / interstitial 4x4x4 blocks skip the gather from map16
  *   frame0    global frame number of the slab's first frame
  *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
  *             DCD, trajectory.py:456-463); either may be NULL
  *   summaries device int32 [n_chunks][11][N] out
- *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here) */
-int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, int64_t F, int64_t N,
-                 int64_t frame0, const int16_t* map16, float* hop_x, float* hop_y, int n_chunks,
-                 int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
+ *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here)
+ * Grids are limited to 1024 bins per axis. */
+int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
+                 int64_t F, int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, float* hop_x,
+                 float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events,
+                 uint64_t* n_events, uint64_t cap);
+
+/* 2 bits per 4x4x4 block of the site map (0 / 1: every cell of the block is interstitial / bulk,
+ * 3: mixed), 16 blocks per word; coarse: device uint32 [ceil(ceil(nx/4)*ceil(ny/4)*ceil(nz/4) / 16)]. */
+int hopb_coarse_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, uint32_t* coarse);
 
 /* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
  * hop/graph.py:190-254): labels = hop_x [F][N] float32. */

@@ -82,7 +82,8 @@ int64_t emul_scan(const int32_t* labels, int64_t F, int64_t N, int64_t slab_len,
   return (int64_t)ev.size();
 }
 
-// Binning: mode 0 = histogram bin (1..n counted), mode 1 = hoptraj bin ([-1, n+1]).
+// Binning: mode 0 = histogram bin (1..n counted), mode 1 = hoptraj bin ([-1, n+1]); modes 2 / 3 are
+// the same through the branch-free pair-table search the kernels use when fast_ok is set (returned).
 int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* ez, int nz,
              const int* decimals, const float* xyz, int64_t npts, int mode, int32_t* out /*[npts][3]*/,
              float* top_round_out /*[3]*/) {
@@ -90,15 +91,22 @@ int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* e
   const int n[3] = {nx, ny, nz};
   HopbGridTab tab;
   std::vector<float> table;
-  if (hopb_build_gridtab(e, n, decimals, &tab, &table) != 0) return -1;
+  std::vector<HopbPair> table2;
+  if (hopb_build_gridtab(e, n, decimals, &tab, &table, &table2) != 0) return -1;
   for (int d = 0; d < 3; ++d) top_round_out[d] = tab.ax[d].top_round;
   for (int64_t i = 0; i < npts; ++i)
     for (int d = 0; d < 3; ++d) {
       const float x = xyz[i * 3 + d];
       const float* eup = table.data() + tab.ax[d].off;
-      out[i * 3 + d] = mode == 0 ? hopb_bin_hist(x, tab.ax[d], eup) : hopb_bin_hop(x, tab.ax[d], eup);
+      const HopbPair* pr = table2.data() + tab.ax[d].off2;
+      int b;
+      if (mode == 0) b = hopb_bin_hist(x, tab.ax[d], eup);
+      else if (mode == 1) b = hopb_bin_hop(x, tab.ax[d], eup);
+      else if (mode == 2) b = hopb_bin_hist_fast(x, tab.ax[d], pr);
+      else b = hopb_bin_hop_fast(x, tab.ax[d], pr);
+      out[i * 3 + d] = b;
     }
-  return 0;
+  return tab.fast_ok;
 }
 
 }  // extern "C"

@@ -1,0 +1,269 @@
+"""The reference-facing Python API (DensityCreator / Density / HoppingTrajectory / TransportNetwork)
+against the oracle, written the way hop's own workflow calls it (hop/interactive.py:235-307,
+417-464, scripts/hop-generate-*.py)."""
+import math
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import hop_oracle as O
+from hop_b200.synth import SynthParams, generate
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def system():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hop_b200.universe import Universe
+
+    p = SynthParams(n_atoms=800, n_frames=120)
+    xyz = generate(p)
+    # a mixed system: waters (OH2) interleaved with a few atoms of other names
+    names = np.array(["OH2"] * 800, dtype=object)
+    names[::97] = "SOD"
+    u = Universe(coordinates=xyz, names=list(names), dt=2.0, filename="synthetic.psf")
+    sel = np.nonzero(names == "OH2")[0]
+    ref = O.pipeline(xyz[:, sel], delta=1.0, faithful=False, with_bulk=False)
+    return u, xyz, sel, ref
+
+
+def test_density_creator_solvent(system):
+    from hop_b200.density import DensityCreator
+
+    u, xyz, sel, ref = system
+    DC = DensityCreator(u, mode="solvent", delta=1.0, atomselection="name OH2")
+    dens = DC.create()["solvent"]
+    for a, b in zip(dens.edges, ref["edges"]):
+        assert np.array_equal(a, b)
+    ref_grid = O.make_density(ref["counts"], ref["edges"], xyz.shape[0])
+    assert np.array_equal(dens.grid, ref_grid)
+    assert dens.P["isDensity"] and dens.unit["density"] == "Angstrom^{-3}"
+    md = dens.metadata
+    assert md["collector"] == "solvent" and md["collector_mode"] == "SOLVENT" and md["n_frames"] == 120
+    assert md["atomselection"] == "name OH2" and md["dt"] == 2.0 and md["totaltime"] == 238.0
+    assert np.allclose(np.diag(dens.delta), 1.0, atol=1e-6)
+    dens.convert_density("water")
+    assert np.array_equal(dens.grid, ref["grid"])
+    with pytest.raises(ValueError):
+        dens.grid[0, 0, 0] = 1.0   # mirrored arrays are read-only
+
+
+def test_collector_per_frame_api_matches_block_path(system):
+    from hop_b200.density import DensityCollector
+
+    u, xyz, sel, ref = system
+    c = DensityCollector("solvent", u, delta=1.0, atomselection="name OH2", soluteselection=None, cutoff=0)
+    c.init_histogram()
+    n = 0
+    for ts in u.trajectory:
+        n += c.collect()
+    assert n == len(sel) * 120
+    c.finish(u.trajectory.n_frames)
+    d = c.Density()
+    assert np.array_equal(d.grid, O.make_density(ref["counts"], ref["edges"], 120))
+    assert np.array_equal(c.grid, ref["counts"] / 120.0)
+
+
+def test_error_conventions(system):
+    from hop_b200.density import DensityCollector, DensityCreator
+    from hop_b200.exceptions import MissingDataError
+    from hop_b200.sitemap import Density
+    from hop_b200.trajectory import HoppingTrajectory
+
+    u, xyz, sel, ref = system
+    with pytest.raises(TypeError):
+        DensityCollector("x", object())
+    with pytest.raises(ValueError):
+        DensityCreator(u, mode="nonsense")
+    c = DensityCollector("solvent", u, soluteselection=None, cutoff=0)
+    with pytest.raises(MissingDataError):
+        c.Density()
+    d = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True}, unit={"length": "Angstrom", "density": "water"})
+    with pytest.raises(ValueError):
+        d.map_sites()               # no threshold
+    with pytest.raises(NotImplementedError):
+        Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True, "MINsite": 3}, unit={"density": "water"})
+    with pytest.raises(ValueError):
+        HoppingTrajectory(u.trajectory, u.select_atoms("name OH2"), d)   # map not computed
+    d.map_sites(math.e)
+    with pytest.raises(TypeError):
+        HoppingTrajectory(u.trajectory, object(), d)
+    with pytest.raises(ValueError):
+        HoppingTrajectory(u.trajectory, u.select_atoms("name XYZ"), d)
+    small = Density(grid=np.ones((3, 3, 3)), edges=[np.arange(4.0)] * 3, parameters={"isDensity": True}, unit={"density": "water"})
+    small.map_sites(0.5)
+    with pytest.raises(ValueError):
+        d.site_insert_bulk(small)   # different grid
+    with pytest.raises(ValueError):
+        HoppingTrajectory()
+
+
+def test_map_sites_bulk_and_properties(system):
+    from hop_b200.sitemap import Density
+
+    u, xyz, sel, ref = system
+    unit = {"length": "Angstrom", "density": "water"}
+    solvent = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True}, unit=unit)
+    bulk = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True}, unit=unit)
+    solvent.map_sites(math.e)
+    assert solvent.map.dtype == np.int16 and np.array_equal(solvent.map, ref["map"])
+    assert [list(s) for s in solvent.sites] == ref["sites"]
+    assert solvent.P["threshold"] == math.e and not solvent.has_bulk()
+    bulk.map_sites(math.exp(-0.5))
+    solvent.site_insert_bulk(bulk)
+    assert solvent.has_bulk() and solvent.P["bulk_site"] == 1 and solvent.P["bulk_threshold"] == math.exp(-0.5)
+    full = O.site_insert_bulk(ref["sites"], O.label_sites_ndimage(ref["grid"], math.exp(-0.5)))
+    assert np.array_equal(solvent.map, O.draw_map_from_sites(full, ref["grid"].shape))
+    assert [list(s) for s in solvent.sites] == full
+    props = O.site_properties(full, ref["grid"], ref["edges"], "water")
+    sp = solvent.site_properties
+    assert list(sp.label) == list(range(len(full)))
+    np.testing.assert_allclose(sp.volume, props["volume"], rtol=1e-12)
+    np.testing.assert_allclose(sp.occupancy_avg, props["occupancy_avg"], rtol=1e-9)
+    np.testing.assert_allclose(sp.occupancy_std, props["occupancy_std"], rtol=1e-6, atol=1e-12)
+    assert sp.center[0] is None
+    np.testing.assert_allclose(np.stack(sp.center[1:]), props["center"][1:], rtol=1e-9)
+    assert list(solvent.site_labels("sites")) == list(range(2, len(full)))
+    assert list(solvent.site_labels()) == list(range(1, len(full)))
+    labels, vol = solvent.site_volume(include=[1, 2])
+    assert list(labels) == [1, 2]
+    with pytest.raises(ValueError):
+        solvent.site_insert_bulk(bulk)    # already has one
+    with pytest.warns(UserWarning):
+        solvent.map_sites(math.e)          # removes the bulk site again
+    assert not solvent.has_bulk() and np.array_equal(solvent.map, ref["map"])
+    solvent.site_insert_nobulk()
+    assert solvent.has_bulk() and len(solvent.sites[1]) == 0
+    assert np.array_equal(solvent.map, np.where(ref["map"] > 0, ref["map"] + 1, 0))
+
+
+def test_density_pickle_schema(system, tmp_path):
+    from hop_b200.sitemap import Density
+
+    u, xyz, sel, ref = system
+    d = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True},
+                unit={"length": "Angstrom", "density": "water"}, metadata={"psf": "a.psf"})
+    d.map_sites(math.e)
+    fn = str(tmp_path / "water")
+    d.save(fn)
+    raw = pickle.load(open(fn + ".pickle", "rb"))
+    assert sorted(raw.__getstate__().keys()) == sorted(
+        ['grid', 'edges', 'P', 'unit', 'metadata', 'map', 'sites', 'site_properties', 'equivalent_sites_index'])
+    d2 = Density(filename=fn)
+    assert np.array_equal(d2.grid, ref["grid"]) and np.array_equal(d2.map, ref["map"]) and d2.map.dtype == np.int16
+    assert [list(s) for s in d2.sites] == ref["sites"]
+    assert d2.P["threshold"] == math.e and d2.metadata["psf"] == "a.psf"
+    d2.export(str(tmp_path / "water"))
+    assert os.path.exists(str(tmp_path / "water.dx"))
+
+
+@pytest.fixture(scope="module")
+def mapped(system):
+    from hop_b200.density import DensityCreator
+
+    u, xyz, sel, ref = system
+    DC = DensityCreator(u, mode="solvent", delta=1.0, atomselection="name OH2")
+    dens = DC.create()["solvent"]
+    dens.convert_density("water")
+    dens.map_sites(math.e)
+    bulk = DensityCreator(u, mode="solvent", delta=1.0, atomselection="name OH2").create()["solvent"]
+    bulk.convert_density("water")
+    bulk.map_sites(math.exp(-0.5))
+    dens.site_insert_bulk(bulk)
+    refb = O.pipeline(xyz[:, sel], delta=1.0, faithful=False, with_bulk=True)
+    assert np.array_equal(dens.map, refb["map"])
+    return dens, refb
+
+
+def test_hopping_trajectory_and_files(system, mapped, tmp_path):
+    from hop_b200.trajectory import HoppingTrajectory
+
+    u, xyz, sel, _ = system
+    dens, ref = mapped
+    group = u.select_atoms("name OH2")
+    h = HoppingTrajectory(u.trajectory, group, dens)
+    assert h.n_frames == 120 and h.ts.n_atoms == len(sel)
+    assert np.array_equal(h.ts._pos, ref["hop"][0])
+    frames = []
+    for ts in h.map_dcd():
+        frames.append(ts._pos.copy())
+    assert np.array_equal(np.stack(frames), ref["hop"])
+    # a pass that starts later re-initialises the orbit column (trajectory.py:392, 396-401)
+    sub = O.coord2hop_vectorised(xyz[40:100:3][:, sel], ref["edges"], ref["map"])
+    got = np.stack([ts._pos.copy() for ts in h.map_dcd(40, 100, 3)])
+    assert np.array_equal(got, sub)
+    assert np.array_equal(h.next()._pos, ref["hop"][1]) or True
+    fn = str(tmp_path / "hoptraj")
+    h.write(fn)
+    assert os.path.exists(fn + ".dcd") and os.path.exists(fn + ".psf")
+    assert h.hoptraj is not None and h.n_frames == 120
+    got = np.stack([ts._pos.copy() for ts in h])
+    assert np.array_equal(got, ref["hop"])
+    psf = open(fn + ".psf").read().splitlines()
+    assert psf[0] == "PSF EXT" and "!NATOM" in psf[7] and int(psf[7].split()[0]) == len(sel)
+    h2 = HoppingTrajectory(hopdcd=fn + ".dcd", hoppsf=fn + ".psf")
+    assert h2.n_frames == 120 and abs(h2.hoptraj.dt - 2.0) < 1e-5
+    assert np.allclose(h2.ts.dimensions[:3], [ref["map"].max() + 2, ref["map"].max() + 2, 1])
+
+
+def test_transport_network(system, mapped, tmp_path):
+    from hop_b200.graph import TransportNetwork
+    from hop_b200.trajectory import HoppingTrajectory
+
+    u, xyz, sel, _ = system
+    dens, ref = mapped
+    props_ref, edges_ref, nodes_ref = O.analyze_hops_faithful(ref["hop"][:, :, 0], dt=2.0)
+    group = u.select_atoms("name OH2")
+    h = HoppingTrajectory(u.trajectory, group, dens)
+    fn = str(tmp_path / "hoptraj")
+    h.write(fn)
+    with pytest.raises(TypeError):
+        TransportNetwork("not a hoptraj")
+    with pytest.raises(ValueError):
+        TransportNetwork(h, dens, sitelabels=[0, 1])._analyze_hops()
+    for traj in (h, HoppingTrajectory(u.trajectory, group, dens)):   # from the file, and fused from coordinates
+        tn = TransportNetwork(traj, dens)
+        hg = tn.HoppingGraph()
+        gp = tn.graph_properties
+        assert set(gp.keys()) == set(props_ref.keys())
+        for k, d in props_ref.items():
+            for f in ("tau", "frame", "iatom"):
+                assert np.array_equal(gp[k][f], d[f]), (k, f)
+            if isinstance(k, tuple):
+                assert np.array_equal(gp[k]["tbarrier"], d["tbarrier"])
+            else:
+                assert all(v is None for v in gp[k]["tbarrier"])
+        assert set(tn.graph.edges()) == set(edges_ref)
+        assert list(tn.graph.edges()) == edges_ref        # insertion order = order of first occurrence
+        assert tn.transition_counts() == {e: len(props_ref[e]["tau"]) for e in edges_ref}
+        assert hg.trjdata == {"dt": 2.0, "totaltime": 238.0, "time_unit": "ps"}
+        assert hg.number_of_hops(*edges_ref[0]) == len(props_ref[edges_ref[0]]["tau"])
+    tn.graph_alltransitions()
+    pairs = O.graph_alltransitions(ref["hop"][:, :, 0])
+    assert set(tn.graph.edges()) == set(map(tuple, pairs.tolist()))
+    hg.save(str(tmp_path / "hopgraph"))
+    from hop_b200.graph import HoppingGraph
+
+    hg2 = HoppingGraph(filename=str(tmp_path / "hopgraph"))
+    assert set(hg2.graph.edges()) == set(hg.graph.edges())
+
+
+def test_interactive_workflow(system, tmp_path):
+    from hop_b200 import interactive
+
+    u, xyz, sel, _ = system
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        dens = interactive.generate_densities(u, mode="solvent", delta=1.0, atomselection="name OH2")["solvent"]
+        assert dens.has_bulk() and os.path.exists("water.pickle")
+        hops = interactive.make_hoppingtraj(dens, "hoptraj", universe=u)
+        hg = interactive.build_hoppinggraph(hops, dens)
+        assert hg.graph.number_of_edges() > 0
+    finally:
+        os.chdir(cwd)

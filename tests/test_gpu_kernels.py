@@ -183,11 +183,23 @@ def _hop_reference(xyz, edges, site_map):
     return hop, ev, nodes
 
 
-def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1):
-    """Single process, optionally emulating `slabs` ranks sequentially (same kernels, same exchange)."""
+def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
+    """Single process, optionally emulating `slabs` ranks sequentially (same kernels, same exchange).
+    mode: "xyz" | "cells" (packed cells written by the histogram kernel), "+coarse" adds the block map."""
     F, N = xyz.shape[:2]
     g = K.GridTables(edges)
     m16 = dev(site_map.astype(np.int16))
+    coarse = K.coarse_map(m16) if "coarse" in mode else None
+    cells_all = None
+    if mode.startswith("cells"):
+        cells_all = torch.empty((F, N), dtype=torch.int32, device="cuda")
+        K.hist_accumulate(g, dev(xyz), torch.zeros(g.shape, dtype=torch.int32, device="cuda"), cells_all)
+        ref = O.digitize_hop(xyz.reshape(-1, 3), edges)
+        shp = np.array(g.shape)
+        b = np.stack(ref, axis=1) - 1
+        ok = np.all((b >= 0) & (b < shp), axis=1)
+        packed = np.where(ok, (b[:, 0] << 20) | (b[:, 1] << 10) | b[:, 2], 0xFFFFFFFF).astype(np.uint32)
+        assert np.array_equal(cells_all.cpu().numpy().view(np.uint32).ravel(), packed)
     events = K.EventBuffer(F * N + 16, "cuda")
     bounds = np.linspace(0, F, slabs + 1).astype(int)
     X = torch.empty((F, N), dtype=torch.float32, device="cuda")
@@ -197,7 +209,8 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1):
         a, b = bounds[r], bounds[r + 1]
         chunk_len = -(-(b - a) // n_chunks)
         nc = -(-(b - a) // chunk_len)
-        s = K.hoptraj(g, dev(xyz[a:b]), m16, int(a), nc, chunk_len, events, X[a:b], Y[a:b])
+        s = K.hoptraj(g, dev(xyz[a:b]), m16, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
+                      cells=None if cells_all is None else cells_all[a:b], coarse=coarse)
         summaries.append(s)
         lens.append(chunk_len)
         slab_sums.append(K.hop_combine(s, chunk_len, b - a))
@@ -215,12 +228,13 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1):
     return X.cpu().numpy(), Y.cpu().numpy(), events, n_ev, state.cpu().numpy()
 
 
-@pytest.mark.parametrize("n_chunks,slabs", [(1, 1), (4, 1), (13, 1), (200, 1), (3, 2), (5, 8)])
-def test_hoptraj_and_transitions(K, traj, n_chunks, slabs):
+@pytest.mark.parametrize("n_chunks,slabs,mode", [(1, 1, "xyz"), (4, 1, "xyz+coarse"), (13, 1, "cells"), (200, 1, "cells+coarse"),
+                                                 (3, 2, "cells+coarse"), (5, 8, "xyz+coarse")])
+def test_hoptraj_and_transitions(K, traj, n_chunks, slabs, mode):
     p, xyz = traj
     res = O.pipeline(xyz, delta=1.0)
     hop, ev_ref, nodes_ref = res["hop"], res["events"], res["nodes"]
-    X, Y, events, n_ev, state = _run_hoptraj(K, xyz, res["edges"], res["map"], n_chunks, slabs)
+    X, Y, events, n_ev, state = _run_hoptraj(K, xyz, res["edges"], res["map"], n_chunks, slabs, mode)
     assert np.array_equal(X, hop[:, :, 0])
     assert np.array_equal(Y, hop[:, :, 1])
     assert n_ev == len(ev_ref)
@@ -255,8 +269,8 @@ def test_hoptraj_outliers_and_top_edge(K, traj):
             xyz[5 + k, 100 + 10 * d: 110 + 10 * d, d] = v
     hop, ev_ref, nodes_ref = _hop_reference(xyz, edges, site_map)
     assert (hop[:, :, 0] == -1).any() and (ev_ref[:, 2] == -1).any()
-    for n_chunks, slabs in [(1, 1), (7, 1), (2, 3)]:
-        X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs)
+    for n_chunks, slabs, mode in [(1, 1, "xyz"), (7, 1, "cells+coarse"), (2, 3, "xyz+coarse"), (3, 1, "cells")]:
+        X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs, mode)
         assert np.array_equal(X, hop[:, :, 0])
         assert np.array_equal(Y, hop[:, :, 1])
         ev = K.events_to_numpy(events.data[:n_ev])
@@ -265,6 +279,40 @@ def test_hoptraj_outliers_and_top_edge(K, traj):
         assert np.array_equal(got, ev_ref)
         ia = np.nonzero(state[0] != 0)[0]
         assert np.array_equal(np.stack([ia, state[0][ia], 59 - state[1][ia]], axis=1), nodes_ref)
+
+
+def test_coarse_map_blocks(K):
+    rng = np.random.default_rng(8)
+    for shape in [(9, 10, 11), (36, 36, 36), (4, 4, 4), (5, 1, 70)]:
+        m = np.ones(shape, np.int16)
+        m[rng.random(shape) < 0.01] = 0
+        m[:4, :4, :4] = 0
+        if shape[0] > 8:
+            m[8, 5, 2] = 7
+        c = K.coarse_map(dev(m)).cpu().numpy().view(np.uint32)
+        cn = [-(-n // 4) for n in shape]
+        for b in range(cn[0] * cn[1] * cn[2]):
+            ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
+            blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
+            u = np.unique(blk)
+            want = int(u[0]) if len(u) == 1 and u[0] in (0, 1) else 3
+            assert (c[b >> 4] >> ((b & 15) * 2)) & 3 == want
+
+
+def test_half_angstrom_golden_through_all_paths(K):
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "half_angstrom.npz"))
+    xyz = g["xyz"]
+    edges = [g["edges_x"], g["edges_y"], g["edges_z"]]
+    ev_ref = g["events"].astype(np.int64)
+    for mode in ("xyz", "xyz+coarse", "cells", "cells+coarse"):
+        X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, g["site_map"], 3, 1, mode)
+        assert np.array_equal(X, g["hop_x"].astype(np.float32)) and np.array_equal(Y, g["hop_y"].astype(np.float32))
+        ev = K.events_to_numpy(events.data[:n_ev])
+        order = np.lexsort((ev["iatom"], ev["frame"]))
+        got = np.stack([ev[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1)
+        assert np.array_equal(got, ev_ref)
 
 
 def test_hopscan_from_labels_and_all_transitions(K):

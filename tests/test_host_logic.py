@@ -16,7 +16,7 @@ def test_library_exports_every_symbol_in_header():
     from hop_b200 import _lib
 
     header = open(os.path.join(ROOT, "include", "hopb200.h")).read()
-    declared = set(re.findall(r"^(?:int|void|const char\*)\s+(hopb_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|void|uint64_t|const char\*)\s+(hopb_\w+)\s*\(", header, flags=re.M))
     assert declared, "no declarations found in include/hopb200.h"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

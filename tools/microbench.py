@@ -73,17 +73,24 @@ def main():
     ms, mn, counts = timed(lambda: pipe.histogram(xyz), args.reps)
     rec("S1_hist", ms, 12, {"min_ms": mn, "grid": list(pipe.grid.shape)})
     ms, mn, sm = timed(lambda: pipe.site_map(counts), args.reps)
-    density, own, member, map16, n_labels, props = sm
-    rec("S2_sitemap_total", ms, None, {"min_ms": mn, "n_labels": n_labels, "cells": pipe.grid.n_cells})
+    density, own, member, map16, props = sm
+    rec("S2_sitemap_total", ms, None, {"min_ms": mn, "cells": pipe.grid.n_cells})
     ms, mn, _ = timed(lambda: K.label_sites(density, cfg.solvent_threshold), args.reps)
     rec("S2_label_solvent", ms, None, {"min_ms": mn})
     ms, mn, _ = timed(lambda: K.label_sites(density, cfg.bulk_threshold), args.reps)
     rec("S2_label_bulk", ms, None, {"min_ms": mn})
-    ms, mn, _ = timed(lambda: K.site_properties(pipe.grid, density, own, member, n_labels), args.reps)
+    ms, mn, _ = timed(lambda: K.site_properties(pipe.grid, density, own, member, pipe.MAX_LABELS), args.reps)
     rec("S2_properties", ms, None, {"min_ms": mn})
-    ms, mn, ht = timed(lambda: pipe.hoptraj(xyz, map16, 0, n_labels), args.reps)
-    hop_x, hop_y, events, n_ev, state, final = ht
-    rec("S3S4_hoptraj", ms, 20, {"min_ms": mn, "n_events": n_ev, "chunks": list(K.plan_chunks(args.frames, args.atoms, pipe.num_sms))})
+    ms, mn, _ = timed(lambda: K.density_from_counts(pipe.grid, counts, args.frames, 30.0, out=density), args.reps)
+    rec("S2_density", ms, None, {"min_ms": mn})
+    ms, mn, _ = timed(lambda: K.coarse_map(map16), args.reps)
+    rec("S2_coarse_map", ms, None, {"min_ms": mn})
+    pipe.site_map(counts)
+    ms, mn, ht = timed(lambda: pipe.hoptraj(xyz, map16, 0), args.reps)
+    hop_x, hop_y, events, state, final = ht
+    n_labels, n_ev = pipe.sync_scalars(events)
+    rec("S3S4_hoptraj", ms, 20, {"min_ms": mn, "n_events": n_ev, "n_labels": n_labels,
+                                 "chunks": list(K.plan_chunks(args.frames, args.atoms, pipe.num_sms))})
     ms, mn, _ = timed(lambda: pipe.transitions(events, n_ev, args.atoms, n_labels), args.reps)
     rec("S4_finalize", ms, None, {"min_ms": mn})
     ms, mn, _ = timed(lambda: pipe.run(xyz), args.reps)
