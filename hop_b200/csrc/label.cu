@@ -93,23 +93,24 @@ ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
     auto M = [&](int64_t idx) { return parent[idx] >= 0; };
     const bool m_up = hz && M(c + 1);
     const bool m_dn = lz && M(c - 1);
-    // the three in-plane offsets (0,1,0), (1,0,0), (1,1,0) and their +z partners
-    const int64_t offs[3] = {sy, sx, sx + sy};
-    const bool inb[3] = {hy, hx, hx && hy};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (!inb[k]) continue;
-      const int64_t nb = c + offs[k];
-      const bool m_nb = M(nb);
-      if (m_nb) {
-        // implied when both cells one step down the run are also connected the same way
-        const bool implied = m_dn && M(nb - 1);
-        if (!implied) uf_union(parent, (int)c, (int)nb);
-      }
-      if (hz && M(nb + 1)) {
-        // (c) ~ (nb+1): implied through nb (z-run of the neighbour row) or through c+1
-        if (!m_nb && !m_up) uf_union(parent, (int)c, (int)(nb + 1));
-      }
+    const bool ly = y > 0;
+    const bool m_y = hy && M(c + sy);              // (0,1,0)
+    const bool m_x = hx && M(c + sx);              // (1,0,0)
+    const bool m_xy = hx && hy && M(c + sx + sy);  // (1,1,0)
+    // An edge is skipped when its end points are already joined by edges that are themselves kept
+    // or skipped by a rule lower in the (y, z) order -- so the argument is well founded:
+    //   rule Z: (c, c+o), o_z = 0, follows from the same edge one cell down both z-runs;
+    //   rule Y: the x-edge follows from the x-edge one row down in y plus the two y-edges;
+    //   diagonals follow from any two-step path over in-plane / z edges.
+    if (m_y && !(m_dn && M(c + sy - 1))) uf_union(parent, (int)c, (int)(c + sy));
+    if (m_x && !(m_dn && M(c + sx - 1)) && !(ly && M(c - sy) && M(c + sx - sy))) uf_union(parent, (int)c, (int)(c + sx));
+    if (m_xy && !m_y && !m_x && !(m_dn && M(c + sx + sy - 1))) uf_union(parent, (int)c, (int)(c + sx + sy));
+    if (hz) {
+      // +z partners: (0,1,1), (1,0,1), (1,1,1)
+      if (hy && !m_y && !m_up && M(c + sy + 1)) uf_union(parent, (int)c, (int)(c + sy + 1));
+      if (hx && !m_x && !m_up && M(c + sx + 1)) uf_union(parent, (int)c, (int)(c + sx + 1));
+      // (1,1,1) is also reached through c+x then (0,1,1), or c+y then (1,0,1)
+      if (hx && hy && !m_xy && !m_up && !m_x && !m_y && M(c + sx + sy + 1)) uf_union(parent, (int)c, (int)(c + sx + sy + 1));
     }
   }
 }

@@ -20,6 +20,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
+from . import exchange
 from . import kernels as K
 from .constants import density_conversion_factor
 
@@ -62,12 +63,7 @@ class PipelineResult:
     timings: dict = field(default_factory=dict)
 
 
-def _dist():
-    import torch.distributed as dist
-
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist
-    return None
+_dist = exchange.dist
 
 
 class HopPipeline:
@@ -119,10 +115,7 @@ class HopPipeline:
         if self._use_cells(xyz):
             self.cells = self._buf("cells", (xyz.shape[0], xyz.shape[1]), torch.int32)
         K.hist_accumulate(self.grid, xyz, counts, self.cells)
-        d = _dist()
-        if d is not None:
-            d.all_reduce(counts)  # int32 sum == uint32 sum modulo 2^32
-        return counts
+        return exchange.reduce_counts(counts)
 
     MAX_LABELS = K.HOPB_MAX_SITES + 2
 
@@ -206,8 +199,7 @@ class HopPipeline:
         else:
             rank, world = d.get_rank(), d.get_world_size()
             slab = K.hop_combine(summaries, chunk_len, F)
-            gathered = self._buf("slabs", (world, K.SUMMARY_INTS, N), torch.int32)
-            d.all_gather_into_tensor(gathered, slab)
+            gathered = exchange.gather_slab_summaries(slab, self._buf("slabs", (world, K.SUMMARY_INTS, N), torch.int32))
             K.hop_advance(gathered[:rank] if rank > 0 else None, state, init=True)
             final_state = self._buf("final_state", (K.STATE_INTS, N), torch.int32)
             K.hop_advance(gathered, final_state, init=True)
@@ -226,9 +218,7 @@ class HopPipeline:
             if e_s0.numel():
                 idx = (e_s0.long() + 1) * W + (e_s.long() + 1)
                 matrix.view(-1).index_put_((idx,), e_count.to(torch.int32))
-            d = _dist()
-            if d is not None:
-                d.all_reduce(matrix)
+            exchange.reduce_count_matrix(matrix)
         return ev, e_s0, e_s, e_start, e_count, matrix
 
     def _mark(self, marks, name):
@@ -284,9 +274,7 @@ class HopPipeline:
                 ev.record(copy_stream)
             main.wait_event(ev)
             K.hist_accumulate(self.grid, xyz[f0:f1], counts, None if self.cells is None else self.cells[f0:f1])
-        d = _dist()
-        if d is not None:
-            d.all_reduce(counts)
+        exchange.reduce_counts(counts)
         res = PipelineResult()
         res.counts = counts
         res.density, res.own, res.member, res.map16, res.site_props = self.site_map(counts)

@@ -110,3 +110,74 @@ int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* e
 }
 
 }  // extern "C"
+
+// ---- kernel-by-kernel CPU mirrors of csrc/hoptraj.cu, for the multi-process (gloo) tests --------------
+extern "C" {
+
+// mirrors hoptraj_kernel<1>: labels [F][N] of one slab -> summaries [n_chunks][11][N] + events
+int64_t emul_slab_scan(const int32_t* labels, int64_t F, int64_t N, int64_t frame0, int n_chunks, int64_t chunk_len,
+                       int32_t* summaries, Ev* ev_out, int64_t cap) {
+  int64_t n_ev = 0;
+  for (int c = 0; c < n_chunks; ++c)
+    for (int64_t a = 0; a < N; ++a) {
+      auto emit = [&](int s0, int s, int frame, int tau, int tbar) {
+        if (n_ev < cap) ev_out[n_ev] = Ev{frame, (int32_t)a, s0, s, tau, tbar};
+        ++n_ev;
+      };
+      HopbSummary T = hopb_summary_empty();
+      int ypre = 0; bool yknown = false;
+      const int64_t f0 = (int64_t)c * chunk_len, f1 = std::min(F, f0 + chunk_len);
+      for (int64_t f = f0; f < f1; ++f) {
+        const int lab = labels[f * N + a];
+        hopb_push_frame(T, lab, (int)(frame0 + f), emit);
+        if (lab > 0) yknown = true;
+        if (!yknown) ++ypre;
+      }
+      T.ypre = ypre;
+      hopb_summary_store(summaries + ((int64_t)c * HOPB_SUMMARY_FIELDS) * N + a, N, T);
+    }
+  return n_ev;
+}
+
+// mirrors hop_combine_kernel
+void emul_combine(const int32_t* summaries, int64_t N, int n_chunks, int64_t chunk_len, int64_t F, int32_t* slab) {
+  for (int64_t a = 0; a < N; ++a) {
+    HopbSummary R = hopb_summary_empty();
+    int64_t done = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const HopbSummary T = hopb_summary_load(summaries + ((int64_t)c * HOPB_SUMMARY_FIELDS) * N + a, N);
+      R = hopb_combine(R, T, (int)done);
+      done += std::min(chunk_len, F - (int64_t)c * chunk_len);
+    }
+    hopb_summary_store(slab + a, N, R);
+  }
+}
+
+// mirrors hop_advance_kernel: state [4][N]
+void emul_advance(const int32_t* summaries, int n, int64_t N, int init, int32_t* state) {
+  for (int64_t a = 0; a < N; ++a) {
+    HopbState S = hopb_state_virgin();
+    if (!init) { S.s0 = state[a]; S.t0 = state[N + a]; S.t1 = state[2 * N + a]; S.on = state[3 * N + a]; }
+    for (int c = 0; c < n; ++c)
+      hopb_apply(S, hopb_summary_load(summaries + ((int64_t)c * HOPB_SUMMARY_FIELDS) * N + a, N), [](int, int, int, int, int) {});
+    state[a] = S.s0; state[N + a] = S.t0; state[2 * N + a] = S.t1; state[3 * N + a] = S.on;
+  }
+}
+
+// mirrors hop_fixup_kernel (events only)
+int64_t emul_fixup(const int32_t* summaries, int n_chunks, int64_t N, int32_t* state, Ev* ev_out, int64_t cap) {
+  int64_t n_ev = 0;
+  for (int64_t a = 0; a < N; ++a) {
+    auto emit = [&](int s0, int s, int frame, int tau, int tbar) {
+      if (n_ev < cap) ev_out[n_ev] = Ev{frame, (int32_t)a, s0, s, tau, tbar};
+      ++n_ev;
+    };
+    HopbState S; S.s0 = state[a]; S.t0 = state[N + a]; S.t1 = state[2 * N + a]; S.on = state[3 * N + a];
+    for (int c = 0; c < n_chunks; ++c)
+      hopb_apply(S, hopb_summary_load(summaries + ((int64_t)c * HOPB_SUMMARY_FIELDS) * N + a, N), emit);
+    state[a] = S.s0; state[N + a] = S.t0; state[2 * N + a] = S.t1; state[3 * N + a] = S.on;
+  }
+  return n_ev;
+}
+
+}  // extern "C"

@@ -21,6 +21,20 @@ __global__ void red_kernel(uint32_t* grid, uint32_t n_cells, int64_t n, int per_
   }
 }
 
+// scattered REDs while streaming 12 B per RED from HBM (the histogram kernel's real mix)
+__global__ void red_stream_kernel(uint32_t* grid, uint32_t n_cells, const float4* __restrict__ in, int64_t n4) {
+  int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = i0; i + 2 * stride < n4; i += 3 * stride) {
+    float4 a = in[i], b = in[i + stride], c = in[i + 2 * stride];
+    uint32_t h0 = hash32(__float_as_uint(a.x) + (uint32_t)i) % n_cells;
+    uint32_t h1 = hash32(__float_as_uint(b.y) + (uint32_t)i * 3u + 1u) % n_cells;
+    uint32_t h2 = hash32(__float_as_uint(c.z) + (uint32_t)i * 5u + 2u) % n_cells;
+    uint32_t h3 = hash32(__float_as_uint(c.w) + (uint32_t)i * 7u + 3u) % n_cells;
+    atomicAdd(grid + h0, 1u); atomicAdd(grid + h1, 1u); atomicAdd(grid + h2, 1u); atomicAdd(grid + h3, 1u);
+  }
+}
+
 __global__ void gather_kernel(const int16_t* __restrict__ map, uint32_t n_cells, int64_t n, int* out) {
   int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -103,6 +117,23 @@ int main() {
       cudaDestroyTextureObject(tex);
     }
     CK(cudaFree(grid));
+  }
+  {
+    const int64_t n4 = n * 3 / 4;
+    float4* in; CK(cudaMalloc(&in, n4 * 16)); CK(cudaMemset(in, 0, n4 * 16));
+    for (uint32_t n_cells : {8120601u, 4060300u, 2000000u}) {
+      uint32_t* grid; CK(cudaMalloc(&grid, (size_t)n_cells * 4)); CK(cudaMemset(grid, 0, (size_t)n_cells * 4));
+      for (int bps : {4, 8}) {
+        float ms = timeit([&] { red_stream_kernel<<<sms * bps, 256>>>(grid, n_cells, in, n4); });
+        printf("RED+STREAM(12B/red) cells=%9u blocks/SM=%d  %.3f ms  %.3e red/s  %.1f GB/s\n", n_cells, bps, ms, n / (ms * 1e-3), n4 * 16 / (ms * 1e-3) / 1e9);
+      }
+      for (int bps : {8}) {
+        float ms = timeit([&] { red_kernel<<<sms * bps, 256>>>(grid, n_cells, n, 0); });
+        printf("RED only            cells=%9u blocks/SM=%d  %.3f ms  %.3e red/s\n", n_cells, bps, ms, n / (ms * 1e-3));
+      }
+      CK(cudaFree(grid));
+    }
+    CK(cudaFree(in));
   }
   {
     cudaFuncSetAttribute(lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
