@@ -79,7 +79,7 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 __global__ void __launch_bounds__(256)
-ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
+ccl_merge_kernel(int* parent, int nx, int ny, int nz, int phase) {
   const int64_t n_cells = (int64_t)nx * ny * nz;
   const int64_t sy = nz, sx = (int64_t)ny * nz;
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
@@ -93,6 +93,10 @@ ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
     auto M = [&](int64_t idx) { return parent[idx] >= 0; };
     const bool m_up = hz && M(c + 1);
     const bool m_dn = lz && M(c - 1);
+    // phase 0: heads of z-runs only -- they tie the rows of a blob into one tree (the skeleton);
+    // phase 1 (after a flatten): every other cell; inside a blob both ends then already share a
+    // root one step away, so the many unions around isolated holes cost two loads each
+    if ((phase == 0) == m_dn) continue;
     const bool ly = y > 0;
     const bool m_y = hy && M(c + sy);              // (0,1,0)
     const bool m_x = hx && M(c + sx);              // (1,0,0)
@@ -116,11 +120,18 @@ ccl_merge_kernel(int* parent, int nx, int ny, int nz) {
 }
 
 // ---- 3. flatten -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* parent, int64_t n_cells) {
+// Only heads of z-runs are ever parents (initial links, unions and path halving all point at
+// heads), so flattening is: heads find their root (few cells, possibly long walks), then every
+// other cell takes its head's root in one hop.
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* parent, int64_t n_cells, int nz, int heads) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
     if (parent[c] < 0) continue;
-    const int r = uf_find(parent, (int)c);
-    parent[c] = r;
+    const bool is_head = (c % nz) == 0 || parent[c - 1] < 0;
+    if (heads) {
+      if (is_head) { const int r = uf_find(parent, (int)c); parent[c] = r; }
+    } else if (!is_head) {
+      parent[c] = ld_parent(parent, ld_parent(parent, (int)c));
+    }
   }
 }
 
@@ -412,8 +423,11 @@ int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz,
   const int64_t n_rows = (int64_t)nx * ny;
   HOPB_K(ccl_rows_kernel)<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 8), 256, 0, s>>>(density, threshold, n_rows, nz, parent);
   const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 8);
-  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz);
-  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells);
+  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz, 0);
+  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 1);
+  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz, 1);
+  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 1);
+  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 0);
   HOPB_K(ccl_size_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, size);
   HOPB_K(ccl_roots_kernel)<<<gcells, 256, 0, s>>>(parent, size, n_cells, minsite, keys, vals, cap, n_roots_dev);
   HOPB_K(ccl_rank_kernel)<<<cap / 256, 256, 0, s>>>(keys, vals, n_roots_dev, cap, keys_alt, vals_alt);

@@ -171,7 +171,8 @@ class TransportNetwork(object):
         st = state.cpu().numpy()
         last = F - 1
         ia = numpy.nonzero(st[0] != SITELABEL['interstitial'])[0]
-        for node in numpy.unique(st[0][ia]) if len(ia) else []:
+        node_vals, first_idx = numpy.unique(st[0][ia], return_index=True) if len(ia) else ([], [])
+        for node in [node_vals[k] for k in numpy.argsort(first_idx)]:   # reference order: first atom that holds it
             sel = ia[st[0][ia] == node]
             self.graph.add_node(int(node))
             self.graph_properties[int(node)] = {
