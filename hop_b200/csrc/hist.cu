@@ -12,9 +12,9 @@
 // next to the HBM stream.  Everything else is kept off the critical path: the bin search is the
 // branch-free pair-table search of hopb_binning.h (~11 instructions per axis).
 //
-// Optionally the kernel also emits, per point, the packed cell index under the hopping-trajectory
-// binning rules (10 bits per axis, 0xFFFFFFFF = outlier).  Stage 3 can then read 4 B per
-// atom-frame instead of re-reading and re-binning 12 B of coordinates.
+// Optionally the kernel also emits, per point, the brick index of its cell under the
+// hopping-trajectory binning rules (4x4x4 bricks, 0xFFFFFFFF = outlier).  Stage 3 can then read
+// 4 B per atom-frame instead of re-reading and re-binning 12 B of coordinates.
 //
 // Data movement: each warp owns 128 consecutive points = 96 float4.  Lanes load float4 j, j+32,
 // j+64 (three fully coalesced 512 B requests), park them in a per-warp shared-memory slab, and read
@@ -37,18 +37,24 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 
 struct AxisReg {
   float lo, inv, nf, top_eq, hop_lo, hop_hi, edge_zone;
-  int n;
+  int n, cn;  // bins, bricks (ceil(n/4)) along this axis
   const HopbPair* pairs;
 };
 
 __device__ __forceinline__ AxisReg load_axis(const HopbAxis& a, const HopbPair* s_pairs) {
   AxisReg r;
   r.lo = a.lo; r.inv = a.inv; r.nf = (float)a.n; r.top_eq = a.top_eq; r.hop_lo = a.hop_lo; r.hop_hi = a.hop_hi;
-  r.n = a.n; r.pairs = s_pairs + a.off2;
+  r.n = a.n; r.cn = (a.n + 3) >> 2; r.pairs = s_pairs + a.off2;
   // smallest x for which a last-edge rule can apply (NaN top_eq / empty interval drop out of fminf)
   r.edge_zone = fminf(a.top_eq, a.hop_lo <= a.hop_hi ? a.hop_lo : a.top_eq);
   if (!(r.edge_zone == r.edge_zone)) r.edge_zone = __int_as_float(0x7f800000);  // +inf: never
   return r;
+}
+
+// brick index of cell (i,j,k): see hoptraj.cu -- brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3))
+__device__ __forceinline__ uint32_t brick_index(int i, int j, int k, int cny, int cnz) {
+  const uint32_t cb = (uint32_t)(((i >> 2) * cny + (j >> 2)) * cnz + (k >> 2));
+  return (cb << 6) | (uint32_t)(((i & 3) << 4) | ((j & 3) << 2) | (k & 3));
 }
 
 // digitize (searchsorted right) in [0, n+1], branch-free
@@ -93,7 +99,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     }
     if (!CELLS) return 0u;
     const bool in = ((unsigned)(px - 1) < (unsigned)ax.n) & ((unsigned)(py - 1) < (unsigned)ay.n) & ((unsigned)(pz - 1) < (unsigned)az.n);
-    return in ? (((uint32_t)(px - 1) << 20) | ((uint32_t)(py - 1) << 10) | (uint32_t)(pz - 1)) : 0xFFFFFFFFu;
+    return in ? brick_index(px - 1, py - 1, pz - 1, ay.cn, az.cn) : 0xFFFFFFFFu;
   }
   const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
   if (ok) {
@@ -101,7 +107,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
   }
   if (!CELLS) return 0u;
-  return ok ? (((uint32_t)(bx - 1) << 20) | ((uint32_t)(by - 1) << 10) | (uint32_t)(bz - 1)) : 0xFFFFFFFFu;
+  return ok ? brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : 0xFFFFFFFFu;
 }
 
 template <bool CELLS, bool FAST>
@@ -185,7 +191,6 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
                                uint32_t* counts, uint32_t* cells) {
   HOPB_REQUIRE(h, g && xyz && counts && n_points >= 0, "bad argument");
   HOPB_REQUIRE(h, ((uintptr_t)xyz & 3) == 0, "xyz must be 4-byte aligned");
-  if (cells) HOPB_REQUIRE(h, g->n[0] <= 1024 && g->n[1] <= 1024 && g->n[2] <= 1024, "packed cells need <= 1024 bins per axis");
   if (n_points == 0) return HOPB_OK;
   // number of leading points until the stream is 16-byte aligned (12 B per point)
   int64_t lead = 0;

@@ -68,10 +68,18 @@ __device__ __forceinline__ int hop_bin(float x, const AxisReg& a) {
   return b - 1;
 }
 
-// packed cell (10 bits per axis, 0xFFFFFFFF = outlier) from coordinates; FAST = pair-table search
+// Brick index of a cell: the site map is stored in 4x4x4 bricks of 64 cells (one 128-byte line of
+// int16 each), brick-major; the index of cell (i,j,k) is brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3)).
+// It is both the gather address into the bricked map and, shifted right by 6, the index into the
+// 2-bit block map.  0xFFFFFFFF marks an outlier.
+__device__ __forceinline__ uint32_t brick_index(int i, int j, int k, int cny, int cnz) {
+  const uint32_t cb = (uint32_t)(((i >> 2) * cny + (j >> 2)) * cnz + (k >> 2));
+  return (cb << 6) | (uint32_t)(((i & 3) << 4) | ((j & 3) << 2) | (k & 3));
+}
+
 template <bool FAST>
 __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
-                                              const AxisReg& ay, const AxisReg& az, const float* s_tab) {
+                                              const AxisReg& ay, const AxisReg& az, const float* s_tab, int cny, int cnz) {
   int bx, by, bz;
   if (FAST) {
     bx = hop_bin(x, ax); by = hop_bin(y, ay); bz = hop_bin(z, az);
@@ -81,34 +89,32 @@ __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const H
     bz = hopb_bin_hop(z, tab.ax[2], s_tab + tab.ax[2].off) - 1;
   }
   const bool ok = ((unsigned)bx < (unsigned)ax.n) & ((unsigned)by < (unsigned)ay.n) & ((unsigned)bz < (unsigned)az.n);
-  return ok ? (((uint32_t)bx << 20) | ((uint32_t)by << 10) | (uint32_t)bz) : 0xFFFFFFFFu;
+  return ok ? brick_index(bx, by, bz, cny, cnz) : 0xFFFFFFFFu;
 }
 
 struct MapView {
-  const int16_t* map16;
-  const uint32_t* s_coarse;  // 2 bits per 4x4x4 block in shared memory, or nullptr
-  int ny, nz, cny, cnz;
+  const int16_t* brick;      // bricked site map
+  const uint32_t* s_coarse;  // 2 bits per brick in shared memory, or nullptr
 };
 
-// site label of a packed cell: the coarse map answers for blocks that are uniformly interstitial
-// (0) or bulk (1); only cells in mixed blocks gather from the int16 site map in L2.
+// site label of a brick index: the block map answers for bricks that are uniformly interstitial
+// (0) or bulk (1); only cells in mixed bricks gather from the bricked int16 map in L2.
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
   if (c == 0xFFFFFFFFu) return -1;  // the -1 shell of buffered_map (trajectory.py:176-177)
-  const int i = (int)(c >> 20), j = (int)((c >> 10) & 1023u), k = (int)(c & 1023u);
   if (m.s_coarse) {
-    const int cb = ((i >> 2) * m.cny + (j >> 2)) * m.cnz + (k >> 2);
-    const uint32_t st = (m.s_coarse[cb >> 4] >> ((cb & 15) * 2)) & 3u;
+    const uint32_t cb = c >> 6;
+    const uint32_t st = (m.s_coarse[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
     if (st != 3u) return (int)st;
   }
-  return (int)__ldg(m.map16 + ((i * m.ny + j) * m.nz + k));
+  return (int)__ldg(m.brick + c);
 }
 
-// SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: packed cells
+// SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: brick indices
 template <int SRC, bool FAST>
 __global__ void __launch_bounds__(1024)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
-               const HopbPair* __restrict__ table2, const int16_t* __restrict__ map16,
+               const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
                const uint32_t* __restrict__ coarse, int coarse_words, float* __restrict__ hop_x,
                float* __restrict__ hop_y, int64_t chunk_len, int32_t* __restrict__ summaries, EventSink sink) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -127,8 +133,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
   MapView mv;
-  mv.map16 = map16; mv.s_coarse = (SRC != 1 && coarse) ? s_coarse : nullptr;
-  mv.ny = tab.ax[1].n; mv.nz = tab.ax[2].n; mv.cny = (tab.ax[1].n + 3) >> 2; mv.cnz = (tab.ax[2].n + 3) >> 2;
+  mv.brick = brick; mv.s_coarse = (SRC != 1 && coarse) ? s_coarse : nullptr;
+  const int cny = (tab.ax[1].n + 3) >> 2, cnz = (tab.ax[2].n + 3) >> 2;
 
   const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y;
@@ -143,16 +149,50 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const int iatom = (int)atom;
   auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
 
-  // one frame through the state machine + outputs
-  auto step = [&](int l, int64_t fr) {
-    hopb_push_frame(T, l, (int)(frame0 + fr), emit);
+  // running output pointers (one frame = N floats further)
+  float* px = hop_x ? hop_x + f_begin * N + atom : nullptr;
+  float* py = hop_y ? hop_y + f_begin * N + atom : nullptr;
+
+  // Generic step: any phase of the summary machine.
+  auto step_generic = [&](int l, int t) {
+    hopb_push_frame(T, l, t, emit);
     if (l > 0) { yorb = l; yknown = true; }
     if (!yknown) ++ypre;
-    if (hop_x) hop_x[fr * N + atom] = (float)l;
-    if (hop_y) hop_y[fr * N + atom] = (float)yorb;
+  };
+  // Fast step, valid once a first site has been seen (SPEC or FULL, orbit known): the machine is
+  // "current site `cur`, on/off, last exit t1"; entering another site is the only rare event.
+  int cur = 0, on = 1, t1 = 0;
+  auto step_fast = [&](int l, int t) {
+    if (l == cur) {
+      on = 1;
+    } else if (l == 0) {
+      if (on) { t1 = t; on = 0; }
+    } else if (l > 0) {
+      const int tx = on ? t : t1;
+      if (T.kind == HOPB_SPEC) {          // second site of the chunk: the open event E2
+        T.t1_2 = tx; T.A2 = l; T.f2 = t; T.kind = HOPB_FULL;
+      } else {
+        emit(cur, l, t, tx - T.t0, t - tx);
+      }
+      cur = l; T.t0 = t; on = 1;
+      yorb = l;
+    }                                      // l == -1: outlier, nothing changes
+  };
+  bool fast = false;
+  auto enter_fast = [&]() {
+    cur = T.kind == HOPB_SPEC ? T.A1 : T.s0; on = T.on; t1 = T.t1; fast = true;
+  };
+  auto leave_fast = [&]() {
+    if (T.kind == HOPB_FULL) T.s0 = cur;
+    T.on = on; T.t1 = t1;
+  };
+  auto store = [&](int l) {
+    if (px) { *px = (float)l; px += N; }
+    if (py) { *py = (float)yorb; py += N; }
   };
 
   int64_t f = f_begin;
+  constexpr int kDeep = 8;
   if (SRC == 0) {
     for (; f + kUnroll <= f_end; f += kUnroll) {
       float cx[kUnroll], cy[kUnroll], cz[kUnroll];
@@ -163,34 +203,49 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       }
       int lab[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab), mv);
+      for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) step(lab[u], f + u);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int t = (int)(frame0 + f + u);
+        if (fast) step_fast(lab[u], t);
+        else { step_generic(lab[u], t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
+        store(lab[u]);
+      }
     }
   } else {
-    // 4-byte inputs (packed cells or labels): blocks of kDeep frames, the next block's loads are
+    // 4-byte inputs (brick indices or labels): blocks of kDeep frames, the next block's loads are
     // issued before the current block is consumed so that ~2 x kDeep x 4 B per thread stay in flight
-    constexpr int kDeep = 8;
-    const uint32_t* src = SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in);
-    uint32_t cur[kDeep], nxt[kDeep];
+    const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f_begin * N + atom;
+    uint32_t curv[kDeep], nxt[kDeep];
     if (f + kDeep <= f_end) {
 #pragma unroll
-      for (int u = 0; u < kDeep; ++u) cur[u] = __ldg(src + (f + u) * N + atom);
+      for (int u = 0; u < kDeep; ++u) curv[u] = __ldg(src + u * N);
     }
     for (; f + kDeep <= f_end; f += kDeep) {
+      src += kDeep * N;
       const bool more = f + 2 * kDeep <= f_end;
       if (more) {
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) nxt[u] = __ldg(src + (f + kDeep + u) * N + atom);
+        for (int u = 0; u < kDeep; ++u) nxt[u] = __ldg(src + u * N);
       }
       int lab[kDeep];
 #pragma unroll
-      for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(cur[u], mv) : (int)__uint_as_float(cur[u]);
+      for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(curv[u], mv) : (int)__uint_as_float(curv[u]);
+      if (fast) {
 #pragma unroll
-      for (int u = 0; u < kDeep; ++u) step(lab[u], f + u);
+        for (int u = 0; u < kDeep; ++u) { step_fast(lab[u], (int)(frame0 + f + u)); store(lab[u]); }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) {
+          const int t = (int)(frame0 + f + u);
+          if (fast) step_fast(lab[u], t);
+          else { step_generic(lab[u], t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
+          store(lab[u]);
+        }
+      }
       if (more) {
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) cur[u] = nxt[u];
+        for (int u = 0; u < kDeep; ++u) curv[u] = nxt[u];
       }
     }
   }
@@ -202,23 +257,28 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       uint32_t c;
       if (SRC == 0) {
         const float* p = xyz + (f * N + atom) * 3;
-        c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab);
+        c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab, cny, cnz);
       } else {
         c = __ldg(cells + f * N + atom);
       }
       l = label_of(c, mv);
     }
-    step(l, f);
+    const int t = (int)(frame0 + f);
+    if (fast) step_fast(l, t);
+    else { step_generic(l, t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
+    store(l);
   }
+  if (fast) leave_fast();
   T.ypre = ypre;
   hopb_summary_store(summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom, N, T);
 }
 
-// 2-bit coarse map: one entry per 4x4x4 block of the site map: 0 / 1 = every cell of the block has
-// that label (interstitial / bulk), 3 = mixed.  16 entries per 32-bit word.
+// Bricked copy of the site map + the 2-bit block map: one thread per brick reads its (up to) 64
+// cells from the C-ordered int16 map, writes them as one 128-byte line and classifies the brick:
+// 0 / 1 = every cell interstitial / bulk, 3 = mixed.  16 bricks per 32-bit word.
 __global__ void __launch_bounds__(256)
-coarse_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
-                  uint32_t* __restrict__ coarse) {
+brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
+                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse) {
   const int64_t n_blocks = (int64_t)cnx * cny * cnz;
   const int64_t n_round = (n_blocks + 31) / 32 * 32;
   const int lane = threadIdx.x & 31;
@@ -231,20 +291,26 @@ coarse_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int
       const int ci = (int)(r / cny);
       int first = -2;
       bool uniform = true;
+      int16_t* out = brick + b * 64;
       for (int di = 0; di < 4; ++di) {
         const int i = ci * 4 + di;
-        if (i >= nx) break;
         for (int dj = 0; dj < 4; ++dj) {
           const int j = cj * 4 + dj;
-          if (j >= ny) break;
+          const bool row_ok = i < nx && j < ny;
           const int16_t* row = map16 + ((int64_t)i * ny + j) * nz;
+          int16_t v4[4];
+#pragma unroll
           for (int dk = 0; dk < 4; ++dk) {
             const int k = ck * 4 + dk;
-            if (k >= nz) break;
-            const int v = row[k];
-            if (first == -2) first = v;
-            else if (v != first) uniform = false;
+            int16_t v = 0;
+            if (row_ok && k < nz) {
+              v = row[k];
+              if (first == -2) first = v;
+              else if (v != first) uniform = false;
+            }
+            v4[dk] = v;
           }
+          *reinterpret_cast<short4*>(out + ((di << 4) | (dj << 2))) = make_short4(v4[0], v4[1], v4[2], v4[3]);
         }
       }
       st = (uniform && (first == 0 || first == 1)) ? (uint32_t)first : 3u;
@@ -361,8 +427,6 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     return HOPB_OK;
   }
   HOPB_REQUIRE(h, g && map16 && (src == 0 ? xyz != nullptr : cells != nullptr), "null argument");
-  const bool packable = g->n[0] <= 1024 && g->n[1] <= 1024 && g->n[2] <= 1024;
-  HOPB_REQUIRE(h, packable, "grids with more than 1024 bins per axis are not supported by the hoptraj kernel");
   const bool fast = g->tab.fast_ok != 0;
   int coarse_words = 0;
   if (coarse) {
@@ -407,12 +471,14 @@ int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_
                         n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
-int hopb_coarse_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, uint32_t* coarse) {
-  HOPB_REQUIRE(h, map16 && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
+int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
+                   uint32_t* coarse) {
+  HOPB_REQUIRE(h, map16 && brick && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
   const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
   const int64_t nb = (int64_t)cnx * cny * cnz;
-  HOPB_K(coarse_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(map16, nx, ny, nz, cnx, cny,
-                                                                                                  cnz, coarse);
+  HOPB_REQUIRE(h, nb * 64 < ((int64_t)1 << 32) - 1, "grid too large for brick indices");
+  HOPB_K(brick_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(map16, nx, ny, nz, cnx, cny,
+                                                                                                 cnz, brick, coarse);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

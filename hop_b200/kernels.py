@@ -85,16 +85,27 @@ def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, c
     return counts
 
 
-def coarse_map(map16: torch.Tensor, coarse=None):
-    """2-bit 4x4x4 block map of a site map (lets hoptraj skip the L2 gather in uniform regions)."""
+def brick_shape(shape):
+    """(n_bricks, words of the 2-bit block map) for a grid shape."""
+    nb = 1
+    for n in shape:
+        nb *= -(-int(n) // 4)
+    return nb, -(-nb // 16)
+
+
+def brick_map(map16: torch.Tensor, brick=None, coarse=None):
+    """Site map in 4x4x4 brick order (what the hoptraj kernel gathers from) and its 2-bit block map
+    (which lets the kernel skip the gather in uniformly bulk / interstitial regions)."""
     _cuda(map16, torch.int16, "map16")
     nx, ny, nz = map16.shape
-    nb = -(-nx // 4) * -(-ny // 4) * -(-nz // 4)
+    nb, words = brick_shape(map16.shape)
+    if brick is None:
+        brick = torch.empty(nb * 64, dtype=torch.int16, device=map16.device)
     if coarse is None:
-        coarse = torch.empty(-(-nb // 16), dtype=torch.int32, device=map16.device)
+        coarse = torch.empty(words, dtype=torch.int32, device=map16.device)
     h = _h(map16)
-    _lib.check(h, _lib.lib().hopb_coarse_map(h, _stream(), nx, ny, nz, _p(map16), _p(coarse)))
-    return coarse
+    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse)))
+    return brick, coarse
 
 
 def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
@@ -240,11 +251,13 @@ class EventBuffer:
         return int(self.count.item())
 
 
-def hoptraj(grid: GridTables, xyz, map16: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
+def hoptraj(grid: GridTables, xyz, brick: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
             events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None):
     """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254).
-    Input is either `xyz` (float32 [F][N][3]) or the packed `cells` (int32 [F][N]) from hist_accumulate."""
-    _cuda(map16, torch.int16, "map16")
+    Input is either `xyz` (float32 [F][N][3]) or the brick indices `cells` (int32 [F][N]) from
+    hist_accumulate; `brick` / `coarse` come from brick_map(Density.map)."""
+    _cuda(brick, torch.int16, "brick")
+    map16 = brick
     if cells is not None:
         _cuda(cells, torch.int32, "cells")
         F, N = cells.shape[0], cells.shape[1]
@@ -253,8 +266,8 @@ def hoptraj(grid: GridTables, xyz, map16: torch.Tensor, frame0: int, n_chunks: i
         _cuda(xyz, torch.float32, "xyz")
         F, N = xyz.shape[0], xyz.shape[1]
         dev = xyz.device
-    if map16.numel() != grid.n_cells:
-        raise ValueError("map does not match the grid")
+    if map16.numel() != brick_shape(grid.shape)[0] * 64:
+        raise ValueError("bricked map does not match the grid (use kernels.brick_map)")
     if coarse is not None:
         _cuda(coarse, torch.int32, "coarse")
     if summaries is None:

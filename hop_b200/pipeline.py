@@ -98,8 +98,6 @@ class HopPipeline:
 
     # -- stages -----------------------------------------------------------------------------------
     def _use_cells(self, xyz):
-        if max(self.grid.shape) > 1024:
-            return False
         if self.cfg.cache_cells is not None:
             return bool(self.cfg.cache_cells)
         need = xyz.shape[0] * xyz.shape[1] * 4
@@ -144,12 +142,10 @@ class HopPipeline:
             out = (self._buf("p_count", (L,), torch.int64), self._buf("p_mean", (L,), torch.float64),
                    self._buf("p_std", (L,), torch.float64), self._buf("p_center", (L, 3), torch.float64))
             props = K.site_properties(self.grid, density, own, member, L, out=out)
-        self.coarse = None
-        nb = 1
-        for n in shape:
-            nb *= -(-n // 4)
-        if cfg.coarse_map and max(shape) <= 1024 and nb // 4 <= 160 * 1024:
-            self.coarse = K.coarse_map(map16, self._buf("coarse", (-(-nb // 16),), torch.int32))
+        nb, words = K.brick_shape(shape)
+        self.brick, coarse = K.brick_map(map16, self._buf("brick", (nb * 64,), torch.int16),
+                                         self._buf("coarse", (words,), torch.int32))
+        self.coarse = coarse if (cfg.coarse_map and words * 4 <= 160 * 1024) else None
         return density, own, member, map16, props
 
     def sync_scalars(self, events):
@@ -187,8 +183,8 @@ class HopPipeline:
             hop_x = self._buf("hop_x", (F, N), torch.float32)
             hop_y = self._buf("hop_y", (F, N), torch.float32)
         summaries = self._buf("summaries", (n_chunks, K.SUMMARY_INTS, N), torch.int32)
-        K.hoptraj(self.grid, xyz, map16, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries,
-                  cells=getattr(self, "cells", None), coarse=getattr(self, "coarse", None))
+        K.hoptraj(self.grid, xyz, self.brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries,
+                  cells=getattr(self, "cells", None), coarse=self.coarse)
 
         # state at slab entry: replay the slabs of the ranks before this one
         state = self._buf("state", (K.STATE_INTS, N), torch.int32)

@@ -160,6 +160,9 @@ class HoppingTrajectory(object):
             self._map16 = self._GD._device_map()
             if self._map16.numel() != self._tables.n_cells:
                 raise ValueError("The density object must have its site map computed.")
+            self._brick, self._coarse = K.brick_map(self._map16)
+            if self._coarse.numel() * 4 > 160 * 1024:
+                self._coarse = None
 
     def _coordinates(self, start, stop, step=1):
         """float32 [n][N][3] coordinates of the tracked group for a frame range, as CUDA tensor."""
@@ -202,7 +205,8 @@ class HoppingTrajectory(object):
             hop_x = t.empty((F, N), dtype=t.float32, device=xyz_dev.device)
             hop_y = t.empty((F, N), dtype=t.float32, device=xyz_dev.device)
         n_chunks, chunk_len = K.plan_chunks(F, N)
-        s = K.hoptraj(self._tables, xyz_dev, self._map16, frame0, n_chunks, chunk_len, events, hop_x, hop_y)
+        s = K.hoptraj(self._tables, xyz_dev, self._brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y,
+                      coarse=self._coarse)
         K.hop_fixup(s, chunk_len, F, state, hop_y, events)
         return hop_x, hop_y
 

@@ -83,10 +83,10 @@ void hopb_grid_destroy(hopb_grid* g);
 int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                          int64_t n_points, uint32_t* counts);
 
-/* Same, and additionally writes for every point its packed cell under the hopping-trajectory
- * binning rules of hop/trajectory.py:428-441 ((ix<<20)|(iy<<10)|iz, 0xFFFFFFFF = outlier) so that
- * hopb_hoptraj need not read the coordinates again.  cells: device uint32 [n_points] (NULL = off);
- * needs <= 1024 bins per axis. */
+/* Same, and additionally writes for every point the brick index of its cell under the
+ * hopping-trajectory binning rules of hop/trajectory.py:428-441 (see hopb_brick_map; 0xFFFFFFFF =
+ * outlier) so that hopb_hoptraj need not read the coordinates again.
+ * cells: device uint32 [n_points] (NULL = off). */
 int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                                int64_t n_points, uint32_t* counts, uint32_t* cells);
 
@@ -153,25 +153,29 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  * The slab is cut into n_chunks chunks of chunk_len frames (the last may be short); every
  * (atom, chunk) runs independently and leaves a summary, hopb_hop_fixup stitches them.
  *   xyz       device float32 [F][N][3]; ignored (may be NULL) when `cells` is given
- *   cells     device uint32 [F][N] (may be NULL): packed _coord2hop cell of every atom-frame as
- *             written by hopb_hist_accumulate_cells -- the coordinates are then not read again
- *   map16     device int16 [G] (Density.map)
- *   coarse    device uint32 (may be NULL): the 2-bit block map of hopb_coarse_map; it lets atoms in
- *             uniformly bulk / interstitial 4x4x4 blocks skip the gather from map16
+ *   cells     device uint32 [F][N] (may be NULL): brick index of every atom-frame as written by
+ *             hopb_hist_accumulate_cells -- the coordinates are then not read again
+ *   brick     device int16: the site map (Density.map) in brick order, from hopb_brick_map
+ *   coarse    device uint32 (may be NULL): the 2-bit block map of hopb_brick_map; it lets atoms in
+ *             uniformly bulk / interstitial bricks skip the gather from the site map
  *   frame0    global frame number of the slab's first frame
  *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
  *             DCD, trajectory.py:456-463); either may be NULL
  *   summaries device int32 [n_chunks][11][N] out
- *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here)
- * Grids are limited to 1024 bins per axis. */
+ *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here) */
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
-                 int64_t F, int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, float* hop_x,
+                 int64_t F, int64_t N, int64_t frame0, const int16_t* brick, const uint32_t* coarse, float* hop_x,
                  float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events,
                  uint64_t* n_events, uint64_t cap);
 
-/* 2 bits per 4x4x4 block of the site map (0 / 1: every cell of the block is interstitial / bulk,
- * 3: mixed), 16 blocks per word; coarse: device uint32 [ceil(ceil(nx/4)*ceil(ny/4)*ceil(nz/4) / 16)]. */
-int hopb_coarse_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, uint32_t* coarse);
+/* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block map.  A brick is a
+ * 4x4x4 block of cells stored as 64 consecutive int16 (one 128-byte line), bricks in C order over
+ * (ceil(nx/4), ceil(ny/4), ceil(nz/4)); cell (i,j,k) lives at brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3)).
+ *   brick   device int16  [n_bricks*64] out (cells outside the grid are 0)
+ *   coarse  device uint32 [ceil(n_bricks/16)] out: 2 bits per brick, 0 / 1 = all interstitial / all
+ *           bulk, 3 = mixed */
+int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
+                   uint32_t* coarse);
 
 /* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
  * hop/graph.py:190-254): labels = hop_x [F][N] float32. */

@@ -189,7 +189,9 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
     F, N = xyz.shape[:2]
     g = K.GridTables(edges)
     m16 = dev(site_map.astype(np.int16))
-    coarse = K.coarse_map(m16) if "coarse" in mode else None
+    brick, coarse = K.brick_map(m16)
+    if "coarse" not in mode:
+        coarse = None
     cells_all = None
     if mode.startswith("cells"):
         cells_all = torch.empty((F, N), dtype=torch.int32, device="cuda")
@@ -198,7 +200,9 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
         shp = np.array(g.shape)
         b = np.stack(ref, axis=1) - 1
         ok = np.all((b >= 0) & (b < shp), axis=1)
-        packed = np.where(ok, (b[:, 0] << 20) | (b[:, 1] << 10) | b[:, 2], 0xFFFFFFFF).astype(np.uint32)
+        cn = -(-shp // 4)
+        cb = ((b[:, 0] >> 2) * cn[1] + (b[:, 1] >> 2)) * cn[2] + (b[:, 2] >> 2)
+        packed = np.where(ok, (cb << 6) | ((b[:, 0] & 3) << 4) | ((b[:, 1] & 3) << 2) | (b[:, 2] & 3), 0xFFFFFFFF).astype(np.uint32)
         assert np.array_equal(cells_all.cpu().numpy().view(np.uint32).ravel(), packed)
     events = K.EventBuffer(F * N + 16, "cuda")
     bounds = np.linspace(0, F, slabs + 1).astype(int)
@@ -209,7 +213,7 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
         a, b = bounds[r], bounds[r + 1]
         chunk_len = -(-(b - a) // n_chunks)
         nc = -(-(b - a) // chunk_len)
-        s = K.hoptraj(g, dev(xyz[a:b]), m16, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
+        s = K.hoptraj(g, dev(xyz[a:b]), brick, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
                       cells=None if cells_all is None else cells_all[a:b], coarse=coarse)
         summaries.append(s)
         lens.append(chunk_len)
@@ -289,8 +293,13 @@ def test_coarse_map_blocks(K):
         m[:4, :4, :4] = 0
         if shape[0] > 8:
             m[8, 5, 2] = 7
-        c = K.coarse_map(dev(m)).cpu().numpy().view(np.uint32)
+        brick, c = K.brick_map(dev(m))
+        c = c.cpu().numpy().view(np.uint32)
+        brick = brick.cpu().numpy()
         cn = [-(-n // 4) for n in shape]
+        ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+        idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | ((ii & 3) << 4) | ((jj & 3) << 2) | (kk & 3)
+        assert np.array_equal(brick[idx], m)
         for b in range(cn[0] * cn[1] * cn[2]):
             ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
             blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]

@@ -83,8 +83,8 @@ def main():
     rec("S2_properties", ms, None, {"min_ms": mn})
     ms, mn, _ = timed(lambda: K.density_from_counts(pipe.grid, counts, args.frames, 30.0, out=density), args.reps)
     rec("S2_density", ms, None, {"min_ms": mn})
-    ms, mn, _ = timed(lambda: K.coarse_map(map16), args.reps)
-    rec("S2_coarse_map", ms, None, {"min_ms": mn})
+    ms, mn, _ = timed(lambda: K.brick_map(map16), args.reps)
+    rec("S2_brick_map", ms, None, {"min_ms": mn})
     pipe.site_map(counts)
     ms, mn, ht = timed(lambda: pipe.hoptraj(xyz, map16, 0), args.reps)
     hop_x, hop_y, events, state, final = ht
