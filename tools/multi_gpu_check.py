@@ -1,0 +1,79 @@
+"""Parity of the frame-sharded pipeline on N GPUs (run under torchrun): every rank processes its
+frame slab with HopPipeline (NCCL all-reduce of counts, all-gather of slab summaries, all-reduce of
+the transition-count matrix) and the union of the ranks' outputs must equal the single-process
+CPU oracle bit for bit.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29517 tools/multi_gpu_check.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    from oracle import hop_oracle as O
+    from hop_b200 import exchange
+    from hop_b200 import kernels as K
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for n_atoms, n_frames, delta in [(1000, 200, 1.0), (400, 67, 0.5)]:
+        p = SynthParams(n_atoms=n_atoms, n_frames=n_frames)
+        xyz = generate(p)
+        if n_frames == 67:   # outliers, also in the very first frame
+            rng = np.random.default_rng(3)
+            m = rng.random(xyz.shape[:2]) < 0.03
+            m[0, :] = False
+            xyz[m] += np.float32(40.0)
+            xyz[0, 3:9] -= np.float32(70.0)
+        edges = grid_edges_from_frame0(xyz[0], delta=delta)
+        f0, f1 = exchange.slab_bounds(n_frames, world, rank)
+        pipe = HopPipeline(edges, n_frames, PipelineConfig(n_chunks=3))
+        res = pipe.run(torch.from_numpy(xyz[f0:f1]).cuda(), f0)
+        ref = O.pipeline(xyz, delta=delta)
+        checks = {
+            "counts": np.array_equal(res.counts.cpu().numpy(), ref["counts"].astype(np.int32)),
+            "map": np.array_equal(res.map16.cpu().numpy(), ref["map"]),
+            "hop_x": np.array_equal(res.hop_x.cpu().numpy(), ref["hop"][f0:f1, :, 0]),
+            "hop_y": np.array_equal(res.hop_y.cpu().numpy(), ref["hop"][f0:f1, :, 1]),
+        }
+        ev = K.events_to_numpy(res.events)
+        mine = np.stack([ev[k] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1).astype(np.int64)
+        er = ref["events"]
+        sel = er[(er[:, 0] >= f0) & (er[:, 0] < f1)]
+        order = np.lexsort((sel[:, 1], sel[:, 0], sel[:, 3], sel[:, 2]))
+        checks["events(own frames)"] = np.array_equal(mine, sel[order])
+        pairs, cnts = O.events_to_counts(er)
+        M = res.count_matrix.cpu().numpy()
+        checks["count_matrix"] = bool(M.sum() == len(er) and all(M[a + 1, b + 1] == c for (a, b), c in zip(pairs, cnts)))
+        st = res.final_state.cpu().numpy()
+        ia = np.nonzero(st[0] != 0)[0]
+        nodes = np.stack([ia, st[0][ia], (n_frames - 1) - st[1][ia]], axis=1)
+        checks["nodes"] = np.array_equal(nodes, ref["nodes"])
+        bad = [k for k, v in checks.items() if not v]
+        print("rank %d/%d  %d atoms x %d frames (slab %d:%d)  %s" % (rank, world, n_atoms, n_frames, f0, f1,
+                                                                    "OK" if not bad else "MISMATCH " + str(bad)), flush=True)
+        ok &= not bad
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if flag.item():
+        sys.exit(1)
+    if rank == 0:
+        print("multi-GPU parity OK on %d ranks" % world)
+
+
+if __name__ == "__main__":
+    main()
