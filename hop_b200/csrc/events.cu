@@ -4,64 +4,134 @@
 // TransportNetwork._analyze_hops appends to graph_properties[(s0, s)] while looping frames (outer)
 // and atoms (inner) (hop/graph.py:212-247), so every per-edge list is ordered by (frame, iatom).
 // The kernels and the fix-up produce events in arbitrary order; here they are sorted by
-// (edge, frame, iatom) with an LSD radix sort -- first on frame*N + iatom, then (stable) on the
-// edge key -- and run-length encoded into COO form: (s0, s) -> count = len(tau), the `N` that
+// (edge, frame, iatom) with a stable LSD radix sort -- first on frame*N + iatom, then on the edge
+// key -- and run-length encoded into COO form: (s0, s) -> count = len(tau), the `N` that
 // HoppingGraph._rate (hop/graph.py:1728,1748) and MCMC (hop/MCMC.py:112-118) consume.
-#include "hopb_common.cuh"
+//
+// There are far fewer events than atom-frames (~1e-3), so the ~30 small passes this takes are
+// launch-latency bound when issued one by one.  The whole finalisation is therefore ONE cooperative
+// kernel: every pass is a phase separated by a grid-wide barrier.
+#include <cooperative_groups.h>
+
+#include "hopb_sort_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-__global__ void __launch_bounds__(256)
-ev_key1_kernel(const hopb_event* __restrict__ ev, int64_t n, int64_t N, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    keys[i] = (uint64_t)ev[i].frame * (uint64_t)N + (uint64_t)ev[i].iatom;
-    vals[i] = (uint32_t)i;
+using namespace hopb_sort;
+
+struct EvArgs {
+  const hopb_event* ev;
+  int64_t n, N;
+  int n_labels, bits1, bits2, tiles_per_block;
+  uint64_t* k[2];
+  uint32_t* v[2];
+  uint32_t* ghist;     // [256][grid]
+  uint32_t* totals;    // [256]
+  uint32_t* blockcnt;  // [grid + 1]
+  hopb_event* sorted;
+  int32_t* e_s0;
+  int32_t* e_s;
+  int64_t* e_start;
+  int64_t* e_count;
+  int32_t* matrix;     // optional dense [(n_labels+1)^2], caller-zeroed
+  int64_t* n_edges_dev;
+};
+
+__device__ __forceinline__ int coop_sort(cg::grid_group& grid, const EvArgs& a, int cur, int bits, SortSmem& sm) {
+  for (int shift = 0; shift < bits; shift += 8) {
+    sort_hist_block(a.k[cur], a.n, shift, a.tiles_per_block, a.ghist, sm);
+    grid.sync();
+    sort_rowscan_rows(a.ghist, (int)gridDim.x, a.totals, sm);
+    grid.sync();
+    sort_scatter_block(a.k[cur], a.v[cur], a.k[cur ^ 1], a.v[cur ^ 1], a.n, shift, a.tiles_per_block, a.ghist, a.totals, sm);
+    grid.sync();
+    cur ^= 1;
   }
+  return cur;
 }
 
-__global__ void __launch_bounds__(256)
-ev_key2_kernel(const hopb_event* __restrict__ ev, const uint32_t* __restrict__ perm, int64_t n, int n_labels,
-               uint64_t* __restrict__ keys) {
-  const uint64_t W = (uint64_t)n_labels + 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const hopb_event e = ev[perm[i]];
-    keys[i] = (uint64_t)(e.s0 + 1) * W + (uint64_t)(e.s + 1);
-  }
-}
+__global__ void __launch_bounds__(kSortThreads)
+ev_finalize_kernel(EvArgs a) {
+  __shared__ SortSmem sm;
+  __shared__ uint32_t s_carry;
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n = a.n;
 
-__global__ void __launch_bounds__(256)
-ev_gather_kernel(const hopb_event* __restrict__ ev, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ keys,
-                 int64_t n, hopb_event* __restrict__ out, uint32_t* __restrict__ head) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    out[i] = ev[perm[i]];
-    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  // key 1: position in the reference's loop order
+  for (int64_t i = gtid; i < n; i += gstride) {
+    a.k[0][i] = (uint64_t)a.ev[i].frame * (uint64_t)a.N + (uint64_t)a.ev[i].iatom;
+    a.v[0][i] = (uint32_t)i;
   }
-}
+  grid.sync();
+  int cur = coop_sort(grid, a, 0, a.bits1, sm);
+  // key 2: the edge
+  const uint64_t W = (uint64_t)a.n_labels + 1;
+  for (int64_t i = gtid; i < n; i += gstride) {
+    const hopb_event e = a.ev[a.v[cur][i]];
+    a.k[cur][i] = (uint64_t)(e.s0 + 1) * W + (uint64_t)(e.s + 1);
+  }
+  grid.sync();
+  cur = coop_sort(grid, a, cur, a.bits2, sm);
+  const uint64_t* keys = a.k[cur];
+  const uint32_t* perm = a.v[cur];
 
-__global__ void __launch_bounds__(256)
-ev_edges_kernel(const hopb_event* __restrict__ sorted, const uint32_t* __restrict__ head, const uint32_t* __restrict__ rank,
-                int64_t n, int32_t* __restrict__ edge_s0, int32_t* __restrict__ edge_s, int64_t* __restrict__ edge_start) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (head[i]) {
-      const uint32_t e = rank[i];
-      edge_s0[e] = sorted[i].s0;
-      edge_s[e] = sorted[i].s;
-      edge_start[e] = i;
+  // gather into the final order; count edge heads per block (blocks own contiguous ranges)
+  const int64_t begin = (int64_t)blockIdx.x * a.tiles_per_block * kSortTile;
+  int64_t end = begin + (int64_t)a.tiles_per_block * kSortTile;
+  if (end > n) end = n;
+  uint32_t heads = 0;
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    a.sorted[i] = a.ev[perm[i]];
+    heads += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  }
+  uint32_t total;
+  block_exclusive_scan(heads, sm.warp, &total);
+  if (threadIdx.x == 0) a.blockcnt[blockIdx.x] = total;
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { const uint32_t c = a.blockcnt[b]; a.blockcnt[b] = run; run += c; }
+    a.blockcnt[gridDim.x] = run;
+    *a.n_edges_dev = (int64_t)run;
+  }
+  grid.sync();
+  // edge records: rank of every head = block base + ordered rank inside the block
+  if (threadIdx.x == 0) s_carry = a.blockcnt[blockIdx.x];
+  __syncthreads();
+  for (int64_t i0 = begin; i0 < end; i0 += blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool head = i < end && (i == 0 || keys[i] != keys[i - 1]);
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(head ? 1u : 0u, sm.warp, &tot);
+    if (head) {
+      const uint32_t e = s_carry + ex;
+      a.e_s0[e] = a.sorted[i].s0;
+      a.e_s[e] = a.sorted[i].s;
+      a.e_start[e] = i;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += tot;
+    __syncthreads();
   }
-}
-
-__global__ void __launch_bounds__(256)
-ev_counts_kernel(const int64_t* __restrict__ edge_start, int64_t n_edges, int64_t n, int64_t* __restrict__ edge_count) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x)
-    edge_count[e] = (e + 1 < n_edges ? edge_start[e + 1] : n) - edge_start[e];
+  grid.sync();
+  const int64_t n_edges = (int64_t)a.blockcnt[gridDim.x];
+  for (int64_t e = gtid; e < n_edges; e += gstride) {
+    const int64_t c = (e + 1 < n_edges ? a.e_start[e + 1] : n) - a.e_start[e];
+    a.e_count[e] = c;
+    if (a.matrix) a.matrix[(int64_t)(a.e_s0[e] + 1) * (int64_t)W + (a.e_s[e] + 1)] = (int32_t)c;
+  }
 }
 
 }  // namespace
 
-extern "C" int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_event* events, uint64_t n_u, int64_t N,
-                                    int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
-                                    int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int64_t* n_edges) {
+extern "C" int hopb_events_finalize_ex(hopb_handle* h, void* stream, const hopb_event* events, uint64_t n_u, int64_t N,
+                                       int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
+                                       int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int32_t* count_matrix,
+                                       int64_t* n_edges) {
   HOPB_REQUIRE(h, n_edges != nullptr, "null argument");
   *n_edges = 0;
   const int64_t n = (int64_t)n_u;
@@ -69,42 +139,51 @@ extern "C" int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_eve
   HOPB_REQUIRE(h, events && events_sorted && edge_s0 && edge_s && edge_start && edge_count, "null argument");
   HOPB_REQUIRE(h, n < ((int64_t)1 << 32) && N > 0 && F_total > 0 && n_labels >= 1, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned char* buf = nullptr;
-  const size_t per = 2 * sizeof(uint64_t) + 4 * sizeof(uint32_t);
-  int rc = hopb_scratch(h, 5, (size_t)(n + 2) * per + 64, (void**)&buf);
-  if (rc) return rc;
-  uint64_t* keys = (uint64_t*)buf;
-  uint64_t* keys_alt = keys + (n + 2);
-  uint32_t* vals = (uint32_t*)(keys_alt + (n + 2));
-  uint32_t* vals_alt = vals + (n + 2);
-  uint32_t* head = vals_alt + (n + 2);
-  uint32_t* rank = head + (n + 2);
-  uint32_t* total_dev = rank + n;  // inside the padding
-  const unsigned g = hopb_grid_for(n, 256, h->num_sms, 8);
 
-  HOPB_K(ev_key1_kernel)<<<g, 256, 0, s>>>(events, n, N, keys, vals);
-  int alt = 0;
-  rc = hopb_radix_sort_pairs(h, s, keys, keys_alt, vals, vals_alt, n, 0, hopb_bits_for((uint64_t)F_total * (uint64_t)N), &alt);
+  int per_sm = 0;
+  HOPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ev_finalize_kernel, kSortThreads, 0));
+  int64_t max_blocks = (int64_t)per_sm * h->num_sms;
+  if (max_blocks > kMaxSortBlocks) max_blocks = kMaxSortBlocks;
+  HOPB_REQUIRE(h, max_blocks >= 1, "cooperative launch not possible");
+  const int64_t ntiles = (n + kSortTile - 1) / kSortTile;
+  const int tiles_per_block = (int)((ntiles + max_blocks - 1) / max_blocks);
+  const int nblocks = (int)((ntiles + tiles_per_block - 1) / tiles_per_block);
+
+  unsigned char* buf = nullptr;
+  const size_t per = 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
+  const size_t bytes = (size_t)(n + 2) * per + ((size_t)256 * nblocks + 256 + nblocks + 8) * sizeof(uint32_t) + 64;
+  int rc = hopb_scratch(h, 5, bytes, (void**)&buf);
   if (rc) return rc;
-  uint64_t* k = alt ? keys_alt : keys; uint64_t* ka = alt ? keys : keys_alt;
-  uint32_t* v = alt ? vals_alt : vals; uint32_t* va = alt ? vals : vals_alt;
-  HOPB_K(ev_key2_kernel)<<<g, 256, 0, s>>>(events, v, n, n_labels, k);
-  int alt2 = 0;
+  EvArgs a;
+  a.ev = events; a.n = n; a.N = N; a.n_labels = n_labels;
+  a.bits1 = hopb_bits_for((uint64_t)F_total * (uint64_t)N);
   const uint64_t W = (uint64_t)n_labels + 1;
-  rc = hopb_radix_sort_pairs(h, s, k, ka, v, va, n, 0, hopb_bits_for(W * W), &alt2);
-  if (rc) return rc;
-  const uint64_t* kf = alt2 ? ka : k;
-  const uint32_t* vf = alt2 ? va : v;
-  HOPB_K(ev_gather_kernel)<<<g, 256, 0, s>>>(events, vf, kf, n, events_sorted, head);
-  rc = hopb_exclusive_scan_u32(h, s, head, rank, n, total_dev);
-  if (rc) return rc;
-  HOPB_K(ev_edges_kernel)<<<g, 256, 0, s>>>(events_sorted, head, rank, n, edge_s0, edge_s, edge_start);
-  uint32_t total = 0;
-  HOPB_CUDA(h, cudaMemcpyAsync(&total, total_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  a.bits2 = hopb_bits_for(W * W);
+  a.tiles_per_block = tiles_per_block;
+  a.k[0] = (uint64_t*)buf;
+  a.k[1] = a.k[0] + (n + 2);
+  a.v[0] = (uint32_t*)(a.k[1] + (n + 2));
+  a.v[1] = a.v[0] + (n + 2);
+  a.ghist = a.v[1] + (n + 2);
+  a.totals = a.ghist + (size_t)256 * nblocks;
+  a.blockcnt = a.totals + 256;
+  int64_t* n_edges_dev = (int64_t*)(((uintptr_t)(a.blockcnt + nblocks + 2) + 7) & ~(uintptr_t)7);
+  a.n_edges_dev = n_edges_dev;
+  a.sorted = events_sorted; a.e_s0 = edge_s0; a.e_s = edge_s; a.e_start = edge_start; a.e_count = edge_count;
+  a.matrix = count_matrix;
+  void* kargs[] = {(void*)&a};
+  hopb_note_launch();
+  HOPB_CUDA(h, cudaLaunchCooperativeKernel((void*)ev_finalize_kernel, dim3((unsigned)nblocks), dim3(kSortThreads), kargs, 0, s));
+  int64_t total = 0;
+  HOPB_CUDA(h, cudaMemcpyAsync(&total, n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   HOPB_CUDA(h, cudaStreamSynchronize(s));
-  *n_edges = (int64_t)total;
-  HOPB_K(ev_counts_kernel)<<<hopb_grid_for((int64_t)total, 256, h->num_sms, 8), 256, 0, s>>>(edge_start, (int64_t)total, n, edge_count);
-  HOPB_LAUNCH_CHECK(h);
-  HOPB_CUDA(h, cudaStreamSynchronize(s));
+  *n_edges = total;
   return HOPB_OK;
+}
+
+extern "C" int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_event* events, uint64_t n_u, int64_t N,
+                                    int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
+                                    int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int64_t* n_edges) {
+  return hopb_events_finalize_ex(h, stream, events, n_u, N, F_total, n_labels, events_sorted, edge_s0, edge_s, edge_start,
+                                 edge_count, nullptr, n_edges);
 }

@@ -1,11 +1,12 @@
 // Device-wide primitives: exclusive scan and a stable LSD radix sort of (u64 key, u32 value) pairs.
 // They serve the site ranking (label.cu), the site cell lists and the event ordering (events.cu);
 // all of those work on #sites / #events items, orders of magnitude fewer than atom-frames.
-#include "hopb_common.cuh"
+
+#include "hopb_sort_device.cuh"
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
+using namespace hopb_sort;
 
 // ------------------------------------------------------------------------------------------------
 // scan
@@ -13,34 +14,6 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
-    uint32_t winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(kFull, winc, o);
-      if (lane >= o) winc += t;
-    }
-    s_warp[lane] = winc - w;  // exclusive warp offsets
-    if (lane == 31) s_warp[32] = winc;
-  }
-  __syncthreads();
-  const uint32_t res = s_warp[warp] + inc - v;
-  if (total) *total = s_warp[32];
-  __syncthreads();
-  return res;
-}
 
 // phase 0: tile sums; phase 1: final scan with tile offsets
 template <int PHASE>
@@ -75,112 +48,24 @@ __global__ void store_total_kernel(const uint32_t* in_last, const uint32_t* out_
   *total = *in_last + *out_last;
 }
 
-// ------------------------------------------------------------------------------------------------
-// radix sort, 8 bits per pass
-// ------------------------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 8;                       // rows of 32 per warp per tile
-constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
-constexpr int kMaxSortBlocks = 1024;
-
-__device__ __forceinline__ unsigned digit_of(uint64_t key, int shift) { return (unsigned)(key >> shift) & 255u; }
-
 __global__ void __launch_bounds__(kSortThreads)
 sort_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, int tiles_per_block, uint32_t* __restrict__ ghist) {
-  __shared__ uint32_t s_hist[256];
-  s_hist[threadIdx.x] = 0;
-  __syncthreads();
-  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * kSortTile;
-  int64_t end = begin + (int64_t)tiles_per_block * kSortTile;
-  if (end > n) end = n;
-  for (int64_t i = begin + threadIdx.x; i < end; i += kSortThreads) atomicAdd(&s_hist[digit_of(keys[i], shift)], 1u);
-  __syncthreads();
-  ghist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = s_hist[threadIdx.x];
+  __shared__ SortSmem sm;
+  sort_hist_block(keys, n, shift, tiles_per_block, ghist, sm);
 }
 
-// one block per digit: exclusive scan along the blocks, digit total to totals[d]
-__global__ void __launch_bounds__(kMaxSortBlocks)
+__global__ void __launch_bounds__(kSortThreads)
 sort_rowscan_kernel(uint32_t* __restrict__ ghist, int nblocks, uint32_t* __restrict__ totals) {
-  __shared__ uint32_t s_warp[33];
-  const int d = blockIdx.x;
-  uint32_t v = (int)threadIdx.x < nblocks ? ghist[(int64_t)d * nblocks + threadIdx.x] : 0u;
-  uint32_t total;
-  uint32_t ex = block_exclusive_scan(v, s_warp, &total);
-  if ((int)threadIdx.x < nblocks) ghist[(int64_t)d * nblocks + threadIdx.x] = ex;
-  if (threadIdx.x == 0) totals[d] = total;
+  __shared__ SortSmem sm;
+  sort_rowscan_rows(ghist, nblocks, totals, sm);
 }
 
 __global__ void __launch_bounds__(kSortThreads)
 sort_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t* __restrict__ keys_out,
                     uint32_t* __restrict__ vals_out, int64_t n, int shift, int tiles_per_block,
                     const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ totals) {
-  __shared__ uint32_t s_off[256];
-  __shared__ uint32_t s_wcnt[kSortWarps][256];
-  __shared__ uint32_t s_warp[33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {
-    // digit base = exclusive scan of the 256 digit totals + this block's offset within the digit
-    uint32_t t = totals[threadIdx.x];
-    uint32_t ex = block_exclusive_scan(t, s_warp, nullptr);
-    s_off[threadIdx.x] = ex + ghist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
-  }
-  __syncthreads();
-  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * kSortTile;
-  for (int t = 0; t < tiles_per_block; ++t) {
-    const int64_t tile0 = begin + (int64_t)t * kSortTile;
-    if (tile0 >= n) break;
-    const int64_t wbase = tile0 + (int64_t)warp * 32 * kSortItems;
-    uint64_t k[kSortItems];
-    uint32_t v[kSortItems];
-    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_wcnt[0][0])[i] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-      const int64_t idx = wbase + r * 32 + lane;
-      const bool valid = idx < n;
-      k[r] = valid ? keys[idx] : 0;
-      v[r] = valid ? vals[idx] : 0;
-      const unsigned act = __ballot_sync(kFull, valid);
-      if (valid) {
-        const unsigned dgt = digit_of(k[r], shift);
-        const unsigned peers = __match_any_sync(act, dgt);
-        if ((peers & ((1u << lane) - 1)) == 0) s_wcnt[warp][dgt] += __popc(peers);
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-    {
-      const int dgt = threadIdx.x;
-      uint32_t run = s_off[dgt];
-#pragma unroll
-      for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = s_wcnt[w][dgt];
-        s_wcnt[w][dgt] = run;
-        run += c;
-      }
-      s_off[dgt] = run;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-      const int64_t idx = wbase + r * 32 + lane;
-      const bool valid = idx < n;
-      const unsigned act = __ballot_sync(kFull, valid);
-      if (valid) {
-        const unsigned dgt = digit_of(k[r], shift);
-        const unsigned peers = __match_any_sync(act, dgt);
-        const unsigned below = peers & ((1u << lane) - 1);
-        const uint32_t pos = s_wcnt[warp][dgt] + __popc(below);
-        keys_out[pos] = k[r];
-        vals_out[pos] = v[r];
-        __syncwarp(act);
-        if (below == 0) s_wcnt[warp][dgt] += __popc(peers);
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-  }
+  __shared__ SortSmem sm;
+  sort_scatter_block(keys, vals, keys_out, vals_out, n, shift, tiles_per_block, ghist, totals, sm);
 }
 
 }  // namespace
@@ -255,7 +140,7 @@ int hopb_radix_sort_pairs(hopb_handle* h, cudaStream_t s, uint64_t* keys, uint64
   uint32_t* vin = vals; uint32_t* vout = vals_alt;
   for (int shift = begin_bit; shift < end_bit; shift += 8) {
     HOPB_K(sort_hist_kernel)<<<nblocks, kSortThreads, 0, s>>>(kin, n, shift, tiles_per_block, ghist);
-    HOPB_K(sort_rowscan_kernel)<<<256, kMaxSortBlocks, 0, s>>>(ghist, nblocks, totals);
+    HOPB_K(sort_rowscan_kernel)<<<256, kSortThreads, 0, s>>>(ghist, nblocks, totals);
     HOPB_K(sort_scatter_kernel)<<<nblocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, tiles_per_block, ghist, totals);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

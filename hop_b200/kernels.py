@@ -321,20 +321,27 @@ def new_state(n_atoms: int, device):
     return torch.zeros((STATE_INTS, n_atoms), dtype=torch.int32, device=device)
 
 
-def events_finalize(events: EventBuffer, n_events: int, n_atoms: int, n_frames_total: int, n_labels: int):
-    """Sort events into reference order; returns (sorted [n,6] int32, edge_s0, edge_s, edge_start, edge_count)."""
+def events_finalize(events: EventBuffer, n_events: int, n_atoms: int, n_frames_total: int, n_labels: int,
+                    count_matrix=None, out=None):
+    """Sort events into reference order; returns (sorted [n,6] int32, edge_s0, edge_s, edge_start, edge_count).
+    `count_matrix` (zeroed CUDA int32 [(n_labels+1)^2]) optionally receives the dense transition counts;
+    `out` may supply the five output buffers (sized for n events) to avoid allocations."""
     dev = events.data.device
     n = int(n_events)
-    sorted_ev = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
     cap_edges = max(1, min(n, (n_labels + 1) ** 2))
-    e_s0 = torch.empty(cap_edges, dtype=torch.int32, device=dev)
-    e_s = torch.empty(cap_edges, dtype=torch.int32, device=dev)
-    e_start = torch.empty(cap_edges, dtype=torch.int64, device=dev)
-    e_count = torch.empty(cap_edges, dtype=torch.int64, device=dev)
+    if out is not None:
+        sorted_ev, e_s0, e_s, e_start, e_count = out
+    else:
+        sorted_ev = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
+        e_s0 = torch.empty(cap_edges, dtype=torch.int32, device=dev)
+        e_s = torch.empty(cap_edges, dtype=torch.int32, device=dev)
+        e_start = torch.empty(cap_edges, dtype=torch.int64, device=dev)
+        e_count = torch.empty(cap_edges, dtype=torch.int64, device=dev)
     n_edges = ctypes.c_int64(0)
     h = _h(events.data)
-    rc = _lib.lib().hopb_events_finalize(h, _stream(), _p(events.data), n, int(n_atoms), int(n_frames_total), int(n_labels),
-                                         _p(sorted_ev), _p(e_s0), _p(e_s), _p(e_start), _p(e_count), ctypes.byref(n_edges))
+    rc = _lib.lib().hopb_events_finalize_ex(h, _stream(), _p(events.data), n, int(n_atoms), int(n_frames_total),
+                                            int(n_labels), _p(sorted_ev), _p(e_s0), _p(e_s), _p(e_start), _p(e_count),
+                                            _p(count_matrix), ctypes.byref(n_edges))
     _lib.check(h, rc)
     k = int(n_edges.value)
     return sorted_ev[:n], e_s0[:k], e_s[:k], e_start[:k], e_count[:k]

@@ -162,8 +162,6 @@ class HopPipeline:
 
             raise TooManySitesError("map_sites: %d sites (bulk map: %d); hop's int16 site map holds at most %d"
                                     % (n_sites, n_bulk, K.HOPB_MAX_SITES))
-        if n_ev > events.capacity:
-            raise _capacity_error(n_ev, events.capacity)
         n_labels = n_sites + (2 if self.cfg.with_bulk else 1)
         return n_labels, n_ev
 
@@ -175,7 +173,9 @@ class HopPipeline:
         else:
             chunk_len = -(-F // cfg.n_chunks)
             n_chunks = -(-F // chunk_len)
-        cap = cfg.event_capacity or max(1 << 16, (F * N) // 8)
+        cap = cfg.event_capacity or max(1 << 20, (F * N) // 64)
+        if self._events is not None:
+            cap = max(cap, self._events.capacity)
         events = self._event_buffer(cap)
         events.reset()
         hop_x = hop_y = None
@@ -205,15 +205,18 @@ class HopPipeline:
         return hop_x, hop_y, events, state, final_state
 
     def transitions(self, events, n_ev, n_atoms, n_labels):
-        ev, e_s0, e_s, e_start, e_count = K.events_finalize(events, n_ev, n_atoms, self.n_frames_total, n_labels)
         W = n_labels + 1
         matrix = None
         if W * W <= (1 << 24):
             matrix = self._buf("count_matrix", (W, W), torch.int32)
             matrix.zero_()
-            if e_s0.numel():
-                idx = (e_s0.long() + 1) * W + (e_s.long() + 1)
-                matrix.view(-1).index_put_((idx,), e_count.to(torch.int32))
+        cap = events.capacity
+        out = (self._buf("ev_sorted", (max(cap, 1), 6), torch.int32), self._buf("e_s0", (max(cap, 1),), torch.int32),
+               self._buf("e_s", (max(cap, 1),), torch.int32), self._buf("e_start", (max(cap, 1),), torch.int64),
+               self._buf("e_count", (max(cap, 1),), torch.int64))
+        ev, e_s0, e_s, e_start, e_count = K.events_finalize(events, n_ev, n_atoms, self.n_frames_total, n_labels,
+                                                            count_matrix=matrix, out=out)
+        if matrix is not None:
             exchange.reduce_count_matrix(matrix)
         return ev, e_s0, e_s, e_start, e_count, matrix
 
@@ -234,8 +237,12 @@ class HopPipeline:
         res.density, res.own, res.member, res.map16, res.site_props = self.site_map(res.counts)
         self._mark(marks, "S2_sitemap")
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
-        self._mark(marks, "S3S4_hoptraj")
         res.n_labels, n_ev = self.sync_scalars(events)
+        if n_ev > events.capacity:      # rare: more transitions than budgeted -- grow the buffer and redo stage 3
+            self._event_buffer(n_ev + n_ev // 8)
+            res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+            res.n_labels, n_ev = self.sync_scalars(events)
+        self._mark(marks, "S3S4_hoptraj")
         res.n_events_local = n_ev
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
          res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]), res.n_labels)
@@ -276,6 +283,10 @@ class HopPipeline:
         res.density, res.own, res.member, res.map16, res.site_props = self.site_map(counts)
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
         res.n_labels, n_ev = self.sync_scalars(events)
+        if n_ev > events.capacity:
+            self._event_buffer(n_ev + n_ev // 8)
+            res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+            res.n_labels, n_ev = self.sync_scalars(events)
         res.n_events_local = n_ev
         if out_x is None:
             out_x = torch.empty((F, N), dtype=torch.float32).pin_memory()

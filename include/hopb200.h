@@ -209,6 +209,14 @@ int hopb_events_finalize(hopb_handle* h, void* stream, const hopb_event* events,
                          int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
                          int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int64_t* n_edges);
 
+/* Same, and additionally fills a dense transition-count matrix: count_matrix (device int32
+ * [(n_labels+1)^2], zeroed by the caller, may be NULL) gets count_matrix[(s0+1)*(n_labels+1) + (s+1)]
+ * = number of (s0 -> s) transitions.  The whole finalisation is one cooperative kernel launch. */
+int hopb_events_finalize_ex(hopb_handle* h, void* stream, const hopb_event* events, uint64_t n, int64_t N,
+                            int64_t F_total, int n_labels, hopb_event* events_sorted, int32_t* edge_s0,
+                            int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int32_t* count_matrix,
+                            int64_t* n_edges);
+
 /* TransportNetwork.graph_alltransitions (hop/graph.py:107-135): bit (a+1)*(n_labels+1)+(b+1) of
  * `bitmap` is set when some atom has label a in frame t-1 and b in frame t.
  * bitmap: device uint32 [ceil((n_labels+1)^2 / 32)], OR-ed into (not cleared). */

@@ -347,6 +347,51 @@ def test_hopscan_from_labels_and_all_transitions(K):
     assert np.array_equal(K.all_transitions(hx, 8), O.graph_alltransitions(lab))
 
 
+def test_pipeline_regrows_event_buffer(K, traj):
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    ref = O.pipeline(xyz, delta=1.0)
+    pipe = HopPipeline(grid_edges_from_frame0(xyz[0], delta=1.0), xyz.shape[0], PipelineConfig(event_capacity=100))
+    res = pipe.run(dev(xyz))
+    assert res.n_events_local == len(ref["events"]) > 100
+    assert np.array_equal(res.hop_y.cpu().numpy(), ref["hop"][:, :, 1])
+    assert res.count_matrix.sum().item() == len(ref["events"])
+
+
+def test_empty_and_degenerate_inputs(K):
+    # zero points, one frame, atoms all outside the grid, a grid with a single cell
+    edges = [np.linspace(0.0, 4.0, 5), np.linspace(0.0, 3.0, 4), np.linspace(0.0, 1.0, 2)]
+    g = K.GridTables(edges)
+    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    K.hist_accumulate(g, torch.empty((0, 3), dtype=torch.float32, device="cuda"), counts)
+    assert counts.sum().item() == 0
+    far = dev(np.full((1, 7, 3), 99.0, np.float32))
+    K.hist_accumulate(g, far, counts)
+    assert counts.sum().item() == 0
+    m16 = dev(np.ones(g.shape, np.int16))
+    brick, coarse = K.brick_map(m16)
+    ev = K.EventBuffer(16, "cuda")
+    X = torch.empty((1, 7), dtype=torch.float32, device="cuda")
+    Y = torch.empty((1, 7), dtype=torch.float32, device="cuda")
+    s = K.hoptraj(g, far, brick, 0, 1, 1, ev, X, Y, coarse=coarse)
+    st = K.new_state(7, "cuda")
+    K.hop_advance(None, st, init=True)
+    K.hop_fixup(s, 1, 1, st, Y, ev)
+    assert (X == -1).all().item() and (Y == 0).all().item() and ev.n() == 0
+    assert (st.cpu().numpy()[0] == -1).all()          # first-frame outliers: s0 = -1 (hop/graph.py:206-208)
+    out = K.events_finalize(ev, 0, 7, 1, 3)
+    assert out[0].shape[0] == 0 and out[1].numel() == 0
+    one = K.GridTables([np.array([0.0, 1.0])] * 3)
+    c1 = torch.zeros(one.shape, dtype=torch.int32, device="cuda")
+    K.hist_accumulate(one, dev(np.array([[0.5, 0.5, 0.5], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [1.5, 0.5, 0.5]], np.float32)), c1)
+    assert c1.item() == 3                              # the point on the last edge counts, the one beyond does not
+    lab, n, vol = K.label_sites(dev(np.ones((1, 1, 1))), 0.5)
+    assert n == 1 and lab.item() == 1 and vol.cpu().tolist() == [0, 1]
+    lab, n, vol = K.label_sites(dev(np.zeros((3, 2, 2))), 0.5)
+    assert n == 0 and (lab == 0).all().item()
+
+
 def test_pipeline_config1_matches_faithful_oracle(K, traj):
     from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
 
