@@ -98,20 +98,24 @@ struct MapView {
 };
 
 // site label of a brick index: the block map answers for bricks that are uniformly interstitial
-// (0) or bulk (1); only cells in mixed bricks gather from the bricked int16 map in L2.
+// (0) or bulk (1); only cells in mixed bricks gather from the bricked int16 map in L2.  Written
+// with selects and one predicated load so that a warp does not diverge on it.
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
-  if (c == 0xFFFFFFFFu) return -1;  // the -1 shell of buffered_map (trajectory.py:176-177)
+  const bool out = c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
+  const uint32_t cc = out ? 0u : c;
+  uint32_t st = 3u;
   if (m.s_coarse) {
-    const uint32_t cb = c >> 6;
-    const uint32_t st = (m.s_coarse[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
-    if (st != 3u) return (int)st;
+    const uint32_t cb = cc >> 6;
+    st = (m.s_coarse[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
   }
-  return (int)__ldg(m.brick + c);
+  int l = (int)st;
+  if (st == 3u && !out) l = (int)__ldg(m.brick + cc);
+  return out ? -1 : l;
 }
 
 // SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: brick indices
 template <int SRC, bool FAST>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kHopThreads, 3)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
@@ -149,126 +153,107 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const int iatom = (int)atom;
   auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
 
-  // running output pointers (one frame = N floats further)
+  // running pointers (one frame = N elements further)
   float* px = hop_x ? hop_x + f_begin * N + atom : nullptr;
   float* py = hop_y ? hop_y + f_begin * N + atom : nullptr;
-
-  // Generic step: any phase of the summary machine.
-  auto step_generic = [&](int l, int t) {
-    hopb_push_frame(T, l, t, emit);
-    if (l > 0) { yorb = l; yknown = true; }
-    if (!yknown) ++ypre;
-  };
-  // Fast step, valid once a first site has been seen (SPEC or FULL, orbit known): the machine is
-  // "current site `cur`, on/off, last exit t1"; entering another site is the only rare event.
-  int cur = 0, on = 1, t1 = 0;
-  auto step_fast = [&](int l, int t) {
-    if (l == cur) {
-      on = 1;
-    } else if (l == 0) {
-      if (on) { t1 = t; on = 0; }
-    } else if (l > 0) {
-      const int tx = on ? t : t1;
-      if (T.kind == HOPB_SPEC) {          // second site of the chunk: the open event E2
-        T.t1_2 = tx; T.A2 = l; T.f2 = t; T.kind = HOPB_FULL;
-      } else {
-        emit(cur, l, t, tx - T.t0, t - tx);
-      }
-      cur = l; T.t0 = t; on = 1;
-      yorb = l;
-    }                                      // l == -1: outlier, nothing changes
-  };
-  bool fast = false;
-  auto enter_fast = [&]() {
-    cur = T.kind == HOPB_SPEC ? T.A1 : T.s0; on = T.on; t1 = T.t1; fast = true;
-  };
-  auto leave_fast = [&]() {
-    if (T.kind == HOPB_FULL) T.s0 = cur;
-    T.on = on; T.t1 = t1;
-  };
   auto store = [&](int l) {
     if (px) { *px = (float)l; px += N; }
     if (py) { *py = (float)yorb; py += N; }
   };
+  // label of frame f, whatever the source
+  auto label_at = [&](int64_t fr) -> int {
+    if (SRC == 1) return (int)__ldg(labels_in + fr * N + atom);
+    uint32_t c;
+    if (SRC == 0) {
+      const float* p = xyz + (fr * N + atom) * 3;
+      c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab, cny, cnz);
+    } else {
+      c = __ldg(cells + fr * N + atom);
+    }
+    return label_of(c, mv);
+  };
 
+  // ---- prologue: the generic summary machine until a first real site has been seen -------------
   int64_t f = f_begin;
-  constexpr int kDeep = 8;
-  if (SRC == 0) {
-    for (; f + kUnroll <= f_end; f += kUnroll) {
-      float cx[kUnroll], cy[kUnroll], cz[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const float* p = xyz + ((f + u) * N + atom) * 3;
-        cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
-      }
-      int lab[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int t = (int)(frame0 + f + u);
-        if (fast) step_fast(lab[u], t);
-        else { step_generic(lab[u], t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
-        store(lab[u]);
-      }
-    }
-  } else {
-    // 4-byte inputs (brick indices or labels): blocks of kDeep frames, the next block's loads are
-    // issued before the current block is consumed so that ~2 x kDeep x 4 B per thread stay in flight
-    const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f_begin * N + atom;
-    uint32_t curv[kDeep], nxt[kDeep];
-    if (f + kDeep <= f_end) {
-#pragma unroll
-      for (int u = 0; u < kDeep; ++u) curv[u] = __ldg(src + u * N);
-    }
-    for (; f + kDeep <= f_end; f += kDeep) {
-      src += kDeep * N;
-      const bool more = f + 2 * kDeep <= f_end;
-      if (more) {
-#pragma unroll
-        for (int u = 0; u < kDeep; ++u) nxt[u] = __ldg(src + u * N);
-      }
-      int lab[kDeep];
-#pragma unroll
-      for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(curv[u], mv) : (int)__uint_as_float(curv[u]);
-      if (fast) {
-#pragma unroll
-        for (int u = 0; u < kDeep; ++u) { step_fast(lab[u], (int)(frame0 + f + u)); store(lab[u]); }
+  while (f < f_end && !(T.kind >= HOPB_SPEC && yknown)) {
+    const int l = label_at(f);
+    hopb_push_frame(T, l, (int)(frame0 + f), emit);
+    if (l > 0) { yorb = l; yknown = true; }
+    if (!yknown) ++ypre;
+    store(l);
+    ++f;
+  }
+
+  // ---- main loop: "current site cur, on/off, last exit t1"; entering another site is the only
+  // rare event.  Written with selects; the rare event is one (mostly not taken) branch. ---------
+  if (f < f_end) {
+    int cur = T.kind == HOPB_SPEC ? T.A1 : T.s0;
+    int on = T.on, t1 = T.t1;
+    auto step = [&](int l, int t) {
+      const bool same = l == cur, zero = l == 0;
+      if (l > 0 && !same) {
+        const int tx = on ? t : t1;
+        if (T.kind == HOPB_SPEC) {          // second site of the chunk: the open event E2
+          T.t1_2 = tx; T.A2 = l; T.f2 = t; T.kind = HOPB_FULL;
+        } else {
+          emit(cur, l, t, tx - T.t0, t - tx);
+        }
+        cur = l; T.t0 = t; on = 1; yorb = l;
       } else {
+        t1 = (zero && on) ? t : t1;
+        on = same ? 1 : (zero ? 0 : on);   // l == -1 (outlier): nothing changes
+      }
+      store(l);
+    };
+    if (SRC == 0) {
+      for (; f + kUnroll <= f_end; f += kUnroll) {
+        float cx[kUnroll], cy[kUnroll], cz[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) {
-          const int t = (int)(frame0 + f + u);
-          if (fast) step_fast(lab[u], t);
-          else { step_generic(lab[u], t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
-          store(lab[u]);
+        for (int u = 0; u < kUnroll; ++u) {
+          const float* p = xyz + ((f + u) * N + atom) * 3;
+          cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
+        }
+        int lab[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) step(lab[u], (int)(frame0 + f + u));
+      }
+    } else {
+      // 4-byte inputs (brick indices or labels): two register blocks of kDeep frames in ping-pong, so
+      // that the loads of one block are in flight while the other is consumed
+      constexpr int kDeep = 8;
+      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
+      auto load_block = [&](uint32_t (&v)[kDeep]) {
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + u * N);
+        src += kDeep * N;
+      };
+      auto run_block = [&](const uint32_t (&v)[kDeep]) {
+        int lab[kDeep];
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(v[u], mv) : (int)__uint_as_float(v[u]);
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) step(lab[u], (int)(frame0 + f + u));
+        f += kDeep;
+      };
+      uint32_t va[kDeep], vb[kDeep];
+      if (f + kDeep <= f_end) {
+        load_block(va);
+        while (true) {
+          if (f + 2 * kDeep > f_end) { run_block(va); break; }
+          load_block(vb);
+          run_block(va);
+          if (f + 2 * kDeep > f_end) { run_block(vb); break; }
+          load_block(va);
+          run_block(vb);
         }
       }
-      if (more) {
-#pragma unroll
-        for (int u = 0; u < kDeep; ++u) curv[u] = nxt[u];
-      }
     }
+    for (; f < f_end; ++f) step(label_at(f), (int)(frame0 + f));
+    if (T.kind == HOPB_FULL) T.s0 = cur;
+    T.on = on; T.t1 = t1;
   }
-  for (; f < f_end; ++f) {
-    int l;
-    if (SRC == 1) {
-      l = (int)__ldg(labels_in + f * N + atom);
-    } else {
-      uint32_t c;
-      if (SRC == 0) {
-        const float* p = xyz + (f * N + atom) * 3;
-        c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab, cny, cnz);
-      } else {
-        c = __ldg(cells + f * N + atom);
-      }
-      l = label_of(c, mv);
-    }
-    const int t = (int)(frame0 + f);
-    if (fast) step_fast(l, t);
-    else { step_generic(l, t); if (T.kind >= HOPB_SPEC && yknown) enter_fast(); }
-    store(l);
-  }
-  if (fast) leave_fast();
   T.ypre = ypre;
   hopb_summary_store(summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom, N, T);
 }
@@ -436,10 +421,8 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   size_t smem = (size_t)coarse_words * 4;
   if (src == 0) smem += (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
   // threads per CTA: big coarse maps are shared by more threads so that an SM still holds >= 1024
-  int threads = kHopThreads;
-  if (smem > 100 * 1024) threads = 1024;
-  else if (smem > 48 * 1024) threads = 512;
-  HOPB_REQUIRE(h, smem <= 200 * 1024, "coarse map too large for shared memory; pass coarse = NULL");
+  const int threads = kHopThreads;
+  HOPB_REQUIRE(h, smem <= 110 * 1024, "block map too large for shared memory; pass coarse = NULL");
   dim3 grid((unsigned)((N + threads - 1) / threads), (unsigned)n_chunks);
 #define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
   do {                                                                                                               \

@@ -80,6 +80,8 @@ def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, c
         _cuda(cells, torch.int32, "cells")
         if cells.numel() != n_points:
             raise ValueError("cells has the wrong size")
+    if n_points == 0:
+        return counts       # a frame with no selected atoms contributes nothing (hop/density.py:128)
     h = _h(xyz)
     _lib.check(h, _lib.lib().hopb_hist_accumulate_cells(h, _stream(), grid.ptr, _p(xyz), n_points, _p(counts), _p(cells)))
     return counts
@@ -216,7 +218,7 @@ def site_cells(own: torch.Tensor, member, n_labels: int):
 
 
 def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32, cta_threads: int = 256,
-                ctas_per_sm: int = 4, max_waves: int = 4):
+                ctas_per_sm: int = 3, max_waves: int = 4):
     """(n_chunks, chunk_len) for the fused hoptraj kernel: one thread per (atom, chunk).
 
     The kernel is latency-bound per thread, so the grid should be a whole number of waves of

@@ -145,7 +145,7 @@ class HopPipeline:
         nb, words = K.brick_shape(shape)
         self.brick, coarse = K.brick_map(map16, self._buf("brick", (nb * 64,), torch.int16),
                                          self._buf("coarse", (words,), torch.int32))
-        self.coarse = coarse if (cfg.coarse_map and words * 4 <= 160 * 1024) else None
+        self.coarse = coarse if (cfg.coarse_map and words * 4 <= 100 * 1024) else None
         return density, own, member, map16, props
 
     def sync_scalars(self, events):

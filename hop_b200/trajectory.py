@@ -161,7 +161,7 @@ class HoppingTrajectory(object):
             if self._map16.numel() != self._tables.n_cells:
                 raise ValueError("The density object must have its site map computed.")
             self._brick, self._coarse = K.brick_map(self._map16)
-            if self._coarse.numel() * 4 > 160 * 1024:
+            if self._coarse.numel() * 4 > 100 * 1024:
                 self._coarse = None
 
     def _coordinates(self, start, stop, step=1):
