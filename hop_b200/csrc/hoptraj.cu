@@ -115,7 +115,7 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 
 // SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: brick indices
 template <int SRC, bool FAST>
-__global__ void __launch_bounds__(kHopThreads, 3)
+__global__ void __launch_bounds__(kHopThreads, 4)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
@@ -220,33 +220,27 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         for (int u = 0; u < kUnroll; ++u) step(lab[u], (int)(frame0 + f + u));
       }
     } else {
-      // 4-byte inputs (brick indices or labels): two register blocks of kDeep frames in ping-pong, so
-      // that the loads of one block are in flight while the other is consumed
+      // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
+      // block are resolved its input registers are reloaded with the next block, so those loads are
+      // in flight while the state machine consumes the current labels
       constexpr int kDeep = 8;
       const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
-      auto load_block = [&](uint32_t (&v)[kDeep]) {
+      uint32_t v[kDeep];
+      if (f + kDeep <= f_end) {
 #pragma unroll
         for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + u * N);
         src += kDeep * N;
-      };
-      auto run_block = [&](const uint32_t (&v)[kDeep]) {
-        int lab[kDeep];
+        for (; f + kDeep <= f_end; f += kDeep) {
+          int lab[kDeep];
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(v[u], mv) : (int)__uint_as_float(v[u]);
+          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(v[u], mv) : (int)__uint_as_float(v[u]);
+          if (f + 2 * kDeep <= f_end) {
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) step(lab[u], (int)(frame0 + f + u));
-        f += kDeep;
-      };
-      uint32_t va[kDeep], vb[kDeep];
-      if (f + kDeep <= f_end) {
-        load_block(va);
-        while (true) {
-          if (f + 2 * kDeep > f_end) { run_block(va); break; }
-          load_block(vb);
-          run_block(va);
-          if (f + 2 * kDeep > f_end) { run_block(vb); break; }
-          load_block(va);
-          run_block(vb);
+            for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + u * N);
+            src += kDeep * N;
+          }
+#pragma unroll
+          for (int u = 0; u < kDeep; ++u) step(lab[u], (int)(frame0 + f + u));
         }
       }
     }

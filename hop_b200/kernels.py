@@ -218,7 +218,7 @@ def site_cells(own: torch.Tensor, member, n_labels: int):
 
 
 def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32, cta_threads: int = 256,
-                ctas_per_sm: int = 3, max_waves: int = 4):
+                ctas_per_sm: int = 4, max_waves: int = 4):
     """(n_chunks, chunk_len) for the fused hoptraj kernel: one thread per (atom, chunk).
 
     The kernel is latency-bound per thread, so the grid should be a whole number of waves of
