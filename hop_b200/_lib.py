@@ -55,6 +55,7 @@ _SIGNATURES = {
     "hopb_create": [_int, ctypes.POINTER(_vp)],
     "hopb_destroy": [_vp],
     "hopb_last_error": [_vp],
+    "hopb_set_hist_l2_budget": [_vp, _i64],
     "hopb_dev_alloc": [_vp, _u64, ctypes.POINTER(_vp)],
     "hopb_dev_free": [_vp, _vp],
     "hopb_memset": [_vp, _vp, _vp, _int, _u64],

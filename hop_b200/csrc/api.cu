@@ -22,6 +22,7 @@ int hopb_create(int device, hopb_handle** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return HOPB_E_CUDA; }
   h->num_sms = prop.multiProcessorCount;
+  h->hist_l2_budget = (int64_t)40 << 20;
   *out = h;
   return HOPB_OK;
 }
@@ -35,6 +36,12 @@ void hopb_destroy(hopb_handle* h) {
 }
 
 const char* hopb_last_error(const hopb_handle* h) { return h ? h->err : "null handle"; }
+
+int hopb_set_hist_l2_budget(hopb_handle* h, int64_t bytes) {
+  HOPB_REQUIRE(h, h && bytes >= 1024, "bad argument");
+  h->hist_l2_budget = bytes;
+  return HOPB_OK;
+}
 
 int hopb_dev_alloc(hopb_handle* h, uint64_t bytes, void** out) {
   HOPB_REQUIRE(h, out != nullptr, "null out");

@@ -27,13 +27,34 @@ namespace {
 constexpr int kHistThreads = 256;
 constexpr int kWarpsPerBlock = kHistThreads / 32;
 
-__device__ __forceinline__ float4 ld_stream(const float4* p) {
+// streaming load: no L1 allocation, evict-first in L2 so that the coordinate stream does not push
+// the count grid (the target of the reductions) out of L2
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4* p, uint64_t pol) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
+               : "l"(p), "l"(pol));
   return v;
 }
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+// Grids larger than L2 are histogrammed in x-slabs: pass 1 (this kernel) reduces only the points
+// whose cell lies in slab [x_lo, x_hi) and leaves the brick index of every point in `cells`; the
+// later passes (hist_cells_kernel) re-read those 4-byte indices, one slab each, so that the
+// reductions of every pass hit an L2-resident part of the grid.
+constexpr uint32_t kCellDone = 0x40000000u;  // histogram contribution already made (edge-zone points)
+constexpr uint32_t kCellOut = 0xFFFFFFFFu;
 
 struct AxisReg {
   float lo, inv, nf, top_eq, hop_lo, hop_hi, edge_zone;
@@ -68,10 +89,12 @@ __device__ __forceinline__ int bin_fast(float x, const AxisReg& a) {
   return b;
 }
 
+struct Slab { int x_lo, x_hi; uint32_t done_flag; };  // reduce cells with x_lo <= i < x_hi now
+
 template <bool CELLS, bool FAST>
 __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                                const AxisReg& ay, const AxisReg& az, const float* s_tab,
-                                               uint32_t* counts) {
+                                               uint32_t* counts, const Slab& slab) {
   int bx, by, bz;
   if (FAST) {
     bx = bin_fast(x, ax); by = bin_fast(y, ay); bz = bin_fast(z, az);
@@ -84,37 +107,57 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
   // They differ only within rounding distance of the last edge (numpy.histogramdd's `x ==
   // edges[-1]` rule, _coord2hop's rounded-equality rule); `edge_zone` is the smallest coordinate at
   // which either rule can fire, so one compare per axis routes those rare points to the slow branch.
-  int hx = bx, hy = by, hz = bz, px = bx, py = by, pz = bz;
   if ((x >= ax.edge_zone) | (y >= ay.edge_zone) | (z >= az.edge_zone)) {
-    hx = (x == ax.top_eq) ? ax.n : bx;
-    hy = (y == ay.top_eq) ? ay.n : by;
-    hz = (z == az.top_eq) ? az.n : bz;
-    px = bx - (((x >= ax.hop_lo) & (x <= ax.hop_hi)) ? 1 : 0);
-    py = by - (((y >= ay.hop_lo) & (y <= ay.hop_hi)) ? 1 : 0);
-    pz = bz - (((z >= az.hop_lo) & (z <= az.hop_hi)) ? 1 : 0);
+    const int hx = (x == ax.top_eq) ? ax.n : bx;
+    const int hy = (y == ay.top_eq) ? ay.n : by;
+    const int hz = (z == az.top_eq) ? az.n : bz;
+    const int px = bx - (((x >= ax.hop_lo) & (x <= ax.hop_hi)) ? 1 : 0);
+    const int py = by - (((y >= ay.hop_lo) & (y <= ay.hop_hi)) ? 1 : 0);
+    const int pz = bz - (((z >= az.hop_lo) & (z <= az.hop_hi)) ? 1 : 0);
     const bool okh = ((unsigned)(hx - 1) < (unsigned)ax.n) & ((unsigned)(hy - 1) < (unsigned)ay.n) & ((unsigned)(hz - 1) < (unsigned)az.n);
-    if (okh) {
+    if (okh) {  // counted now, whatever the slab; the later passes skip it (kCellDone)
       const uint32_t cell = ((uint32_t)(hx - 1) * (uint32_t)ay.n + (uint32_t)(hy - 1)) * (uint32_t)az.n + (uint32_t)(hz - 1);
       atomicAdd(counts + cell, 1u);
     }
     if (!CELLS) return 0u;
     const bool in = ((unsigned)(px - 1) < (unsigned)ax.n) & ((unsigned)(py - 1) < (unsigned)ay.n) & ((unsigned)(pz - 1) < (unsigned)az.n);
-    return in ? brick_index(px - 1, py - 1, pz - 1, ay.cn, az.cn) : 0xFFFFFFFFu;
+    return in ? (brick_index(px - 1, py - 1, pz - 1, ay.cn, az.cn) | slab.done_flag) : kCellOut;
   }
   const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
-  if (ok) {
+  if (ok & (bx - 1 >= slab.x_lo) & (bx - 1 < slab.x_hi)) {
     const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)ay.n + (uint32_t)(by - 1)) * (uint32_t)az.n + (uint32_t)(bz - 1);
     atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
   }
   if (!CELLS) return 0u;
-  return ok ? brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : 0xFFFFFFFFu;
+  return ok ? brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : kCellOut;
+}
+
+// later passes of a slabbed histogram: 4 B per point in, one reduction per point of this slab
+__global__ void __launch_bounds__(256)
+hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, Slab slab, int ny, int nz, int cny, int cnz,
+                  uint32_t* __restrict__ counts) {
+  const uint64_t pol = make_evict_first_policy();
+  const uint32_t plane = (uint32_t)(cny * cnz);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = ld_stream_u32(cells + p, pol);
+    if (c & 0xC0000000u) continue;  // outlier or already counted
+    const uint32_t cb = c >> 6;
+    const uint32_t ci = cb / plane;
+    const int i = (int)(ci * 4 + ((c >> 4) & 3u));
+    if (i < slab.x_lo || i >= slab.x_hi) continue;
+    const uint32_t r = cb - ci * plane;
+    const uint32_t cj = r / (uint32_t)cnz;
+    const uint32_t ck = r - cj * (uint32_t)cnz;
+    const uint32_t j = cj * 4 + ((c >> 2) & 3u), k = ck * 4 + (c & 3u);
+    atomicAdd(counts + ((uint32_t)i * (uint32_t)ny + j) * (uint32_t)nz + k, 1u);
+  }
 }
 
 template <bool CELLS, bool FAST>
 __global__ void __launch_bounds__(kHistThreads, 4)
 hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbGridTab tab,
             const float* __restrict__ table, const HopbPair* __restrict__ table2, uint32_t* __restrict__ counts,
-            uint32_t* __restrict__ cells) {
+            uint32_t* __restrict__ cells, Slab slab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* stage = reinterpret_cast<float4*>(smem_raw);                         // [warps][96] float4
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(stage + kWarpsPerBlock * 96);  // pair tables
@@ -127,6 +170,7 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
 
+  const uint64_t pol = make_evict_first_policy();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4* wbuf = stage + warp * 96;
@@ -138,9 +182,9 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + warp; b < nblk; b += total_warps) {
     const float4* src = base + b * 96;
-    const float4 v0 = ld_stream(src + lane);
-    const float4 v1 = ld_stream(src + 32 + lane);
-    const float4 v2 = ld_stream(src + 64 + lane);
+    const float4 v0 = ld_stream(src + lane, pol);
+    const float4 v1 = ld_stream(src + 32 + lane, pol);
+    const float4 v2 = ld_stream(src + 64 + lane, pol);
     wbuf[lane] = v0;
     wbuf[32 + lane] = v1;
     wbuf[64 + lane] = v2;
@@ -149,7 +193,7 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = 3 * (lane + 32 * j);
-      const uint32_t c = hist_point<CELLS, FAST>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts);
+      const uint32_t c = hist_point<CELLS, FAST>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts, slab);
       if (CELLS) cout[32 * j] = c;
     }
     __syncwarp();
@@ -159,7 +203,7 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   const int64_t n_rem = lead + (n_points - tail0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rem; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i < lead ? i : tail0 + (i - lead);
-    const uint32_t c = hist_point<CELLS, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts);
+    const uint32_t c = hist_point<CELLS, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts, slab);
     if (CELLS) cells[p] = c;
   }
 }
@@ -191,6 +235,10 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
                                uint32_t* counts, uint32_t* cells) {
   HOPB_REQUIRE(h, g && xyz && counts && n_points >= 0, "bad argument");
   HOPB_REQUIRE(h, ((uintptr_t)xyz & 3) == 0, "xyz must be 4-byte aligned");
+  if (cells) {
+    const int64_t nbk = (int64_t)((g->n[0] + 3) / 4) * ((g->n[1] + 3) / 4) * ((g->n[2] + 3) / 4);
+    HOPB_REQUIRE(h, nbk * 64 < ((int64_t)1 << 30), "grid too large for 30-bit brick indices");
+  }
   if (n_points == 0) return HOPB_OK;
   // number of leading points until the stream is 16-byte aligned (12 B per point)
   int64_t lead = 0;
@@ -205,13 +253,32 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
   if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned nb = (unsigned)blocks;
+  // x-slabs: keep the part of the grid that receives reductions in one pass well inside L2
+  const int64_t row_bytes = (int64_t)g->n[1] * g->n[2] * 4;
+  int n_pass = 1;
+  if (cells) {
+    const int64_t budget = h->hist_l2_budget;
+    n_pass = (int)((row_bytes * g->n[0] + budget - 1) / budget);
+    if (n_pass < 1) n_pass = 1;
+    if (n_pass > g->n[0]) n_pass = g->n[0];
+  }
+  const int slab_w = (g->n[0] + n_pass - 1) / n_pass;
+  Slab slab;
+  slab.x_lo = 0; slab.x_hi = n_pass == 1 ? g->n[0] : slab_w; slab.done_flag = n_pass == 1 ? 0u : kCellDone;
   hopb_note_launch();
   if (cells) {
-    if (fast) hist_kernel<true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
-    else hist_kernel<true, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+    if (fast) hist_kernel<true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
+    else hist_kernel<true, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
   } else {
-    if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
-    else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells);
+    if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
+    else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
+  }
+  for (int p = 1; p < n_pass; ++p) {
+    slab.x_lo = p * slab_w;
+    slab.x_hi = (p + 1) * slab_w < g->n[0] ? (p + 1) * slab_w : g->n[0];
+    if (slab.x_lo >= slab.x_hi) break;
+    HOPB_K(hist_cells_kernel)<<<hopb_grid_for(n_points, 256, h->num_sms, 8), 256, 0, s>>>(
+        cells, n_points, slab, g->n[1], g->n[2], (g->n[1] + 3) / 4, (g->n[2] + 3) / 4, counts);
   }
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;

@@ -20,6 +20,7 @@ struct hopb_handle {
   char err[512];
   void* scratch[HOPB_NUM_SCRATCH];
   size_t scratch_bytes[HOPB_NUM_SCRATCH];
+  int64_t hist_l2_budget;  // bytes of the count grid that one histogram pass may reduce into
 };
 
 struct hopb_grid {

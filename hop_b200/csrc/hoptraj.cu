@@ -102,7 +102,7 @@ struct MapView {
 // with selects and one predicated load so that a warp does not diverge on it.
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
   const bool out = c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
-  const uint32_t cc = out ? 0u : c;
+  const uint32_t cc = out ? 0u : (c & 0x3FFFFFFFu);  // bit 30: bookkeeping of the slabbed histogram
   uint32_t st = 3u;
   if (m.s_coarse) {
     const uint32_t cb = cc >> 6;

@@ -87,6 +87,12 @@ def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, c
     return counts
 
 
+def set_hist_l2_budget(nbytes: int, device=None):
+    """Largest part of the count grid one histogram pass reduces into (slabbed passes beyond it)."""
+    h = _lib.handle(device)
+    _lib.check(h, _lib.lib().hopb_set_hist_l2_budget(h, int(nbytes)))
+
+
 def brick_shape(shape):
     """(n_bricks, words of the 2-bit block map) for a grid shape."""
     nb = 1

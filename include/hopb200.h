@@ -85,10 +85,16 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
 
 /* Same, and additionally writes for every point the brick index of its cell under the
  * hopping-trajectory binning rules of hop/trajectory.py:428-441 (see hopb_brick_map; 0xFFFFFFFF =
- * outlier) so that hopb_hoptraj need not read the coordinates again.
+ * outlier; bit 30 is bookkeeping of the slabbed histogram and ignored by hopb_hoptraj) so that
+ * hopb_hoptraj need not read the coordinates again.
  * cells: device uint32 [n_points] (NULL = off). */
 int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                                int64_t n_points, uint32_t* counts, uint32_t* cells);
+
+/* Count grids larger than this many bytes (default 40 MiB) are histogrammed in x-slabs when `cells`
+ * is given: one pass over the coordinates, then one pass over the 4-byte cell indices per further
+ * slab, so that every pass reduces into an L2-resident part of the grid. */
+int hopb_set_hist_l2_budget(hopb_handle* h, int64_t bytes);
 
 /* density = counts / n_frames / dx[i] / dy[j] / dz[k] * factor, in float64 and in exactly that
  * order: DensityCollector.finish (hop/density.py:133-137), Grid.make_density

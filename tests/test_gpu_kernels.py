@@ -58,6 +58,40 @@ def test_histogram_counts(K, traj, delta):
     assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
 
 
+def test_histogram_slabbed_passes(K, traj):
+    """Grids beyond the L2 budget are reduced slab by slab from the cached cell indices."""
+    p, xyz = traj
+    xyz = xyz[:50].copy()
+    _, _, edges = O.grid_geometry(xyz[0], delta=0.5)
+    top = [np.float32(e[-1]) for e in edges]
+    xyz[3, 10:14, 0] = top[0]                         # on / next to the last edge: the two binning rules differ
+    xyz[4, 10:14, 1] = np.nextafter(top[1], np.float32(0))
+    xyz[5, 10:14, 2] = np.nextafter(top[2], np.float32(1e9))
+    ref = O.histogram_vectorised(xyz, edges)
+    g = K.GridTables(edges)
+    try:
+        for budget in (1 << 12, 1 << 16, 1 << 20):
+            K.set_hist_l2_budget(budget)
+            counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+            cells = torch.empty(xyz.shape[:2], dtype=torch.int32, device="cuda")
+            K.hist_accumulate(g, dev(xyz), counts, cells)
+            assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref), budget
+            # the cached cells still drive the hopping trajectory correctly
+            res = O.pipeline(xyz, delta=0.5)
+            m16 = dev(res["map"])
+            brick, coarse = K.brick_map(m16)
+            ev = K.EventBuffer(xyz.shape[0] * xyz.shape[1], "cuda")
+            X = torch.empty(xyz.shape[:2], dtype=torch.float32, device="cuda")
+            Y = torch.empty(xyz.shape[:2], dtype=torch.float32, device="cuda")
+            s = K.hoptraj(g, None, brick, 0, 2, 25, ev, X, Y, cells=cells, coarse=coarse)
+            st = K.new_state(xyz.shape[1], "cuda")
+            K.hop_advance(None, st, init=True)
+            K.hop_fixup(s, 25, 50, st, Y, ev)
+            assert np.array_equal(X.cpu().numpy(), res["hop"][:, :, 0]) and np.array_equal(Y.cpu().numpy(), res["hop"][:, :, 1])
+    finally:
+        K.set_hist_l2_budget(40 << 20)
+
+
 def test_histogram_edge_semantics(K):
     rng = np.random.default_rng(3)
     coords0 = (rng.random((300, 3)) * [17.3, 9.1, 23.7] - 1.9999).astype(np.float32)
