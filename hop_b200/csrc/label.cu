@@ -22,20 +22,26 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// Every per-cell pass below is "one warp per (x, y) row, lanes along z": accesses are contiguous,
+// no per-cell division is needed, and rows without a single above-threshold cell (most rows of a
+// hydration-site mask) are skipped after one byte read.
+
 // ---- 1. threshold + z-runs ----------------------------------------------------------------------
-// one warp per (x, y) row of nz cells
 __global__ void __launch_bounds__(256)
-ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_rows, int nz, int* __restrict__ parent) {
+ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_rows, int nz, int* __restrict__ parent,
+                uint8_t* __restrict__ rowflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     const int64_t base = row * nz;
     int carry = -1;  // start (z) of the run that reaches the previous chunk's last cell, or -1
+    unsigned any = 0;
     for (int z0 = 0; z0 < nz; z0 += 32) {
       const int z = z0 + lane;
       const bool m = z < nz && density[base + z] >= threshold;
       const unsigned bits = __ballot_sync(kFull, m);
+      any |= bits;
       const unsigned below = ~bits & ((1u << lane) - 1);  // non-mask cells below this lane
       int start;
       if (below == 0) start = carry >= 0 ? carry : z0;
@@ -44,6 +50,7 @@ ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_
       const int s31 = __shfl_sync(kFull, start, 31);
       carry = (bits >> 31) ? s31 : -1;
     }
+    if (lane == 0) rowflag[row] = any ? 1 : 0;
   }
 }
 
@@ -79,42 +86,54 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 __global__ void __launch_bounds__(256)
-ccl_merge_kernel(int* parent, int nx, int ny, int nz, int phase) {
-  const int64_t n_cells = (int64_t)nx * ny * nz;
+ccl_merge_kernel(int* parent, const uint8_t* __restrict__ rowflag, int nx, int ny, int nz, int phase) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_rows = (int64_t)nx * ny;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t sy = nz, sx = (int64_t)ny * nz;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    if (parent[c] < 0) continue;
-    const int z = (int)(c % nz);
-    const int64_t r = c / nz;
-    const int y = (int)(r % ny);
-    const int x = (int)(r / ny);
-    const bool hx = x + 1 < nx, hy = y + 1 < ny, hz = z + 1 < nz, lz = z > 0;
-    // mask of the neighbours that matter (parent >= 0)
-    auto M = [&](int64_t idx) { return parent[idx] >= 0; };
-    const bool m_up = hz && M(c + 1);
-    const bool m_dn = lz && M(c - 1);
-    // phase 0: heads of z-runs only -- they tie the rows of a blob into one tree (the skeleton);
-    // phase 1 (after a flatten): every other cell; inside a blob both ends then already share a
-    // root one step away, so the many unions around isolated holes cost two loads each
-    if ((phase == 0) == m_dn) continue;
-    const bool ly = y > 0;
-    const bool m_y = hy && M(c + sy);              // (0,1,0)
-    const bool m_x = hx && M(c + sx);              // (1,0,0)
-    const bool m_xy = hx && hy && M(c + sx + sy);  // (1,1,0)
-    // An edge is skipped when its end points are already joined by edges that are themselves kept
-    // or skipped by a rule lower in the (y, z) order -- so the argument is well founded:
-    //   rule Z: (c, c+o), o_z = 0, follows from the same edge one cell down both z-runs;
-    //   rule Y: the x-edge follows from the x-edge one row down in y plus the two y-edges;
-    //   diagonals follow from any two-step path over in-plane / z edges.
-    if (m_y && !(m_dn && M(c + sy - 1))) uf_union(parent, (int)c, (int)(c + sy));
-    if (m_x && !(m_dn && M(c + sx - 1)) && !(ly && M(c - sy) && M(c + sx - sy))) uf_union(parent, (int)c, (int)(c + sx));
-    if (m_xy && !m_y && !m_x && !(m_dn && M(c + sx + sy - 1))) uf_union(parent, (int)c, (int)(c + sx + sy));
-    if (hz) {
-      // +z partners: (0,1,1), (1,0,1), (1,1,1)
-      if (hy && !m_y && !m_up && M(c + sy + 1)) uf_union(parent, (int)c, (int)(c + sy + 1));
-      if (hx && !m_x && !m_up && M(c + sx + 1)) uf_union(parent, (int)c, (int)(c + sx + 1));
-      // (1,1,1) is also reached through c+x then (0,1,1), or c+y then (1,0,1)
-      if (hx && hy && !m_xy && !m_up && !m_x && !m_y && M(c + sx + sy + 1)) uf_union(parent, (int)c, (int)(c + sx + sy + 1));
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    if (!rowflag[row]) continue;
+    const int y = (int)(row % ny);
+    const int x = (int)(row / ny);
+    const bool hx = x + 1 < nx, hy = y + 1 < ny, ly = y > 0;
+    // neighbour rows without any mask cell cannot contribute an edge
+    const bool ry = hy && rowflag[row + 1];
+    const bool rx = hx && rowflag[row + ny];
+    const bool rxy = hx && hy && rowflag[row + ny + 1];
+    if (!(ry | rx | rxy)) continue;
+    const int64_t base = row * nz;
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      if (z >= nz) continue;
+      const int64_t c = base + z;
+      if (parent[c] < 0) continue;
+      const bool hz = z + 1 < nz, lz = z > 0;
+      auto M = [&](int64_t idx) { return parent[idx] >= 0; };
+      const bool m_up = hz && M(c + 1);
+      const bool m_dn = lz && M(c - 1);
+      // phase 0: heads of z-runs only -- they tie the rows of a blob into one tree (the skeleton);
+      // phase 1 (after a flatten): every other cell; inside a blob both ends then already share a
+      // root one step away, so the many unions around isolated holes cost two loads each
+      if ((phase == 0) == m_dn) continue;
+      const bool m_y = ry && M(c + sy);              // (0,1,0)
+      const bool m_x = rx && M(c + sx);              // (1,0,0)
+      const bool m_xy = rxy && M(c + sx + sy);       // (1,1,0)
+      // An edge is skipped when its end points are already joined by edges that are themselves kept
+      // or skipped by a rule lower in the (y, z) order -- so the argument is well founded:
+      //   rule Z: (c, c+o), o_z = 0, follows from the same edge one cell down both z-runs;
+      //   rule Y: the x-edge follows from the x-edge one row down in y plus the two y-edges;
+      //   diagonals follow from any two-step path over in-plane / z edges.
+      if (m_y && !(m_dn && M(c + sy - 1))) uf_union(parent, (int)c, (int)(c + sy));
+      if (m_x && !(m_dn && M(c + sx - 1)) && !(ly && M(c - sy) && M(c + sx - sy))) uf_union(parent, (int)c, (int)(c + sx));
+      if (m_xy && !m_y && !m_x && !(m_dn && M(c + sx + sy - 1))) uf_union(parent, (int)c, (int)(c + sx + sy));
+      if (hz) {
+        // +z partners: (0,1,1), (1,0,1), (1,1,1)
+        if (ry && !m_y && !m_up && M(c + sy + 1)) uf_union(parent, (int)c, (int)(c + sy + 1));
+        if (rx && !m_x && !m_up && M(c + sx + 1)) uf_union(parent, (int)c, (int)(c + sx + 1));
+        // (1,1,1) is also reached through c+x then (0,1,1), or c+y then (1,0,1)
+        if (rxy && !m_xy && !m_up && !m_x && !m_y && M(c + sx + sy + 1)) uf_union(parent, (int)c, (int)(c + sx + sy + 1));
+      }
     }
   }
 }
@@ -123,66 +142,86 @@ ccl_merge_kernel(int* parent, int nx, int ny, int nz, int phase) {
 // Only heads of z-runs are ever parents (initial links, unions and path halving all point at
 // heads), so flattening is: heads find their root (few cells, possibly long walks), then every
 // other cell takes its head's root in one hop.
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* parent, int64_t n_cells, int nz, int heads) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    if (parent[c] < 0) continue;
-    const bool is_head = (c % nz) == 0 || parent[c - 1] < 0;
-    if (heads) {
-      if (is_head) { const int r = uf_find(parent, (int)c); parent[c] = r; }
-    } else if (!is_head) {
-      parent[c] = ld_parent(parent, ld_parent(parent, (int)c));
+__global__ void __launch_bounds__(256)
+ccl_flatten_kernel(int* parent, const uint8_t* __restrict__ rowflag, int64_t n_rows, int nz, int heads) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    if (!rowflag[row]) continue;
+    const int64_t base = row * nz;
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      if (z >= nz) continue;
+      const int64_t c = base + z;
+      if (parent[c] < 0) continue;
+      const bool is_head = z == 0 || parent[c - 1] < 0;
+      if (heads) {
+        if (is_head) { const int r = uf_find(parent, (int)c); parent[c] = r; }
+      } else if (!is_head) {
+        parent[c] = ld_parent(parent, ld_parent(parent, (int)c));
+      }
     }
   }
 }
 
 // ---- 4. sizes ---------------------------------------------------------------------------------------
-// size[root] += cells; aggregated per warp (neighbouring z cells share a root) and per block.
+// size[root] += cells of the row with that root; lanes with equal roots are merged first
+// (neighbouring z cells share a root), so a solid row costs one atomic per 32 cells.
 __global__ void __launch_bounds__(256)
-ccl_size_kernel(const int* __restrict__ parent, int64_t n_cells, int* __restrict__ size) {
-  __shared__ int s_root[8];
-  __shared__ int s_cnt[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = ((n_cells + blockDim.x - 1) / blockDim.x) * blockDim.x;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += stride) {
-    const int r = c < n_cells ? parent[c] : -1;
-    // the dominant root of the warp (lane 0's peers) goes through shared memory; others go direct
-    const unsigned peers = __match_any_sync(kFull, r);
-    const bool leader = (peers & ((1u << lane) - 1)) == 0;
-    const int r0 = __shfl_sync(kFull, r, 0);
-    if (lane == 0) { s_root[warp] = r; s_cnt[warp] = __popc(peers); }
-    if (leader && r >= 0 && r != r0) atomicAdd(size + r, __popc(peers));
-    __syncthreads();
-    if (warp == 0) {
-      const int rr = lane < 8 ? s_root[lane] : -1;
-      const int cc = lane < 8 ? s_cnt[lane] : 0;
-      const unsigned p2 = __match_any_sync(kFull, rr);
-      int sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int rj = __shfl_sync(kFull, rr, j);
-        const int cj = __shfl_sync(kFull, cc, j);
-        if (rj == rr) sum += cj;
+ccl_size_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ rowflag, int64_t n_rows, int nz,
+                int* __restrict__ size) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    if (!rowflag[row]) continue;
+    const int64_t base = row * nz;
+    int run_root = -1, run_cnt = 0;  // lane 0 carries the row's running (root, count) across chunks
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      const int r = z < nz ? parent[base + z] : -1;
+      const unsigned peers = __match_any_sync(kFull, r);
+      const bool leader = (peers & ((1u << lane) - 1)) == 0;
+      const int r0 = __shfl_sync(kFull, r, 0);
+      const int n0 = __popc(__shfl_sync(kFull, peers, 0));
+      if (leader && r >= 0 && lane != 0) atomicAdd(size + r, __popc(peers));
+      if (lane == 0) {
+        if (r0 == run_root) run_cnt += n0;
+        else {
+          if (run_root >= 0) atomicAdd(size + run_root, run_cnt);
+          run_root = r0; run_cnt = n0;
+        }
       }
-      if (rr >= 0 && (p2 & ((1u << lane) - 1)) == 0) atomicAdd(size + rr, sum);
     }
-    __syncthreads();
+    if (lane == 0 && run_root >= 0) atomicAdd(size + run_root, run_cnt);
   }
 }
 
 // roots with size >= minsite become sites; smaller components are dropped (label 0)
 __global__ void __launch_bounds__(256)
-ccl_roots_kernel(const int* __restrict__ parent, int* __restrict__ size, int64_t n_cells, int minsite,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ n_roots) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    if (parent[c] != (int)c) continue;
-    const int sz = size[c];
-    if (sz < minsite) { size[c] = 0; continue; }
-    const uint32_t slot = atomicAdd(n_roots, 1u);
-    if (slot < cap) {
-      // ascending sort on this key = size descending, then root index descending
-      keys[slot] = ((uint64_t)(uint32_t)(n_cells - sz) << 32) | (uint32_t)(n_cells - 1 - c);
-      vals[slot] = (uint32_t)c;
+ccl_roots_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ rowflag, int* __restrict__ size,
+                 int64_t n_rows, int nz, int64_t n_cells, int minsite, uint64_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ n_roots) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    if (!rowflag[row]) continue;
+    const int64_t base = row * nz;
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      if (z >= nz) continue;
+      const int64_t c = base + z;
+      if (parent[c] != (int)c) continue;
+      const int sz = size[c];
+      if (sz < minsite) { size[c] = 0; continue; }
+      const uint32_t slot = atomicAdd(n_roots, 1u);
+      if (slot < cap) {
+        // ascending sort on this key = size descending, then root index descending
+        keys[slot] = ((uint64_t)(uint32_t)(n_cells - sz) << 32) | (uint32_t)(n_cells - 1 - c);
+        vals[slot] = (uint32_t)c;
+      }
     }
   }
 }
@@ -232,10 +271,24 @@ __global__ void ccl_assign_kernel(const uint64_t* __restrict__ keys, const uint3
 }
 
 __global__ void __launch_bounds__(256)
-ccl_relabel_kernel(const int* __restrict__ parent, const int* __restrict__ rootlabel, int64_t n_cells, int32_t* __restrict__ labels) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    const int r = parent[c];
-    labels[c] = r >= 0 ? rootlabel[r] : 0;
+ccl_relabel_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ rowflag, const int* __restrict__ rootlabel,
+                   int64_t n_rows, int nz, int32_t* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int64_t base = row * nz;
+    const bool any = rowflag[row] != 0;
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+      const int z = z0 + lane;
+      if (z >= nz) continue;
+      int l = 0;
+      if (any) {
+        const int r = parent[base + z];
+        if (r >= 0) l = rootlabel[r];
+      }
+      labels[base + z] = l;
+    }
   }
 }
 
@@ -403,11 +456,13 @@ int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz,
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_cells = (int64_t)nx * ny * nz;
   HOPB_REQUIRE(h, n_cells < ((int64_t)1 << 31), "grid too large");
-  // scratch: parent[G], size[G] (slot 0); root keys/vals + counter (slot 1)
+  // scratch: parent[G], size[G], rowflag[rows] (slot 0); root keys/vals + counter (slot 1)
+  const int64_t n_rows = (int64_t)nx * ny;
   int* parent = nullptr;
-  int rc = hopb_scratch(h, 0, (size_t)n_cells * 2 * sizeof(int), (void**)&parent);
+  int rc = hopb_scratch(h, 0, (size_t)n_cells * 2 * sizeof(int) + (size_t)n_rows + 16, (void**)&parent);
   if (rc) return rc;
   int* size = parent + n_cells;
+  uint8_t* rowflag = reinterpret_cast<uint8_t*>(size + n_cells);
   const uint32_t cap = HOPB_MAX_SITES + 1;
   unsigned char* rs = nullptr;
   rc = hopb_scratch(h, 1, (size_t)cap * 2 * (sizeof(uint64_t) + sizeof(uint32_t)) + 64, (void**)&rs);
@@ -420,19 +475,18 @@ int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz,
 
   HOPB_CUDA(h, cudaMemsetAsync(size, 0, (size_t)n_cells * sizeof(int), s));
   HOPB_CUDA(h, cudaMemsetAsync(n_roots_dev, 0, sizeof(uint32_t), s));
-  const int64_t n_rows = (int64_t)nx * ny;
-  HOPB_K(ccl_rows_kernel)<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 8), 256, 0, s>>>(density, threshold, n_rows, nz, parent);
-  const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 8);
-  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz, 0);
-  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 1);
-  HOPB_K(ccl_merge_kernel)<<<gcells, 256, 0, s>>>(parent, nx, ny, nz, 1);
-  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 1);
-  HOPB_K(ccl_flatten_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, nz, 0);
-  HOPB_K(ccl_size_kernel)<<<gcells, 256, 0, s>>>(parent, n_cells, size);
-  HOPB_K(ccl_roots_kernel)<<<gcells, 256, 0, s>>>(parent, size, n_cells, minsite, keys, vals, cap, n_roots_dev);
+  const unsigned grows = hopb_grid_for(n_rows * 32, 256, h->num_sms, 8);
+  HOPB_K(ccl_rows_kernel)<<<grows, 256, 0, s>>>(density, threshold, n_rows, nz, parent, rowflag);
+  HOPB_K(ccl_merge_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, nx, ny, nz, 0);
+  HOPB_K(ccl_flatten_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, n_rows, nz, 1);
+  HOPB_K(ccl_merge_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, nx, ny, nz, 1);
+  HOPB_K(ccl_flatten_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, n_rows, nz, 1);
+  HOPB_K(ccl_flatten_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, n_rows, nz, 0);
+  HOPB_K(ccl_size_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, n_rows, nz, size);
+  HOPB_K(ccl_roots_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, size, n_rows, nz, n_cells, minsite, keys, vals, cap, n_roots_dev);
   HOPB_K(ccl_rank_kernel)<<<cap / 256, 256, 0, s>>>(keys, vals, n_roots_dev, cap, keys_alt, vals_alt);
   HOPB_K(ccl_assign_kernel)<<<cap / 256, 256, 0, s>>>(keys_alt, vals_alt, n_roots_dev, cap, n_cells, size, volumes, n_sites_dev);
-  HOPB_K(ccl_relabel_kernel)<<<gcells, 256, 0, s>>>(parent, size, n_cells, labels);
+  HOPB_K(ccl_relabel_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, size, n_rows, nz, labels);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

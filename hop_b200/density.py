@@ -196,11 +196,13 @@ class DensityCollector(object):
             _torch().cuda.current_stream().synchronize()
             self._pending_n = 0
 
-    def collect_block(self, xyz_dev):
-        """Bin a whole block of frames already in HBM: CUDA float32 [n][N][3] of the selected atoms."""
+    def collect_block(self, xyz_dev, cells=None):
+        """Bin a whole block of frames already in HBM: CUDA float32 [n][N][3] of the selected atoms.
+        `cells` (CUDA int32 [n][N]) optionally receives the brick index of every atom-frame, which
+        HoppingTrajectory reads instead of the coordinates."""
         from . import kernels as K
 
-        K.hist_accumulate(self._tables, xyz_dev, self._counts)
+        K.hist_accumulate(self._tables, xyz_dev, self._counts, cells)
 
     def finish(self, n_frames):
         if self.isComplete():
@@ -315,10 +317,17 @@ class DensityCreator(object):
             N = len(idx)
             if N == 0:
                 continue
-            total_bytes = F * N * 12
+            total_bytes = F * N * 16
             free, _ = t.cuda.mem_get_info()
             keep = self.keep_coordinates and total_bytes < 0.4 * free
             stager = _FrameStager(N, keep_on_device=keep, n_frames_hint=F)
+            cells_blocks = []
+
+            def consume(d, c=c):
+                cells = t.empty(d.shape[:2], dtype=t.int32, device=d.device) if keep else None
+                c.collect_block(d, cells)
+                if keep:
+                    cells_blocks.append(cells)
             identity = self.universe._is_identity(idx) if hasattr(self.universe, "_is_identity") else False
             f = 0
             while f < F:
@@ -329,14 +338,15 @@ class DensityCreator(object):
                     host[:n] = block
                 else:
                     numpy.take(block, idx, axis=1, out=host[:n])
-                stager.flush(n, c.collect_block)
+                stager.flush(n, consume)
                 f += n
             t.cuda.current_stream().synchronize()
             if keep:
                 cache = getattr(traj, "_hopb_device_cache", None)
                 if cache is None:
                     cache = traj._hopb_device_cache = {}
-                cache[idx.tobytes()] = stager.keep
+                cache[idx.tobytes()] = {"xyz": stager.keep, "cells": cells_blocks,
+                                        "edges": [numpy.array(e) for e in c.edges]}
 
     def DensityWithBulk(self, density_unit='water', solvent_threshold=numpy.e, bulk_threshold=0.6):
         """Solvent density with the bulk site inserted (hop/density.py:306-356)."""

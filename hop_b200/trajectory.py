@@ -164,23 +164,41 @@ class HoppingTrajectory(object):
             if self._coarse.numel() * 4 > 100 * 1024:
                 self._coarse = None
 
+    @staticmethod
+    def _slice_blocks(blocks, start, stop):
+        t = _torch()
+        out, f0 = [], 0
+        for b in blocks:
+            f1 = f0 + b.shape[0]
+            lo, hi = max(start, f0), min(stop, f1)
+            if lo < hi:
+                out.append(b[lo - f0: hi - f0])
+            f0 = f1
+        return out[0] if len(out) == 1 else t.cat(out)
+
+    def _cached(self):
+        """Device copies DensityCreator left behind for this atom group (coordinates, cell indices)."""
+        cache = getattr(self.traj, "_hopb_device_cache", None)
+        if cache is None:
+            return None
+        return cache.get(numpy.asarray(self.tgroup.indices).tobytes())
+
+    def _cells(self, start, stop, step=1):
+        """Brick indices [n][N] written by the density pass, if they were computed on this very grid."""
+        entry = self._cached()
+        if entry is None or step != 1 or not entry["cells"]:
+            return None
+        if not all(numpy.array_equal(a, b) for a, b in zip(entry["edges"], self.edges)):
+            return None
+        return self._slice_blocks(entry["cells"], start, stop)
+
     def _coordinates(self, start, stop, step=1):
         """float32 [n][N][3] coordinates of the tracked group for a frame range, as CUDA tensor."""
         t = _torch()
         idx = numpy.asarray(self.tgroup.indices)
-        cache = getattr(self.traj, "_hopb_device_cache", None)
-        if cache is not None and step == 1 and idx.tobytes() in cache:
-            blocks = cache[idx.tobytes()]
-            out, f0 = [], 0
-            for b in blocks:
-                f1 = f0 + b.shape[0]
-                lo, hi = max(start, f0), min(stop, f1)
-                if lo < hi:
-                    out.append(b[lo - f0: hi - f0])
-                f0 = f1
-            if len(out) == 1:
-                return out[0]
-            return t.cat(out)
+        entry = self._cached()
+        if entry is not None and step == 1:
+            return self._slice_blocks(entry["xyz"], start, stop)
         if hasattr(self.traj, "coordinate_array"):
             block = self.traj.coordinate_array(start, stop, step)
         else:
@@ -195,18 +213,19 @@ class HoppingTrajectory(object):
         pinned = t.from_numpy(numpy.ascontiguousarray(block, dtype=numpy.float32)).pin_memory()
         return pinned.cuda(non_blocking=True)
 
-    def _map_block(self, xyz_dev, frame0, state, events, hop_x=None, hop_y=None):
+    def _map_block(self, xyz_dev, frame0, state, events, hop_x=None, hop_y=None, cells_dev=None):
         """One slab through the fused kernel + fix-up.  `state` is carried from slab to slab."""
         from . import kernels as K
 
-        F, N = int(xyz_dev.shape[0]), int(xyz_dev.shape[1])
+        src = cells_dev if cells_dev is not None else xyz_dev
+        F, N = int(src.shape[0]), int(src.shape[1])
         t = _torch()
         if hop_x is None:
-            hop_x = t.empty((F, N), dtype=t.float32, device=xyz_dev.device)
-            hop_y = t.empty((F, N), dtype=t.float32, device=xyz_dev.device)
+            hop_x = t.empty((F, N), dtype=t.float32, device=src.device)
+            hop_y = t.empty((F, N), dtype=t.float32, device=src.device)
         n_chunks, chunk_len = K.plan_chunks(F, N)
         s = K.hoptraj(self._tables, xyz_dev, self._brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y,
-                      coarse=self._coarse)
+                      cells=None if cells_dev is None else cells_dev.contiguous(), coarse=self._coarse)
         K.hop_fixup(s, chunk_len, F, state, hop_y, events)
         return hop_x, hop_y
 
@@ -234,10 +253,11 @@ class HoppingTrajectory(object):
         while done < n:
             m = min(block, n - done)
             f0 = start + done * step
-            xyz = self._coordinates(f0, f0 + (m - 1) * step + 1, step)
+            cells = self._cells(f0, f0 + (m - 1) * step + 1, step)
+            xyz = None if cells is not None else self._coordinates(f0, f0 + (m - 1) * step + 1, step)
             # frame numbers only matter to the (discarded) transition events here; starting at 1
             # keeps the start-of-trajectory rule for outliers out of a pass that begins mid-way
-            hx, hy = self._map_block(xyz, done + 1, state, events)
+            hx, hy = self._map_block(xyz, done + 1, state, events, cells_dev=cells)
             x[done:done + m] = hx.cpu().numpy()
             y[done:done + m] = hy.cpu().numpy()
             done += m
@@ -278,8 +298,9 @@ class HoppingTrajectory(object):
         events = K.EventBuffer(cap, "cuda")
         for f0 in range(0, F, block):
             m = min(block, F - f0)
-            xyz = self._coordinates(f0, f0 + m)
-            hx, hy = self._map_block(xyz, f0, state, events)
+            cells = self._cells(f0, f0 + m)
+            xyz = None if cells is not None else self._coordinates(f0, f0 + m)
+            hx, hy = self._map_block(xyz, f0, state, events, cells_dev=cells)
             x[f0:f0 + m].copy_(hx, non_blocking=True)
             y[f0:f0 + m].copy_(hy, non_blocking=True)
         t.cuda.current_stream().synchronize()
@@ -292,7 +313,9 @@ class HoppingTrajectory(object):
                 K.hop_advance(None, state, init=True)
                 for f0 in range(0, F, block):
                     m = min(block, F - f0)
-                    self._map_block(self._coordinates(f0, f0 + m), f0, state, events)
+                    cells = self._cells(f0, f0 + m)
+                    self._map_block(None if cells is not None else self._coordinates(f0, f0 + m), f0, state, events,
+                                    cells_dev=cells)
                 n_ev = events.n()
             self._events_cache = (events, n_ev, state)
         return x.numpy(), y.numpy()
