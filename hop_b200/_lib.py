@@ -115,15 +115,16 @@ def lib():
     return _lib
 
 
-def handle(device_index=None):
-    """One hopb_handle per CUDA device (created on first use)."""
+def handle(device_index=None, lane=0):
+    """One hopb_handle per CUDA device (created on first use).  `lane` > 0 gives an additional
+    handle with its own scratch memory, for work enqueued concurrently on a second stream."""
     import torch
 
     if not torch.cuda.is_available():
         raise RuntimeError("hop_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")
     if device_index is None:
         device_index = torch.cuda.current_device()
-    key = (os.getpid(), int(device_index))
+    key = (os.getpid(), int(device_index), int(lane))
     library = lib()
     h = _handles.get(key)
     if h is None:

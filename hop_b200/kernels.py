@@ -142,14 +142,14 @@ def label_sites(density: torch.Tensor, threshold: float, minsite: int = 1):
 
 
 def label_sites_async(density: torch.Tensor, threshold: float, minsite: int, labels: torch.Tensor,
-                      n_sites_dev: torch.Tensor, volumes=None):
+                      n_sites_dev: torch.Tensor, volumes=None, lane: int = 0):
     """Density.map_sites without a host round trip: `n_sites_dev` (CUDA int32[1]) receives the
     number of sites; a value above HOPB_MAX_SITES means the int16 map cannot hold them."""
     _cuda(density, torch.float64, "density")
     _cuda(labels, torch.int32, "labels")
     _cuda(n_sites_dev, torch.int32, "n_sites_dev")
     nx, ny, nz = density.shape
-    h = _h(density)
+    h = _lib.handle(density.device.index, lane)   # lane > 0: own scratch, safe on a concurrent stream
     rc = _lib.lib().hopb_label_sites_async(h, _stream(), nx, ny, nz, _p(density), float(threshold), int(minsite),
                                            _p(labels), _p(n_sites_dev), _p(volumes))
     _lib.check(h, rc)

@@ -127,29 +127,49 @@ class HopPipeline:
         density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor,
                                         out=self._buf("density", shape, torch.float64))
         self.n_sites_dev = self._buf("n_sites_dev", (2,), torch.int32)
-        own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, self._buf("own", shape, torch.int32),
-                                  self.n_sites_dev[0:1])
+        main = torch.cuda.current_stream(self.device)
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device)
+        own_buf = self._buf("own", shape, torch.int32)
         if cfg.with_bulk:
-            bulk_labels = K.label_sites_async(density, cfg.bulk_threshold, cfg.minsite,
-                                              self._buf("bulk_labels", shape, torch.int32), self.n_sites_dev[1:2])
+            # the two labellings are independent: the (sparse, cheap) hydration-site map runs on a
+            # side stream with its own scratch while the bulk map occupies the main stream
+            bulk_buf = self._buf("bulk_labels", shape, torch.int32)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, own_buf, self.n_sites_dev[0:1], lane=1)
+            bulk_labels = K.label_sites_async(density, cfg.bulk_threshold, cfg.minsite, bulk_buf, self.n_sites_dev[1:2])
+            main.wait_stream(side)
             member, map16 = K.insert_bulk(own, bulk_labels, 1, self._buf("member", shape, torch.uint8),
                                           self._buf("map16", shape, torch.int16))
         else:
+            own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, own_buf, self.n_sites_dev[0:1])
             member, map16 = None, K.labels_to_map16(own, self._buf("map16", shape, torch.int16))
+        nb, words = K.brick_shape(shape)
+        brick_buf = self._buf("brick", (nb * 64,), torch.int16)
+        coarse_buf = self._buf("coarse", (words,), torch.int32)
         props = None
         if cfg.annotate:
+            # the per-site reductions are not needed by stage 3: they run beside the brick map
             L = self.MAX_LABELS
             out = (self._buf("p_count", (L,), torch.int64), self._buf("p_mean", (L,), torch.float64),
                    self._buf("p_std", (L,), torch.float64), self._buf("p_center", (L, 3), torch.float64))
-            props = K.site_properties(self.grid, density, own, member, L, out=out)
-        nb, words = K.brick_shape(shape)
-        self.brick, coarse = K.brick_map(map16, self._buf("brick", (nb * 64,), torch.int16),
-                                         self._buf("coarse", (words,), torch.int32))
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                props = K.site_properties(self.grid, density, own, member, L, out=out)
+            self._props_done = torch.cuda.Event()
+            self._props_done.record(side)
+        self.brick, coarse = K.brick_map(map16, brick_buf, coarse_buf)
         self.coarse = coarse if (cfg.coarse_map and words * 4 <= 100 * 1024) else None
         return density, own, member, map16, props
 
     def sync_scalars(self, events):
         """The one host synchronisation of a run: number of sites and number of events."""
+        ev = getattr(self, "_props_done", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)   # annotation ran beside stage 3
+            self._props_done = None
         host = getattr(self, "_scalars_host", None)
         if host is None:
             host = self._scalars_host = torch.zeros(4, dtype=torch.int64).pin_memory()
