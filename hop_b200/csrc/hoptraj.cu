@@ -114,8 +114,8 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 }
 
 // SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: brick indices
-template <int SRC, bool FAST>
-__global__ void __launch_bounds__(kHopThreads, 4)
+template <int SRC, bool FAST, int DEEP = 8, int MINB = 4>
+__global__ void __launch_bounds__(kHopThreads, MINB)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
@@ -223,7 +223,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
       // block are resolved its input registers are reloaded with the next block, so those loads are
       // in flight while the state machine consumes the current labels
-      constexpr int kDeep = 8;
+      constexpr int kDeep = DEEP;
       const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
       uint32_t v[kDeep];
       if (f + kDeep <= f_end) {

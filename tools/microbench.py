@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--delta", type=float, default=0.5)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--chunks", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM assumed by the chunk planner")
     ap.add_argument("--out", default="gpurun_out/micro.json")
     args = ap.parse_args()
     peaks = {}
@@ -55,6 +56,9 @@ def main():
     print("generated", tuple(xyz.shape), "in %.2fs" % (time.time() - t0), flush=True)
     edges = grid_edges_from_frame0(xyz[0].cpu().numpy(), delta=args.delta)
     cfg = PipelineConfig(n_chunks=args.chunks or None)
+    if args.ctas:
+        import functools
+        K.plan_chunks = functools.partial(K.plan_chunks, ctas_per_sm=args.ctas)
     pipe = HopPipeline(edges, args.frames, cfg)
     AF = args.atoms * args.frames
     rows = {}
