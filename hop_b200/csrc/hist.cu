@@ -20,6 +20,8 @@
 // j+64 (three fully coalesced 512 B requests), park them in a per-warp shared-memory slab, and read
 // the points back at a stride of 3 words (conflict-free) so that lane l handles points l, l+32,
 // l+64, l+96; the packed cells go out as four coalesced 128 B stores per warp.
+#include <cstdlib>
+
 #include "hopb_common.cuh"
 
 namespace {
@@ -247,9 +249,10 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
   const bool fast = g->tab.fast_ok != 0;
   const size_t smem = kWarpsPerBlock * 96 * sizeof(float4) + (size_t)g->tab.table2_len * sizeof(HopbPair) +
                       (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
-  int64_t blocks = (nblk + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int64_t cap = (int64_t)h->num_sms * 8;  // 8 x 256 threads = one full SM
-  if (blocks > cap) blocks = cap;
+  // ~4 groups of 128 points per warp: many short-lived blocks balance better across the SMs than a
+  // persistent grid (measured on B200: 1.76 ms vs 2.11 ms for 3e8 points)
+  static const int per_warp = getenv("HOPB_HIST_PER_WARP") ? atoi(getenv("HOPB_HIST_PER_WARP")) : 4;  // tuning hook
+  int64_t blocks = (nblk + (int64_t)kWarpsPerBlock * per_warp - 1) / ((int64_t)kWarpsPerBlock * per_warp);
   if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned nb = (unsigned)blocks;
