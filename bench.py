@@ -276,12 +276,27 @@ def run_gpu(args):
                   pipe._bufs["summaries"], cells=pipe.cells, coarse=pipe.coarse)
     k_hop = time_kernel(hop_once, max(args.steps, 3))
     peak, peak_src = measured_peak()
+    # DRAM bytes per launch of the two kernels from the committed `ncu --set full` capture of this
+    # same workload (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     kernels = {"hist_kernel": (k_hist, 12), "hoptraj_kernel": (k_hop, 20)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]
     achieved = atom_frames_local * dom_bytes / (dom_ms * 1e-3) / 1e9
+    red_peak = 1.9e11   # scattered RED/s into a 32 MB grid, nothing else running (tools/ubench.cu on this B200 pool)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic.get(dom, {}).get("dram_bytes_per_launch"),
+                "peak_source": peak_src,
+                "note": ("hist_kernel is bound by L2 atomic throughput, not HBM: one scattered red.global.add per "
+                         "atom-frame (0.004 atoms/cell/frame leaves nothing to privatise); see l2_atomic"),
+                "l2_atomic": {"achieved_red_per_s": atom_frames_local / (k_hist * 1e-3), "peak_red_per_s": red_peak,
+                              "frac": atom_frames_local / (k_hist * 1e-3) / red_peak,
+                              "peak_source": "tools/ubench.cu, profiles/r1_ubench_b200.txt"},
                 "algorithmic_bytes_per_atom_frame": dom_bytes, "launch_ms": dom_ms,
                 "kernels": {k: {"ms": v[0], "GBps": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9,
                                 "frac": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9 / peak} for k, v in kernels.items()},
