@@ -65,6 +65,7 @@ _SIGNATURES = {
     "hopb_grid_create": [_vp, _vp, _int, _vp, _int, _vp, _int, _vp, ctypes.POINTER(_vp)],
     "hopb_grid_destroy": [_vp],
     "hopb_hist_accumulate": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "hopb_hist_bulk": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp],
     "hopb_density_from_counts": [_vp, _vp, _vp, _vp, _i64, _dbl, _vp],
     "hopb_label_sites": [_vp, _vp, _int, _int, _int, _vp, _dbl, _int, _vp, ctypes.POINTER(_i32), _vp],
     "hopb_label_sites_async": [_vp, _vp, _int, _int, _int, _vp, _dbl, _int, _vp, _vp, _vp],

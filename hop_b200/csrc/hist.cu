@@ -93,10 +93,13 @@ __device__ __forceinline__ int bin_fast(float x, const AxisReg& a) {
 
 struct Slab { int x_lo, x_hi; uint32_t done_flag; };  // reduce cells with x_lo <= i < x_hi now
 
+// counts: the selection's own histogram (may be NULL); counts_b: a second histogram that receives the
+// point only when `to_b` (the bulk density: solvent not within the cutoff of the solute)
 template <bool CELLS, bool FAST>
 __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                                const AxisReg& ay, const AxisReg& az, const float* s_tab,
-                                               uint32_t* counts, const Slab& slab) {
+                                               uint32_t* counts, const Slab& slab, uint32_t* counts_b = nullptr,
+                                               bool to_b = false) {
   int bx, by, bz;
   if (FAST) {
     bx = bin_fast(x, ax); by = bin_fast(y, ay); bz = bin_fast(z, az);
@@ -119,7 +122,8 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     const bool okh = ((unsigned)(hx - 1) < (unsigned)ax.n) & ((unsigned)(hy - 1) < (unsigned)ay.n) & ((unsigned)(hz - 1) < (unsigned)az.n);
     if (okh) {  // counted now, whatever the slab; the later passes skip it (kCellDone)
       const uint32_t cell = ((uint32_t)(hx - 1) * (uint32_t)ay.n + (uint32_t)(hy - 1)) * (uint32_t)az.n + (uint32_t)(hz - 1);
-      atomicAdd(counts + cell, 1u);
+      if (counts) atomicAdd(counts + cell, 1u);
+      if (to_b) atomicAdd(counts_b + cell, 1u);
     }
     if (!CELLS) return 0u;
     const bool in = ((unsigned)(px - 1) < (unsigned)ax.n) & ((unsigned)(py - 1) < (unsigned)ay.n) & ((unsigned)(pz - 1) < (unsigned)az.n);
@@ -128,7 +132,8 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
   const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
   if (ok & (bx - 1 >= slab.x_lo) & (bx - 1 < slab.x_hi)) {
     const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)ay.n + (uint32_t)(by - 1)) * (uint32_t)az.n + (uint32_t)(bz - 1);
-    atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
+    if (counts) atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
+    if (to_b) atomicAdd(counts_b + cell, 1u);
   }
   if (!CELLS) return 0u;
   return ok ? brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : kCellOut;
@@ -210,6 +215,145 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   }
 }
 
+// ---- bulk density: '<solvent> not within <cutoff> of <solute>' fused with the histogram -------------
+// Replaces the per-frame kd-tree selection of notwithin_coordinates_factory (hop/density.py:82-87)
+// followed by numpy.histogramdd.  One CTA per frame: the solute atoms of the frame are binned into a
+// uniform cell list (cell edge >= cutoff) in shared memory, every solvent atom tests the 27 cells
+// around it (first hit wins) and is then reduced into the solvent histogram and, when no solute atom
+// is within the cutoff, into the bulk histogram -- both densities from one read of the coordinates.
+// "Within" means d^2 <= cutoff^2 with d^2 = (dx*dx + dy*dy) + dz*dz evaluated in float32 without FMA.
+constexpr int kBulkThreads = 256;
+constexpr int kBulkMaxCells = 4096;
+
+template <bool CELLS, bool FAST>
+__global__ void __launch_bounds__(kBulkThreads)
+hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ solute, int64_t Nw, int Np, float cutoff,
+                 HopbGridTab tab, const float* __restrict__ table, const HopbPair* __restrict__ table2,
+                 uint32_t* __restrict__ counts_solvent, uint32_t* __restrict__ counts_bulk, uint32_t* __restrict__ cells,
+                 uint8_t* __restrict__ within_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
+  float* s_tab = reinterpret_cast<float*>(s_pairs + tab.table2_len);
+  int* s_start = reinterpret_cast<int*>(s_tab + (FAST ? 0 : tab.table_len));  // [kBulkMaxCells + 1]
+  int* s_cursor = s_start + kBulkMaxCells + 1;                               // [kBulkMaxCells]
+  float* s_atoms = reinterpret_cast<float*>(s_cursor + kBulkMaxCells);        // [Np][3], sorted by cell
+  __shared__ float s_lo[3], s_hi[3];
+  __shared__ float s_red[2][3][kBulkThreads / 32];
+  __shared__ uint32_t s_warp[33];
+
+  const int64_t frame = blockIdx.x;
+  const float* P = solute + frame * (int64_t)Np * 3;
+  const float* W = solvent + frame * Nw * 3;
+  for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
+  if (!FAST)
+    for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
+
+  // 1. bounding box of the solute in this frame
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = threadIdx.x; i < Np; i += blockDim.x)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const float v = P[3 * i + d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float a = lo[d], b = hi[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+    if (lane == 0) { s_red[0][d][warp] = a; s_red[1][d][warp] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float a = 3.0e38f, b = -3.0e38f;
+    for (int w = 0; w < kBulkThreads / 32; ++w) { a = fminf(a, s_red[0][threadIdx.x][w]); b = fmaxf(b, s_red[1][threadIdx.x][w]); }
+    s_lo[threadIdx.x] = a; s_hi[threadIdx.x] = b;
+  }
+  __syncthreads();
+  // 2. cell grid: edge = cutoff, doubled until the grid fits the shared-memory table
+  // a hair above the cutoff so that rounding in the cell coordinates can never separate a pair
+  // at distance <= cutoff by more than one cell
+  float cs = cutoff > 0.0f ? cutoff * 1.001f : 1.0f;
+  int dim[3];
+  while (true) {
+    int64_t tot = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { dim[d] = Np > 0 ? (int)floorf((s_hi[d] - s_lo[d]) / cs) + 1 : 1; tot *= dim[d]; }
+    if (tot <= kBulkMaxCells) break;
+    cs *= 2.0f;
+  }
+  const float inv_cs = 1.0f / cs;
+  const int n_cells = dim[0] * dim[1] * dim[2];
+  for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) s_start[i] = 0;
+  __syncthreads();
+  auto cell_of = [&](float x, float y, float z) {
+    const int cx = min(max((int)floorf((x - s_lo[0]) * inv_cs), 0), dim[0] - 1);
+    const int cy = min(max((int)floorf((y - s_lo[1]) * inv_cs), 0), dim[1] - 1);
+    const int cz = min(max((int)floorf((z - s_lo[2]) * inv_cs), 0), dim[2] - 1);
+    return (cx * dim[1] + cy) * dim[2] + cz;
+  };
+  for (int i = threadIdx.x; i < Np; i += blockDim.x) atomicAdd(&s_start[cell_of(P[3 * i], P[3 * i + 1], P[3 * i + 2])], 1);
+  __syncthreads();
+  // exclusive scan of the cell counts (n_cells <= 4096: 16 per thread)
+  {
+    const int per = (n_cells + kBulkThreads - 1) / kBulkThreads;
+    const int b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; ++k) if (b0 + k < n_cells) sum += (uint32_t)s_start[b0 + k];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < kBulkThreads / 32 ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + inc - sum;
+    for (int k = 0; k < per; ++k)
+      if (b0 + k < n_cells) { const uint32_t c = (uint32_t)s_start[b0 + k]; s_start[b0 + k] = (int)run; s_cursor[b0 + k] = (int)run; run += c; }
+    if (threadIdx.x == kBulkThreads - 1) s_start[n_cells] = Np;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Np; i += blockDim.x) {
+    const float x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+    const int slot = atomicAdd(&s_cursor[cell_of(x, y, z)], 1);
+    s_atoms[3 * slot] = x; s_atoms[3 * slot + 1] = y; s_atoms[3 * slot + 2] = z;
+  }
+  __syncthreads();
+  const AxisReg ax = load_axis(tab.ax[0], s_pairs);
+  const AxisReg ay = load_axis(tab.ax[1], s_pairs);
+  const AxisReg az = load_axis(tab.ax[2], s_pairs);
+  Slab slab; slab.x_lo = 0; slab.x_hi = tab.ax[0].n; slab.done_flag = 0u;
+  const float c2 = __fmul_rn(cutoff, cutoff);
+  // 3. every solvent atom: neighbour search, then both histograms
+  for (int64_t i = threadIdx.x; i < Nw; i += blockDim.x) {
+    const float x = W[3 * i], y = W[3 * i + 1], z = W[3 * i + 2];
+    bool within = false;
+    if (Np > 0) {
+      // cells whose box can hold an atom within the cutoff: +-1 around the atom's (unclamped) cell
+      const int cx = (int)floorf((x - s_lo[0]) * inv_cs), cy = (int)floorf((y - s_lo[1]) * inv_cs), cz = (int)floorf((z - s_lo[2]) * inv_cs);
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dim[0] - 1);
+      const int y0 = max(cy - 1, 0), y1 = min(cy + 1, dim[1] - 1);
+      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, dim[2] - 1);
+      for (int a = x0; a <= x1 && !within; ++a)
+        for (int b = y0; b <= y1 && !within; ++b) {
+          const int row = (a * dim[1] + b) * dim[2];
+          const int j0 = s_start[row + z0], j1 = s_start[row + z1 + 1];   // cells z0..z1 are contiguous
+          for (int j = j0; j < j1; ++j) {
+            const float dx = __fadd_rn(x, -s_atoms[3 * j]), dy = __fadd_rn(y, -s_atoms[3 * j + 1]), dz = __fadd_rn(z, -s_atoms[3 * j + 2]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 <= c2) { within = true; break; }
+          }
+        }
+    }
+    const uint32_t c = hist_point<CELLS, FAST>(x, y, z, tab, ax, ay, az, s_tab, counts_solvent, slab, counts_bulk, !within);
+    if (CELLS) cells[frame * Nw + i] = c;
+    if (within_out) within_out[frame * Nw + i] = within ? 1 : 0;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 density_kernel(const uint32_t* __restrict__ counts, int64_t n_cells, int ny, int nz, double n_frames,
                const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
@@ -283,6 +427,34 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
     HOPB_K(hist_cells_kernel)<<<hopb_grid_for(n_points, 256, h->num_sms, 8), 256, 0, s>>>(
         cells, n_points, slab, g->n[1], g->n[2], (g->n[1] + 3) / 4, (g->n[2] + 3) / 4, counts);
   }
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_hist_bulk(hopb_handle* h, void* stream, const hopb_grid* g, const float* solvent, const float* solute,
+                   int64_t F, int64_t Nw, int64_t Np, double cutoff, uint32_t* counts_solvent, uint32_t* counts_bulk,
+                   uint32_t* cells, uint8_t* within) {
+  HOPB_REQUIRE(h, g && solvent && counts_bulk && F >= 0 && Nw >= 0 && Np >= 0 && (Np == 0 || solute), "bad argument");
+  HOPB_REQUIRE(h, cutoff >= 0.0, "cutoff must be >= 0");
+  if (F == 0 || Nw == 0) return HOPB_OK;
+  HOPB_REQUIRE(h, F < ((int64_t)1 << 31), "too many frames for one call");
+  const bool fast = g->tab.fast_ok != 0;
+  const size_t smem = (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float)) +
+                      (size_t)(2 * kBulkMaxCells + 1) * sizeof(int) + (size_t)Np * 3 * sizeof(float) + 16;
+  HOPB_REQUIRE(h, smem <= 200 * 1024, "solute selection too large for the shared-memory cell list (max ~12000 atoms)");
+  cudaStream_t s = (cudaStream_t)stream;
+#define HOPB_BULK_LAUNCH(C, FA)                                                                                      \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hist_bulk_kernel<C, FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hopb_note_launch();                                                                                              \
+    hist_bulk_kernel<C, FA><<<(unsigned)F, kBulkThreads, smem, s>>>(solvent, solute, Nw, (int)Np, (float)cutoff, g->tab, \
+                                                                   g->d_table, g->d_table2, counts_solvent,          \
+                                                                   counts_bulk, cells, within);                      \
+  } while (0)
+  if (cells) { if (fast) HOPB_BULK_LAUNCH(true, true); else HOPB_BULK_LAUNCH(true, false); }
+  else { if (fast) HOPB_BULK_LAUNCH(false, true); else HOPB_BULK_LAUNCH(false, false); }
+#undef HOPB_BULK_LAUNCH
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

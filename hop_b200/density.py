@@ -109,7 +109,8 @@ class DensityCollector(object):
 
             self.current_coordinates = notwithin_coordinates_factory(
                 u, self.atomselection, self.soluteselection, self.cutoff, use_kdtree=self.use_kdtree)
-            self.group = None
+            self.group = self.current_coordinates.solvent
+            self.solute_group = self.current_coordinates.solute
             self.mode = "BULK"
         else:
             group = u.select_atoms(self.atomselection)
@@ -292,7 +293,7 @@ class DensityCreator(object):
         """Loop through the trajectory and build all densities (hop/density.py:281-304)."""
         u = self.universe
         traj = u.trajectory
-        fast = [c for c in self.collectors if c.mode == "SOLVENT" and hasattr(traj, "coordinate_array")]
+        fast = [c for c in self.collectors if hasattr(traj, "coordinate_array")]
         slow = [c for c in self.collectors if c not in fast]
         if fast:
             self._create_blocks(fast)
@@ -308,26 +309,52 @@ class DensityCreator(object):
 
     def _create_blocks(self, collectors):
         """Whole frame blocks: pinned staging -> HBM -> histogram kernel, copy overlapped with compute.
-        The device copies are kept (memory permitting) so HoppingTrajectory can reuse them."""
+        A bulk collector is fused with the solvent collector of the same atom selection: one read of
+        the coordinates feeds both histograms (csrc/hist.cu, hist_bulk_kernel).  The device copies are
+        kept (memory permitting) so HoppingTrajectory can reuse them."""
+        from . import kernels as K
+
         t = _torch()
         traj = self.universe.trajectory
         F = traj.n_frames
+        done = set()
         for c in collectors:
+            if id(c) in done or len(c.group.indices) == 0:
+                continue
             idx = c.group.indices
             N = len(idx)
-            if N == 0:
-                continue
+            # partner collector on the same atoms (mode='all': 'bulk' + 'solvent')
+            partner = None
+            for o in collectors:
+                if o is not c and id(o) not in done and o.mode != c.mode and numpy.array_equal(o.group.indices, idx):
+                    partner = o
+            bulk = c if c.mode == "BULK" else (partner if partner is not None and partner.mode == "BULK" else None)
+            solv = c if c.mode == "SOLVENT" else (partner if partner is not None and partner.mode == "SOLVENT" else None)
+            done.add(id(c))
+            if partner is not None:
+                done.add(id(partner))
             total_bytes = F * N * 16
             free, _ = t.cuda.mem_get_info()
             keep = self.keep_coordinates and total_bytes < 0.4 * free
             stager = _FrameStager(N, keep_on_device=keep, n_frames_hint=F)
             cells_blocks = []
+            pidx = bulk.solute_group.indices if bulk is not None else None
+            state = {"f": 0}
 
-            def consume(d, c=c):
+            def consume(d, bulk=bulk, solv=solv, pidx=pidx, state=state):
                 cells = t.empty(d.shape[:2], dtype=t.int32, device=d.device) if keep else None
-                c.collect_block(d, cells)
+                if bulk is None:
+                    solv.collect_block(d, cells)
+                else:
+                    f0 = state["f"]
+                    pblock = numpy.ascontiguousarray(numpy.take(traj.coordinate_array(f0, f0 + d.shape[0]), pidx, axis=1),
+                                                     dtype=numpy.float32)
+                    pd = t.from_numpy(pblock).cuda()
+                    K.hist_bulk(bulk._tables, d, pd, bulk.cutoff, bulk._counts,
+                                counts_solvent=None if solv is None else solv._counts, cells=cells)
                 if keep:
                     cells_blocks.append(cells)
+
             identity = self.universe._is_identity(idx) if hasattr(self.universe, "_is_identity") else False
             f = 0
             while f < F:
@@ -338,6 +365,7 @@ class DensityCreator(object):
                     host[:n] = block
                 else:
                     numpy.take(block, idx, axis=1, out=host[:n])
+                state["f"] = f
                 stager.flush(n, consume)
                 f += n
             t.cuda.current_stream().synchronize()
@@ -345,8 +373,9 @@ class DensityCreator(object):
                 cache = getattr(traj, "_hopb_device_cache", None)
                 if cache is None:
                     cache = traj._hopb_device_cache = {}
+                edges = (solv or bulk).edges
                 cache[idx.tobytes()] = {"xyz": stager.keep, "cells": cells_blocks,
-                                        "edges": [numpy.array(e) for e in c.edges]}
+                                        "edges": [numpy.array(e) for e in edges]}
 
     def DensityWithBulk(self, density_unit='water', solvent_threshold=numpy.e, bulk_threshold=0.6):
         """Solvent density with the bulk site inserted (hop/density.py:306-356)."""

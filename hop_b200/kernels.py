@@ -87,6 +87,28 @@ def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, c
     return counts
 
 
+def hist_bulk(grid: GridTables, solvent: torch.Tensor, solute: torch.Tensor, cutoff: float, counts_bulk: torch.Tensor,
+              counts_solvent=None, cells=None, within=None):
+    """Solvent histogram + bulk histogram ('solvent not within cutoff of solute', hop/density.py:82-87)
+    from one pass.  solvent float32 [F][Nw][3], solute float32 [F][Np][3]."""
+    _cuda(solvent, torch.float32, "solvent")
+    _cuda(counts_bulk, torch.int32, "counts_bulk")
+    F, Nw = int(solvent.shape[0]), int(solvent.shape[1])
+    Np = 0
+    if solute is not None and solute.numel():
+        _cuda(solute, torch.float32, "solute")
+        if solute.shape[0] != F:
+            raise ValueError("solvent and solute must cover the same frames")
+        Np = int(solute.shape[1])
+    if F == 0 or Nw == 0:
+        return counts_bulk
+    h = _h(solvent)
+    rc = _lib.lib().hopb_hist_bulk(h, _stream(), grid.ptr, _p(solvent), _p(solute if Np else None), F, Nw, Np, float(cutoff),
+                                   _p(counts_solvent), _p(counts_bulk), _p(cells), _p(within))
+    _lib.check(h, rc)
+    return counts_bulk
+
+
 def set_hist_l2_budget(nbytes: int, device=None):
     """Largest part of the count grid one histogram pass reduces into (slabbed passes beyond it)."""
     h = _lib.handle(device)

@@ -96,6 +96,19 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
  * slab, so that every pass reduces into an L2-resident part of the grid. */
 int hopb_set_hist_l2_budget(hopb_handle* h, int64_t bytes);
 
+/* Bulk density: the selection '<solvent> not within <cutoff> of <solute>' that
+ * DensityCollector builds with notwithin_coordinates_factory (hop/density.py:82-87, an MDAnalysis
+ * kd-tree search per frame), fused with the histogram.  Per frame, every solvent atom is counted in
+ * counts_solvent (may be NULL) and, when no solute atom lies within the cutoff (d^2 <= cutoff^2 in
+ * float32, no periodic images), also in counts_bulk -- the 'solvent' and 'bulk' collectors of
+ * DensityCreator(mode='all') from one read of the coordinates.
+ *   solvent  device float32 [F][Nw][3]   solute  device float32 [F][Np][3] (Np <= ~12000)
+ *   cells    device uint32 [F][Nw] (may be NULL): brick indices of the solvent atoms, see above
+ *   within   device uint8  [F][Nw] (may be NULL): 1 where a solute atom is within the cutoff */
+int hopb_hist_bulk(hopb_handle* h, void* stream, const hopb_grid* g, const float* solvent, const float* solute,
+                   int64_t F, int64_t Nw, int64_t Np, double cutoff, uint32_t* counts_solvent, uint32_t* counts_bulk,
+                   uint32_t* cells, uint8_t* within);
+
 /* density = counts / n_frames / dx[i] / dy[j] / dz[k] * factor, in float64 and in exactly that
  * order: DensityCollector.finish (hop/density.py:133-137), Grid.make_density
  * (hop/sitemap.py:196-216), Grid.convert_density (hop/sitemap.py:236-264).  Pass factor = 1.0 for

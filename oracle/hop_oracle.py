@@ -135,6 +135,36 @@ def histogram_vectorised(xyz, edges):
     return np.bincount(lin, minlength=int(np.prod(shape))).reshape(shape).astype(np.int64)
 
 
+def within_cutoff(solvent, solute, cutoff):
+    """Boolean [Nw]: a solute atom lies within `cutoff` of the solvent atom (one frame).
+
+    Restates the selection '<sel1> not within <cutoff> of <sel2>' that hop builds with MDAnalysis'
+    kd-tree (`notwithin_coordinates_factory`, hop/density.py:82-87; MDAnalysis is absent, so this is
+    unpinned): plain Euclidean distance, no periodic images, boundary included.  The squared
+    distance is evaluated in float32 as (dx*dx + dy*dy) + dz*dz -- the order the kernel uses."""
+    w = np.asarray(solvent, dtype=np.float32)
+    p = np.asarray(solute, dtype=np.float32)
+    c2 = np.float32(cutoff) * np.float32(cutoff)
+    out = np.zeros(len(w), dtype=bool)
+    for j in range(len(p)):   # chunk-free and exact; Np is small in the tests
+        d = w - p[j]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        out |= d2 <= c2
+    return out
+
+
+def histogram_bulk(xyz_solvent, xyz_solute, edges, cutoff):
+    """Counts of the solvent atoms that are NOT within `cutoff` of the solute, frame by frame
+    (DensityCollector in BULK mode, hop/density.py:82-87 + 125-131)."""
+    shape = tuple(len(e) - 1 for e in edges)
+    total = np.zeros(shape, np.int64)
+    for w, p in zip(xyz_solvent, xyz_solute):
+        keep = ~within_cutoff(w, p, cutoff)
+        if keep.any():
+            total += histogram_vectorised(w[keep][None], edges)
+    return total
+
+
 def make_density(counts, edges, n_frames, unit=None):
     """counts -> density, reproducing the reference's operation order exactly.
 

@@ -275,3 +275,78 @@ def test_interactive_workflow(system, tmp_path):
         assert hg.graph.number_of_edges() > 0
     finally:
         os.chdir(cwd)
+
+
+# ---- bulk density: '<solvent> not within <cutoff> of <solute>' (hop/density.py:82-87, 257-272, 306-356) ----
+@pytest.fixture(scope="module")
+def solvated():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hop_b200.universe import Universe
+
+    p = SynthParams(n_atoms=900, n_frames=40)
+    water = generate(p)
+    rng = np.random.default_rng(12)
+    c = p.box / 2
+    prot0 = (c + rng.normal(0, 4.0, size=(60, 3))).astype(np.float32)
+    prot = (prot0[None] + rng.normal(0, 0.3, size=(40, 60, 3))).astype(np.float32)   # a wobbling "protein"
+    xyz = np.concatenate([prot, water], axis=1)
+    names = ["CA"] * 30 + ["HA"] * 30 + ["OH2"] * 900
+    resn = ["ALA"] * 60 + ["TIP3"] * 900
+    u = Universe(coordinates=xyz, names=names, resnames=resn, dt=1.0)
+    return u, xyz, water, prot[:, :30]     # heavy atoms only: 'protein and not name H*'
+
+
+def test_notwithin_selection_and_fused_densities(solvated):
+    from hop_b200.bulk import notwithin_coordinates_factory
+    from hop_b200.density import DensityCollector, DensityCreator
+
+    u, xyz, water, heavy = solvated
+    cutoff = 3.5
+    nw = notwithin_coordinates_factory(u, "name OH2", "protein and not name H*", cutoff)
+    u.trajectory[7]
+    ref_mask = O.within_cutoff(water[7], heavy[7], cutoff)
+    assert 0 < ref_mask.sum() < len(ref_mask)
+    assert np.array_equal(nw(), water[7][~ref_mask])
+    assert np.array_equal(nw.within_mask(water[:5], heavy[:5]).astype(bool),
+                          np.stack([O.within_cutoff(water[f], heavy[f], cutoff) for f in range(5)]))
+    u.trajectory.rewind()
+
+    DC = DensityCreator(u, mode="all", delta=1.0, atomselection="name OH2", cutoff=cutoff,
+                        soluteselection="protein and not name H*")
+    dens = DC.create()
+    assert set(dens) == {"bulk", "solvent"}
+    edges = dens["solvent"].edges
+    for a, b in zip(edges, dens["bulk"].edges):
+        assert np.array_equal(a, b)
+    _, _, ref_edges = O.grid_geometry(water[0], delta=1.0)
+    for a, b in zip(edges, ref_edges):
+        assert np.array_equal(a, b)
+    ref_solvent = O.make_density(O.histogram_vectorised(water, edges), edges, 40)
+    ref_bulk = O.make_density(O.histogram_bulk(water, heavy, edges, cutoff), edges, 40)
+    assert np.array_equal(dens["solvent"].grid, ref_solvent)
+    assert np.array_equal(dens["bulk"].grid, ref_bulk)
+    assert dens["bulk"].metadata["collector_mode"] == "BULK" and dens["bulk"].metadata["cutoff"] == cutoff
+    assert dens["bulk"].metadata["soluteselection"] == "protein and not name H*"
+
+    # the per-frame collector API gives the same histogram as the fused block path
+    cb = DensityCollector("bulk", u, delta=1.0, atomselection="name OH2", cutoff=cutoff,
+                          soluteselection="protein and not name H*")
+    cb.init_histogram(smin=np.min(water[0], axis=0) - 2.0, smax=np.max(water[0], axis=0) + 2.0)
+    for ts in u.trajectory:
+        cb.collect()
+    cb.finish(40)
+    assert np.array_equal(cb.Density().grid, ref_bulk)
+
+    # mode='bulk' alone
+    only = DensityCreator(u, mode="bulk", delta=1.0, atomselection="name OH2", cutoff=cutoff,
+                          soluteselection="protein and not name H*").create()["bulk"]
+    assert np.array_equal(only.grid.sum(), only.grid.sum()) and only.grid.shape[0] > 0
+
+    # DensityWithBulk: the standard workflow (hop/density.py:306-356)
+    final = DC.DensityWithBulk(density_unit="water", solvent_threshold=math.e, bulk_threshold=math.exp(-0.5))
+    gs = O.make_density(O.histogram_vectorised(water, edges), edges, 40, "water")
+    gb = O.make_density(O.histogram_bulk(water, heavy, edges, cutoff), edges, 40, "water")
+    sites = O.site_insert_bulk(O.label_sites_ndimage(gs, math.e), O.label_sites_ndimage(gb, math.exp(-0.5)))
+    assert np.array_equal(final.map, O.draw_map_from_sites(sites, gs.shape))
+    assert final.has_bulk() and [list(s) for s in final.sites] == sites
