@@ -337,7 +337,7 @@ hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ so
       const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dim[0] - 1);
       const int y0 = max(cy - 1, 0), y1 = min(cy + 1, dim[1] - 1);
       const int z0 = max(cz - 1, 0), z1 = min(cz + 1, dim[2] - 1);
-      for (int a = x0; a <= x1 && !within; ++a)
+      for (int a = x0; a <= x1 && !within && z0 <= z1; ++a)
         for (int b = y0; b <= y1 && !within; ++b) {
           const int row = (a * dim[1] + b) * dim[2];
           const int j0 = s_start[row + z0], j1 = s_start[row + z1 + 1];   // cells z0..z1 are contiguous
