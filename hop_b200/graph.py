@@ -7,9 +7,10 @@ reference's emission order (csrc/events.cu) and come back as the ``graph_propert
 edge tuple ``(i, j)`` or node ``i`` -> ``{'tau', 'tbarrier', 'frame', 'iatom'}`` arrays, times in ps.
 The transition-count matrix is ``len(tau)`` per edge.
 
-``HoppingGraph`` here is the container the network hands its results to (graph, properties,
-trjdata, site_properties); the rate fits of hop.graph.HoppingGraph (hop/graph.py:1677-1748) are a
-"next" row of the scope table.
+``HoppingGraph`` takes the network's results (graph, properties, trjdata, site_properties) and puts
+a rate constant on every edge the way hop.graph.HoppingGraph does (hop/graph.py:1677-1748): a
+least-squares fit of the survival function of the waiting times, on the host with scipy like the
+reference, fed by the event arrays the GPU produced.
 """
 from __future__ import annotations
 
@@ -189,29 +190,107 @@ class TransportNetwork(object):
 
 
 class HoppingGraph(object):
-    """Container for the hopping graph that TransportNetwork produces (hop/graph.py:492-612):
-    ``graph`` (networkx.DiGraph), ``properties`` (per edge/node event arrays), ``trjdata`` and
-    ``site_properties``.  ``number_of_hops(i, j)`` is the transition count N_ij."""
+    """Directed graph of sites with rate constants on the edges (hop/graph.py:492-640, 1677-1748).
+
+    ``graph`` is a networkx.DiGraph whose edges carry ``k`` (rate constant in 1/ps), ``N`` (number of
+    transitions = the transition count) and ``fit`` (a :class:`fit_func`); ``properties`` holds the
+    per-edge / per-node event arrays of TransportNetwork; ``trjdata`` and ``site_properties`` travel
+    along.  As in the reference the rate of an edge comes from a least-squares fit (scipy's
+    ``leastsq``, i.e. MINPACK, on the host) of a double or single exponential to the survival
+    function of the waiting times; the survival function is evaluated by sorting instead of the
+    reference's O(N * T) sum of step functions -- the values are identical."""
 
     def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None):
-        if graph is not None and properties is not None:
-            self.graph = graph
+        import networkx as NX
+
+        self.trjdata = trjdata if isinstance(trjdata, dict) else None
+        self.site_properties = site_properties
+        self._filename = filename
+        if not (graph is None or properties is None):
+            self.graph = NX.DiGraph(name='Transitions between sites')
             self.properties = properties
-            self.trjdata = trjdata
-            self.site_properties = site_properties
+            self.graph.add_nodes_from(graph.nodes)
+            ebunch = [(e[0], e[1], self._rate(properties[e]['tau'])) for e in graph.edges]
+            self.graph.add_edges_from(ebunch)
         elif filename is not None:
             self.load(filename)
         else:
-            raise ValueError('Either a graph and properties or a filename is required.')
+            raise ValueError('provide edges and properties or a filename')
 
-    def number_of_hops(self, i, j):
-        return len(self.properties[(i, j)]['tau'])
+    # ---- access to the data of an edge (hop/graph.py:617-700) ------------------------------------
+    def rate(self, edge):
+        """Fastest rate on an edge, in 1/ns."""
+        f = self.waitingtime_fit(edge)
+        if len(f.parameters) == 1:
+            k = f.parameters[0]
+        elif len(f.parameters) == 3:
+            a, k1, k2 = f.parameters
+            k = k1 if a > 0.5 else k2
+        else:
+            raise ValueError('Unknown waitingtime fit, ' + str(f))
+        return 1000 * k
+
+    def waitingtime_fit(self, edge):
+        """The fit_func instance of an edge (from_site, to_site[, data])."""
+        return self.graph[edge[0]][edge[1]]['fit']
+
+    def number_of_hops(self, *edge):
+        """Number of transitions recorded on the edge = the transition count N_ij."""
+        if len(edge) == 1:
+            edge = edge[0]
+        return self.graph[edge[0]][edge[1]]['N']
+
+    def from_site(self, edge):
+        return edge[0]
+
+    def to_site(self, edge):
+        return edge[1]
 
     def waitingtimes(self, i, j):
         return self.properties[(i, j)]['tau']
 
     def barriertimes(self, i, j):
         return self.properties[(i, j)]['tbarrier']
+
+    def rates(self, n, use_filtered_graph=False):
+        """{(from, to): k} of all edges entering or leaving site n, in 1/ps."""
+        out = {}
+        for a, b, d in self.graph.in_edges(n, data=True):
+            out[(a, b)] = d['k']
+        for a, b, d in self.graph.out_edges(n, data=True):
+            out[(a, b)] = d['k']
+        return out
+
+    def _rate(self, taus, method='survivalfunction', block_w=200):
+        """Rate i --> j from the hopping times tau_ji: dict(k, N, fit)  (hop/graph.py:1677-1748).
+
+        Fit a*exp(-k1 t) + (1-a)*exp(-k2 t) to the survival function S(t) when there are more than 10
+        events, fall back to exp(-k t) when the double exponential is very asymmetric
+        (|0.5 - a| > 0.49) or has a negative rate."""
+        if method != 'survivalfunction':
+            raise NotImplementedError('Method "%s" is not implemented.' % method)
+        taus = numpy.asarray(taus)
+        dt = 1.0
+        tmax = numpy.max(taus) + 1.0 * dt
+        N = len(taus)
+        x = numpy.arange(0, tmax + 1, dt)
+        S = survivalfunction(taus, block_w=block_w)
+        Sx = S(x)
+        enough_data = (len(taus) > 10)
+        is_single_exp = False
+        if enough_data:
+            fit = fitExp2(x, Sx)
+            a, k1, k2 = fit.parameters
+            is_single_exp = abs(0.5 - a) > 0.49
+            all_k = numpy.array([k1, k2])
+            if numpy.any(all_k < 0):
+                is_single_exp = True
+            else:
+                k = all_k[all_k > 0].max()
+        if not enough_data or is_single_exp:
+            fit = fitExp(x, Sx)
+            k, = fit.parameters
+        return dict(k=k, N=N, fit=fit)
 
     def filename(self, filename=None, ext=None, set_default=False, use_my_ext=False):
         from .utilities import filename_function
@@ -232,3 +311,110 @@ class HoppingGraph(object):
         self.properties = data['properties']
         self.trjdata = data.get('trjdata')
         self.site_properties = data.get('site_properties')
+
+
+class fit_func(object):
+    """Fit a function f to data (x, y) by least squares (hop/graph.py:2354-2397); ``parameters``
+    holds the fitted parameters."""
+
+    def __init__(self, x, y):
+        import scipy.optimize
+
+        _x = numpy.asarray(x)
+        _y = numpy.asarray(y)
+        p0 = self.initial_values()
+        fitfunc = self.f_factory()
+
+        def errfunc(p, x, y):
+            return fitfunc(p, x) - y
+
+        p, msg = scipy.optimize.leastsq(errfunc, p0[:], args=(_x, _y))
+        try:
+            p[0]
+            self.parameters = p
+        except (TypeError, IndexError):
+            self.parameters = [p]
+        self.message = msg
+
+    def f_factory(self):
+        def fitfunc(p, x):
+            raise NotImplementedError("base class must be extended for each fit function")
+        return fitfunc
+
+    def initial_values(self):
+        raise NotImplementedError("base class must be extended for each fit function")
+
+    def fit(self, x):
+        """Applies the fit to all x values"""
+        return self.f_factory()(self.parameters, numpy.asarray(x))
+
+
+class fitExp(fit_func):
+    """y = f(x) = exp(-p[0]*x)"""
+
+    def f_factory(self):
+        def fitfunc(p, x):
+            return numpy.exp(-p[0] * x)
+        return fitfunc
+
+    def initial_values(self):
+        return [1.0]
+
+    def __repr__(self):
+        return "<fitExp " + str(self.parameters) + ">"
+
+
+class fitExp2(fit_func):
+    """y = f(x) = p[0]*exp(-p[1]*x) + (1-p[0])*exp(-p[2]*x)"""
+
+    def f_factory(self):
+        def fitfunc(p, x):
+            return p[0] * numpy.exp(-p[1] * x) + (1 - p[0]) * numpy.exp(-p[2] * x)
+        return fitfunc
+
+    def initial_values(self):
+        return [0.5, 0.1, 1e-4]
+
+    def __repr__(self):
+        return "<fitExp2" + str(self.parameters) + ">"
+
+
+class fitlin(fit_func):
+    """y = f(x) = p[0]*x + p[1]"""
+
+    def f_factory(self):
+        def fitfunc(p, x):
+            return p[0] * x + p[1]
+        return fitfunc
+
+    def initial_values(self):
+        return [1.0, 0.0]
+
+    def __repr__(self):
+        return "<fitlin" + str(self.parameters) + ">"
+
+
+def Unitstep(x, x0):
+    """Heaviside step function Theta(x - x0): 1 if x > x0, 0.5 if x == x0, 0 if x < x0
+    (hop/graph.py:2501-2518)."""
+    return 0.5 * (1 + numpy.sign(numpy.asarray(x) - x0))
+
+
+def survivalfunction(waitingtimes, block_w=200, block_t=1000):
+    """S(t): the fraction of particles that have not yet left the site after time t, from a list
+    of waiting times (hop/graph.py:2433-2499): S(t) = <Theta(t0 - t)>_{t0}.
+
+    The reference sums one step function per waiting time for every t (O(N * T), blocked to save
+    memory); here the waiting times are sorted once and S(t) = (#{t0 > t} + 0.5 #{t0 == t}) / N comes
+    from two binary searches -- the same numbers (sums of 0, 0.5 and 1 are exact)."""
+    w = numpy.sort(numpy.asarray(waitingtimes, dtype=float))
+    n = len(w)
+
+    def S(t):
+        _t = numpy.asarray(t, dtype=float)
+        right = numpy.searchsorted(w, _t, side='right')   # #{t0 <= t}
+        left = numpy.searchsorted(w, _t, side='left')     # #{t0 <  t}
+        return ((n - right) + 0.5 * (right - left)) / n
+
+    S.__doc__ = "Survival function S(t).  t can be a array."
+    return S

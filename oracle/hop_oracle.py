@@ -504,6 +504,55 @@ def graph_alltransitions(hop_x):
 
 
 # =================================================================================================
+# Rates from waiting times (row f.2 of the scope table)
+# =================================================================================================
+def survival_faithful(taus, t):
+    """S(t) = <Theta(t0 - t)> over the waiting times t0, the way hop.graph.survivalfunction
+    (hop/graph.py:2433-2499) builds it: one step function per waiting time, Theta(0) = 1/2
+    (Unitstep, hop/graph.py:2501-2518), summed and divided by N."""
+    taus = np.asarray(taus, dtype=float)
+    t = np.asarray(t, dtype=float)
+    total = np.zeros(t.shape)
+    for t0 in taus:
+        total += 0.5 * (1 + np.sign(t0 - t))
+    return total / len(taus)
+
+
+def rate_faithful(taus):
+    """HoppingGraph._rate (hop/graph.py:1677-1748): least-squares fit (scipy.optimize.leastsq, as in
+    fit_func, hop/graph.py:2354-2397) of a*exp(-k1 t) + (1-a)*exp(-k2 t) to S(t) on t = 0, 1, ...,
+    max(tau)+1 when there are more than 10 events; exp(-k t) when there are not, when the double
+    exponential is asymmetric (|0.5 - a| > 0.49) or has a negative rate.  Returns (k, N, parameters)."""
+    import scipy.optimize
+
+    taus = np.asarray(taus)
+    x = np.arange(0, np.max(taus) + 1.0 + 1, 1.0)
+    y = survival_faithful(taus, x)
+
+    def exp2(p, x):
+        return p[0] * np.exp(-p[1] * x) + (1 - p[0]) * np.exp(-p[2] * x)
+
+    def exp1(p, x):
+        return np.exp(-p[0] * x)
+
+    def lsq(f, p0):
+        p, _ = scipy.optimize.leastsq(lambda p, x, y: f(p, x) - y, p0, args=(x, y))
+        return np.atleast_1d(p)
+
+    single = len(taus) <= 10
+    if not single:
+        p = lsq(exp2, [0.5, 0.1, 1e-4])
+        a, k1, k2 = p
+        single = abs(0.5 - a) > 0.49 or k1 < 0 or k2 < 0
+        if not single:
+            k = max(kk for kk in (k1, k2) if kk > 0)
+    if single:
+        p = lsq(exp1, [1.0])
+        k = p[0]
+    return k, len(taus), p
+
+
+# =================================================================================================
 # Whole pipeline (used by tests, smoke and the CPU baseline)
 # =================================================================================================
 def pipeline(xyz, delta=1.0, padding=2.0, solvent_threshold=math.e, bulk_threshold=math.exp(-0.5),

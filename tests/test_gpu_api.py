@@ -251,6 +251,10 @@ def test_transport_network(system, mapped, tmp_path):
         assert tn.transition_counts() == {e: len(props_ref[e]["tau"]) for e in edges_ref}
         assert hg.trjdata["time_unit"] == "ps" and abs(hg.trjdata["dt"] - 2.0) < 1e-6 and abs(hg.trjdata["totaltime"] - 238.0) < 1e-3
         assert hg.number_of_hops(*edges_ref[0]) == len(props_ref[edges_ref[0]]["tau"])
+        for e in edges_ref[:6]:                           # rates from the GPU's events vs the oracle's fit
+            k_ref, n_ref, _ = O.rate_faithful(props_ref[e]["tau"])
+            assert hg.graph[e[0]][e[1]]["N"] == n_ref
+            assert abs(hg.graph[e[0]][e[1]]["k"] - k_ref) <= 1e-6 * abs(k_ref)
     tn.graph_alltransitions()
     pairs = O.graph_alltransitions(ref["hop"][:, :, 0])
     assert set(tn.graph.edges()) == set(map(tuple, pairs.tolist()))

@@ -165,3 +165,45 @@ def test_synth_generator_properties():
     assert xyz.min() >= 0.0 and xyz.max() < p.box
     assert np.array_equal(generate(p, 10, 20), xyz[10:20])
     assert np.allclose(xyz[0, 1], 0.0) and xyz[0, 2].min() > p.box * 0.999
+
+
+def test_survivalfunction_and_rates_match_oracle():
+    """hop_b200.graph.HoppingGraph rates vs the oracle's restatement of hop/graph.py:1677-1748
+    (tolerance 1e-6 relative, north_star); the survival function must be identical."""
+    import warnings
+
+    import networkx as NX
+
+    from hop_b200.graph import HoppingGraph, Unitstep, fitExp2, survivalfunction
+
+    rng = np.random.default_rng(7)
+    cases = {
+        (2, 3): 2.0 * np.round(rng.exponential(30, 400)),                       # single population
+        (3, 2): np.concatenate([np.round(rng.exponential(4, 300)), np.round(rng.exponential(90, 300))]) + 1.0,
+        (2, 4): np.array([3.0, 1.0, 8.0, 2.0]),                                  # <= 10 events -> single exponential
+        (4, 2): np.full(25, 5.0),                                                # all equal: step at t = 5
+    }
+    for taus in cases.values():
+        x = np.arange(0, taus.max() + 2, 1.0)
+        S = survivalfunction(taus)
+        assert np.array_equal(S(x), O.survival_faithful(taus, x))
+        assert np.array_equal(S(x + 0.5), O.survival_faithful(taus, x + 0.5))
+    assert Unitstep(1.0, 1.0) == 0.5 and Unitstep(2.0, 1.0) == 1.0 and Unitstep(0.0, 1.0) == 0.0
+    g = NX.DiGraph()
+    g.add_edges_from(cases.keys())
+    props = {e: {"tau": t, "tbarrier": 0 * t, "frame": t, "iatom": t} for e, t in cases.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hg = HoppingGraph(g, props, trjdata={"dt": 1.0})
+        for e, taus in cases.items():
+            k, n, p = O.rate_faithful(taus)
+            d = hg.graph[e[0]][e[1]]
+            assert d["N"] == n == hg.number_of_hops(e)
+            assert abs(d["k"] - k) <= 1e-6 * abs(k), (e, d["k"], k)
+            assert np.allclose(d["fit"].parameters, p, rtol=1e-6, atol=0)
+            f = hg.waitingtime_fit(e)
+            kk = f.parameters[0] if len(f.parameters) == 1 else (f.parameters[1] if f.parameters[0] > 0.5 else f.parameters[2])
+            assert hg.rate(e) == 1000 * kk
+    assert len(hg.waitingtime_fit((2, 4)).parameters) == 1
+    assert isinstance(hg.waitingtime_fit((3, 2)), fitExp2)
+    assert set(hg.rates(2)) == set(cases)
