@@ -271,36 +271,51 @@ class HopPipeline:
 
     def run_host(self, xyz_host, frame0=0, out_x=None, out_y=None, block_bytes=256 << 20):
         """End-to-end run from HOST coordinates to HOST results (what the Python classes do for a
-        user): xyz_host is a pinned CPU float32 tensor [F_local][N][3].
+        user): xyz_host is a pinned CPU float32 tensor [F_local][N][3].  Returns
+        (PipelineResult, host dict); see run_host_begin."""
+        return self.run_host_begin(xyz_host, frame0, out_x, out_y, block_bytes).finish()
 
-        Coordinates go to HBM in blocks on a copy stream while the histogram kernel consumes the
-        blocks already there; they stay resident for stage 3.  The hopping trajectory comes back
-        into pinned host tensors (out_x / out_y, [F_local][N] float32) together with the sorted
-        events and the COO transition counts.  Returns (PipelineResult, host dict)."""
+    def run_host_begin(self, xyz_host, frame0=0, out_x=None, out_y=None, block_bytes=256 << 20):
+        """Start an end-to-end run and return a HostRun; HostRun.finish() waits for the hopping
+        trajectory to be in host memory and returns (PipelineResult, host dict).
+
+        Coordinates go to HBM in blocks on an upload stream while the histogram kernel consumes the
+        blocks already there; they stay resident for stage 3.  The events are sorted and the small
+        results (sorted events, COO transition counts, final per-atom state) copied to the host, then
+        the hopping trajectory planes stream back into pinned host tensors (out_x / out_y,
+        [F_local][N] float32) on a download stream.  Uploads and downloads use different streams
+        (and copy engines), so a caller that begins run k+1 before finishing run k -- with a second
+        pair of out_x / out_y -- overlaps the download of k with the upload of k+1; PCIe is full
+        duplex.  The device buffers are shared between runs: stage 3 of the next run waits for the
+        download of this one."""
         F, N = int(xyz_host.shape[0]), int(xyz_host.shape[1])
         dev = self.device
         xyz = self._buf("xyz_resident", (F, N, 3), torch.float32)
         counts = self._buf("counts", self.grid.shape, torch.int32)
         counts.zero_()
         self.cells = self._buf("cells", (F, N), torch.int32) if self._use_cells(xyz) else None
-        copy_stream = getattr(self, "_copy_stream", None)
-        if copy_stream is None:
-            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(device=dev)
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+            self._d2h_done = None
+        h2d, d2h = self._h2d_stream, self._d2h_stream
         main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)
+        h2d.wait_stream(main)
         block = max(1, block_bytes // (N * 12))
         for f0 in range(0, F, block):
             f1 = min(F, f0 + block)
-            with torch.cuda.stream(copy_stream):
+            with torch.cuda.stream(h2d):
                 xyz[f0:f1].copy_(xyz_host[f0:f1], non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(copy_stream)
+                ev.record(h2d)
             main.wait_event(ev)
             K.hist_accumulate(self.grid, xyz[f0:f1], counts, None if self.cells is None else self.cells[f0:f1])
         exchange.reduce_counts(counts)
         res = PipelineResult()
         res.counts = counts
         res.density, res.own, res.member, res.map16, res.site_props = self.site_map(counts)
+        if self._d2h_done is not None:
+            main.wait_event(self._d2h_done)      # the previous run's planes are still being downloaded
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
         res.n_labels, n_ev = self.sync_scalars(events)
         if n_ev > events.capacity:
@@ -311,20 +326,31 @@ class HopPipeline:
         if out_x is None:
             out_x = torch.empty((F, N), dtype=torch.float32).pin_memory()
             out_y = torch.empty((F, N), dtype=torch.float32).pin_memory()
-        # hoptraj planes stream back while the events are sorted on the compute stream
-        done = torch.cuda.Event()
-        done.record(main)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
-            out_x.copy_(res.hop_x, non_blocking=True)
-            out_y.copy_(res.hop_y, non_blocking=True)
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
          res.count_matrix) = self.transitions(events, n_ev, N, res.n_labels)
+        # small results first (these copies synchronise), then the planes: 8 B per atom-frame
         host = dict(hop_x=out_x, hop_y=out_y, events=res.events.cpu(), edge_s0=res.edge_s0.cpu(),
                     edge_s=res.edge_s.cpu(), edge_count=res.edge_count.cpu(), final_state=res.final_state.cpu())
-        copy_stream.synchronize()
-        main.synchronize()
-        return res, host
+        d2h.wait_stream(main)
+        with torch.cuda.stream(d2h):
+            out_x.copy_(res.hop_x, non_blocking=True)
+            out_y.copy_(res.hop_y, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(d2h)
+        self._d2h_done = done
+        return HostRun(res, host, done)
+
+
+class HostRun(object):
+    """A run_host_begin in flight: finish() returns (PipelineResult, host dict) once the hopping
+    trajectory planes are in host memory."""
+
+    def __init__(self, result, host, done):
+        self.result, self.host, self._done = result, host, done
+
+    def finish(self):
+        self._done.synchronize()
+        return self.result, self.host
 
 
 def _capacity_error(n, cap):

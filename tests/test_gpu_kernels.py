@@ -456,3 +456,36 @@ def test_pipeline_config1_matches_faithful_oracle(K, traj):
     assert M.sum() == len(ev)
     for (a, b), c in zip(edge_keys, e_count):
         assert M[a + 1, b + 1] == c
+
+
+def test_run_host_overlapped_runs_match_resident_run(K, traj):
+    """HopPipeline.run_host (host in, host out) gives what run() gives on resident data, also when a
+    second run begins before the first one's hopping trajectory has been downloaded."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    ref = O.pipeline(xyz, delta=1.0, faithful=False)
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig())
+    host_xyz = torch.from_numpy(np.ascontiguousarray(xyz)).pin_memory()
+    # a different second trajectory on the same grid: the same frames in reverse order (checked
+    # against the resident run below)
+    host_rev = torch.from_numpy(np.ascontiguousarray(xyz[::-1])).pin_memory()
+    outs = [(torch.empty(xyz.shape[:2], dtype=torch.float32).pin_memory(), torch.empty(xyz.shape[:2], dtype=torch.float32).pin_memory())
+            for _ in range(2)]
+    a = pipe.run_host_begin(host_xyz, 0, *outs[0], block_bytes=1 << 16)
+    b = pipe.run_host_begin(host_rev, 0, *outs[1], block_bytes=1 << 16)
+    ra, ha = a.finish()
+    rb, hb = b.finish()
+    assert np.array_equal(ha["hop_x"].numpy(), ref["hop"][:, :, 0]) and np.array_equal(ha["hop_y"].numpy(), ref["hop"][:, :, 1])
+    n_edge_events = len(O.analyze_hops_vectorised(ref["hop"][:, :, 0])[0])
+    assert ha["events"].shape[0] == n_edge_events and int(ha["edge_count"].sum()) == n_edge_events
+    # the second run alone, resident: identical planes and events
+    res = pipe.run(dev(np.ascontiguousarray(xyz[::-1])))
+    assert torch.equal(res.hop_x.cpu(), hb["hop_x"]) and torch.equal(res.hop_y.cpu(), hb["hop_y"])
+    assert torch.equal(res.events.cpu(), hb["events"]) and torch.equal(res.edge_count.cpu(), hb["edge_count"])
+    r1, h1 = pipe.run_host(host_xyz)
+    assert torch.equal(h1["hop_x"], ha["hop_x"]) and torch.equal(h1["hop_y"], ha["hop_y"])
+    assert torch.equal(h1["events"], ha["events"])
