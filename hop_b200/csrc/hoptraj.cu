@@ -16,6 +16,8 @@
 //
 // Roofline per atom-frame: 12 B read + 8 B written to HBM; the site-map gather (2 B out of a 32 B
 // sector) is served by L2 (map16 of 201^3 cells = 16 MB).
+#include <type_traits>
+
 #include "hopb_common.cuh"
 
 namespace {
@@ -100,21 +102,25 @@ struct MapView {
 // site label of a brick index: the block map answers for bricks that are uniformly interstitial
 // (0) or bulk (1); only cells in mixed bricks gather from the bricked int16 map in L2.  Written
 // with selects and one predicated load so that a warp does not diverge on it.
+template <bool COARSE>
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
   const bool out = c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
   const uint32_t cc = out ? 0u : (c & 0x3FFFFFFFu);  // bit 30: bookkeeping of the slabbed histogram
   uint32_t st = 3u;
-  if (m.s_coarse) {
+  if (COARSE) {
     const uint32_t cb = cc >> 6;
     st = (m.s_coarse[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
   }
-  int l = (int)st;
+  // everything that does not depend on the gather comes first: the load is the last thing that
+  // writes l, so nothing waits for it until the label is used
+  int l = out ? -1 : (int)st;
   if (st == 3u && !out) l = (int)__ldg(m.brick + cc);
-  return out ? -1 : l;
+  return l;
 }
 
-// SRC = 0: coordinates; SRC = 1: labels of an existing hoptraj x column; SRC = 2: brick indices
-template <int SRC, bool FAST, int DEEP = 8, int MINB = 4>
+// XY: both output planes are present (the product path), so the stores need no pointer tests;
+// COARSE: the 2-bit block map is present (it fits in shared memory)
+template <int SRC, bool FAST, bool XY, bool COARSE, int DEEP = 8, int MINB = 4>
 __global__ void __launch_bounds__(kHopThreads, MINB)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
@@ -130,14 +136,14 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     if (!FAST)
       for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
   }
-  if (SRC != 1 && coarse)
+  if (SRC != 1 && COARSE)
     for (int i = threadIdx.x; i < coarse_words; i += blockDim.x) s_coarse[i] = coarse[i];
   if (SRC != 1) __syncthreads();
   const AxisReg ax = load_axis(tab.ax[0], s_pairs);
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
   MapView mv;
-  mv.brick = brick; mv.s_coarse = (SRC != 1 && coarse) ? s_coarse : nullptr;
+  mv.brick = brick; mv.s_coarse = (SRC != 1 && COARSE) ? s_coarse : nullptr;
   const int cny = (tab.ax[1].n + 3) >> 2, cnz = (tab.ax[2].n + 3) >> 2;
 
   const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,8 +163,13 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   float* px = hop_x ? hop_x + f_begin * N + atom : nullptr;
   float* py = hop_y ? hop_y + f_begin * N + atom : nullptr;
   auto store = [&](int l) {
-    if (px) { *px = (float)l; px += N; }
-    if (py) { *py = (float)yorb; py += N; }
+    if (XY) {
+      *px = (float)l; px += N;
+      *py = (float)yorb; py += N;
+    } else {
+      if (px) { *px = (float)l; px += N; }
+      if (py) { *py = (float)yorb; py += N; }
+    }
   };
   // label of frame f, whatever the source
   auto label_at = [&](int64_t fr) -> int {
@@ -170,7 +181,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     } else {
       c = __ldg(cells + fr * N + atom);
     }
-    return label_of(c, mv);
+    return label_of<COARSE>(c, mv);
   };
 
   // ---- prologue: the generic summary machine until a first real site has been seen -------------
@@ -184,8 +195,10 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     ++f;
   }
 
-  // ---- main loop: "current site cur, on/off, last exit t1"; entering another site is the only
-  // rare event.  Written with selects; the rare event is one (mostly not taken) branch. ---------
+  // ---- main loop: "current site cur, on/off, last exit t1".  Entering another site is the only
+  // rare event (~1e-3 per atom-frame), so frames go through in blocks: when no label of a block is
+  // a site other than cur, neither cur nor the orbit site changes inside the block and the block is
+  // a handful of selects and two stores per frame; otherwise the block replays frame by frame. ----
   if (f < f_end) {
     int cur = T.kind == HOPB_SPEC ? T.A1 : T.s0;
     int on = T.on, t1 = T.t1;
@@ -205,6 +218,30 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       }
       store(l);
     };
+    const uint32_t Nu = (uint32_t)N;
+    auto block = [&](const int* lab, auto kc, int t) {
+      constexpr int K = decltype(kc)::value;
+      bool rare = false;
+#pragma unroll
+      for (int u = 0; u < K; ++u) rare |= (lab[u] > 0) & (lab[u] != cur);
+      if (!rare && XY) {
+        const float yf = (float)yorb;
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const int l = lab[u];
+          const bool same = l == cur, zero = l == 0;
+          t1 = (zero && on) ? t + u : t1;
+          on = same ? 1 : (zero ? 0 : on);
+          px[(uint64_t)Nu * (uint32_t)u] = (float)l;
+          py[(uint64_t)Nu * (uint32_t)u] = yf;
+        }
+        px += (uint64_t)Nu * K;
+        py += (uint64_t)Nu * K;
+      } else {
+#pragma unroll
+        for (int u = 0; u < K; ++u) step(lab[u], t + u);
+      }
+    };
     if (SRC == 0) {
       for (; f + kUnroll <= f_end; f += kUnroll) {
         float cx[kUnroll], cy[kUnroll], cz[kUnroll];
@@ -215,9 +252,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         }
         int lab[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) lab[u] = label_of(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) step(lab[u], (int)(frame0 + f + u));
+        for (int u = 0; u < kUnroll; ++u) lab[u] = label_of<COARSE>(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
+        block(lab, std::integral_constant<int, kUnroll>(), (int)(frame0 + f));
       }
     } else {
       // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
@@ -228,19 +264,18 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       uint32_t v[kDeep];
       if (f + kDeep <= f_end) {
 #pragma unroll
-        for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + u * N);
-        src += kDeep * N;
+        for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
+        src += (uint64_t)Nu * kDeep;
         for (; f + kDeep <= f_end; f += kDeep) {
           int lab[kDeep];
 #pragma unroll
-          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of(v[u], mv) : (int)__uint_as_float(v[u]);
+          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of<COARSE>(v[u], mv) : (int)__uint_as_float(v[u]);
           if (f + 2 * kDeep <= f_end) {
 #pragma unroll
-            for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + u * N);
-            src += kDeep * N;
+            for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
+            src += (uint64_t)Nu * kDeep;
           }
-#pragma unroll
-          for (int u = 0; u < kDeep; ++u) step(lab[u], (int)(frame0 + f + u));
+          block(lab, std::integral_constant<int, kDeep>(), (int)(frame0 + f));
         }
       }
     }
@@ -400,8 +435,12 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     memset(&tab, 0, sizeof(tab));
     dim3 grid((unsigned)((N + kHopThreads - 1) / kHopThreads), (unsigned)n_chunks);
     hopb_note_launch();
-    hoptraj_kernel<1, true><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
-                                                      nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
+    if (hop_x && hop_y)
+      hoptraj_kernel<1, true, true, false><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
+                                                              nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
+    else
+      hoptraj_kernel<1, true, false, false><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
+                                                               nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
@@ -418,17 +457,26 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   const int threads = kHopThreads;
   HOPB_REQUIRE(h, smem <= 110 * 1024, "block map too large for shared memory; pass coarse = NULL");
   dim3 grid((unsigned)((N + threads - 1) / threads), (unsigned)n_chunks);
-#define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
+#define HOPB_HT_LAUNCH_XY(SRC, FAST, XY, CO)                                                                          \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table,       \
-                                                         g->d_table2, map16, coarse, coarse_words, hop_x, hop_y,      \
-                                                         chunk_len, summaries, sink);                                \
+    hoptraj_kernel<SRC, FAST, XY, CO><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
+                                                             g->d_table2, map16, coarse, coarse_words, hop_x, hop_y,  \
+                                                             chunk_len, summaries, sink);                            \
+  } while (0)
+#define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
+  do {                                                                                                               \
+    if (hop_x && hop_y) {                                                                                            \
+      if (coarse) HOPB_HT_LAUNCH_XY(SRC, FAST, true, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, true, false);          \
+    } else {                                                                                                         \
+      if (coarse) HOPB_HT_LAUNCH_XY(SRC, FAST, false, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, false, false);        \
+    }                                                                                                                \
   } while (0)
   if (src == 0) { if (fast) HOPB_HT_LAUNCH(0, true); else HOPB_HT_LAUNCH(0, false); }
   else HOPB_HT_LAUNCH(2, true);
+#undef HOPB_HT_LAUNCH_XY
 #undef HOPB_HT_LAUNCH
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;

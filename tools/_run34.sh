@@ -1,0 +1,5 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q --timeout 300 --timeout-method=thread -k "hoptraj or pipeline or golden or hopscan" > gpurun_out/t34.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t34.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/b34.json 2> gpurun_out/b34.err; echo "bench rc=$?" >> gpurun_out/t34.log
+tail -5 gpurun_out/t34.log
