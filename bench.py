@@ -273,7 +273,7 @@ def run_gpu(args):
     def hop_once():
         ev_tmp.reset()
         K.hoptraj(pipe.grid, xyz, pipe.brick, frame0, n_chunks, chunk_len, ev_tmp, res.hop_x, res.hop_y,
-                  pipe._bufs["summaries"], cells=pipe.cells, coarse=pipe.coarse)
+                  pipe._bufs["summaries"], cells=pipe.cells)
     k_hop = time_kernel(hop_once, max(args.steps, 3))
     peak, peak_src = measured_peak()
     # DRAM bytes per launch of the two kernels from the committed `ncu --set full` capture of this

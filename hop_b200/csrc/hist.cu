@@ -74,11 +74,6 @@ __device__ __forceinline__ AxisReg load_axis(const HopbAxis& a, const HopbPair* 
   return r;
 }
 
-// brick index of cell (i,j,k): see hoptraj.cu -- brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3))
-__device__ __forceinline__ uint32_t brick_index(int i, int j, int k, int cny, int cnz) {
-  const uint32_t cb = (uint32_t)(((i >> 2) * cny + (j >> 2)) * cnz + (k >> 2));
-  return (cb << 6) | (uint32_t)(((i & 3) << 4) | ((j & 3) << 2) | (k & 3));
-}
 
 // digitize (searchsorted right) in [0, n+1], branch-free
 __device__ __forceinline__ int bin_fast(float x, const AxisReg& a) {
@@ -127,7 +122,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     }
     if (!CELLS) return 0u;
     const bool in = ((unsigned)(px - 1) < (unsigned)ax.n) & ((unsigned)(py - 1) < (unsigned)ay.n) & ((unsigned)(pz - 1) < (unsigned)az.n);
-    return in ? (brick_index(px - 1, py - 1, pz - 1, ay.cn, az.cn) | slab.done_flag) : kCellOut;
+    return in ? (hopb_brick_index(px - 1, py - 1, pz - 1, ay.cn, az.cn) | slab.done_flag) : kCellOut;
   }
   const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
   if (ok & (bx - 1 >= slab.x_lo) & (bx - 1 < slab.x_hi)) {
@@ -136,7 +131,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     if (to_b) atomicAdd(counts_b + cell, 1u);
   }
   if (!CELLS) return 0u;
-  return ok ? brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : kCellOut;
+  return ok ? hopb_brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : kCellOut;
 }
 
 // later passes of a slabbed histogram: 4 B per point in, one reduction per point of this slab
@@ -150,12 +145,14 @@ hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, Slab sla
     if (c & 0xC0000000u) continue;  // outlier or already counted
     const uint32_t cb = c >> 6;
     const uint32_t ci = cb / plane;
-    const int i = (int)(ci * 4 + ((c >> 4) & 3u));
+    int di, dj, dk;
+    hopb_brick_decode(c, di, dj, dk);
+    const int i = (int)(ci * 4) + di;
     if (i < slab.x_lo || i >= slab.x_hi) continue;
     const uint32_t r = cb - ci * plane;
     const uint32_t cj = r / (uint32_t)cnz;
     const uint32_t ck = r - cj * (uint32_t)cnz;
-    const uint32_t j = cj * 4 + ((c >> 2) & 3u), k = ck * 4 + (c & 3u);
+    const uint32_t j = cj * 4 + (uint32_t)dj, k = ck * 4 + (uint32_t)dk;
     atomicAdd(counts + ((uint32_t)i * (uint32_t)ny + j) * (uint32_t)nz + k, 1u);
   }
 }

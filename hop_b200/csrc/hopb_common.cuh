@@ -91,3 +91,21 @@ static inline unsigned hopb_grid_for(int64_t n, int block, int num_sms, int per_
   if (need < 1) need = 1;
   return (unsigned)(need < cap ? need : cap);
 }
+
+// ---- bricked site map ---------------------------------------------------------------------------
+// The site map is stored in 4x4x4 bricks of 64 cells (one 128-byte line of int16 each), brick-major.
+// Inside a brick the cells are ordered by 2x2x2 sub-brick first: the index of cell (i,j,k) is
+//   brick*64 + (i1 j1 k1 i0 j0 k0)   with i1 = bit 1 of i, i0 = bit 0 of i, ...
+// so index >> 3 numbers the 2x2x2 sub-bricks (the 1-bit "fine" block map) and index >> 6 the bricks
+// (the 2-bit "coarse" block map).  0xFFFFFFFF marks an outlier; bit 30 is bookkeeping of the slabbed
+// histogram.
+__device__ __forceinline__ uint32_t hopb_brick_index(int i, int j, int k, int cny, int cnz) {
+  const uint32_t cb = (uint32_t)(((i >> 2) * cny + (j >> 2)) * cnz + (k >> 2));
+  return (cb << 6) | (uint32_t)(((i & 2) << 4) | ((j & 2) << 3) | ((k & 2) << 2) | ((i & 1) << 2) | ((j & 1) << 1) | (k & 1));
+}
+// position inside the brick -> (di, dj, dk) in 0..3
+__device__ __forceinline__ void hopb_brick_decode(uint32_t c, int& di, int& dj, int& dk) {
+  di = (int)(((c >> 4) & 2u) | ((c >> 2) & 1u));
+  dj = (int)(((c >> 3) & 2u) | ((c >> 1) & 1u));
+  dk = (int)(((c >> 2) & 2u) | (c & 1u));
+}

@@ -14,6 +14,9 @@
 // second distinct site depends on it, so each (atom, chunk) leaves a 44-byte summary and
 // hop_fixup_kernel stitches the chunks (and, across GPUs, the slabs) exactly.
 //
+// (L2 evict-first hints on the streamed loads / stores were measured and made this kernel 5-25 %
+// slower on B200; plain ld.global.nc / st.global it is.)
+//
 // Roofline per atom-frame: 12 B read + 8 B written to HBM; the site-map gather (2 B out of a 32 B
 // sector) is served by L2 (map16 of 201^3 cells = 16 MB).
 #include <type_traits>
@@ -70,15 +73,6 @@ __device__ __forceinline__ int hop_bin(float x, const AxisReg& a) {
   return b - 1;
 }
 
-// Brick index of a cell: the site map is stored in 4x4x4 bricks of 64 cells (one 128-byte line of
-// int16 each), brick-major; the index of cell (i,j,k) is brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3)).
-// It is both the gather address into the bricked map and, shifted right by 6, the index into the
-// 2-bit block map.  0xFFFFFFFF marks an outlier.
-__device__ __forceinline__ uint32_t brick_index(int i, int j, int k, int cny, int cnz) {
-  const uint32_t cb = (uint32_t)(((i >> 2) * cny + (j >> 2)) * cnz + (k >> 2));
-  return (cb << 6) | (uint32_t)(((i & 3) << 4) | ((j & 3) << 2) | (k & 3));
-}
-
 template <bool FAST>
 __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                               const AxisReg& ay, const AxisReg& az, const float* s_tab, int cny, int cnz) {
@@ -91,64 +85,88 @@ __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const H
     bz = hopb_bin_hop(z, tab.ax[2], s_tab + tab.ax[2].off) - 1;
   }
   const bool ok = ((unsigned)bx < (unsigned)ax.n) & ((unsigned)by < (unsigned)ay.n) & ((unsigned)bz < (unsigned)az.n);
-  return ok ? brick_index(bx, by, bz, cny, cnz) : 0xFFFFFFFFu;
+  return ok ? hopb_brick_index(bx, by, bz, cny, cnz) : 0xFFFFFFFFu;
 }
 
+// how a brick index becomes a label
+enum { MAP_GATHER = 0,   // always gather from the bricked int16 map (L2)
+       MAP_COARSE = 1,   // 2 bits per 4x4x4 brick in shared memory: 0 / 1 = uniformly interstitial / bulk, 3 = mixed
+       MAP_FINE = 2 };   // 1 bit per 2x2x2 sub-brick in shared memory: all 8 cells carry fine_value
+
 struct MapView {
-  const int16_t* brick;      // bricked site map
-  const uint32_t* s_coarse;  // 2 bits per brick in shared memory, or nullptr
+  const int16_t* brick;     // bricked site map
+  const uint32_t* s_map;    // block map in shared memory (coarse or fine), or nullptr
+  int fine_value;
 };
 
-// site label of a brick index: the block map answers for bricks that are uniformly interstitial
-// (0) or bulk (1); only cells in mixed bricks gather from the bricked int16 map in L2.  Written
-// with selects and one predicated load so that a warp does not diverge on it.
-template <bool COARSE>
+// Site label of a brick index.  The block map answers for the cells of uniform (sub-)bricks; only the
+// others gather from the bricked int16 map in L2.  A gather costs one 32-byte sector per lane, and
+// sectors -- not bytes -- are what the kernel is short of, so the fine map (2.6 % of the bulk cells
+// of a 0.5 A water grid sit in a mixed 2x2x2 sub-brick, 20 % in a mixed 4x4x4 brick) is preferred
+// whenever it fits into shared memory.  Selects and one predicated load: no divergence, and the
+// load is the last thing that writes l so nothing waits for it before the label is used.
+template <int MAP>
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
   const bool out = c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
   const uint32_t cc = out ? 0u : (c & 0x3FFFFFFFu);  // bit 30: bookkeeping of the slabbed histogram
-  uint32_t st = 3u;
-  if (COARSE) {
+  int l;
+  bool need;
+  if (MAP == MAP_FINE) {
+    const uint32_t sb = cc >> 3;
+    const bool uni = (m.s_map[sb >> 5] >> (sb & 31u)) & 1u;
+    l = m.fine_value;
+    need = !uni;
+  } else if (MAP == MAP_COARSE) {
     const uint32_t cb = cc >> 6;
-    st = (m.s_coarse[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
+    const uint32_t st = (m.s_map[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
+    l = (int)st;
+    need = st == 3u;
+  } else {
+    l = 0;
+    need = true;
   }
-  // everything that does not depend on the gather comes first: the load is the last thing that
-  // writes l, so nothing waits for it until the label is used
-  int l = out ? -1 : (int)st;
-  if (st == 3u && !out) l = (int)__ldg(m.brick + cc);
+  l = out ? -1 : l;
+  if (need && !out) l = (int)__ldg(m.brick + cc);
   return l;
 }
 
 // XY: both output planes are present (the product path), so the stores need no pointer tests;
-// COARSE: the 2-bit block map is present (it fits in shared memory)
-template <int SRC, bool FAST, bool XY, bool COARSE, int DEEP = 8, int MINB = 4>
-__global__ void __launch_bounds__(kHopThreads, MINB)
+// MAP: which block map sits in shared memory.
+// Work items are (warp of 32 consecutive atoms, chunk), numbered chunk-major and dealt to the warps
+// of the grid in order, so the CTA size (256 with a small block map, up to 1024 with a large one: one
+// copy of the map per CTA) does not change which items exist.
+template <int SRC, bool FAST, bool XY, int MAP, bool PIPE = false, int DEEP = 8>
+__global__ void __launch_bounds__(1024, 1)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
-               const uint32_t* __restrict__ coarse, int coarse_words, float* __restrict__ hop_x,
-               float* __restrict__ hop_y, int64_t chunk_len, int32_t* __restrict__ summaries, EventSink sink) {
+               const uint32_t* __restrict__ blockmap, int map_words, int fine_value, float* __restrict__ hop_x,
+               float* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
+               EventSink sink) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
   float* s_tab = reinterpret_cast<float*>(s_pairs + (SRC == 0 ? tab.table2_len : 0));
-  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_tab + ((SRC == 0 && !FAST) ? tab.table_len : 0));
+  uint32_t* s_map = reinterpret_cast<uint32_t*>(s_tab + ((SRC == 0 && !FAST) ? tab.table_len : 0));
   if (SRC == 0) {
     for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
     if (!FAST)
       for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
   }
-  if (SRC != 1 && COARSE)
-    for (int i = threadIdx.x; i < coarse_words; i += blockDim.x) s_coarse[i] = coarse[i];
+  if (SRC != 1 && MAP != MAP_GATHER)
+    for (int i = threadIdx.x; i < map_words; i += blockDim.x) s_map[i] = blockmap[i];
   if (SRC != 1) __syncthreads();
   const AxisReg ax = load_axis(tab.ax[0], s_pairs);
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
   MapView mv;
-  mv.brick = brick; mv.s_coarse = (SRC != 1 && COARSE) ? s_coarse : nullptr;
+  mv.brick = brick; mv.s_map = (SRC != 1 && MAP != MAP_GATHER) ? s_map : nullptr; mv.fine_value = fine_value;
   const int cny = (tab.ax[1].n + 3) >> 2, cnz = (tab.ax[2].n + 3) >> 2;
 
-  const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int chunk = blockIdx.y;
-  if (atom >= N) return;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t atom_warps = (N + 31) >> 5;
+  const int chunk = (int)(item / atom_warps);
+  const int64_t atom = (item - (int64_t)chunk * atom_warps) * 32 + (threadIdx.x & 31);
+  if (chunk >= n_chunks || atom >= N) return;
   const int64_t f_begin = (int64_t)chunk * chunk_len;
   int64_t f_end = f_begin + chunk_len;
   if (f_end > F) f_end = F;
@@ -181,7 +199,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     } else {
       c = __ldg(cells + fr * N + atom);
     }
-    return label_of<COARSE>(c, mv);
+    return label_of<MAP>(c, mv);
   };
 
   // ---- prologue: the generic summary machine until a first real site has been seen -------------
@@ -252,15 +270,46 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         }
         int lab[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) lab[u] = label_of<COARSE>(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
+        for (int u = 0; u < kUnroll; ++u) lab[u] = label_of<MAP>(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
         block(lab, std::integral_constant<int, kUnroll>(), (int)(frame0 + f));
       }
     } else {
+      constexpr int kDeep = DEEP;
+      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
+      if (PIPE) {
+      // 4-byte inputs (brick indices or labels) in blocks of kDeep frames, two blocks ahead: while
+      // the state machine consumes the labels of block b, the site-map gathers of block b+1 and the
+      // input loads of block b+2 are in flight
+      if (f + kDeep <= f_end) {
+        uint32_t v[kDeep];
+        int nxt[kDeep];
+        auto load = [&]() {
+#pragma unroll
+          for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
+          src += (uint64_t)Nu * kDeep;
+        };
+        auto resolve = [&]() {
+#pragma unroll
+          for (int u = 0; u < kDeep; ++u) nxt[u] = SRC == 2 ? label_of<MAP>(v[u], mv) : (int)__uint_as_float(v[u]);
+        };
+        load();
+        resolve();
+        if (f + 2 * kDeep <= f_end) load();
+        for (; f + kDeep <= f_end; f += kDeep) {
+          int lab[kDeep];
+#pragma unroll
+          for (int u = 0; u < kDeep; ++u) lab[u] = nxt[u];
+          if (f + 2 * kDeep <= f_end) {
+            resolve();
+            if (f + 3 * kDeep <= f_end) load();
+          }
+          block(lab, std::integral_constant<int, kDeep>(), (int)(frame0 + f));
+        }
+      }
+      } else {
       // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
       // block are resolved its input registers are reloaded with the next block, so those loads are
       // in flight while the state machine consumes the current labels
-      constexpr int kDeep = DEEP;
-      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
       uint32_t v[kDeep];
       if (f + kDeep <= f_end) {
 #pragma unroll
@@ -269,7 +318,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         for (; f + kDeep <= f_end; f += kDeep) {
           int lab[kDeep];
 #pragma unroll
-          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of<COARSE>(v[u], mv) : (int)__uint_as_float(v[u]);
+          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of<MAP>(v[u], mv) : (int)__uint_as_float(v[u]);
           if (f + 2 * kDeep <= f_end) {
 #pragma unroll
             for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
@@ -277,6 +326,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
           }
           block(lab, std::integral_constant<int, kDeep>(), (int)(frame0 + f));
         }
+      }
       }
     }
     for (; f < f_end; ++f) step(label_at(f), (int)(frame0 + f));
@@ -287,12 +337,14 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   hopb_summary_store(summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom, N, T);
 }
 
-// Bricked copy of the site map + the 2-bit block map: one thread per brick reads its (up to) 64
-// cells from the C-ordered int16 map, writes them as one 128-byte line and classifies the brick:
-// 0 / 1 = every cell interstitial / bulk, 3 = mixed.  16 bricks per 32-bit word.
+// Bricked copy of the site map + its block maps: one thread per 4x4x4 brick reads its (up to) 64
+// cells from the C-ordered int16 map, writes them as one 128-byte line (sub-brick order, see
+// hopb_brick_index) and classifies the brick -- coarse: 0 / 1 = every cell interstitial / bulk,
+// 3 = mixed, 16 bricks per 32-bit word; fine: one bit per 2x2x2 sub-brick, set when all of its cells
+// carry fine_value, one byte per brick.  Cells beyond the grid are never looked up and do not count.
 __global__ void __launch_bounds__(256)
 brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
-                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse) {
+                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse, uint8_t* __restrict__ fine, int fine_value) {
   const int64_t n_blocks = (int64_t)cnx * cny * cnz;
   const int64_t n_round = (n_blocks + 31) / 32 * 32;
   const int lane = threadIdx.x & 31;
@@ -305,6 +357,7 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
       const int ci = (int)(r / cny);
       int first = -2;
       bool uniform = true;
+      uint32_t spoiled = 0;  // bit s: sub-brick s has a cell that is not fine_value
       int16_t* out = brick + b * 64;
       for (int di = 0; di < 4; ++di) {
         const int i = ci * 4 + di;
@@ -321,13 +374,18 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
               v = row[k];
               if (first == -2) first = v;
               else if (v != first) uniform = false;
+              if (v != fine_value) spoiled |= 1u << (((di & 2) << 1) | (dj & 2) | (dk >> 1));
             }
             v4[dk] = v;
           }
-          *reinterpret_cast<short4*>(out + ((di << 4) | (dj << 2))) = make_short4(v4[0], v4[1], v4[2], v4[3]);
+          // (di, dj) fixes i1 j1 . i0 j0 .; dk = 0,1 and dk = 2,3 are two runs of two cells 8 apart
+          int16_t* o = out + (((di & 2) << 4) | ((dj & 2) << 3) | ((di & 1) << 2) | ((dj & 1) << 1));
+          *reinterpret_cast<short2*>(o) = make_short2(v4[0], v4[1]);
+          *reinterpret_cast<short2*>(o + 8) = make_short2(v4[2], v4[3]);
         }
       }
       st = (uniform && (first == 0 || first == 1)) ? (uint32_t)first : 3u;
+      if (fine) fine[b] = (uint8_t)(~spoiled & 0xFFu);
     }
     uint32_t w = st << ((lane & 15) * 2);
 #pragma unroll
@@ -419,8 +477,9 @@ extern "C" {
 
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
                           const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t frame0,
-                          const int16_t* map16, const uint32_t* coarse, float* hop_x, float* hop_y, int n_chunks,
-                          int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
+                          const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value, float* hop_x,
+                          float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events,
+                          uint64_t* n_events, uint64_t cap) {
   HOPB_REQUIRE(h, F > 0 && N > 0 && summaries && n_events, "bad argument");
   HOPB_REQUIRE(h, n_chunks >= 1 && chunk_len >= 1 && (int64_t)n_chunks * chunk_len >= F &&
                       (int64_t)(n_chunks - 1) * chunk_len < F, "chunks must tile the slab exactly");
@@ -429,81 +488,100 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
   cudaStream_t s = (cudaStream_t)stream;
+  const int64_t items = ((N + 31) / 32) * n_chunks;  // (warp of atoms, chunk)
   if (src == 1) {
     HOPB_REQUIRE(h, labels_in, "null argument");
     HopbGridTab tab;
     memset(&tab, 0, sizeof(tab));
-    dim3 grid((unsigned)((N + kHopThreads - 1) / kHopThreads), (unsigned)n_chunks);
+    const unsigned grid = (unsigned)((items + kHopThreads / 32 - 1) / (kHopThreads / 32));
     hopb_note_launch();
     if (hop_x && hop_y)
-      hoptraj_kernel<1, true, true, false><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
-                                                              nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
+      hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
+          nullptr, nullptr, nullptr, nullptr, 0, 0, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     else
-      hoptraj_kernel<1, true, false, false><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab, nullptr, nullptr,
-                                                               nullptr, nullptr, 0, hop_x, hop_y, chunk_len, summaries, sink);
+      hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
+          nullptr, nullptr, nullptr, nullptr, 0, 0, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
   HOPB_REQUIRE(h, g && map16 && (src == 0 ? xyz != nullptr : cells != nullptr), "null argument");
+  HOPB_REQUIRE(h, fine_value == 0 || fine_value == 1, "fine_value must be 0 or 1");
   const bool fast = g->tab.fast_ok != 0;
-  int coarse_words = 0;
-  if (coarse) {
-    const int64_t nb = (int64_t)((g->n[0] + 3) / 4) * ((g->n[1] + 3) / 4) * ((g->n[2] + 3) / 4);
-    coarse_words = (int)((nb + 15) / 16);
-  }
-  size_t smem = (size_t)coarse_words * 4;
+  const int64_t nb = (int64_t)((g->n[0] + 3) / 4) * ((g->n[1] + 3) / 4) * ((g->n[2] + 3) / 4);
+  size_t smem = 0;
   if (src == 0) smem += (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
-  // threads per CTA: big coarse maps are shared by more threads so that an SM still holds >= 1024
-  const int threads = kHopThreads;
-  HOPB_REQUIRE(h, smem <= 110 * 1024, "block map too large for shared memory; pass coarse = NULL");
-  dim3 grid((unsigned)((N + threads - 1) / threads), (unsigned)n_chunks);
-#define HOPB_HT_LAUNCH_XY(SRC, FAST, XY, CO)                                                                          \
+  // Block map: the fine one when it fits beside the tables (one copy per CTA, so big maps mean big
+  // CTAs: an SM holds 1024 threads of this kernel either way), else the coarse one, else none.
+  const size_t kSmemSm = 220 * 1024;
+  int mode = MAP_GATHER, map_words = 0, threads = kHopThreads;
+  const uint32_t* blockmap = nullptr;
+  const size_t fine_bytes = (size_t)((nb * 8 + 31) / 32) * 4, coarse_bytes = (size_t)((nb + 15) / 16) * 4;
+  if (fine && smem + fine_bytes <= kSmemSm) {
+    mode = MAP_FINE; map_words = (int)(fine_bytes / 4); blockmap = reinterpret_cast<const uint32_t*>(fine);
+    smem += fine_bytes;
+  } else if (coarse && smem + coarse_bytes <= kSmemSm) {
+    mode = MAP_COARSE; map_words = (int)(coarse_bytes / 4); blockmap = coarse;
+    smem += coarse_bytes;
+  }
+  const size_t per_cta = smem + 1024;  // + the driver's reservation
+  threads = per_cta * 4 <= 227 * 1024 ? 256 : (per_cta * 2 <= 227 * 1024 ? 512 : 1024);
+  const unsigned grid = (unsigned)((items + threads / 32 - 1) / (threads / 32));
+  static const bool pipe = getenv("HOPB_K3_PIPE") && atoi(getenv("HOPB_K3_PIPE")) != 0;  // experiment hook
+#define HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, PIPE)                                                                        \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST, XY, CO><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
-                                                             g->d_table2, map16, coarse, coarse_words, hop_x, hop_y,  \
-                                                             chunk_len, summaries, sink);                            \
+    hoptraj_kernel<SRC, FAST, XY, MAP, PIPE><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
+        g->d_table2, map16, blockmap, map_words, fine_value, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);     \
+  } while (0)
+#define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP)                                                                         \
+  do {                                                                                                               \
+    if (SRC == 2 && pipe) HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, (SRC == 2)); else HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, false); \
+  } while (0)
+#define HOPB_HT_LAUNCH_XY(SRC, FAST, XY)                                                                             \
+  do {                                                                                                               \
+    if (mode == MAP_FINE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_FINE);                                                 \
+    else if (mode == MAP_COARSE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_COARSE);                                        \
+    else HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_GATHER);                                                                \
   } while (0)
 #define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
   do {                                                                                                               \
-    if (hop_x && hop_y) {                                                                                            \
-      if (coarse) HOPB_HT_LAUNCH_XY(SRC, FAST, true, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, true, false);          \
-    } else {                                                                                                         \
-      if (coarse) HOPB_HT_LAUNCH_XY(SRC, FAST, false, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, false, false);        \
-    }                                                                                                                \
+    if (hop_x && hop_y) HOPB_HT_LAUNCH_XY(SRC, FAST, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, false);                \
   } while (0)
   if (src == 0) { if (fast) HOPB_HT_LAUNCH(0, true); else HOPB_HT_LAUNCH(0, false); }
   else HOPB_HT_LAUNCH(2, true);
-#undef HOPB_HT_LAUNCH_XY
 #undef HOPB_HT_LAUNCH
+#undef HOPB_HT_LAUNCH_XY
+#undef HOPB_HT_LAUNCH_M
+#undef HOPB_HT_LAUNCH_P
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
 
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
-                 int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, float* hop_x, float* hop_y,
-                 int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events,
-                 uint64_t cap) {
-  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, frame0, map16, coarse, hop_x, hop_y,
-                        n_chunks, chunk_len, summaries, events, n_events, cap);
+                 int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
+                 int fine_value, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
+                 hopb_event* events, uint64_t* n_events, uint64_t cap) {
+  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, frame0, map16, coarse, fine, fine_value,
+                        hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N, int64_t frame0, int n_chunks,
                         int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
-  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, frame0, nullptr, nullptr, nullptr, nullptr,
-                        n_chunks, chunk_len, summaries, events, n_events, cap);
+  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, frame0, nullptr, nullptr, nullptr, 0, nullptr,
+                        nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse) {
+                   uint32_t* coarse, uint8_t* fine, int fine_value) {
   HOPB_REQUIRE(h, map16 && brick && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
+  HOPB_REQUIRE(h, fine_value == 0 || fine_value == 1, "fine_value must be 0 or 1");
   const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
   const int64_t nb = (int64_t)cnx * cny * cnz;
   HOPB_REQUIRE(h, nb * 64 < ((int64_t)1 << 32) - 1, "grid too large for brick indices");
-  HOPB_K(brick_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(map16, nx, ny, nz, cnx, cny,
-                                                                                                 cnz, brick, coarse);
+  HOPB_K(brick_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+      map16, nx, ny, nz, cnx, cny, cnz, brick, coarse, fine, fine_value);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

@@ -123,9 +123,23 @@ def brick_shape(shape):
     return nb, -(-nb // 16)
 
 
-def brick_map(map16: torch.Tensor, brick=None, coarse=None):
-    """Site map in 4x4x4 brick order (what the hoptraj kernel gathers from) and its 2-bit block map
-    (which lets the kernel skip the gather in uniformly bulk / interstitial regions)."""
+class BrickMap(object):
+    """The site map as stage 3 reads it: `brick` (int16, 4x4x4 brick order), `coarse` (2 bits per
+    brick), `fine` (1 bit per 2x2x2 sub-brick: all cells carry `fine_value`).  Unpacks as
+    (brick, coarse)."""
+
+    def __init__(self, brick, coarse, fine, fine_value):
+        self.brick, self.coarse, self.fine, self.fine_value = brick, coarse, fine, int(fine_value)
+
+    def __iter__(self):
+        return iter((self.brick, self.coarse))
+
+
+def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None, fine_value=1):
+    """Site map in 4x4x4 brick order (what the hoptraj kernel gathers from) and its block maps, which
+    let the kernel skip the gather where a whole (sub-)brick carries one label: `coarse`, 2 bits per
+    brick (uniformly interstitial / bulk / mixed), and `fine`, 1 bit per 2x2x2 sub-brick (uniformly
+    `fine_value`: 1 when the map has a bulk site, else 0)."""
     _cuda(map16, torch.int16, "map16")
     nx, ny, nz = map16.shape
     nb, words = brick_shape(map16.shape)
@@ -133,9 +147,12 @@ def brick_map(map16: torch.Tensor, brick=None, coarse=None):
         brick = torch.empty(nb * 64, dtype=torch.int16, device=map16.device)
     if coarse is None:
         coarse = torch.empty(words, dtype=torch.int32, device=map16.device)
+    if fine is None:
+        fine = torch.zeros((nb + 3) // 4 * 4, dtype=torch.uint8, device=map16.device)
     h = _h(map16)
-    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse)))
-    return brick, coarse
+    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse), _p(fine),
+                                            int(fine_value)))
+    return BrickMap(brick, coarse, fine, fine_value)
 
 
 def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
@@ -245,20 +262,22 @@ def site_cells(own: torch.Tensor, member, n_labels: int):
     return cells[: n_cells.value], offsets
 
 
-def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32, cta_threads: int = 256,
-                ctas_per_sm: int = 4, max_waves: int = 4):
-    """(n_chunks, chunk_len) for the fused hoptraj kernel: one thread per (atom, chunk).
+def plan_chunks(n_frames: int, n_atoms: int, num_sms: int = 148, min_chunk: int = 32, warps_per_sm: int = 32,
+                max_waves: int = 4):
+    """(n_chunks, chunk_len) for the fused hoptraj kernel: one thread per (atom, chunk), dealt out as
+    work items of (32 consecutive atoms, chunk) to the warps of the grid.
 
-    The kernel is latency-bound per thread, so the grid should be a whole number of waves of
-    resident CTAs (num_sms * ctas_per_sm): pick the chunk count with the best wave efficiency,
-    preferring fewer chunks (less stitching) when efficiencies are within 2 %."""
-    ctas_per_chunk = -(-n_atoms // cta_threads)
-    capacity = num_sms * ctas_per_sm
-    max_chunks = max(1, min(n_frames // min_chunk, 65535, (max_waves * capacity) // max(ctas_per_chunk, 1)))
+    The kernel is latency-bound per thread, so the items should fill a whole number of waves of
+    resident warps (num_sms * warps_per_sm; the kernel holds 1024 threads per SM): pick the chunk
+    count with the best wave efficiency, preferring fewer chunks (less stitching) when efficiencies
+    are within 2 %."""
+    items_per_chunk = -(-n_atoms // 32)
+    capacity = num_sms * warps_per_sm
+    max_chunks = max(1, min(n_frames // min_chunk, 65535, (max_waves * capacity) // max(items_per_chunk, 1)))
     best, best_eff = 1, 0.0
     for c in range(1, max_chunks + 1):
-        ctas = c * ctas_per_chunk
-        eff = ctas / (-(-ctas // capacity) * capacity)
+        items = c * items_per_chunk
+        eff = items / (-(-items // capacity) * capacity)
         if eff > best_eff + 0.02:
             best, best_eff = c, eff
     chunk_len = -(-n_frames // best)
@@ -281,11 +300,19 @@ class EventBuffer:
         return int(self.count.item())
 
 
-def hoptraj(grid: GridTables, xyz, brick: torch.Tensor, frame0: int, n_chunks: int, chunk_len: int,
-            events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None):
+def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len: int,
+            events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None, fine=None,
+            fine_value=1, block_map="auto"):
     """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254).
     Input is either `xyz` (float32 [F][N][3]) or the brick indices `cells` (int32 [F][N]) from
-    hist_accumulate; `brick` / `coarse` come from brick_map(Density.map)."""
+    hist_accumulate.  `brick` is the BrickMap of brick_map(Density.map) -- block_map = "auto" (the
+    fine block map when it fits into shared memory, else the coarse one), "fine", "coarse" or "none"
+    -- or the bricked int16 tensor with `coarse` / `fine` given separately."""
+    if isinstance(brick, BrickMap):
+        bm = brick
+        brick, fine_value = bm.brick, bm.fine_value
+        coarse = bm.coarse if block_map in ("auto", "coarse") else None
+        fine = bm.fine if block_map in ("auto", "fine") else None
     _cuda(brick, torch.int16, "brick")
     map16 = brick
     if cells is not None:
@@ -296,16 +323,22 @@ def hoptraj(grid: GridTables, xyz, brick: torch.Tensor, frame0: int, n_chunks: i
         _cuda(xyz, torch.float32, "xyz")
         F, N = xyz.shape[0], xyz.shape[1]
         dev = xyz.device
-    if map16.numel() != brick_shape(grid.shape)[0] * 64:
+    nb = brick_shape(grid.shape)[0]
+    if map16.numel() != nb * 64:
         raise ValueError("bricked map does not match the grid (use kernels.brick_map)")
     if coarse is not None:
         _cuda(coarse, torch.int32, "coarse")
+    if fine is not None:
+        _cuda(fine, torch.uint8, "fine")
+        if fine.numel() != (nb + 3) // 4 * 4:
+            raise ValueError("fine block map does not match the grid (use kernels.brick_map)")
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
     h = _h(map16)
     rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N,
-                                 int(frame0), _p(map16), _p(coarse), _p(hop_x), _p(hop_y), int(n_chunks),
-                                 int(chunk_len), _p(summaries), _p(events.data), _p(events.count), events.capacity)
+                                 int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(hop_x), _p(hop_y),
+                                 int(n_chunks), int(chunk_len), _p(summaries), _p(events.data), _p(events.count),
+                                 events.capacity)
     _lib.check(h, rc)
     return summaries
 

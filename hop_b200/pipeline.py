@@ -37,7 +37,8 @@ class PipelineConfig:
     n_chunks: int | None = None
     event_capacity: int | None = None
     cache_cells: bool | None = None  # stage 1 also writes the packed hoptraj cell per atom-frame (4 B)
-    coarse_map: bool = True          # 2-bit block map in shared memory for stage 3
+    coarse_map: bool = True          # block map in shared memory for stage 3 (False: always gather)
+    block_map: str = "auto"          # "auto" (fine when it fits, else coarse), "fine", "coarse", "none"
 
 
 @dataclass
@@ -160,8 +161,9 @@ class HopPipeline:
                 props = K.site_properties(self.grid, density, own, member, L, out=out)
             self._props_done = torch.cuda.Event()
             self._props_done.record(side)
-        self.brick, coarse = K.brick_map(map16, brick_buf, coarse_buf)
-        self.coarse = coarse if (cfg.coarse_map and words * 4 <= 100 * 1024) else None
+        fine_buf = self._buf("fine", ((nb + 3) // 4 * 4,), torch.uint8)
+        # most atoms sit in the bulk site when there is one, else in the interstitial
+        self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf, fine_value=1 if cfg.with_bulk else 0)
         return density, own, member, map16, props
 
     def sync_scalars(self, events):
@@ -204,7 +206,7 @@ class HopPipeline:
             hop_y = self._buf("hop_y", (F, N), torch.float32)
         summaries = self._buf("summaries", (n_chunks, K.SUMMARY_INTS, N), torch.int32)
         K.hoptraj(self.grid, xyz, self.brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries,
-                  cells=getattr(self, "cells", None), coarse=self.coarse)
+                  cells=getattr(self, "cells", None), block_map=cfg.block_map if cfg.coarse_map else "none")
 
         # state at slab entry: replay the slabs of the ranks before this one
         state = self._buf("state", (K.STATE_INTS, N), torch.int32)

@@ -160,9 +160,7 @@ class HoppingTrajectory(object):
             self._map16 = self._GD._device_map()
             if self._map16.numel() != self._tables.n_cells:
                 raise ValueError("The density object must have its site map computed.")
-            self._brick, self._coarse = K.brick_map(self._map16)
-            if self._coarse.numel() * 4 > 100 * 1024:
-                self._coarse = None
+            self._brick = K.brick_map(self._map16, fine_value=1 if self._GD.has_bulk() else 0)
 
     @staticmethod
     def _slice_blocks(blocks, start, stop):
@@ -225,7 +223,7 @@ class HoppingTrajectory(object):
             hop_y = t.empty((F, N), dtype=t.float32, device=src.device)
         n_chunks, chunk_len = K.plan_chunks(F, N)
         s = K.hoptraj(self._tables, xyz_dev, self._brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y,
-                      cells=None if cells_dev is None else cells_dev.contiguous(), coarse=self._coarse)
+                      cells=None if cells_dev is None else cells_dev.contiguous())
         K.hop_fixup(s, chunk_len, F, state, hop_y, events)
         return hop_x, hop_y
 

@@ -176,25 +176,34 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  *             hopb_hist_accumulate_cells -- the coordinates are then not read again
  *   brick     device int16: the site map (Density.map) in brick order, from hopb_brick_map
  *   coarse    device uint32 (may be NULL): the 2-bit block map of hopb_brick_map; it lets atoms in
- *             uniformly bulk / interstitial bricks skip the gather from the site map
+ *             uniformly bulk / interstitial 4x4x4 bricks skip the gather from the site map
+ *   fine      device uint8 (may be NULL): the 1-bit block map of hopb_brick_map over 2x2x2 sub-bricks
+ *             (padded to a multiple of 4 bytes), with the fine_value it was built for.  Used instead
+ *             of `coarse` whenever it fits into shared memory (grids up to ~230^3 cells): far fewer
+ *             atoms then need the gather.
  *   frame0    global frame number of the slab's first frame
  *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
  *             DCD, trajectory.py:456-463); either may be NULL
  *   summaries device int32 [n_chunks][11][N] out
  *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here) */
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
-                 int64_t F, int64_t N, int64_t frame0, const int16_t* brick, const uint32_t* coarse, float* hop_x,
-                 float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events,
-                 uint64_t* n_events, uint64_t cap);
+                 int64_t F, int64_t N, int64_t frame0, const int16_t* brick, const uint32_t* coarse,
+                 const uint8_t* fine, int fine_value, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
+                 int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
 
-/* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block map.  A brick is a
+/* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block maps.  A brick is a
  * 4x4x4 block of cells stored as 64 consecutive int16 (one 128-byte line), bricks in C order over
- * (ceil(nx/4), ceil(ny/4), ceil(nz/4)); cell (i,j,k) lives at brick*64 + ((i&3)<<4 | (j&3)<<2 | (k&3)).
+ * (ceil(nx/4), ceil(ny/4), ceil(nz/4)); inside a brick the cells are ordered by 2x2x2 sub-brick:
+ * cell (i,j,k) lives at brick*64 + (i1<<5 | j1<<4 | k1<<3 | i0<<2 | j0<<1 | k0) with i1 = (i>>1)&1,
+ * i0 = i&1, ...
  *   brick   device int16  [n_bricks*64] out (cells outside the grid are 0)
  *   coarse  device uint32 [ceil(n_bricks/16)] out: 2 bits per brick, 0 / 1 = all interstitial / all
- *           bulk, 3 = mixed */
+ *           bulk, 3 = mixed
+ *   fine    device uint8  [n_bricks rounded up to a multiple of 4] out, may be NULL: bit s of byte b
+ *           is set when all cells of sub-brick s = (i1<<2 | j1<<1 | k1) of brick b carry the label
+ *           fine_value (0 = interstitial or 1 = bulk: whichever most atoms sit in) */
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse);
+                   uint32_t* coarse, uint8_t* fine, int fine_value);
 
 /* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
  * hop/graph.py:190-254): labels = hop_x [F][N] float32. */

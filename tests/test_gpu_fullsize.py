@@ -93,14 +93,14 @@ def test_result_does_not_depend_on_chunking_or_input_path(full):
     K, pipe, xyz, edges, res, _ = full
     ref_x, ref_y = res.hop_x, res.hop_y
     ref_ev = K.events_to_numpy(res.events)
-    for n_chunks, use_cells in [(1, True), (7, False), (23, True)]:
+    for n_chunks, use_cells, block_map in [(1, True, "coarse"), (7, False, "none"), (23, True, "fine"), (5, False, "fine")]:
         ev = K.EventBuffer(max(len(ref_ev) + 16, 1 << 20), "cuda")
         X = torch.empty_like(ref_x)
         Y = torch.empty_like(ref_y)
         chunk_len = -(-FRAMES // n_chunks)
         nc = -(-FRAMES // chunk_len)
         s = K.hoptraj(pipe.grid, xyz, pipe.brick, 0, nc, chunk_len, ev, X, Y,
-                      cells=pipe.cells if use_cells else None, coarse=pipe.coarse if n_chunks != 7 else None)
+                      cells=pipe.cells if use_cells else None, block_map=block_map)
         st = K.new_state(ATOMS, "cuda")
         K.hop_advance(None, st, init=True)
         K.hop_fixup(s, chunk_len, FRAMES, st, Y, ev)

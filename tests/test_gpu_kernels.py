@@ -79,11 +79,11 @@ def test_histogram_slabbed_passes(K, traj):
             # the cached cells still drive the hopping trajectory correctly
             res = O.pipeline(xyz, delta=0.5)
             m16 = dev(res["map"])
-            brick, coarse = K.brick_map(m16)
+            brick = K.brick_map(m16)
             ev = K.EventBuffer(xyz.shape[0] * xyz.shape[1], "cuda")
             X = torch.empty(xyz.shape[:2], dtype=torch.float32, device="cuda")
             Y = torch.empty(xyz.shape[:2], dtype=torch.float32, device="cuda")
-            s = K.hoptraj(g, None, brick, 0, 2, 25, ev, X, Y, cells=cells, coarse=coarse)
+            s = K.hoptraj(g, None, brick, 0, 2, 25, ev, X, Y, cells=cells)
             st = K.new_state(xyz.shape[1], "cuda")
             K.hop_advance(None, st, init=True)
             K.hop_fixup(s, 25, 50, st, Y, ev)
@@ -219,13 +219,13 @@ def _hop_reference(xyz, edges, site_map):
 
 def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
     """Single process, optionally emulating `slabs` ranks sequentially (same kernels, same exchange).
-    mode: "xyz" | "cells" (packed cells written by the histogram kernel), "+coarse" adds the block map."""
+    mode: "xyz" | "cells" (packed cells written by the histogram kernel), "+coarse" / "+fine" add a block map."""
     F, N = xyz.shape[:2]
     g = K.GridTables(edges)
     m16 = dev(site_map.astype(np.int16))
-    brick, coarse = K.brick_map(m16)
-    if "coarse" not in mode:
-        coarse = None
+    # the fine block map is built for the label most cells of this map carry
+    bm = K.brick_map(m16, fine_value=1 if (site_map == 1).sum() > (site_map == 0).sum() else 0)
+    block_map = "coarse" if "coarse" in mode else ("fine" if "fine" in mode else "none")
     cells_all = None
     if mode.startswith("cells"):
         cells_all = torch.empty((F, N), dtype=torch.int32, device="cuda")
@@ -236,7 +236,8 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
         ok = np.all((b >= 0) & (b < shp), axis=1)
         cn = -(-shp // 4)
         cb = ((b[:, 0] >> 2) * cn[1] + (b[:, 1] >> 2)) * cn[2] + (b[:, 2] >> 2)
-        packed = np.where(ok, (cb << 6) | ((b[:, 0] & 3) << 4) | ((b[:, 1] & 3) << 2) | (b[:, 2] & 3), 0xFFFFFFFF).astype(np.uint32)
+        low = ((b[:, 0] & 2) << 4) | ((b[:, 1] & 2) << 3) | ((b[:, 2] & 2) << 2) | ((b[:, 0] & 1) << 2) | ((b[:, 1] & 1) << 1) | (b[:, 2] & 1)
+        packed = np.where(ok, (cb << 6) | low, 0xFFFFFFFF).astype(np.uint32)
         assert np.array_equal(cells_all.cpu().numpy().view(np.uint32).ravel(), packed)
     events = K.EventBuffer(F * N + 16, "cuda")
     bounds = np.linspace(0, F, slabs + 1).astype(int)
@@ -247,8 +248,8 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
         a, b = bounds[r], bounds[r + 1]
         chunk_len = -(-(b - a) // n_chunks)
         nc = -(-(b - a) // chunk_len)
-        s = K.hoptraj(g, dev(xyz[a:b]), brick, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
-                      cells=None if cells_all is None else cells_all[a:b], coarse=coarse)
+        s = K.hoptraj(g, dev(xyz[a:b]), bm, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
+                      cells=None if cells_all is None else cells_all[a:b], block_map=block_map)
         summaries.append(s)
         lens.append(chunk_len)
         slab_sums.append(K.hop_combine(s, chunk_len, b - a))
@@ -267,7 +268,8 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
 
 
 @pytest.mark.parametrize("n_chunks,slabs,mode", [(1, 1, "xyz"), (4, 1, "xyz+coarse"), (13, 1, "cells"), (200, 1, "cells+coarse"),
-                                                 (3, 2, "cells+coarse"), (5, 8, "xyz+coarse")])
+                                                 (3, 2, "cells+coarse"), (5, 8, "xyz+coarse"), (1, 1, "xyz+fine"),
+                                                 (9, 1, "cells+fine"), (4, 3, "cells+fine")])
 def test_hoptraj_and_transitions(K, traj, n_chunks, slabs, mode):
     p, xyz = traj
     res = O.pipeline(xyz, delta=1.0)
@@ -307,7 +309,8 @@ def test_hoptraj_outliers_and_top_edge(K, traj):
             xyz[5 + k, 100 + 10 * d: 110 + 10 * d, d] = v
     hop, ev_ref, nodes_ref = _hop_reference(xyz, edges, site_map)
     assert (hop[:, :, 0] == -1).any() and (ev_ref[:, 2] == -1).any()
-    for n_chunks, slabs, mode in [(1, 1, "xyz"), (7, 1, "cells+coarse"), (2, 3, "xyz+coarse"), (3, 1, "cells")]:
+    for n_chunks, slabs, mode in [(1, 1, "xyz"), (7, 1, "cells+coarse"), (2, 3, "xyz+coarse"), (3, 1, "cells"), (5, 1, "cells+fine"),
+                                  (2, 2, "xyz+fine")]:
         X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs, mode)
         assert np.array_equal(X, hop[:, :, 0])
         assert np.array_equal(Y, hop[:, :, 1])
@@ -327,19 +330,28 @@ def test_coarse_map_blocks(K):
         m[:4, :4, :4] = 0
         if shape[0] > 8:
             m[8, 5, 2] = 7
-        brick, c = K.brick_map(dev(m))
-        c = c.cpu().numpy().view(np.uint32)
-        brick = brick.cpu().numpy()
-        cn = [-(-n // 4) for n in shape]
-        ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
-        idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | ((ii & 3) << 4) | ((jj & 3) << 2) | (kk & 3)
-        assert np.array_equal(brick[idx], m)
-        for b in range(cn[0] * cn[1] * cn[2]):
-            ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
-            blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
-            u = np.unique(blk)
-            want = int(u[0]) if len(u) == 1 and u[0] in (0, 1) else 3
-            assert (c[b >> 4] >> ((b & 15) * 2)) & 3 == want
+        for fine_value in (1, 0):
+            bm = K.brick_map(dev(m), fine_value=fine_value)
+            brick, c = bm
+            c = c.cpu().numpy().view(np.uint32)
+            fine = bm.fine.cpu().numpy()
+            brick = brick.cpu().numpy()
+            cn = [-(-n // 4) for n in shape]
+            ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+            # 4x4x4 bricks, cells inside a brick ordered by 2x2x2 sub-brick: (i1 j1 k1 i0 j0 k0)
+            low = ((ii & 2) << 4) | ((jj & 2) << 3) | ((kk & 2) << 2) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1)
+            idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | low
+            assert np.array_equal(brick[idx], m)
+            for b in range(cn[0] * cn[1] * cn[2]):
+                ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
+                blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
+                u = np.unique(blk)
+                want = int(u[0]) if len(u) == 1 and u[0] in (0, 1) else 3
+                assert (c[b >> 4] >> ((b & 15) * 2)) & 3 == want
+                for sub in range(8):
+                    i1, j1, k1 = sub >> 2, (sub >> 1) & 1, sub & 1
+                    sb = blk[i1 * 2:i1 * 2 + 2, j1 * 2:j1 * 2 + 2, k1 * 2:k1 * 2 + 2]
+                    assert (fine[b] >> sub) & 1 == int((sb == fine_value).all()), (shape, b, sub)
 
 
 def test_half_angstrom_golden_through_all_paths(K):
@@ -349,7 +361,7 @@ def test_half_angstrom_golden_through_all_paths(K):
     xyz = g["xyz"]
     edges = [g["edges_x"], g["edges_y"], g["edges_z"]]
     ev_ref = g["events"].astype(np.int64)
-    for mode in ("xyz", "xyz+coarse", "cells", "cells+coarse"):
+    for mode in ("xyz", "xyz+coarse", "cells", "cells+coarse", "xyz+fine", "cells+fine"):
         X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, g["site_map"], 3, 1, mode)
         assert np.array_equal(X, g["hop_x"].astype(np.float32)) and np.array_equal(Y, g["hop_y"].astype(np.float32))
         ev = K.events_to_numpy(events.data[:n_ev])
@@ -408,7 +420,7 @@ def test_empty_and_degenerate_inputs(K):
     ev = K.EventBuffer(16, "cuda")
     X = torch.empty((1, 7), dtype=torch.float32, device="cuda")
     Y = torch.empty((1, 7), dtype=torch.float32, device="cuda")
-    s = K.hoptraj(g, far, brick, 0, 1, 1, ev, X, Y, coarse=coarse)
+    s = K.hoptraj(g, far, K.brick_map(m16), 0, 1, 1, ev, X, Y)
     st = K.new_state(7, "cuda")
     K.hop_advance(None, st, init=True)
     K.hop_fixup(s, 1, 1, st, Y, ev)

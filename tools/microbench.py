@@ -58,7 +58,7 @@ def main():
     cfg = PipelineConfig(n_chunks=args.chunks or None)
     if args.ctas:
         import functools
-        K.plan_chunks = functools.partial(K.plan_chunks, ctas_per_sm=args.ctas)
+        K.plan_chunks = functools.partial(K.plan_chunks, warps_per_sm=8 * args.ctas)
     pipe = HopPipeline(edges, args.frames, cfg)
     AF = args.atoms * args.frames
     rows = {}
