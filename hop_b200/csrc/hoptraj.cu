@@ -135,12 +135,13 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 // Work items are (warp of 32 consecutive atoms, chunk), numbered chunk-major and dealt to the warps
 // of the grid in order, so the CTA size (256 with a small block map, up to 1024 with a large one: one
 // copy of the map per CTA) does not change which items exist.
-template <int SRC, bool FAST, bool XY, int MAP, bool PIPE = false, int DEEP = 8>
+template <int SRC, bool FAST, bool XY, int MAP, int DEEP = 8>
 __global__ void __launch_bounds__(1024, 1)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
-               const uint32_t* __restrict__ blockmap, int map_words, int fine_value, float* __restrict__ hop_x,
+               const uint32_t* __restrict__ blockmap, int map_words, int fine_value, uint32_t fine_auto_min,
+               float* __restrict__ hop_x,
                float* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
                EventSink sink) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -151,6 +152,11 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
     if (!FAST)
       for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
+  }
+  if (SRC != 1 && MAP == MAP_FINE) {
+    // two maps (sub-brick uniformly 0 / uniformly 1) and the number of bulk cells behind them
+    if (fine_value < 0) fine_value = blockmap[2 * map_words] >= fine_auto_min ? 1 : 0;
+    blockmap += fine_value * map_words;
   }
   if (SRC != 1 && MAP != MAP_GATHER)
     for (int i = threadIdx.x; i < map_words; i += blockDim.x) s_map[i] = blockmap[i];
@@ -167,9 +173,9 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const int chunk = (int)(item / atom_warps);
   const int64_t atom = (item - (int64_t)chunk * atom_warps) * 32 + (threadIdx.x & 31);
   if (chunk >= n_chunks || atom >= N) return;
-  const int64_t f_begin = (int64_t)chunk * chunk_len;
-  int64_t f_end = f_begin + chunk_len;
-  if (f_end > F) f_end = F;
+  // frame numbers inside the slab fit 32 bits (checked by the launcher)
+  const int f_begin = (int)((int64_t)chunk * chunk_len);
+  const int f_end = (int)((int64_t)f_begin + chunk_len > F ? F : (int64_t)f_begin + chunk_len);
 
   HopbSummary T = hopb_summary_empty();
   int ypre = 0, yorb = 0;
@@ -178,8 +184,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
 
   // running pointers (one frame = N elements further)
-  float* px = hop_x ? hop_x + f_begin * N + atom : nullptr;
-  float* py = hop_y ? hop_y + f_begin * N + atom : nullptr;
+  float* px = hop_x ? hop_x + (int64_t)f_begin * N + atom : nullptr;
+  float* py = hop_y ? hop_y + (int64_t)f_begin * N + atom : nullptr;
   auto store = [&](int l) {
     if (XY) {
       *px = (float)l; px += N;
@@ -202,152 +208,185 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     return label_of<MAP>(c, mv);
   };
 
-  // ---- prologue: the generic summary machine until a first real site has been seen -------------
-  int64_t f = f_begin;
-  while (f < f_end && !(T.kind >= HOPB_SPEC && yknown)) {
-    const int l = label_at(f);
-    hopb_push_frame(T, l, (int)(frame0 + f), emit);
+  // Two regimes per (atom, chunk).  Until a first real site has been seen the generic summary
+  // machine of hopb_machine.h runs (kinds EMPTY / PRE / SPEC); from then on the state is "current
+  // site cur, on/off, last exit t1" in registers (regime A).  Frames go through in blocks: entering
+  // another site is the only rare event (~1e-3 per atom-frame), so when no label of a block is a site
+  // other than cur (A), or no label is a site at all and none has been seen yet (atoms that spend the
+  // whole chunk in the interstitial, e.g. ions), the block is a few selects and two stores per
+  // frame; otherwise it replays frame by frame.
+  bool inA = false;
+  int cur = 0, on = 1, t1 = 0;
+  auto stepA = [&](int l, int t) {
+    const bool same = l == cur, zero = l == 0;
+    if (l > 0 && !same) {
+      const int tx = on ? t : t1;
+      if (T.kind == HOPB_SPEC) {          // second site of the chunk: the open event E2
+        T.t1_2 = tx; T.A2 = l; T.f2 = t; T.kind = HOPB_FULL;
+      } else {
+        emit(cur, l, t, tx - T.t0, t - tx);
+      }
+      cur = l; T.t0 = t; on = 1; yorb = l;
+    } else {
+      t1 = (zero && on) ? t : t1;
+      on = same ? 1 : (zero ? 0 : on);   // l == -1 (outlier): nothing changes
+    }
+    store(l);
+  };
+  auto generic = [&](int l, int t) {
+    if (inA) { stepA(l, t); return; }
+    hopb_push_frame(T, l, t, emit);
     if (l > 0) { yorb = l; yknown = true; }
     if (!yknown) ++ypre;
     store(l);
-    ++f;
-  }
+    if (T.kind >= HOPB_SPEC && yknown) {
+      inA = true;
+      cur = T.kind == HOPB_SPEC ? T.A1 : T.s0;
+      on = T.on; t1 = T.t1;
+      // these four never change again: out of the registers now (the kernel sits at the 64-register
+      // limit of 1024 resident threads per SM)
+      int32_t* sp = summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom;
+      sp[1 * N] = T.z; sp[2 * N] = T.A1; sp[3 * N] = T.f1; sp[10 * N] = ypre;
+    }
+  };
+  const uint32_t Nu = (uint32_t)N;
+  // regime A, one block of K frames at global frame t; lab[] are its labels
+  auto blockA = [&](const int* lab, auto kc, int, int t) {
+    constexpr int K = decltype(kc)::value;
+    bool rare = false;
+#pragma unroll
+    for (int u = 0; u < K; ++u) rare |= (lab[u] > 0) & (lab[u] != cur);
+    if (!rare && XY) {
+      const float yf = (float)yorb;
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const int l = lab[u];
+        const bool same = l == cur, zero = l == 0;
+        t1 = (zero && on) ? t + u : t1;
+        on = same ? 1 : (zero ? 0 : on);
+        px[(uint64_t)Nu * (uint32_t)u] = (float)l;
+        py[(uint64_t)Nu * (uint32_t)u] = yf;
+      }
+      px += (uint64_t)Nu * K;
+      py += (uint64_t)Nu * K;
+    } else {
+#pragma unroll
+      for (int u = 0; u < K; ++u) stepA(lab[u], t + u);
+    }
+  };
+  // before regime A, one block of K frames starting at slab frame fb: quick when there is nothing
+  // but interstitial / outlier frames and no site has been seen so far (global frame 0 is special: an
+  // outlier there is the pseudo-site -1, hop/graph.py:206-208)
+  auto blockB = [&](const int* lab, auto kc, int fb, int t) {
+    constexpr int K = decltype(kc)::value;
+    bool quiet = (T.kind <= HOPB_PRE) & (t != 0);
+#pragma unroll
+    for (int u = 0; u < K; ++u) quiet &= lab[u] <= 0;
+    if (quiet && XY) {
+      const float yf = (float)yorb;
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const int l = lab[u];
+        const bool first0 = (l == 0) & (T.kind == HOPB_EMPTY);
+        T.z = first0 ? t + u : T.z;
+        T.kind = first0 ? (int)HOPB_PRE : T.kind;
+        px[(uint64_t)Nu * (uint32_t)u] = (float)l;
+        py[(uint64_t)Nu * (uint32_t)u] = yf;
+      }
+      ypre += K;
+      px += (uint64_t)Nu * K;
+      py += (uint64_t)Nu * K;
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < K; ++u) generic(label_at(fb + u), t + u);
+    }
+  };
+  // lanes of both kinds in one warp
+  auto blockU = [&](const int* lab, auto kc, int fb, int t) {
+    if (inA) blockA(lab, kc, fb, t); else blockB(lab, kc, fb, t);
+  };
 
-  // ---- main loop: "current site cur, on/off, last exit t1".  Entering another site is the only
-  // rare event (~1e-3 per atom-frame), so frames go through in blocks: when no label of a block is
-  // a site other than cur, neither cur nor the orbit site changes inside the block and the block is
-  // a handful of selects and two stores per frame; otherwise the block replays frame by frame. ----
-  if (f < f_end) {
-    int cur = T.kind == HOPB_SPEC ? T.A1 : T.s0;
-    int on = T.on, t1 = T.t1;
-    auto step = [&](int l, int t) {
-      const bool same = l == cur, zero = l == 0;
-      if (l > 0 && !same) {
-        const int tx = on ? t : t1;
-        if (T.kind == HOPB_SPEC) {          // second site of the chunk: the open event E2
-          T.t1_2 = tx; T.A2 = l; T.f2 = t; T.kind = HOPB_FULL;
-        } else {
-          emit(cur, l, t, tx - T.t0, t - tx);
-        }
-        cur = l; T.t0 = t; on = 1; yorb = l;
-      } else {
-        t1 = (zero && on) ? t : t1;
-        on = same ? 1 : (zero ? 0 : on);   // l == -1 (outlier): nothing changes
-      }
-      store(l);
-    };
-    const uint32_t Nu = (uint32_t)N;
-    auto block = [&](const int* lab, auto kc, int t) {
-      constexpr int K = decltype(kc)::value;
-      bool rare = false;
-#pragma unroll
-      for (int u = 0; u < K; ++u) rare |= (lab[u] > 0) & (lab[u] != cur);
-      if (!rare && XY) {
-        const float yf = (float)yorb;
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-          const int l = lab[u];
-          const bool same = l == cur, zero = l == 0;
-          t1 = (zero && on) ? t + u : t1;
-          on = same ? 1 : (zero ? 0 : on);
-          px[(uint64_t)Nu * (uint32_t)u] = (float)l;
-          py[(uint64_t)Nu * (uint32_t)u] = yf;
-        }
-        px += (uint64_t)Nu * K;
-        py += (uint64_t)Nu * K;
-      } else {
-#pragma unroll
-        for (int u = 0; u < K; ++u) step(lab[u], t + u);
-      }
-    };
+  int f = f_begin;
+  // stream whole blocks of frames through `body` while `more()` (warp-uniform) holds and the chunk lasts
+  auto stream_blocks = [&](auto&& body, auto&& more) {
+    if (!more()) return;
     if (SRC == 0) {
-      for (; f + kUnroll <= f_end; f += kUnroll) {
+      while (f + kUnroll <= f_end) {
         float cx[kUnroll], cy[kUnroll], cz[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-          const float* p = xyz + ((f + u) * N + atom) * 3;
+          const float* p = xyz + ((int64_t)(f + u) * N + atom) * 3;
           cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
         }
         int lab[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) lab[u] = label_of<MAP>(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
-        block(lab, std::integral_constant<int, kUnroll>(), (int)(frame0 + f));
+        body(lab, std::integral_constant<int, kUnroll>(), f, (int)(frame0 + f));
+        f += kUnroll;
+        if (!more()) break;
       }
     } else {
+      // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
+      // block are resolved its input registers are reloaded with the next block, so those loads are
+      // in flight while the state machine consumes the current labels.  (Going one block deeper --
+      // gathers of block b+1 and loads of block b+2 in flight during block b -- was measured: slower.)
       constexpr int kDeep = DEEP;
-      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + f * N + atom;
-      if (PIPE) {
-      // 4-byte inputs (brick indices or labels) in blocks of kDeep frames, two blocks ahead: while
-      // the state machine consumes the labels of block b, the site-map gathers of block b+1 and the
-      // input loads of block b+2 are in flight
-      if (f + kDeep <= f_end) {
-        uint32_t v[kDeep];
-        int nxt[kDeep];
-        auto load = [&]() {
+      if (f + kDeep > f_end) return;
+      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + (int64_t)f * N + atom;
+      uint32_t v[kDeep];
+#pragma unroll
+      for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
+      src += (uint64_t)Nu * kDeep;
+      while (f + kDeep <= f_end) {
+        int lab[kDeep];
+#pragma unroll
+        for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of<MAP>(v[u], mv) : (int)__uint_as_float(v[u]);
+        if (f + 2 * kDeep <= f_end) {
 #pragma unroll
           for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
           src += (uint64_t)Nu * kDeep;
-        };
-        auto resolve = [&]() {
-#pragma unroll
-          for (int u = 0; u < kDeep; ++u) nxt[u] = SRC == 2 ? label_of<MAP>(v[u], mv) : (int)__uint_as_float(v[u]);
-        };
-        load();
-        resolve();
-        if (f + 2 * kDeep <= f_end) load();
-        for (; f + kDeep <= f_end; f += kDeep) {
-          int lab[kDeep];
-#pragma unroll
-          for (int u = 0; u < kDeep; ++u) lab[u] = nxt[u];
-          if (f + 2 * kDeep <= f_end) {
-            resolve();
-            if (f + 3 * kDeep <= f_end) load();
-          }
-          block(lab, std::integral_constant<int, kDeep>(), (int)(frame0 + f));
         }
-      }
-      } else {
-      // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
-      // block are resolved its input registers are reloaded with the next block, so those loads are
-      // in flight while the state machine consumes the current labels
-      uint32_t v[kDeep];
-      if (f + kDeep <= f_end) {
-#pragma unroll
-        for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
-        src += (uint64_t)Nu * kDeep;
-        for (; f + kDeep <= f_end; f += kDeep) {
-          int lab[kDeep];
-#pragma unroll
-          for (int u = 0; u < kDeep; ++u) lab[u] = SRC == 2 ? label_of<MAP>(v[u], mv) : (int)__uint_as_float(v[u]);
-          if (f + 2 * kDeep <= f_end) {
-#pragma unroll
-            for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
-            src += (uint64_t)Nu * kDeep;
-          }
-          block(lab, std::integral_constant<int, kDeep>(), (int)(frame0 + f));
-        }
-      }
+        body(lab, std::integral_constant<int, kDeep>(), f, (int)(frame0 + f));
+        f += kDeep;
+        if (!more()) break;
       }
     }
-    for (; f < f_end; ++f) step(label_at(f), (int)(frame0 + f));
+  };
+  // Three loops, chosen per warp: no lane has seen a site yet; some have; all have.  (One loop that
+  // serves both kinds of lanes needs more than the 64 registers there are, so the common all-A case
+  // gets its own lean loop; per-lane loops instead would make a mixed warp walk its chunk twice.)
+  const unsigned lanes = __activemask();
+  stream_blocks(blockB, [&]() { return !__any_sync(lanes, inA); });
+  stream_blocks(blockU, [&]() { return !__all_sync(lanes, inA); });
+  stream_blocks(blockA, [&]() { return true; });
+  for (; f < f_end; ++f) generic(label_at(f), (int)(frame0 + f));
+  int32_t* sp = summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom;
+  if (inA) {
     if (T.kind == HOPB_FULL) T.s0 = cur;
-    T.on = on; T.t1 = t1;
+    sp[0 * N] = T.kind | (on << 2);
+    sp[4 * N] = T.A2; sp[5 * N] = T.f2; sp[6 * N] = T.t1_2;
+    sp[7 * N] = T.s0; sp[8 * N] = T.t0; sp[9 * N] = t1;
+  } else {
+    T.ypre = ypre;
+    hopb_summary_store(sp, N, T);
   }
-  T.ypre = ypre;
-  hopb_summary_store(summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom, N, T);
 }
 
 // Bricked copy of the site map + its block maps: one thread per 4x4x4 brick reads its (up to) 64
 // cells from the C-ordered int16 map, writes them as one 128-byte line (sub-brick order, see
 // hopb_brick_index) and classifies the brick -- coarse: 0 / 1 = every cell interstitial / bulk,
 // 3 = mixed, 16 bricks per 32-bit word; fine: one bit per 2x2x2 sub-brick, set when all of its cells
-// carry fine_value, one byte per brick.  Cells beyond the grid are never looked up and do not count.
+// carry the same label v, one byte per brick, one map for v = 0 (fine[b]) and one for v = 1
+// (fine[nb_pad + b]).  The number of cells with label 1 goes to the counter behind the two maps:
+// stage 3 uses the v = 1 map when the bulk site covers at least 1/8 of the grid (then most atoms
+// sit in it), else the v = 0 map.  Cells beyond the grid are never looked up and do not count.
 __global__ void __launch_bounds__(256)
 brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
-                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse, uint8_t* __restrict__ fine, int fine_value) {
+                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse, uint8_t* __restrict__ fine, int64_t nb_pad) {
   const int64_t n_blocks = (int64_t)cnx * cny * cnz;
   const int64_t n_round = (n_blocks + 31) / 32 * 32;
   const int lane = threadIdx.x & 31;
+  uint32_t n_ones = 0;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += (int64_t)gridDim.x * blockDim.x) {
     uint32_t st = 0;
     if (b < n_blocks) {
@@ -357,7 +396,7 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
       const int ci = (int)(r / cny);
       int first = -2;
       bool uniform = true;
-      uint32_t spoiled = 0;  // bit s: sub-brick s has a cell that is not fine_value
+      uint32_t not0 = 0, not1 = 0;  // bit s: sub-brick s has a cell that is not 0 / not 1
       int16_t* out = brick + b * 64;
       for (int di = 0; di < 4; ++di) {
         const int i = ci * 4 + di;
@@ -374,7 +413,9 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
               v = row[k];
               if (first == -2) first = v;
               else if (v != first) uniform = false;
-              if (v != fine_value) spoiled |= 1u << (((di & 2) << 1) | (dj & 2) | (dk >> 1));
+              const uint32_t sub = 1u << (((di & 2) << 1) | (dj & 2) | (dk >> 1));
+              if (v != 0) not0 |= sub;
+              if (v != 1) not1 |= sub; else ++n_ones;
             }
             v4[dk] = v;
           }
@@ -385,12 +426,20 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
         }
       }
       st = (uniform && (first == 0 || first == 1)) ? (uint32_t)first : 3u;
-      if (fine) fine[b] = (uint8_t)(~spoiled & 0xFFu);
+      if (fine) {
+        fine[b] = (uint8_t)(~not0 & 0xFFu);
+        fine[nb_pad + b] = (uint8_t)(~not1 & 0xFFu);
+      }
     }
     uint32_t w = st << ((lane & 15) * 2);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) w |= __shfl_xor_sync(kFull, w, o);
     if ((lane & 15) == 0 && b < n_blocks) coarse[b >> 4] = w;
+  }
+  if (fine) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_ones += __shfl_xor_sync(kFull, n_ones, o);
+    if (lane == 0 && n_ones) atomicAdd(reinterpret_cast<uint32_t*>(fine + 2 * nb_pad), n_ones);
   }
 }
 
@@ -497,15 +546,15 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     hopb_note_launch();
     if (hop_x && hop_y)
       hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     else
       hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
   HOPB_REQUIRE(h, g && map16 && (src == 0 ? xyz != nullptr : cells != nullptr), "null argument");
-  HOPB_REQUIRE(h, fine_value == 0 || fine_value == 1, "fine_value must be 0 or 1");
+  HOPB_REQUIRE(h, fine_value >= -1 && fine_value <= 1, "fine_value must be 0, 1 or -1 (automatic)");
   const bool fast = g->tab.fast_ok != 0;
   const int64_t nb = (int64_t)((g->n[0] + 3) / 4) * ((g->n[1] + 3) / 4) * ((g->n[2] + 3) / 4);
   size_t smem = 0;
@@ -523,21 +572,18 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     mode = MAP_COARSE; map_words = (int)(coarse_bytes / 4); blockmap = coarse;
     smem += coarse_bytes;
   }
+  const uint32_t fine_auto_min = (uint32_t)(((int64_t)g->n[0] * g->n[1] * g->n[2] + 7) / 8);
   const size_t per_cta = smem + 1024;  // + the driver's reservation
   threads = per_cta * 4 <= 227 * 1024 ? 256 : (per_cta * 2 <= 227 * 1024 ? 512 : 1024);
   const unsigned grid = (unsigned)((items + threads / 32 - 1) / (threads / 32));
-  static const bool pipe = getenv("HOPB_K3_PIPE") && atoi(getenv("HOPB_K3_PIPE")) != 0;  // experiment hook
-#define HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, PIPE)                                                                        \
-  do {                                                                                                               \
-    if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST, XY, MAP, PIPE><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
-        g->d_table2, map16, blockmap, map_words, fine_value, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);     \
-  } while (0)
 #define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP)                                                                         \
   do {                                                                                                               \
-    if (SRC == 2 && pipe) HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, (SRC == 2)); else HOPB_HT_LAUNCH_P(SRC, FAST, XY, MAP, false); \
+    if (smem > 48 * 1024)                                                                                            \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hopb_note_launch();                                                                                              \
+    hoptraj_kernel<SRC, FAST, XY, MAP><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
+        g->d_table2, map16, blockmap, map_words, fine_value, fine_auto_min, hop_x, hop_y, n_chunks, chunk_len,       \
+        summaries, sink);                                                                                            \
   } while (0)
 #define HOPB_HT_LAUNCH_XY(SRC, FAST, XY)                                                                             \
   do {                                                                                                               \
@@ -554,7 +600,6 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
 #undef HOPB_HT_LAUNCH
 #undef HOPB_HT_LAUNCH_XY
 #undef HOPB_HT_LAUNCH_M
-#undef HOPB_HT_LAUNCH_P
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -574,14 +619,15 @@ int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_
 }
 
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse, uint8_t* fine, int fine_value) {
+                   uint32_t* coarse, uint8_t* fine) {
   HOPB_REQUIRE(h, map16 && brick && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
-  HOPB_REQUIRE(h, fine_value == 0 || fine_value == 1, "fine_value must be 0 or 1");
   const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
   const int64_t nb = (int64_t)cnx * cny * cnz;
   HOPB_REQUIRE(h, nb * 64 < ((int64_t)1 << 32) - 1, "grid too large for brick indices");
+  const int64_t nb_pad = (nb + 3) / 4 * 4;
+  if (fine) HOPB_CUDA(h, cudaMemsetAsync(fine + 2 * nb_pad, 0, 16, (cudaStream_t)stream));
   HOPB_K(brick_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
-      map16, nx, ny, nz, cnx, cny, cnz, brick, coarse, fine, fine_value);
+      map16, nx, ny, nz, cnx, cny, cnz, brick, coarse, fine, nb_pad);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

@@ -123,23 +123,29 @@ def brick_shape(shape):
     return nb, -(-nb // 16)
 
 
+def fine_map_bytes(shape):
+    """Size of the fine block map buffer of brick_map: two 1-bit maps + the bulk-cell counter."""
+    nb = brick_shape(shape)[0]
+    return 2 * ((nb + 3) // 4 * 4) + 16
+
+
 class BrickMap(object):
     """The site map as stage 3 reads it: `brick` (int16, 4x4x4 brick order), `coarse` (2 bits per
-    brick), `fine` (1 bit per 2x2x2 sub-brick: all cells carry `fine_value`).  Unpacks as
-    (brick, coarse)."""
+    brick), `fine` (1 bit per 2x2x2 sub-brick, one map for "all cells interstitial" and one for "all
+    cells bulk").  Unpacks as (brick, coarse)."""
 
-    def __init__(self, brick, coarse, fine, fine_value):
-        self.brick, self.coarse, self.fine, self.fine_value = brick, coarse, fine, int(fine_value)
+    def __init__(self, brick, coarse, fine):
+        self.brick, self.coarse, self.fine = brick, coarse, fine
 
     def __iter__(self):
         return iter((self.brick, self.coarse))
 
 
-def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None, fine_value=1):
+def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None):
     """Site map in 4x4x4 brick order (what the hoptraj kernel gathers from) and its block maps, which
     let the kernel skip the gather where a whole (sub-)brick carries one label: `coarse`, 2 bits per
     brick (uniformly interstitial / bulk / mixed), and `fine`, 1 bit per 2x2x2 sub-brick (uniformly
-    `fine_value`: 1 when the map has a bulk site, else 0)."""
+    interstitial, uniformly bulk: two maps, the kernel picks the one most atoms fall under)."""
     _cuda(map16, torch.int16, "map16")
     nx, ny, nz = map16.shape
     nb, words = brick_shape(map16.shape)
@@ -148,11 +154,10 @@ def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None, fine_valu
     if coarse is None:
         coarse = torch.empty(words, dtype=torch.int32, device=map16.device)
     if fine is None:
-        fine = torch.zeros((nb + 3) // 4 * 4, dtype=torch.uint8, device=map16.device)
+        fine = torch.zeros(fine_map_bytes(map16.shape), dtype=torch.uint8, device=map16.device)
     h = _h(map16)
-    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse), _p(fine),
-                                            int(fine_value)))
-    return BrickMap(brick, coarse, fine, fine_value)
+    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse), _p(fine)))
+    return BrickMap(brick, coarse, fine)
 
 
 def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
@@ -302,15 +307,16 @@ class EventBuffer:
 
 def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len: int,
             events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None, fine=None,
-            fine_value=1, block_map="auto"):
+            fine_value=-1, block_map="auto"):
     """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254).
     Input is either `xyz` (float32 [F][N][3]) or the brick indices `cells` (int32 [F][N]) from
     hist_accumulate.  `brick` is the BrickMap of brick_map(Density.map) -- block_map = "auto" (the
     fine block map when it fits into shared memory, else the coarse one), "fine", "coarse" or "none"
-    -- or the bricked int16 tensor with `coarse` / `fine` given separately."""
+    -- or the bricked int16 tensor with `coarse` / `fine` given separately.  fine_value picks the fine
+    map (0: interstitial, 1: bulk, -1: decided on the device from the size of the bulk site)."""
     if isinstance(brick, BrickMap):
         bm = brick
-        brick, fine_value = bm.brick, bm.fine_value
+        brick = bm.brick
         coarse = bm.coarse if block_map in ("auto", "coarse") else None
         fine = bm.fine if block_map in ("auto", "fine") else None
     _cuda(brick, torch.int16, "brick")
@@ -330,7 +336,7 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
         _cuda(coarse, torch.int32, "coarse")
     if fine is not None:
         _cuda(fine, torch.uint8, "fine")
-        if fine.numel() != (nb + 3) // 4 * 4:
+        if fine.numel() != fine_map_bytes(grid.shape):
             raise ValueError("fine block map does not match the grid (use kernels.brick_map)")
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)

@@ -161,9 +161,8 @@ class HopPipeline:
                 props = K.site_properties(self.grid, density, own, member, L, out=out)
             self._props_done = torch.cuda.Event()
             self._props_done.record(side)
-        fine_buf = self._buf("fine", ((nb + 3) // 4 * 4,), torch.uint8)
-        # most atoms sit in the bulk site when there is one, else in the interstitial
-        self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf, fine_value=1 if cfg.with_bulk else 0)
+        fine_buf = self._buf("fine", (K.fine_map_bytes(shape),), torch.uint8)
+        self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf)
         return density, own, member, map16, props
 
     def sync_scalars(self, events):

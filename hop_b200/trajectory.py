@@ -160,7 +160,7 @@ class HoppingTrajectory(object):
             self._map16 = self._GD._device_map()
             if self._map16.numel() != self._tables.n_cells:
                 raise ValueError("The density object must have its site map computed.")
-            self._brick = K.brick_map(self._map16, fine_value=1 if self._GD.has_bulk() else 0)
+            self._brick = K.brick_map(self._map16)
 
     @staticmethod
     def _slice_blocks(blocks, start, stop):

@@ -177,10 +177,11 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  *   brick     device int16: the site map (Density.map) in brick order, from hopb_brick_map
  *   coarse    device uint32 (may be NULL): the 2-bit block map of hopb_brick_map; it lets atoms in
  *             uniformly bulk / interstitial 4x4x4 bricks skip the gather from the site map
- *   fine      device uint8 (may be NULL): the 1-bit block map of hopb_brick_map over 2x2x2 sub-bricks
- *             (padded to a multiple of 4 bytes), with the fine_value it was built for.  Used instead
- *             of `coarse` whenever it fits into shared memory (grids up to ~230^3 cells): far fewer
- *             atoms then need the gather.
+ *   fine      device uint8 (may be NULL): the 1-bit block maps of hopb_brick_map over 2x2x2 sub-bricks.
+ *             Used instead of `coarse` whenever one of them fits into shared memory (grids up to
+ *             ~230^3 cells): far fewer atoms then need the gather.  fine_value selects the map:
+ *             0 (sub-bricks uniformly interstitial), 1 (uniformly bulk) or -1 = decided on the device
+ *             (1 when the bulk site covers at least 1/8 of the grid).
  *   frame0    global frame number of the slab's first frame
  *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
  *             DCD, trajectory.py:456-463); either may be NULL
@@ -199,11 +200,12 @@ int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* 
  *   brick   device int16  [n_bricks*64] out (cells outside the grid are 0)
  *   coarse  device uint32 [ceil(n_bricks/16)] out: 2 bits per brick, 0 / 1 = all interstitial / all
  *           bulk, 3 = mixed
- *   fine    device uint8  [n_bricks rounded up to a multiple of 4] out, may be NULL: bit s of byte b
- *           is set when all cells of sub-brick s = (i1<<2 | j1<<1 | k1) of brick b carry the label
- *           fine_value (0 = interstitial or 1 = bulk: whichever most atoms sit in) */
+ *   fine    device uint8  [2 * nb_pad + 16] out, nb_pad = n_bricks rounded up to a multiple of 4; may be
+ *           NULL.  Two maps: bit s of byte v * nb_pad + b is set when all cells of sub-brick
+ *           s = (i1<<2 | j1<<1 | k1) of brick b carry the label v (0 = interstitial, 1 = bulk); the
+ *           uint32 at byte 2 * nb_pad counts the cells with label 1. */
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse, uint8_t* fine, int fine_value);
+                   uint32_t* coarse, uint8_t* fine);
 
 /* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
  * hop/graph.py:190-254): labels = hop_x [F][N] float32. */

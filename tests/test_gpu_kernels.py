@@ -223,9 +223,9 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
     F, N = xyz.shape[:2]
     g = K.GridTables(edges)
     m16 = dev(site_map.astype(np.int16))
-    # the fine block map is built for the label most cells of this map carry
-    bm = K.brick_map(m16, fine_value=1 if (site_map == 1).sum() > (site_map == 0).sum() else 0)
+    bm = K.brick_map(m16)
     block_map = "coarse" if "coarse" in mode else ("fine" if "fine" in mode else "none")
+    fine_value = {"fine0": 0, "fine1": 1}.get(mode.split("+")[-1], -1)
     cells_all = None
     if mode.startswith("cells"):
         cells_all = torch.empty((F, N), dtype=torch.int32, device="cuda")
@@ -249,7 +249,7 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
         chunk_len = -(-(b - a) // n_chunks)
         nc = -(-(b - a) // chunk_len)
         s = K.hoptraj(g, dev(xyz[a:b]), bm, int(a), nc, chunk_len, events, X[a:b], Y[a:b],
-                      cells=None if cells_all is None else cells_all[a:b], block_map=block_map)
+                      cells=None if cells_all is None else cells_all[a:b], block_map=block_map, fine_value=fine_value)
         summaries.append(s)
         lens.append(chunk_len)
         slab_sums.append(K.hop_combine(s, chunk_len, b - a))
@@ -269,7 +269,7 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
 
 @pytest.mark.parametrize("n_chunks,slabs,mode", [(1, 1, "xyz"), (4, 1, "xyz+coarse"), (13, 1, "cells"), (200, 1, "cells+coarse"),
                                                  (3, 2, "cells+coarse"), (5, 8, "xyz+coarse"), (1, 1, "xyz+fine"),
-                                                 (9, 1, "cells+fine"), (4, 3, "cells+fine")])
+                                                 (9, 1, "cells+fine"), (4, 3, "cells+fine"), (2, 1, "cells+fine0"), (3, 1, "xyz+fine1")])
 def test_hoptraj_and_transitions(K, traj, n_chunks, slabs, mode):
     p, xyz = traj
     res = O.pipeline(xyz, delta=1.0)
@@ -330,28 +330,32 @@ def test_coarse_map_blocks(K):
         m[:4, :4, :4] = 0
         if shape[0] > 8:
             m[8, 5, 2] = 7
-        for fine_value in (1, 0):
-            bm = K.brick_map(dev(m), fine_value=fine_value)
-            brick, c = bm
-            c = c.cpu().numpy().view(np.uint32)
-            fine = bm.fine.cpu().numpy()
-            brick = brick.cpu().numpy()
-            cn = [-(-n // 4) for n in shape]
-            ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
-            # 4x4x4 bricks, cells inside a brick ordered by 2x2x2 sub-brick: (i1 j1 k1 i0 j0 k0)
-            low = ((ii & 2) << 4) | ((jj & 2) << 3) | ((kk & 2) << 2) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1)
-            idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | low
-            assert np.array_equal(brick[idx], m)
-            for b in range(cn[0] * cn[1] * cn[2]):
-                ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
-                blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
-                u = np.unique(blk)
-                want = int(u[0]) if len(u) == 1 and u[0] in (0, 1) else 3
-                assert (c[b >> 4] >> ((b & 15) * 2)) & 3 == want
-                for sub in range(8):
-                    i1, j1, k1 = sub >> 2, (sub >> 1) & 1, sub & 1
-                    sb = blk[i1 * 2:i1 * 2 + 2, j1 * 2:j1 * 2 + 2, k1 * 2:k1 * 2 + 2]
-                    assert (fine[b] >> sub) & 1 == int((sb == fine_value).all()), (shape, b, sub)
+        bm = K.brick_map(dev(m))
+        brick, c = bm
+        c = c.cpu().numpy().view(np.uint32)
+        fine = bm.fine.cpu().numpy()
+        brick = brick.cpu().numpy()
+        cn = [-(-n // 4) for n in shape]
+        nb = cn[0] * cn[1] * cn[2]
+        nb_pad = (nb + 3) // 4 * 4
+        assert fine.size == 2 * nb_pad + 16
+        assert int(fine[2 * nb_pad:2 * nb_pad + 4].view(np.uint32)[0]) == int((m == 1).sum())
+        ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+        # 4x4x4 bricks, cells inside a brick ordered by 2x2x2 sub-brick: (i1 j1 k1 i0 j0 k0)
+        low = ((ii & 2) << 4) | ((jj & 2) << 3) | ((kk & 2) << 2) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1)
+        idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | low
+        assert np.array_equal(brick[idx], m)
+        for b in range(nb):
+            ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
+            blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
+            u = np.unique(blk)
+            want = int(u[0]) if len(u) == 1 and u[0] in (0, 1) else 3
+            assert (c[b >> 4] >> ((b & 15) * 2)) & 3 == want
+            for sub in range(8):
+                i1, j1, k1 = sub >> 2, (sub >> 1) & 1, sub & 1
+                sb = blk[i1 * 2:i1 * 2 + 2, j1 * 2:j1 * 2 + 2, k1 * 2:k1 * 2 + 2]
+                for v in (0, 1):
+                    assert (fine[v * nb_pad + b] >> sub) & 1 == int((sb == v).all()), (shape, b, sub, v)
 
 
 def test_half_angstrom_golden_through_all_paths(K):
