@@ -134,26 +134,51 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
   return ok ? hopb_brick_index(bx - 1, by - 1, bz - 1, ay.cn, az.cn) : kCellOut;
 }
 
-// later passes of a slabbed histogram: 4 B per point in, one reduction per point of this slab
+// later passes of a slabbed histogram: 4 B per point in, one reduction per point of this slab.
+// Slabs are brick-aligned in x, so "in this slab" is a range test on the brick index; only the
+// points that pass it (1 / n_pass of them) are decoded into a cell.
+struct CellSlab { uint32_t c_lo, c_hi; };  // brick-index range [c_lo, c_hi) of the slab
+
+__device__ __forceinline__ void hist_cell(uint32_t c, const CellSlab& sl, uint32_t plane, int ny, int nz, int cnz,
+                                          uint32_t* __restrict__ counts) {
+  // outliers (0xFFFFFFFF) and already counted points (bit 30) are >= 2^30 > c_hi
+  if (c < sl.c_lo || c >= sl.c_hi) return;
+  const uint32_t cb = c >> 6;
+  const uint32_t ci = cb / plane;
+  int di, dj, dk;
+  hopb_brick_decode(c, di, dj, dk);
+  const uint32_t r = cb - ci * plane;
+  const uint32_t cj = r / (uint32_t)cnz;
+  const uint32_t ck = r - cj * (uint32_t)cnz;
+  const uint32_t i = ci * 4 + (uint32_t)di, j = cj * 4 + (uint32_t)dj, k = ck * 4 + (uint32_t)dk;
+  atomicAdd(counts + (i * (uint32_t)ny + j) * (uint32_t)nz + k, 1u);
+}
+
 __global__ void __launch_bounds__(256)
-hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, Slab slab, int ny, int nz, int cny, int cnz,
-                  uint32_t* __restrict__ counts) {
+hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, int64_t lead, CellSlab sl, int ny, int nz, int cny,
+                  int cnz, uint32_t* __restrict__ counts) {
   const uint64_t pol = make_evict_first_policy();
   const uint32_t plane = (uint32_t)(cny * cnz);
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t c = ld_stream_u32(cells + p, pol);
-    if (c & 0xC0000000u) continue;  // outlier or already counted
-    const uint32_t cb = c >> 6;
-    const uint32_t ci = cb / plane;
-    int di, dj, dk;
-    hopb_brick_decode(c, di, dj, dk);
-    const int i = (int)(ci * 4) + di;
-    if (i < slab.x_lo || i >= slab.x_hi) continue;
-    const uint32_t r = cb - ci * plane;
-    const uint32_t cj = r / (uint32_t)cnz;
-    const uint32_t ck = r - cj * (uint32_t)cnz;
-    const uint32_t j = cj * 4 + (uint32_t)dj, k = ck * 4 + (uint32_t)dk;
-    atomicAdd(counts + ((uint32_t)i * (uint32_t)ny + j) * (uint32_t)nz + k, 1u);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  // [lead, lead + 4 * n4) is 16-byte aligned: four points per load
+  const int64_t n4 = (n_points - lead) / 4;
+  const uint4* c4 = reinterpret_cast<const uint4*>(cells + lead);
+  for (int64_t q = tid; q < n4; q += nth) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(c4 + q), "l"(pol));
+    hist_cell(v.x, sl, plane, ny, nz, cnz, counts);
+    hist_cell(v.y, sl, plane, ny, nz, cnz, counts);
+    hist_cell(v.z, sl, plane, ny, nz, cnz, counts);
+    hist_cell(v.w, sl, plane, ny, nz, cnz, counts);
+  }
+  const int64_t tail0 = lead + 4 * n4;
+  const int64_t n_rem = lead + (n_points - tail0);
+  for (int64_t i = tid; i < n_rem; i += nth) {
+    const int64_t p = i < lead ? i : tail0 + (i - lead);
+    hist_cell(ld_stream_u32(cells + p, pol), sl, plane, ny, nz, cnz, counts);
   }
 }
 
@@ -406,7 +431,10 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
     if (n_pass < 1) n_pass = 1;
     if (n_pass > g->n[0]) n_pass = g->n[0];
   }
-  const int slab_w = (g->n[0] + n_pass - 1) / n_pass;
+  // slabs are whole bricks (multiples of 4 cells) wide, so that the later passes can tell "in my slab"
+  // from the brick index alone
+  int slab_w = (g->n[0] + n_pass - 1) / n_pass;
+  if (n_pass > 1) slab_w = (slab_w + 3) / 4 * 4;
   Slab slab;
   slab.x_lo = 0; slab.x_hi = n_pass == 1 ? g->n[0] : slab_w; slab.done_flag = n_pass == 1 ? 0u : kCellDone;
   hopb_note_launch();
@@ -417,12 +445,21 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
     if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
     else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
   }
-  for (int p = 1; p < n_pass; ++p) {
-    slab.x_lo = p * slab_w;
-    slab.x_hi = (p + 1) * slab_w < g->n[0] ? (p + 1) * slab_w : g->n[0];
-    if (slab.x_lo >= slab.x_hi) break;
-    HOPB_K(hist_cells_kernel)<<<hopb_grid_for(n_points, 256, h->num_sms, 8), 256, 0, s>>>(
-        cells, n_points, slab, g->n[1], g->n[2], (g->n[1] + 3) / 4, (g->n[2] + 3) / 4, counts);
+  if (n_pass > 1) {
+    const int cny = (g->n[1] + 3) / 4, cnz = (g->n[2] + 3) / 4;
+    const uint32_t plane64 = (uint32_t)(cny * cnz) * 64u;
+    int64_t lead4 = 0;  // points until the index stream is 16-byte aligned
+    while (lead4 < n_points && (((uintptr_t)cells + 4 * (uintptr_t)lead4) & 15) != 0) ++lead4;
+    for (int p = 1; p < n_pass; ++p) {
+      const int x_lo = p * slab_w;
+      const int x_hi = (p + 1) * slab_w < g->n[0] ? (p + 1) * slab_w : g->n[0];
+      if (x_lo >= x_hi) break;
+      CellSlab cs;
+      cs.c_lo = (uint32_t)(x_lo / 4) * plane64;
+      cs.c_hi = (uint32_t)((x_hi + 3) / 4) * plane64;
+      HOPB_K(hist_cells_kernel)<<<hopb_grid_for((n_points + 3) / 4, 256, h->num_sms, 8), 256, 0, s>>>(
+          cells, n_points, lead4, cs, g->n[1], g->n[2], cny, cnz, counts);
+    }
   }
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;

@@ -91,7 +91,7 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
 int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                                int64_t n_points, uint32_t* counts, uint32_t* cells);
 
-/* Count grids larger than this many bytes (default 40 MiB) are histogrammed in x-slabs when `cells`
+/* Count grids larger than this many bytes (default 64 MiB) are histogrammed in x-slabs when `cells`
  * is given: one pass over the coordinates, then one pass over the 4-byte cell indices per further
  * slab, so that every pass reduces into an L2-resident part of the grid. */
 int hopb_set_hist_l2_budget(hopb_handle* h, int64_t bytes);

@@ -89,7 +89,7 @@ def test_histogram_slabbed_passes(K, traj):
             K.hop_fixup(s, 25, 50, st, Y, ev)
             assert np.array_equal(X.cpu().numpy(), res["hop"][:, :, 0]) and np.array_equal(Y.cpu().numpy(), res["hop"][:, :, 1])
     finally:
-        K.set_hist_l2_budget(40 << 20)
+        K.set_hist_l2_budget(64 << 20)
 
 
 def test_histogram_edge_semantics(K):
