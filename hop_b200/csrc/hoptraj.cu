@@ -91,11 +91,12 @@ __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const H
 // how a brick index becomes a label
 enum { MAP_GATHER = 0,   // always gather from the bricked int16 map (L2)
        MAP_COARSE = 1,   // 2 bits per 4x4x4 brick in shared memory: 0 / 1 = uniformly interstitial / bulk, 3 = mixed
-       MAP_FINE = 2 };   // 1 bit per 2x2x2 sub-brick in shared memory: all 8 cells carry fine_value
+       MAP_FINE = 2,     // 1 bit per 2x2x2 sub-brick in shared memory: all 8 cells carry fine_value
+       MAP_CELL2 = 3 };  // grids whose block maps do not fit: 2 bits per cell in L2 (0, 1, 3 = a hydration site)
 
 struct MapView {
   const int16_t* brick;     // bricked site map
-  const uint32_t* s_map;    // block map in shared memory (coarse or fine), or nullptr
+  const uint32_t* s_map;    // block map in shared memory (coarse or fine); MAP_CELL2: the 2-bit cell map in global memory
   int fine_value;
 };
 
@@ -121,6 +122,12 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
     const uint32_t st = (m.s_map[cb >> 4] >> ((cb & 15u) * 2u)) & 3u;
     l = (int)st;
     need = st == 3u;
+  } else if (MAP == MAP_CELL2) {
+    // 16 cells per word, brick order: a 16x smaller gather target than the int16 map (16 MB instead
+    // of 130 MB at 402^3), so it stays in L2; only atoms on hydration sites go on to the int16 map
+    const uint32_t code = (__ldg(m.s_map + (cc >> 4)) >> ((cc & 15u) * 2u)) & 3u;
+    l = (int)code;
+    need = code == 3u;
   } else {
     l = 0;
     need = true;
@@ -158,14 +165,15 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
     if (fine_value < 0) fine_value = blockmap[2 * map_words] >= fine_auto_min ? 1 : 0;
     blockmap += fine_value * map_words;
   }
-  if (SRC != 1 && MAP != MAP_GATHER)
+  if (SRC != 1 && (MAP == MAP_COARSE || MAP == MAP_FINE))
     for (int i = threadIdx.x; i < map_words; i += blockDim.x) s_map[i] = blockmap[i];
   if (SRC != 1) __syncthreads();
   const AxisReg ax = load_axis(tab.ax[0], s_pairs);
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
   MapView mv;
-  mv.brick = brick; mv.s_map = (SRC != 1 && MAP != MAP_GATHER) ? s_map : nullptr; mv.fine_value = fine_value;
+  mv.brick = brick; mv.fine_value = fine_value;
+  mv.s_map = (SRC == 1 || MAP == MAP_GATHER) ? nullptr : (MAP == MAP_CELL2 ? blockmap : s_map);
   const int cny = (tab.ax[1].n + 3) >> 2, cnz = (tab.ax[2].n + 3) >> 2;
 
   const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -382,7 +390,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
 // sit in it), else the v = 0 map.  Cells beyond the grid are never looked up and do not count.
 __global__ void __launch_bounds__(256)
 brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int cnx, int cny, int cnz,
-                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse, uint8_t* __restrict__ fine, int64_t nb_pad) {
+                 int16_t* __restrict__ brick, uint32_t* __restrict__ coarse, uint8_t* __restrict__ fine, int64_t nb_pad,
+                 uint4* __restrict__ cell2) {
   const int64_t n_blocks = (int64_t)cnx * cny * cnz;
   const int64_t n_round = (n_blocks + 31) / 32 * 32;
   const int lane = threadIdx.x & 31;
@@ -397,6 +406,7 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
       int first = -2;
       bool uniform = true;
       uint32_t not0 = 0, not1 = 0;  // bit s: sub-brick s has a cell that is not 0 / not 1
+      uint32_t c2[4] = {0u, 0u, 0u, 0u};  // 2 bits per cell, brick order: 0, 1, 3 = any other label
       int16_t* out = brick + b * 64;
       for (int di = 0; di < 4; ++di) {
         const int i = ci * 4 + di;
@@ -405,6 +415,7 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
           const bool row_ok = i < nx && j < ny;
           const int16_t* row = map16 + ((int64_t)i * ny + j) * nz;
           int16_t v4[4];
+          uint32_t part = 0;
 #pragma unroll
           for (int dk = 0; dk < 4; ++dk) {
             const int k = ck * 4 + dk;
@@ -418,7 +429,12 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
               if (v != 1) not1 |= sub; else ++n_ones;
             }
             v4[dk] = v;
+            const uint32_t code = v == 0 ? 0u : (v == 1 ? 1u : 3u);
+            part |= code << (2 * (((dk & 2) << 2) | ((di & 1) << 2) | ((dj & 1) << 1) | (dk & 1)));
           }
+          // position inside the brick = (i1 j1 | k1 i0 j0 k0): word i1 j1, 2-bit slot k1 i0 j0 k0
+          const int widx = (di & 2) | (dj >> 1);
+          if (widx == 0) c2[0] |= part; else if (widx == 1) c2[1] |= part; else if (widx == 2) c2[2] |= part; else c2[3] |= part;
           // (di, dj) fixes i1 j1 . i0 j0 .; dk = 0,1 and dk = 2,3 are two runs of two cells 8 apart
           int16_t* o = out + (((di & 2) << 4) | ((dj & 2) << 3) | ((di & 1) << 2) | ((dj & 1) << 1));
           *reinterpret_cast<short2*>(o) = make_short2(v4[0], v4[1]);
@@ -430,6 +446,7 @@ brick_map_kernel(const int16_t* __restrict__ map16, int nx, int ny, int nz, int 
         fine[b] = (uint8_t)(~not0 & 0xFFu);
         fine[nb_pad + b] = (uint8_t)(~not1 & 0xFFu);
       }
+      if (cell2) cell2[b] = make_uint4(c2[0], c2[1], c2[2], c2[3]);
     }
     uint32_t w = st << ((lane & 15) * 2);
 #pragma unroll
@@ -526,9 +543,9 @@ extern "C" {
 
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
                           const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t frame0,
-                          const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value, float* hop_x,
-                          float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events,
-                          uint64_t* n_events, uint64_t cap) {
+                          const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value,
+                          const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
+                          int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   HOPB_REQUIRE(h, F > 0 && N > 0 && summaries && n_events, "bad argument");
   HOPB_REQUIRE(h, n_chunks >= 1 && chunk_len >= 1 && (int64_t)n_chunks * chunk_len >= F &&
                       (int64_t)(n_chunks - 1) * chunk_len < F, "chunks must tile the slab exactly");
@@ -571,6 +588,8 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   } else if (coarse && smem + coarse_bytes <= kSmemSm) {
     mode = MAP_COARSE; map_words = (int)(coarse_bytes / 4); blockmap = coarse;
     smem += coarse_bytes;
+  } else if (cell2) {
+    mode = MAP_CELL2; blockmap = cell2;
   }
   const uint32_t fine_auto_min = (uint32_t)(((int64_t)g->n[0] * g->n[1] * g->n[2] + 7) / 8);
   const size_t per_cta = smem + 1024;  // + the driver's reservation
@@ -589,6 +608,7 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   do {                                                                                                               \
     if (mode == MAP_FINE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_FINE);                                                 \
     else if (mode == MAP_COARSE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_COARSE);                                        \
+    else if (mode == MAP_CELL2) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_CELL2);                                          \
     else HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_GATHER);                                                                \
   } while (0)
 #define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
@@ -606,20 +626,20 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
 
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
                  int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
-                 int fine_value, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
-                 hopb_event* events, uint64_t* n_events, uint64_t cap) {
+                 int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
+                 int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, frame0, map16, coarse, fine, fine_value,
-                        hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
+                        cell2, hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N, int64_t frame0, int n_chunks,
                         int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, frame0, nullptr, nullptr, nullptr, 0, nullptr,
-                        nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
+                        nullptr, nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse, uint8_t* fine) {
+                   uint32_t* coarse, uint8_t* fine, uint32_t* cell2) {
   HOPB_REQUIRE(h, map16 && brick && coarse && nx > 0 && ny > 0 && nz > 0, "bad argument");
   const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
   const int64_t nb = (int64_t)cnx * cny * cnz;
@@ -627,7 +647,7 @@ int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const i
   const int64_t nb_pad = (nb + 3) / 4 * 4;
   if (fine) HOPB_CUDA(h, cudaMemsetAsync(fine + 2 * nb_pad, 0, 16, (cudaStream_t)stream));
   HOPB_K(brick_map_kernel)<<<hopb_grid_for(nb, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
-      map16, nx, ny, nz, cnx, cny, cnz, brick, coarse, fine, nb_pad);
+      map16, nx, ny, nz, cnx, cny, cnz, brick, coarse, fine, nb_pad, reinterpret_cast<uint4*>(cell2));
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

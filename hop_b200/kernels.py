@@ -132,20 +132,23 @@ def fine_map_bytes(shape):
 class BrickMap(object):
     """The site map as stage 3 reads it: `brick` (int16, 4x4x4 brick order), `coarse` (2 bits per
     brick), `fine` (1 bit per 2x2x2 sub-brick, one map for "all cells interstitial" and one for "all
-    cells bulk").  Unpacks as (brick, coarse)."""
+    cells bulk"), `cell2` (2 bits per cell, for grids whose block maps do not fit into shared memory).
+    Unpacks as (brick, coarse)."""
 
-    def __init__(self, brick, coarse, fine):
-        self.brick, self.coarse, self.fine = brick, coarse, fine
+    def __init__(self, brick, coarse, fine, cell2=None):
+        self.brick, self.coarse, self.fine, self.cell2 = brick, coarse, fine, cell2
 
     def __iter__(self):
         return iter((self.brick, self.coarse))
 
 
-def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None):
+def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None, cell2=None):
     """Site map in 4x4x4 brick order (what the hoptraj kernel gathers from) and its block maps, which
     let the kernel skip the gather where a whole (sub-)brick carries one label: `coarse`, 2 bits per
     brick (uniformly interstitial / bulk / mixed), and `fine`, 1 bit per 2x2x2 sub-brick (uniformly
-    interstitial, uniformly bulk: two maps, the kernel picks the one most atoms fall under)."""
+    interstitial, uniformly bulk: two maps, the kernel picks the one most atoms fall under).  `cell2`
+    (2 bits per cell: interstitial / bulk / other) is the small gather target for grids too large for
+    either."""
     _cuda(map16, torch.int16, "map16")
     nx, ny, nz = map16.shape
     nb, words = brick_shape(map16.shape)
@@ -155,9 +158,12 @@ def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None):
         coarse = torch.empty(words, dtype=torch.int32, device=map16.device)
     if fine is None:
         fine = torch.zeros(fine_map_bytes(map16.shape), dtype=torch.uint8, device=map16.device)
+    if cell2 is None:
+        cell2 = torch.empty(nb * 4, dtype=torch.int32, device=map16.device)
     h = _h(map16)
-    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse), _p(fine)))
-    return BrickMap(brick, coarse, fine)
+    _lib.check(h, _lib.lib().hopb_brick_map(h, _stream(), nx, ny, nz, _p(map16), _p(brick), _p(coarse), _p(fine),
+                                            _p(cell2)))
+    return BrickMap(brick, coarse, fine, cell2)
 
 
 def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
@@ -307,11 +313,12 @@ class EventBuffer:
 
 def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len: int,
             events: EventBuffer, hop_x=None, hop_y=None, summaries=None, cells=None, coarse=None, fine=None,
-            fine_value=-1, block_map="auto"):
+            fine_value=-1, block_map="auto", cell2=None):
     """Fused _coord2hop + transition scan over one slab (hop/trajectory.py:403-468, hop/graph.py:212-254).
     Input is either `xyz` (float32 [F][N][3]) or the brick indices `cells` (int32 [F][N]) from
     hist_accumulate.  `brick` is the BrickMap of brick_map(Density.map) -- block_map = "auto" (the
-    fine block map when it fits into shared memory, else the coarse one), "fine", "coarse" or "none"
+    fine block map when it fits into shared memory, else the coarse one, else the 2-bit cell map),
+    "fine", "coarse", "cell2" or "none"
     -- or the bricked int16 tensor with `coarse` / `fine` given separately.  fine_value picks the fine
     map (0: interstitial, 1: bulk, -1: decided on the device from the size of the bulk site)."""
     if isinstance(brick, BrickMap):
@@ -319,6 +326,7 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
         brick = bm.brick
         coarse = bm.coarse if block_map in ("auto", "coarse") else None
         fine = bm.fine if block_map in ("auto", "fine") else None
+        cell2 = bm.cell2 if block_map in ("auto", "cell2") else None
     _cuda(brick, torch.int16, "brick")
     map16 = brick
     if cells is not None:
@@ -338,11 +346,15 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
         _cuda(fine, torch.uint8, "fine")
         if fine.numel() != fine_map_bytes(grid.shape):
             raise ValueError("fine block map does not match the grid (use kernels.brick_map)")
+    if cell2 is not None:
+        _cuda(cell2, torch.int32, "cell2")
+        if cell2.numel() != nb * 4:
+            raise ValueError("2-bit cell map does not match the grid (use kernels.brick_map)")
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
     h = _h(map16)
     rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N,
-                                 int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(hop_x), _p(hop_y),
+                                 int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(cell2), _p(hop_x), _p(hop_y),
                                  int(n_chunks), int(chunk_len), _p(summaries), _p(events.data), _p(events.count),
                                  events.capacity)
     _lib.check(h, rc)

@@ -162,7 +162,7 @@ class HopPipeline:
             self._props_done = torch.cuda.Event()
             self._props_done.record(side)
         fine_buf = self._buf("fine", (K.fine_map_bytes(shape),), torch.uint8)
-        self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf)
+        self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf, self._buf("cell2", (nb * 4,), torch.int32))
         return density, own, member, map16, props
 
     def sync_scalars(self, events):

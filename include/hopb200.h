@@ -182,6 +182,8 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  *             ~230^3 cells): far fewer atoms then need the gather.  fine_value selects the map:
  *             0 (sub-bricks uniformly interstitial), 1 (uniformly bulk) or -1 = decided on the device
  *             (1 when the bulk site covers at least 1/8 of the grid).
+ *   cell2     device uint32 (may be NULL): the 2-bit cell map of hopb_brick_map, the gather target for
+ *             grids whose block maps do not fit into shared memory (beyond ~370^3 cells)
  *   frame0    global frame number of the slab's first frame
  *   hop_x/y   device float32 [F][N] out (site / orbit site: the X and Y records of the hoptraj
  *             DCD, trajectory.py:456-463); either may be NULL
@@ -189,8 +191,8 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
  *   events    device hopb_event [cap]; n_events device uint64 (running count, NOT reset here) */
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
                  int64_t F, int64_t N, int64_t frame0, const int16_t* brick, const uint32_t* coarse,
-                 const uint8_t* fine, int fine_value, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
-                 int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
+                 const uint8_t* fine, int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks,
+                 int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
 
 /* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block maps.  A brick is a
  * 4x4x4 block of cells stored as 64 consecutive int16 (one 128-byte line), bricks in C order over
@@ -203,9 +205,12 @@ int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* 
  *   fine    device uint8  [2 * nb_pad + 16] out, nb_pad = n_bricks rounded up to a multiple of 4; may be
  *           NULL.  Two maps: bit s of byte v * nb_pad + b is set when all cells of sub-brick
  *           s = (i1<<2 | j1<<1 | k1) of brick b carry the label v (0 = interstitial, 1 = bulk); the
- *           uint32 at byte 2 * nb_pad counts the cells with label 1. */
+ *           uint32 at byte 2 * nb_pad counts the cells with label 1.
+ *   cell2   device uint32 [n_bricks * 4] out, 16-byte aligned, may be NULL: 2 bits per cell in brick
+ *           order (cell index c: word c >> 4, bits 2 * (c & 15)): 0 = interstitial, 1 = bulk, 3 = any
+ *           other label (look it up in `brick`) */
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
-                   uint32_t* coarse, uint8_t* fine);
+                   uint32_t* coarse, uint8_t* fine, uint32_t* cell2);
 
 /* Same scan driven by an existing hopping trajectory (TransportNetwork on a loaded hoptraj,
  * hop/graph.py:190-254): labels = hop_x [F][N] float32. */

@@ -224,7 +224,7 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
     g = K.GridTables(edges)
     m16 = dev(site_map.astype(np.int16))
     bm = K.brick_map(m16)
-    block_map = "coarse" if "coarse" in mode else ("fine" if "fine" in mode else "none")
+    block_map = "coarse" if "coarse" in mode else ("fine" if "fine" in mode else ("cell2" if "cell2" in mode else "none"))
     fine_value = {"fine0": 0, "fine1": 1}.get(mode.split("+")[-1], -1)
     cells_all = None
     if mode.startswith("cells"):
@@ -269,7 +269,7 @@ def _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs=1, mode="xyz"):
 
 @pytest.mark.parametrize("n_chunks,slabs,mode", [(1, 1, "xyz"), (4, 1, "xyz+coarse"), (13, 1, "cells"), (200, 1, "cells+coarse"),
                                                  (3, 2, "cells+coarse"), (5, 8, "xyz+coarse"), (1, 1, "xyz+fine"),
-                                                 (9, 1, "cells+fine"), (4, 3, "cells+fine"), (2, 1, "cells+fine0"), (3, 1, "xyz+fine1")])
+                                                 (9, 1, "cells+fine"), (4, 3, "cells+fine"), (2, 1, "cells+fine0"), (3, 1, "xyz+fine1"), (6, 1, "cells+cell2"), (2, 2, "xyz+cell2")])
 def test_hoptraj_and_transitions(K, traj, n_chunks, slabs, mode):
     p, xyz = traj
     res = O.pipeline(xyz, delta=1.0)
@@ -345,6 +345,9 @@ def test_coarse_map_blocks(K):
         low = ((ii & 2) << 4) | ((jj & 2) << 3) | ((kk & 2) << 2) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1)
         idx = ((((ii >> 2) * cn[1] + (jj >> 2)) * cn[2] + (kk >> 2)) << 6) | low
         assert np.array_equal(brick[idx], m)
+        c2 = bm.cell2.cpu().numpy().view(np.uint32)
+        code = (c2[idx >> 4] >> ((idx & 15) * 2)) & 3
+        assert np.array_equal(code, np.where(m == 0, 0, np.where(m == 1, 1, 3)))
         for b in range(nb):
             ci, cj, ck = b // (cn[1] * cn[2]), (b // cn[2]) % cn[1], b % cn[2]
             blk = m[ci * 4:ci * 4 + 4, cj * 4:cj * 4 + 4, ck * 4:ck * 4 + 4]
@@ -365,7 +368,7 @@ def test_half_angstrom_golden_through_all_paths(K):
     xyz = g["xyz"]
     edges = [g["edges_x"], g["edges_y"], g["edges_z"]]
     ev_ref = g["events"].astype(np.int64)
-    for mode in ("xyz", "xyz+coarse", "cells", "cells+coarse", "xyz+fine", "cells+fine"):
+    for mode in ("xyz", "xyz+coarse", "cells", "cells+coarse", "xyz+fine", "cells+fine", "cells+cell2"):
         X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, g["site_map"], 3, 1, mode)
         assert np.array_equal(X, g["hop_x"].astype(np.float32)) and np.array_equal(Y, g["hop_y"].astype(np.float32))
         ev = K.events_to_numpy(events.data[:n_ev])
