@@ -619,6 +619,36 @@ class Density(Grid):
                 selected.discard(self.P['bulk_site'])
         return numpy.array(sorted(selected), dtype=int)
 
+    def stats(self, data=None):
+        """Statistics for the density, excluding bulk, interstitial and subsites
+        (hop/sitemap.py:1301-1339): rho_cut, rho_cut_bulk, N_sites, N_equivalence_sites, N_subsites,
+        site_volume_avg/std, site_occupancy_rho_avg/std.  `data` (a dict) receives the per-site
+        arrays site_volume, site_occupancy_rho_avg, site_occupancy_rho_std."""
+        if self.site_properties is None:
+            raise AttributeError('Stats require site_properties annotation.')
+        stats = dict()
+        nodes = self.site_labels(exclude=['bulk', 'interstitial', 'subsites'])
+        try:
+            stats['rho_cut'] = self.P['threshold']
+            stats['rho_cut_bulk'] = self.P['bulk_threshold']
+        except KeyError:
+            warnings.warn("No bulk site defined", category=MissingDataWarning)
+        stats['N_sites'] = len(nodes)
+        stats['N_equivalence_sites'] = 0   # equivalence sites are not part of this package
+        stats['N_subsites'] = 0
+        sp = self.site_properties.take(nodes)
+        stats['site_volume_avg'] = numpy.average(sp.volume)
+        stats['site_volume_std'] = numpy.std(sp.volume)
+        stats['site_occupancy_rho_avg'] = numpy.average(sp.occupancy_avg)
+        stats['site_occupancy_rho_std'] = numpy.std(sp.occupancy_avg)
+        try:
+            data['site_volume'] = sp.volume
+            data['site_occupancy_rho_avg'] = sp.occupancy_avg
+            data['site_occupancy_rho_std'] = sp.occupancy_std
+        except TypeError:
+            pass
+        return stats
+
     def _draw_map_from_sites(self):
         """Repaint the map from the (possibly edited) site list (hop/sitemap.py:1574-1587)."""
         self._own = None

@@ -176,3 +176,16 @@ def flatten(l):
         else:
             out.append(x)
     return out
+
+
+def easy_load(names, baseclass, keymethod):
+    """Instantiate a class either from an existing instance or a pickled file
+    (hop/utilities.py:263-296): objects that implement `keymethod` are taken as they are, anything
+    else is treated as a file name for ``baseclass(filename=name)``.  A single name gives a single
+    instance, a list gives a list."""
+    def load(name):
+        return name if hasattr(name, keymethod) else baseclass(filename=name)
+
+    if iterable(names) and not hasattr(names, keymethod):
+        return [load(x) for x in names]
+    return load(names)

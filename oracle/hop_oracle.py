@@ -504,6 +504,30 @@ def graph_alltransitions(hop_x):
 
 
 # =================================================================================================
+# Threshold scans (row f.4 of the scope table)
+# =================================================================================================
+def density_stats(sites, props, bulk_label=None):
+    """Density.stats (hop/sitemap.py:1301-1339) on the sites without interstitial and bulk."""
+    nodes = [l for l in range(len(sites)) if l != SITELABEL["interstitial"] and l != bulk_label]
+    vol = props["volume"][nodes]
+    occ = props["occupancy_avg"][nodes]
+    return dict(N_sites=len(nodes), site_volume_avg=np.average(vol), site_volume_std=np.std(vol),
+                site_occupancy_rho_avg=np.average(occ), site_occupancy_rho_std=np.std(occ))
+
+
+def scan_thresholds(grid, edges, bulk_sites, cutoffs, density_unit="Angstrom^{-3}", minsite=1):
+    """DensityScanner.scan for one density (hop/analysis.py:165-195): per cut-off map_sites,
+    site_insert_bulk, stats."""
+    out = {}
+    for rhocut in cutoffs:
+        sites = label_sites_ndimage(grid, rhocut, minsite)
+        sites = site_insert_bulk(sites, bulk_sites)
+        props = site_properties(sites, grid, edges, density_unit)
+        out[rhocut] = density_stats(sites, props, bulk_label=SITELABEL["bulk"])
+    return out
+
+
+# =================================================================================================
 # Rates from waiting times (row f.2 of the scope table)
 # =================================================================================================
 def survival_faithful(taus, t):

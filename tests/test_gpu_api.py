@@ -142,6 +142,45 @@ def test_map_sites_bulk_and_properties(system):
     assert np.array_equal(solvent.map, np.where(ref["map"] > 0, ref["map"] + 1, 0))
 
 
+def test_threshold_scan_matches_oracle(system, tmp_path):
+    """DensityScanner.scan (hop/analysis.py:165-195): per cut-off map_sites + site_insert_bulk + stats."""
+    import warnings
+
+    from hop_b200.analysis import DensityScanner
+    from hop_b200.sitemap import Density
+
+    u, xyz, sel, ref = system
+    unit = {"length": "Angstrom", "density": "water"}
+    solvent = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True}, unit=unit)
+    bulk = Density(grid=ref["grid"], edges=ref["edges"], parameters={"isDensity": True}, unit=unit)
+    bulk.map_sites(math.exp(-0.5))
+    cutoffs = [1.5, 2.0, math.e, 3.5]
+    scanner = DensityScanner(solvent, bulk)
+    with pytest.raises(ValueError):
+        DensityScanner(solvent).scan(cutoffs)          # bulk densities are required
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                 # "Removed bulk site in order to map sites"
+        scanner.scan(cutoffs)
+    want = O.scan_thresholds(ref["grid"], ref["edges"], O.label_sites_ndimage(ref["grid"], math.exp(-0.5)), cutoffs, "water")
+    assert sorted(scanner.scanstats) == sorted(cutoffs)
+    for c in cutoffs:
+        got = scanner.scanstats[c][0]
+        assert got["rho_cut"] == c and got["rho_cut_bulk"] == math.exp(-0.5)
+        assert got["N_sites"] == want[c]["N_sites"] and got["N_equivalence_sites"] == 0
+        for k in ("site_volume_avg", "site_volume_std", "site_occupancy_rho_avg", "site_occupancy_rho_std"):
+            assert got[k] == pytest.approx(want[c][k], rel=1e-6), (c, k)
+    arr = scanner.scanarrays[0]
+    assert list(arr.rho_cut) == sorted(cutoffs) and list(arr.N_sites) == [want[c]["N_sites"] for c in sorted(cutoffs)]
+    assert arr.N_sites[0] >= arr.N_sites[-1] or True     # more sites at lower cut-offs is typical, not guaranteed
+    data = {}
+    solvent.stats(data=data)
+    assert len(data["site_volume"]) == scanner.scanstats[cutoffs[-1]][0]["N_sites"]
+    scanner.save(str(tmp_path / "scan"))
+    again = DensityScanner()
+    again.load(str(tmp_path / "scan"))
+    assert sorted(again.scanstats) == sorted(cutoffs) and list(again.scanarrays[0].N_sites) == list(arr.N_sites)
+
+
 def test_density_pickle_schema(system, tmp_path):
     from hop_b200.sitemap import Density
 
