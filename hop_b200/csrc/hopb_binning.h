@@ -43,6 +43,7 @@ struct HopbGridTab {
   int32_t table_len;   // total floats in the packed up32 table
   int32_t table2_len;  // total float2 entries in the packed pair table
   int32_t fast_ok;     // 1 if the one-step corrected guess is proven exact for these edges
+  float sure_eps;      // > 0: hopb_bin_sure() with this margin is proven exact for these edges; 0: off
 };
 
 struct HopbPair { float lo, hi; };  // pair table entry b: (up32(e[b-1]) or -inf, up32(e[b]) or +inf)
@@ -66,6 +67,19 @@ HOPB_HD int hopb_bin_right_fast(float x, const HopbAxis& a, const HopbPair* pair
   b += (x >= e.hi) ? 1 : 0;
   b -= (x < e.lo) ? 1 : 0;
   return b;
+}
+
+// The bin without any table: the guess g = (x - lo) * inv is monotone in x, so when its fractional
+// part keeps a margin eps from 0 and 1 -- and the host has checked, at the two float32 neighbours of
+// every edge, that points the guess would misplace always land inside that margin -- floor(g) IS the
+// searchsorted result, and x is also clear of the last-edge rules.  Returns the bin (1..n), or 0 when
+// the point needs the table (about 2 * eps of the points per axis, everything outside the grid, NaN).
+HOPB_HD int hopb_bin_sure(float x, float lo, float inv, float nf, float eps) {
+  const float g = (x - lo) * inv;
+  const float fl = floorf(g);
+  const float fr = g - fl;  // exact
+  const bool sure = (g >= 0.0f) & (g < nf) & (fabsf(fr - 0.5f) <= 0.5f - eps);
+  return sure ? (int)fl + 1 : 0;
 }
 
 // numpy.histogramdd bin (1..n counted) and _coord2hop bin (1..n are map cells) on the fast path

@@ -108,5 +108,31 @@ static inline int hopb_build_gridtab(const double* const edges[3], const int n[3
   }
   tab->table_len = (int)table->size();
   tab->table2_len = table2 ? (int)table2->size() : 0;
+  // Margin for the table-free bin (hopb_bin_sure): the smallest eps for which, on every axis,
+  //   (A) g(up32(e_k)) > k - eps   -- points at/above edge k that the guess leaves in bin k have frac > 1 - eps,
+  //   (B) g(prev32(up32(e_k))) < k + eps   -- points below edge k that the guess puts in bin k+1 have frac < eps,
+  //   (C) g(first coordinate of a last-edge rule) > n - eps   -- those points are never "sure".
+  // g is monotone in x, so checking the two float32 neighbours of every edge covers all x.
+  tab->sure_eps = 0.0f;
+  if (tab->fast_ok) {
+    const float candidates[] = {1.0f / 4096, 1.0f / 1024, 1.0f / 256, 1.0f / 64};
+    for (float eps : candidates) {
+      bool ok = true;
+      for (int d = 0; d < 3 && ok; ++d) {
+        const HopbAxis& a = tab->ax[d];
+        const float* eup = table->data() + a.off;
+        auto g = [&](float x) { return (x - a.lo) * a.inv; };
+        for (int k = 0; k <= a.n && ok; ++k) {
+          if (!(g(eup[k]) > (float)k - eps)) ok = false;
+          if (!(g(hopb_prev32(eup[k])) < (float)k + eps)) ok = false;
+        }
+        float zone = std::numeric_limits<float>::infinity();
+        if (a.top_eq == a.top_eq) zone = a.top_eq;
+        if (a.hop_lo <= a.hop_hi && a.hop_lo < zone) zone = a.hop_lo;
+        if (std::isfinite(zone) && !(g(zone) > (float)a.n - eps)) ok = false;
+      }
+      if (ok) { tab->sure_eps = eps; break; }
+    }
+  }
   return 0;
 }

@@ -83,7 +83,9 @@ int64_t emul_scan(const int32_t* labels, int64_t F, int64_t N, int64_t slab_len,
 }
 
 // Binning: mode 0 = histogram bin (1..n counted), mode 1 = hoptraj bin ([-1, n+1]); modes 2 / 3 are
-// the same through the branch-free pair-table search the kernels use when fast_ok is set (returned).
+// the same through the branch-free pair-table search the kernels use when fast_ok is set (returned);
+// mode 4 = histogram bin through the table-free "sure" bin with the pair-table search as fallback (what
+// hist_kernel does), mode 5 = 1 where the sure bin applies, else 0.
 int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* ez, int nz,
              const int* decimals, const float* xyz, int64_t npts, int mode, int32_t* out /*[npts][3]*/,
              float* top_round_out /*[3]*/) {
@@ -103,7 +105,13 @@ int emul_bin(const double* ex, int nx, const double* ey, int ny, const double* e
       if (mode == 0) b = hopb_bin_hist(x, tab.ax[d], eup);
       else if (mode == 1) b = hopb_bin_hop(x, tab.ax[d], eup);
       else if (mode == 2) b = hopb_bin_hist_fast(x, tab.ax[d], pr);
-      else b = hopb_bin_hop_fast(x, tab.ax[d], pr);
+      else if (mode == 3) b = hopb_bin_hop_fast(x, tab.ax[d], pr);
+      else {
+        const HopbAxis& a = tab.ax[d];
+        const int s = tab.sure_eps > 0.0f ? hopb_bin_sure(x, a.lo, a.inv, (float)a.n, tab.sure_eps) : 0;
+        if (mode == 4) b = s ? s : hopb_bin_hist_fast(x, a, pr);
+        else b = s ? 1 : 0;
+      }
       out[i * 3 + d] = b;
     }
   return tab.fast_ok;

@@ -131,6 +131,18 @@ def test_binning_matches_numpy(emul, delta, origin):
         b_out = (b < 1) | (b > n)
         assert np.array_equal(a_out, b_out)
         assert np.array_equal(a[~a_out], b[~b_out])
+    # the table-free "sure" bin (with the table as fallback) is the histogram bin everywhere, it is
+    # never taken for a hoptraj bin that differs from the histogram bin, and it covers nearly all points
+    a, _ = _bins(emul, edges, xyz, 0)
+    b, _ = _bins(emul, edges, xyz, 4)
+    n = np.array([len(e) - 1 for e in edges])
+    a_out, b_out = (a < 1) | (a > n), (b < 1) | (b > n)
+    assert np.array_equal(a_out, b_out) and np.array_equal(a[~a_out], b[~b_out])
+    sure, _ = _bins(emul, edges, xyz, 5)
+    hopb, _ = _bins(emul, edges, xyz, 1)
+    assert np.array_equal(hopb[sure == 1], a[sure == 1])
+    inside = (xyz[:20000] > np.array([e[0] for e in edges])).all(axis=1) & (xyz[:20000] < np.array([e[-1] for e in edges])).all(axis=1)
+    assert sure[:20000][inside].mean() > 0.95
     # histogram semantics
     got, _ = _bins(emul, edges, xyz, 0)
     for d in range(3):
