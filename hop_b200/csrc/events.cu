@@ -35,8 +35,15 @@ struct EvArgs {
   int32_t* e_s;
   int64_t* e_start;
   int64_t* e_count;
-  int32_t* matrix;     // optional dense [(n_labels+1)^2], caller-zeroed
+  int32_t* matrix;     // optional dense count matrix, row stride matrix_stride (0: n_labels + 1, caller-zeroed)
   int64_t* n_edges_dev;
+  // device-side arguments (hopb_events_finalize_dev): n and n_labels are read from device memory,
+  // so the host need not wait for stage 3 before it launches this kernel
+  const unsigned long long* n_dev;  // number of events (NULL: use n)
+  int64_t cap;                      // capacity of the event buffer
+  const int32_t* n_sites_dev;       // number of hydration sites; n_labels = *n_sites_dev + label_offset
+  int label_offset, max_sites, matrix_stride;
+  int64_t* result_dev;              // [4]: n_events, n_edges, n_labels, status
 };
 
 __device__ __forceinline__ int coop_sort(cg::grid_group& grid, const EvArgs& a, int cur, int bits, SortSmem& sm) {
@@ -59,6 +66,30 @@ ev_finalize_kernel(EvArgs a) {
   cg::grid_group grid = cg::this_grid();
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  if (a.n_dev) {
+    // every thread derives the same launch parameters from the device scalars
+    const unsigned long long n_all = *a.n_dev;
+    const int n_sites = *a.n_sites_dev;
+    int status = 0;
+    if (n_all > (unsigned long long)a.cap) status |= HOPB_FIN_OVERFLOW;   // stage 3 must be redone with a larger buffer
+    if (n_sites > a.max_sites) status |= HOPB_FIN_TOO_MANY_SITES;
+    a.n = status ? 0 : (int64_t)n_all;
+    a.n_labels = n_sites + a.label_offset;
+    const uint64_t W = (uint64_t)a.n_labels + 1;
+    a.bits2 = hopb_bits_for(W * W);
+    if (a.matrix && (int64_t)W > a.matrix_stride) { status |= HOPB_FIN_MATRIX_SKIPPED; a.matrix = nullptr; }
+    const int64_t ntiles = (a.n + kSortTile - 1) / kSortTile;
+    a.tiles_per_block = (int)((ntiles + gridDim.x - 1) / gridDim.x);
+    if (a.tiles_per_block < 1) a.tiles_per_block = 1;
+    if (gtid == 0) {
+      a.result_dev[0] = (int64_t)n_all; a.result_dev[1] = 0; a.result_dev[2] = a.n_labels; a.result_dev[3] = status;
+    }
+    if (a.matrix) {  // the whole buffer: it is all-reduced across ranks as it is
+      const int64_t cells = (int64_t)a.matrix_stride * a.matrix_stride;
+      for (int64_t i = gtid; i < cells; i += gstride) a.matrix[i] = 0;
+    }
+    if (a.n == 0) return;   // uniform: every thread of the grid leaves before the first barrier
+  }
   const int64_t n = a.n;
 
   // key 1: position in the reference's loop order
@@ -97,6 +128,7 @@ ev_finalize_kernel(EvArgs a) {
     for (unsigned b = 0; b < gridDim.x; ++b) { const uint32_t c = a.blockcnt[b]; a.blockcnt[b] = run; run += c; }
     a.blockcnt[gridDim.x] = run;
     *a.n_edges_dev = (int64_t)run;
+    if (a.result_dev) a.result_dev[1] = (int64_t)run;
   }
   grid.sync();
   // edge records: rank of every head = block base + ordered rank inside the block
@@ -122,7 +154,8 @@ ev_finalize_kernel(EvArgs a) {
   for (int64_t e = gtid; e < n_edges; e += gstride) {
     const int64_t c = (e + 1 < n_edges ? a.e_start[e + 1] : n) - a.e_start[e];
     a.e_count[e] = c;
-    if (a.matrix) a.matrix[(int64_t)(a.e_s0[e] + 1) * (int64_t)W + (a.e_s[e] + 1)] = (int32_t)c;
+    const int64_t stride = a.matrix_stride ? (int64_t)a.matrix_stride : (int64_t)W;
+    if (a.matrix) a.matrix[(int64_t)(a.e_s0[e] + 1) * stride + (a.e_s[e] + 1)] = (int32_t)c;
   }
 }
 
@@ -171,6 +204,8 @@ extern "C" int hopb_events_finalize_ex(hopb_handle* h, void* stream, const hopb_
   a.n_edges_dev = n_edges_dev;
   a.sorted = events_sorted; a.e_s0 = edge_s0; a.e_s = edge_s; a.e_start = edge_start; a.e_count = edge_count;
   a.matrix = count_matrix;
+  a.n_dev = nullptr; a.cap = n; a.n_sites_dev = nullptr; a.label_offset = 0; a.max_sites = 0; a.matrix_stride = 0;
+  a.result_dev = nullptr;
   void* kargs[] = {(void*)&a};
   hopb_note_launch();
   HOPB_CUDA(h, cudaLaunchCooperativeKernel((void*)ev_finalize_kernel, dim3((unsigned)nblocks), dim3(kSortThreads), kargs, 0, s));
@@ -178,6 +213,49 @@ extern "C" int hopb_events_finalize_ex(hopb_handle* h, void* stream, const hopb_
   HOPB_CUDA(h, cudaMemcpyAsync(&total, n_edges_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   HOPB_CUDA(h, cudaStreamSynchronize(s));
   *n_edges = total;
+  return HOPB_OK;
+}
+
+extern "C" int hopb_events_finalize_dev(hopb_handle* h, void* stream, const hopb_event* events,
+                                        const uint64_t* n_events_dev, uint64_t cap_u, int64_t N, int64_t F_total,
+                                        const int32_t* n_sites_dev, int label_offset, hopb_event* events_sorted,
+                                        int32_t* edge_s0, int32_t* edge_s, int64_t* edge_start, int64_t* edge_count,
+                                        int32_t* count_matrix, int matrix_stride, int64_t* result_dev) {
+  HOPB_REQUIRE(h, events && n_events_dev && n_sites_dev && events_sorted && edge_s0 && edge_s && edge_start && edge_count &&
+                      result_dev, "null argument");
+  const int64_t cap = (int64_t)cap_u;
+  HOPB_REQUIRE(h, cap >= 1 && cap < ((int64_t)1 << 32) && N > 0 && F_total > 0 && label_offset >= 1, "bad argument");
+  HOPB_REQUIRE(h, count_matrix == nullptr || matrix_stride >= 2, "bad matrix stride");
+  cudaStream_t s = (cudaStream_t)stream;
+  int per_sm = 0;
+  HOPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ev_finalize_kernel, kSortThreads, 0));
+  HOPB_REQUIRE(h, per_sm >= 1, "cooperative launch not possible");
+  // one block per SM: the passes are barrier-latency bound at the event counts of this path
+  const int nblocks = h->num_sms < kMaxSortBlocks ? h->num_sms : kMaxSortBlocks;
+  unsigned char* buf = nullptr;
+  const size_t per = 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
+  const size_t bytes = (size_t)(cap + 2) * per + ((size_t)256 * nblocks + 256 + nblocks + 8) * sizeof(uint32_t) + 64;
+  int rc = hopb_scratch(h, 5, bytes, (void**)&buf);
+  if (rc) return rc;
+  EvArgs a;
+  a.ev = events; a.n = 0; a.N = N; a.n_labels = 0; a.bits2 = 0; a.tiles_per_block = 1;
+  a.bits1 = hopb_bits_for((uint64_t)F_total * (uint64_t)N);
+  a.k[0] = (uint64_t*)buf;
+  a.k[1] = a.k[0] + (cap + 2);
+  a.v[0] = (uint32_t*)(a.k[1] + (cap + 2));
+  a.v[1] = a.v[0] + (cap + 2);
+  a.ghist = a.v[1] + (cap + 2);
+  a.totals = a.ghist + (size_t)256 * nblocks;
+  a.blockcnt = a.totals + 256;
+  a.n_edges_dev = (int64_t*)(((uintptr_t)(a.blockcnt + nblocks + 2) + 7) & ~(uintptr_t)7);
+  a.sorted = events_sorted; a.e_s0 = edge_s0; a.e_s = edge_s; a.e_start = edge_start; a.e_count = edge_count;
+  a.matrix = count_matrix;
+  a.n_dev = (const unsigned long long*)n_events_dev; a.cap = cap; a.n_sites_dev = n_sites_dev;
+  a.label_offset = label_offset; a.max_sites = HOPB_MAX_SITES; a.matrix_stride = count_matrix ? matrix_stride : 0;
+  a.result_dev = result_dev;
+  void* kargs[] = {(void*)&a};
+  hopb_note_launch();
+  HOPB_CUDA(h, cudaLaunchCooperativeKernel((void*)ev_finalize_kernel, dim3((unsigned)nblocks), dim3(kSortThreads), kargs, 0, s));
   return HOPB_OK;
 }
 

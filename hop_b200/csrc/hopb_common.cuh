@@ -78,7 +78,7 @@ int hopb_exclusive_scan_u32(hopb_handle* h, cudaStream_t s, const uint32_t* in, 
 int hopb_radix_sort_pairs(hopb_handle* h, cudaStream_t s, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals,
                           uint32_t* vals_alt, int64_t n, int begin_bit, int end_bit, int* in_alt);
 
-static inline int hopb_bits_for(uint64_t v) {  // number of bits needed to represent values in [0, v]
+static __host__ __device__ inline int hopb_bits_for(uint64_t v) {  // number of bits needed to represent values in [0, v]
   int b = 0;
   while (v) { ++b; v >>= 1; }
   return b < 1 ? 1 : b;

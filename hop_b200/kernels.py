@@ -428,6 +428,25 @@ def events_finalize(events: EventBuffer, n_events: int, n_atoms: int, n_frames_t
     return sorted_ev[:n], e_s0[:k], e_s[:k], e_start[:k], e_count[:k]
 
 
+FIN_OVERFLOW, FIN_TOO_MANY_SITES, FIN_MATRIX_SKIPPED = 1, 2, 4
+
+
+def events_finalize_dev(events: EventBuffer, n_atoms: int, n_frames_total: int, n_sites_dev: torch.Tensor,
+                        label_offset: int, out, count_matrix, result_dev: torch.Tensor):
+    """events_finalize without any host round trip: the event count (events.count) and the number of
+    sites (n_sites_dev, int32) are read on the device.  `out` = five capacity-sized output buffers,
+    `count_matrix` = square int32 buffer (or None) filled with its own row stride, `result_dev` = int64
+    [4] receiving (n_events, n_edges, n_labels, status bits FIN_*)."""
+    sorted_ev, e_s0, e_s, e_start, e_count = out
+    stride = 0 if count_matrix is None else int(count_matrix.shape[0])
+    h = _h(events.data)
+    rc = _lib.lib().hopb_events_finalize_dev(h, _stream(), _p(events.data), _p(events.count), events.capacity,
+                                             int(n_atoms), int(n_frames_total), _p(n_sites_dev), int(label_offset),
+                                             _p(sorted_ev), _p(e_s0), _p(e_s), _p(e_start), _p(e_count),
+                                             _p(count_matrix), stride, _p(result_dev))
+    _lib.check(h, rc)
+
+
 def all_transitions(hop_x: torch.Tensor, n_labels: int):
     """Sorted (K,2) int64 array of (label[t-1], label[t]) pairs (hop/graph.py:107-135)."""
     _cuda(hop_x, torch.float32, "hop_x")

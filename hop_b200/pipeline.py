@@ -15,7 +15,7 @@ No collective touches the coordinate stream.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
@@ -39,29 +39,86 @@ class PipelineConfig:
     cache_cells: bool | None = None  # stage 1 also writes the packed hoptraj cell per atom-frame (4 B)
     coarse_map: bool = True          # block map in shared memory for stage 3 (False: always gather)
     block_map: str = "auto"          # "auto" (fine when it fits, else coarse), "fine", "coarse", "none"
+    async_results: bool = True       # from the second run on: no host synchronisation inside run()
 
 
-@dataclass
-class PipelineResult:
-    counts: torch.Tensor = None
-    density: torch.Tensor = None
-    own: torch.Tensor = None
-    member: torch.Tensor = None
-    map16: torch.Tensor = None
-    n_labels: int = 0                 # len(sites): interstitial + bulk + hydration sites
-    hop_x: torch.Tensor = None
-    hop_y: torch.Tensor = None
-    events: torch.Tensor = None       # this rank's events, sorted by (edge, frame, iatom)
-    edge_s0: torch.Tensor = None
-    edge_s: torch.Tensor = None
-    edge_start: torch.Tensor = None
-    edge_count: torch.Tensor = None   # this rank's COO counts
-    count_matrix: torch.Tensor = None  # global dense [(S+2),(S+2)] int32 (row/col = label+1), if small enough
-    state: torch.Tensor = None        # [4][N] machine state after this rank's slab
-    final_state: torch.Tensor = None  # state after the last slab (node records: hop/graph.py:259-274)
-    site_props: tuple = None
-    n_events_local: int = 0
-    timings: dict = field(default_factory=dict)
+class PipelineResult(object):
+    """What a run leaves behind.  The tensors are the pipeline's own buffers: they stay valid until the
+    next run.  The fields that depend on counts only the device knows when run() returns -- n_labels,
+    n_events_local, events, edge_*, count_matrix, site_props -- are resolved on first access (one
+    wait for the finalisation stream), so that back-to-back runs never stall the host."""
+
+    _LAZY = ("n_labels", "n_events_local", "events", "edge_s0", "edge_s", "edge_start", "edge_count", "count_matrix",
+             "site_props")
+
+    def __init__(self):
+        self.counts = None
+        self.density = None
+        self.own = None
+        self.member = None
+        self.map16 = None
+        self.hop_x = None
+        self.hop_y = None
+        self.state = None         # [4][N] machine state after this rank's slab
+        self.final_state = None   # state after the last slab (node records: hop/graph.py:259-274)
+        self.timings = {}
+        self._pending = None
+        # lazily resolved (see class docstring):
+        #   n_labels        len(sites): interstitial + bulk + hydration sites
+        #   events          this rank's events, sorted by (edge, frame, iatom)
+        #   edge_s0, edge_s, edge_start, edge_count   this rank's COO counts
+        #   count_matrix    global dense [(S+2),(S+2)] int32 (row/col = label+1), if small enough
+        #   site_props, n_events_local
+
+    def __getattr__(self, name):
+        # only reached when the attribute has not been set yet
+        if name in PipelineResult._LAZY:
+            pending = self.__dict__.get("_pending")
+            if pending is not None:
+                self.__dict__["_pending"] = None
+                pending.resolve(self)
+                return self.__dict__[name]
+        raise AttributeError(name)
+
+    def wait(self):
+        """Resolve the lazy fields now."""
+        return self.n_labels
+
+
+class _PendingFinalize(object):
+    """The finalisation of one run in flight on the pipeline's side stream."""
+
+    def __init__(self, pipe, done, host, events, out, matrix, props, props_done, redo):
+        self.pipe, self.done, self.host, self.events, self.out = pipe, done, host, events, out
+        self.matrix, self.props, self.props_done, self.redo = matrix, props, props_done, redo
+
+    def resolve(self, res):
+        self.done.synchronize()
+        n_all, n_edges, n_labels, status = (int(v) for v in self.host.tolist())
+        pipe = self.pipe
+        pipe._fin_hosts.append(self.host)
+        if status & K.FIN_TOO_MANY_SITES:
+            from ._lib import TooManySitesError
+
+            raise TooManySitesError("map_sites: more than %d sites; hop's int16 site map cannot hold them"
+                                    % K.HOPB_MAX_SITES)
+        if status & (K.FIN_OVERFLOW | K.FIN_MATRIX_SKIPPED):
+            # rare: more transitions than budgeted, or more sites than the count matrix was sized for
+            # -- redo the tail of the run synchronously with what is known now
+            pipe._w_known = n_labels + 1
+            self.redo(res, n_all if status & K.FIN_OVERFLOW else None)
+            return
+        sorted_ev, e_s0, e_s, e_start, e_count = self.out
+        res.events = sorted_ev[:n_all]
+        res.edge_s0, res.edge_s = e_s0[:n_edges], e_s[:n_edges]
+        res.edge_start, res.edge_count = e_start[:n_edges], e_count[:n_edges]
+        W = n_labels + 1
+        res.count_matrix = None if self.matrix is None else self.matrix[:W, :W]
+        res.n_labels, res.n_events_local = n_labels, n_all
+        if self.props_done is not None:
+            self.props_done.synchronize()
+        res.site_props = self.props
+        pipe._w_known = W
 
 
 _dist = exchange.dist
@@ -81,6 +138,9 @@ class HopPipeline:
         self.device = self.grid.device
         self._events = None
         self._bufs = {}
+        self._w_known = None      # n_labels + 1 of the last resolved run: sizes the count matrix of the next
+        self._s4_done = None      # finalisation of the previous run (reads the event buffer)
+        self._run_index = 0
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     # -- buffers reused across runs (steady-state runs do not allocate) --------------------------
@@ -127,7 +187,8 @@ class HopPipeline:
         factor = density_conversion_factor("Angstrom^{-3}", cfg.density_unit)
         density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor,
                                         out=self._buf("density", shape, torch.float64))
-        self.n_sites_dev = self._buf("n_sites_dev", (2,), torch.int32)
+        # two buffers, alternating: the finalisation of the previous run may still read its own
+        self.n_sites_dev = self._buf("n_sites_dev%d" % (self._run_index & 1), (2,), torch.int32)
         main = torch.cuda.current_stream(self.device)
         side = getattr(self, "_side_stream", None)
         if side is None:
@@ -198,6 +259,9 @@ class HopPipeline:
         if self._events is not None:
             cap = max(cap, self._events.capacity)
         events = self._event_buffer(cap)
+        if self._s4_done is not None:     # the previous run's finalisation reads the event buffer
+            torch.cuda.current_stream(self.device).wait_event(self._s4_done)
+            self._s4_done = None
         events.reset()
         hop_x = hop_y = None
         if cfg.write_hoptraj:
@@ -241,33 +305,103 @@ class HopPipeline:
             exchange.reduce_count_matrix(matrix)
         return ev, e_s0, e_s, e_start, e_count, matrix
 
-    def _mark(self, marks, name):
-        if marks is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append((name, ev))
-
-    def run(self, xyz, frame0=0, marks=None):
-        """xyz: CUDA float32 [F_local][N][3] (this rank's slab, starting at global frame `frame0`).
-        `marks` (a list) receives (stage name, CUDA event) pairs recorded on the current stream at
-        every stage boundary, for per-stage device timing."""
-        res = PipelineResult()
-        self._mark(marks, "start")
-        res.counts = self.histogram(xyz)
-        self._mark(marks, "S1_histogram")
-        res.density, res.own, res.member, res.map16, res.site_props = self.site_map(res.counts)
-        self._mark(marks, "S2_sitemap")
-        res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+    def _finalize_sync(self, res, events, xyz, frame0):
+        """Tail of a run with the host in the loop: wait for stage 3, read the counts, sort."""
         res.n_labels, n_ev = self.sync_scalars(events)
         if n_ev > events.capacity:      # rare: more transitions than budgeted -- grow the buffer and redo stage 3
             self._event_buffer(n_ev + n_ev // 8)
             res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
             res.n_labels, n_ev = self.sync_scalars(events)
-        self._mark(marks, "S3S4_hoptraj")
         res.n_events_local = n_ev
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
          res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]), res.n_labels)
-        self._mark(marks, "S4_transitions")
+        res.site_props = self._props
+        res._pending = None
+        self._w_known = res.n_labels + 1
+
+    def _finalize_async(self, res, events, xyz, frame0):
+        """Tail of a run without the host: the event ordering is queued on a side stream with its sizes
+        read on the device (csrc/events.cu), the four result scalars come back through pinned memory
+        and are looked at when a lazy field of the result is first used.  The next run may start right
+        away; only its stage 3 waits for this finalisation (it reuses the event buffer)."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        s4 = getattr(self, "_s4_stream", None)
+        if s4 is None:
+            s4 = self._s4_stream = torch.cuda.Stream(device=dev)
+            self._fin_hosts = []      # pool of pinned 4-word result buffers; one per unresolved result
+        props_done = getattr(self, "_props_done", None)
+        self._props_done = None
+        if props_done is not None:
+            main.wait_event(props_done)   # the next run's stage 2 overwrites what the annotation reads
+        w_cap = 256
+        while w_cap < self._w_known + self._w_known // 4 + 8:
+            w_cap *= 2
+        # two sets of outputs, alternating: the results of a run stay intact while the next one is finalised
+        par = "%d" % (self._run_index & 1)
+        matrix = self._buf("count_matrix_cap" + par, (w_cap, w_cap), torch.int32) if w_cap * w_cap <= (1 << 24) else None
+        cap = max(events.capacity, 1)
+        out = (self._buf("ev_sorted" + par, (cap, 6), torch.int32), self._buf("e_s0" + par, (cap,), torch.int32),
+               self._buf("e_s" + par, (cap,), torch.int32), self._buf("e_start" + par, (cap,), torch.int64),
+               self._buf("e_count" + par, (cap,), torch.int64))
+        result_dev = self._buf("fin_result", (4,), torch.int64)
+        host = self._fin_hosts.pop() if self._fin_hosts else torch.zeros(4, dtype=torch.int64).pin_memory()
+        s4.wait_stream(main)
+        with torch.cuda.stream(s4):
+            K.events_finalize_dev(events, int(xyz.shape[1]), self.n_frames_total, self.n_sites_dev[0:1],
+                                  2 if self.cfg.with_bulk else 1, out, matrix, result_dev)
+            if matrix is not None:
+                exchange.reduce_count_matrix(matrix)
+            host.copy_(result_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(s4)
+        self._s4_done = done
+
+        run_index = self._run_index
+
+        def redo(res_, n_needed):
+            if self._run_index != run_index + 1:
+                if n_needed is not None:
+                    self._event_buffer(n_needed + n_needed // 8)   # at least the next runs will fit
+                raise _capacity_error(n_needed or 0, events.capacity) if n_needed is not None else RuntimeError(
+                    "the count matrix of an earlier run was sized for fewer sites and its buffers have been reused")
+            if n_needed is not None:
+                self._event_buffer(n_needed + n_needed // 8)
+                res_.hop_x, res_.hop_y, ev2, res_.state, res_.final_state = self.hoptraj(xyz, res_.map16, frame0)
+            else:
+                ev2 = events
+            self._finalize_sync(res_, ev2, xyz, frame0)
+
+        res._pending = _PendingFinalize(self, done, host, events, out, matrix, self._props, props_done, redo)
+
+    def _finalize(self, res, events, xyz, frame0):
+        if self.cfg.async_results and self._w_known is not None:
+            self._finalize_async(res, events, xyz, frame0)
+        else:
+            self._finalize_sync(res, events, xyz, frame0)
+        self._run_index += 1
+
+    def _mark(self, marks, name, stream=None):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+            marks.append((name, ev))
+
+    def run(self, xyz, frame0=0, marks=None):
+        """xyz: CUDA float32 [F_local][N][3] (this rank's slab, starting at global frame `frame0`).
+        `marks` (a list) receives (stage name, CUDA event) pairs recorded at every stage boundary, for
+        per-stage device timing (the last one on the finalisation stream when that runs beside the
+        next run)."""
+        res = PipelineResult()
+        self._mark(marks, "start")
+        res.counts = self.histogram(xyz)
+        self._mark(marks, "S1_histogram")
+        res.density, res.own, res.member, res.map16, self._props = self.site_map(res.counts)
+        self._mark(marks, "S2_sitemap")
+        res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+        self._mark(marks, "S3S4_hoptraj")
+        self._finalize(res, events, xyz, frame0)
+        self._mark(marks, "S4_transitions", getattr(self, "_s4_stream", None) if res._pending is not None else None)
         return res
 
     def run_host(self, xyz_host, frame0=0, out_x=None, out_y=None, block_bytes=256 << 20):
@@ -281,27 +415,33 @@ class HopPipeline:
         trajectory to be in host memory and returns (PipelineResult, host dict).
 
         Coordinates go to HBM in blocks on an upload stream while the histogram kernel consumes the
-        blocks already there; they stay resident for stage 3.  The events are sorted and the small
-        results (sorted events, COO transition counts, final per-atom state) copied to the host, then
-        the hopping trajectory planes stream back into pinned host tensors (out_x / out_y,
-        [F_local][N] float32) on a download stream.  Uploads and downloads use different streams
-        (and copy engines), so a caller that begins run k+1 before finishing run k -- with a second
-        pair of out_x / out_y -- overlaps the download of k with the upload of k+1; PCIe is full
-        duplex.  The device buffers are shared between runs: stage 3 of the next run waits for the
-        download of this one."""
+        blocks already there; they stay resident for stage 3.  The hopping trajectory planes stream
+        back into pinned host tensors (out_x / out_y, [F_local][N] float32) on a download stream; the
+        sorted events, COO transition counts and final per-atom state follow at finish().  From the
+        second run on nothing in here waits for the device (PipelineConfig.async_results), uploads
+        and downloads use different streams and copy engines, and the resident coordinates are double
+        buffered: a caller that begins run k+1 before finishing run k -- with a second pair of out_x /
+        out_y -- overlaps the upload of k+1 with the stage 2-4 tail and the download of k (PCIe is full
+        duplex)."""
         F, N = int(xyz_host.shape[0]), int(xyz_host.shape[1])
         dev = self.device
-        xyz = self._buf("xyz_resident", (F, N, 3), torch.float32)
+        par = self._run_index & 1
+        xyz = self._buf("xyz_resident%d" % par, (F, N, 3), torch.float32)
         counts = self._buf("counts", self.grid.shape, torch.int32)
         counts.zero_()
-        self.cells = self._buf("cells", (F, N), torch.int32) if self._use_cells(xyz) else None
+        self.cells = self._buf("cells%d" % par, (F, N), torch.int32) if self._use_cells(xyz) else None
         if getattr(self, "_h2d_stream", None) is None:
             self._h2d_stream = torch.cuda.Stream(device=dev)
             self._d2h_stream = torch.cuda.Stream(device=dev)
+            self._small_stream = torch.cuda.Stream(device=dev)
             self._d2h_done = None
+            self._xyz_free = [None, None]
         h2d, d2h = self._h2d_stream, self._d2h_stream
         main = torch.cuda.current_stream(dev)
-        h2d.wait_stream(main)
+        if self._xyz_free[par] is not None:
+            h2d.wait_event(self._xyz_free[par])       # stage 3 of the run before last read this buffer
+        elif self._run_index < 2:
+            h2d.wait_stream(main)
         block = max(1, block_bytes // (N * 12))
         for f0 in range(0, F, block):
             f1 = min(F, f0 + block)
@@ -314,44 +454,53 @@ class HopPipeline:
         exchange.reduce_counts(counts)
         res = PipelineResult()
         res.counts = counts
-        res.density, res.own, res.member, res.map16, res.site_props = self.site_map(counts)
+        res.density, res.own, res.member, res.map16, self._props = self.site_map(counts)
         if self._d2h_done is not None:
             main.wait_event(self._d2h_done)      # the previous run's planes are still being downloaded
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
-        res.n_labels, n_ev = self.sync_scalars(events)
-        if n_ev > events.capacity:
-            self._event_buffer(n_ev + n_ev // 8)
-            res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
-            res.n_labels, n_ev = self.sync_scalars(events)
-        res.n_events_local = n_ev
+        free = torch.cuda.Event()
+        free.record(main)
+        self._xyz_free[par] = free
         if out_x is None:
             out_x = torch.empty((F, N), dtype=torch.float32).pin_memory()
             out_y = torch.empty((F, N), dtype=torch.float32).pin_memory()
-        (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
-         res.count_matrix) = self.transitions(events, n_ev, N, res.n_labels)
-        # small results first (these copies synchronise), then the planes: 8 B per atom-frame
-        host = dict(hop_x=out_x, hop_y=out_y, events=res.events.cpu(), edge_s0=res.edge_s0.cpu(),
-                    edge_s=res.edge_s.cpu(), edge_count=res.edge_count.cpu(), final_state=res.final_state.cpu())
         d2h.wait_stream(main)
         with torch.cuda.stream(d2h):
             out_x.copy_(res.hop_x, non_blocking=True)
             out_y.copy_(res.hop_y, non_blocking=True)
+            # fixed-size small result; the buffer is rewritten by the next run's stage 3
+            state_host = self._host_buf("final_state%d" % par, tuple(res.final_state.shape), torch.int32)
+            state_host.copy_(res.final_state, non_blocking=True)
             done = torch.cuda.Event()
             done.record(d2h)
         self._d2h_done = done
-        return HostRun(res, host, done)
+        self._finalize(res, events, xyz, frame0)
+        return HostRun(self, res, dict(hop_x=out_x, hop_y=out_y, final_state=state_host), done)
+
+    def _host_buf(self, name, shape, dtype):
+        bufs = self.__dict__.setdefault("_host_bufs", {})
+        t = bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = bufs[name] = torch.empty(shape, dtype=dtype).pin_memory()
+        return t
 
 
 class HostRun(object):
     """A run_host_begin in flight: finish() returns (PipelineResult, host dict) once the hopping
-    trajectory planes are in host memory."""
+    trajectory planes and the sorted events / transition counts are in host memory."""
 
-    def __init__(self, result, host, done):
-        self.result, self.host, self._done = result, host, done
+    def __init__(self, pipe, result, host, done):
+        self.pipe, self.result, self.host, self._done = pipe, result, host, done
 
     def finish(self):
+        res, host = self.result, self.host
+        if "events" not in host:
+            res.wait()                                   # finalisation of this run (not of later ones)
+            with torch.cuda.stream(self.pipe._small_stream):   # a stream of its own: nothing queued ahead
+                host.update(events=res.events.cpu(), edge_s0=res.edge_s0.cpu(), edge_s=res.edge_s.cpu(),
+                            edge_count=res.edge_count.cpu())
         self._done.synchronize()
-        return self.result, self.host
+        return res, host
 
 
 def _capacity_error(n, cap):

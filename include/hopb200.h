@@ -252,6 +252,24 @@ int hopb_events_finalize_ex(hopb_handle* h, void* stream, const hopb_event* even
                             int32_t* edge_s, int64_t* edge_start, int64_t* edge_count, int32_t* count_matrix,
                             int64_t* n_edges);
 
+/* The same finalisation with its sizes read on the device, so that the host can queue it behind
+ * stage 3 without waiting for the event count or the number of sites (no synchronisation at all):
+ *   n_events_dev  device uint64: number of events produced (the running count hopb_hoptraj adds to)
+ *   cap           capacity of `events`, `events_sorted` and the four edge arrays
+ *   n_sites_dev   device int32: number of hydration sites (hopb_label_sites_async);
+ *                 n_labels = *n_sites_dev + label_offset (2 with a bulk site, else 1)
+ *   count_matrix  device int32 [matrix_stride^2] or NULL: zeroed and filled here with row stride
+ *                 matrix_stride (a fixed size, so that it can be all-reduced across ranks before the host
+ *                 knows n_labels)
+ *   result_dev    device int64 [4] out: n_events, n_edges, n_labels, status (bit mask of HOPB_FIN_*) */
+#define HOPB_FIN_OVERFLOW 1        /* more events than `cap`: nothing was sorted; redo stage 3 with a larger buffer */
+#define HOPB_FIN_TOO_MANY_SITES 2  /* *n_sites_dev > HOPB_MAX_SITES */
+#define HOPB_FIN_MATRIX_SKIPPED 4  /* n_labels + 1 > matrix_stride: count_matrix was not filled */
+int hopb_events_finalize_dev(hopb_handle* h, void* stream, const hopb_event* events, const uint64_t* n_events_dev,
+                             uint64_t cap, int64_t N, int64_t F_total, const int32_t* n_sites_dev, int label_offset,
+                             hopb_event* events_sorted, int32_t* edge_s0, int32_t* edge_s, int64_t* edge_start,
+                             int64_t* edge_count, int32_t* count_matrix, int matrix_stride, int64_t* result_dev);
+
 /* TransportNetwork.graph_alltransitions (hop/graph.py:107-135): bit (a+1)*(n_labels+1)+(b+1) of
  * `bitmap` is set when some atom has label a in frame t-1 and b in frame t.
  * bitmap: device uint32 [ceil((n_labels+1)^2 / 32)], OR-ed into (not cleared). */

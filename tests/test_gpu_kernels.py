@@ -508,3 +508,47 @@ def test_run_host_overlapped_runs_match_resident_run(K, traj):
     r1, h1 = pipe.run_host(host_xyz)
     assert torch.equal(h1["hop_x"], ha["hop_x"]) and torch.equal(h1["hop_y"], ha["hop_y"])
     assert torch.equal(h1["events"], ha["events"])
+
+
+def test_pipeline_async_results_are_lazy_and_correct(K, traj):
+    """From the second run on the pipeline does not wait for the device: the counts-dependent result
+    fields resolve on first use, and the results of a run survive the next run being queued."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    a, b = dev(np.ascontiguousarray(xyz)), dev(np.ascontiguousarray(xyz[::-1]))
+
+    def snapshot(res):
+        return dict(n_labels=res.n_labels, n_ev=res.n_events_local, events=res.events.clone(), e_s0=res.edge_s0.clone(),
+                    e_s=res.edge_s.clone(), e_count=res.edge_count.clone(), e_start=res.edge_start.clone(),
+                    M=res.count_matrix.clone(), props=[t.clone() for t in res.site_props])
+
+    def same(x, y):
+        return (x["n_labels"] == y["n_labels"] and x["n_ev"] == y["n_ev"] and torch.equal(x["events"], y["events"])
+                and torch.equal(x["e_s0"], y["e_s0"]) and torch.equal(x["e_s"], y["e_s"]) and torch.equal(x["e_count"], y["e_count"])
+                and torch.equal(x["e_start"], y["e_start"]) and torch.equal(x["M"], y["M"])
+                and all(torch.equal(s, t, ) or (torch.isnan(s) == torch.isnan(t)).all() for s, t in zip(x["props"], y["props"])))
+
+    want = {}
+    for name, inp in (("a", a), ("b", b)):
+        sync_pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig(async_results=False))
+        want[name] = snapshot(sync_pipe.run(inp))
+    pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig())
+    r1 = pipe.run(a)                       # first run: synchronous (learns the sizes)
+    assert r1._pending is None and same(snapshot(r1), want["a"])
+    r2 = pipe.run(b)
+    assert r2._pending is not None         # nothing resolved yet
+    r3 = pipe.run(a)
+    assert same(snapshot(r2), want["b"])   # resolved after the next run was queued
+    assert same(snapshot(r3), want["a"])
+    # more events than budgeted, noticed late: the tail of the run is redone
+    small = HopPipeline(edges, xyz.shape[0], PipelineConfig())
+    small.run(a)
+    small._events = K.EventBuffer(64, "cuda")
+    small.cfg.event_capacity = 64
+    r = small.run(b)
+    assert r._pending is not None and same(snapshot(r), want["b"])
+    assert small._events.capacity >= want["b"]["n_ev"]
