@@ -328,7 +328,9 @@ class HopPipeline:
         main = torch.cuda.current_stream(dev)
         s4 = getattr(self, "_s4_stream", None)
         if s4 is None:
-            s4 = self._s4_stream = torch.cuda.Stream(device=dev)
+            # high priority: its cooperative kernel needs one block on every SM at once and would
+            # otherwise wait until the next run's histogram (tens of thousands of short-lived CTAs) drains
+            s4 = self._s4_stream = torch.cuda.Stream(device=dev, priority=-1)
             self._fin_hosts = []      # pool of pinned 4-word result buffers; one per unresolved result
         props_done = getattr(self, "_props_done", None)
         self._props_done = None
