@@ -234,6 +234,9 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    from hop_b200.exchange import bind_host_to_gpu
+
+    numa = bind_host_to_gpu(local)   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -378,7 +381,7 @@ def run_gpu(args):
               + host["final_state"].numel() * 4)
     e2e = {"value": atom_frames_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(xyz_host.numel() * 4), "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps,
+           "steps": e2e_steps, "host_binding": numa,
            "api": ("HopPipeline.run_host_begin/finish (pinned host float32 [F][N][3] in; host hop_x/hop_y, sorted events, "
                    "COO counts out; download of step k overlaps upload of step k+1)")}
 
