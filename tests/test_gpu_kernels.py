@@ -322,6 +322,35 @@ def test_hoptraj_outliers_and_top_edge(K, traj):
         assert np.array_equal(np.stack([ia, state[0][ia], 59 - state[1][ia]], axis=1), nodes_ref)
 
 
+def test_hoptraj_mostly_interstitial_map(K, traj):
+    """A map without a bulk site (ions, or site_insert_nobulk): most atoms never see a site, a few
+    hop between sites, some are outliers from frame 0 on -- the "no site seen yet" block path, warps
+    with lanes in both regimes, and long chunks entirely in the interstitial."""
+    p, xyz = traj
+    xyz = xyz.copy()
+    res0 = O.pipeline(xyz, delta=1.0, with_bulk=False)
+    edges, site_map = res0["edges"], res0["map"]
+    assert (site_map == 1).sum() < 0.05 * site_map.size          # label 1 is an ordinary small site here
+    rng = np.random.default_rng(4)
+    xyz[:, 5:9] += np.float32(70.0)                               # outliers for the whole trajectory
+    mask = rng.random(xyz.shape[:2]) < 0.01
+    xyz[mask] -= np.float32(90.0)
+    hop, ev_ref, nodes_ref = _hop_reference(xyz, edges, site_map)
+    assert (hop[:, :, 0] == 0).mean() > 0.8 and len(ev_ref) > 50
+    F = xyz.shape[0]
+    for n_chunks, slabs, mode in [(1, 1, "cells+fine"), (3, 1, "cells+fine0"), (1, 1, "xyz+fine"), (5, 2, "cells+coarse"),
+                                  (2, 1, "cells+cell2"), (4, 1, "cells"), (1, 3, "xyz")]:
+        X, Y, events, n_ev, state = _run_hoptraj(K, xyz, edges, site_map, n_chunks, slabs, mode)
+        assert np.array_equal(X, hop[:, :, 0]), mode
+        assert np.array_equal(Y, hop[:, :, 1]), mode
+        ev = K.events_to_numpy(events.data[:n_ev])
+        order = np.lexsort((ev["iatom"], ev["frame"]))
+        got = np.stack([ev[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1)
+        assert np.array_equal(got, ev_ref), mode
+        ia = np.nonzero(state[0] != 0)[0]
+        assert np.array_equal(np.stack([ia, state[0][ia], (F - 1) - state[1][ia]], axis=1), nodes_ref), mode
+
+
 def test_coarse_map_blocks(K):
     rng = np.random.default_rng(8)
     for shape in [(9, 10, 11), (36, 36, 36), (4, 4, 4), (5, 1, 70)]:
