@@ -389,22 +389,31 @@ hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ so
   }
 }
 
+// One warp per (i, j) row of the grid: no per-cell index division, the two row divisors are loaded
+// once, loads and stores are contiguous.  The four divisions stay IEEE double divisions in the
+// reference's order (bit-identical densities); they are what the kernel spends its time on.
 __global__ void __launch_bounds__(256)
-density_kernel(const uint32_t* __restrict__ counts, int64_t n_cells, int ny, int nz, double n_frames,
+density_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int nz, double n_frames,
                const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
                double factor, int apply_factor, double* __restrict__ density) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(c % nz);
-    const int64_t r = c / nz;
-    const int j = (int)(r % ny);
-    const int i = (int)(r / ny);
-    double v = (double)counts[c];
-    v = v / n_frames;   // DensityCollector.finish
-    v = v / wx[i];      // Grid.make_density, axis 0 then 1 then 2
-    v = v / wy[j];
-    v = v / wz[k];
-    if (apply_factor) v = v * factor;  // Grid.convert_density
-    density[c] = v;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp; row < n_rows; row += n_warps) {
+    const int j = (int)(row % ny);
+    const int i = (int)(row / ny);
+    const double dx = wx[i], dy = wy[j];
+    const uint32_t* src = counts + row * nz;
+    double* dst = density + row * nz;
+    for (int k = lane; k < nz; k += 32) {
+      double v = (double)src[k];
+      v = v / n_frames;   // DensityCollector.finish
+      v = v / dx;         // Grid.make_density, axis 0 then 1 then 2
+      v = v / dy;
+      v = v / wz[k];
+      if (apply_factor) v = v * factor;  // Grid.convert_density
+      dst[k] = v;
+    }
   }
 }
 
@@ -514,9 +523,9 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
 int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
                              int64_t n_frames, double factor, double* density) {
   HOPB_REQUIRE(h, g && counts && density && n_frames > 0, "bad argument");
-  const int64_t n_cells = (int64_t)g->n[0] * g->n[1] * g->n[2];
-  HOPB_K(density_kernel)<<<hopb_grid_for(n_cells, 256, h->num_sms, 16), 256, 0, (cudaStream_t)stream>>>(
-      counts, n_cells, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
+  const int64_t n_rows = (int64_t)g->n[0] * g->n[1];
+  HOPB_K(density_kernel)<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 16), 256, 0, (cudaStream_t)stream>>>(
+      counts, n_rows, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
       factor != 1.0 ? 1 : 0, density);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
