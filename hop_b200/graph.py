@@ -19,7 +19,7 @@ import pickle
 
 import numpy
 
-from . import sitemap, trajectory
+from . import _ratefit, sitemap, trajectory
 from .constants import SITELABEL
 
 logger = logging.getLogger("MDAnalysis.app.hop.graph")
@@ -200,7 +200,7 @@ class HoppingGraph(object):
     function of the waiting times; the survival function is evaluated by sorting instead of the
     reference's O(N * T) sum of step functions -- the values are identical."""
 
-    def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None):
+    def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None, workers=None):
         import networkx as NX
 
         self.trjdata = trjdata if isinstance(trjdata, dict) else None
@@ -210,7 +210,9 @@ class HoppingGraph(object):
             self.graph = NX.DiGraph(name='Transitions between sites')
             self.properties = properties
             self.graph.add_nodes_from(graph.nodes)
-            ebunch = [(e[0], e[1], self._rate(properties[e]['tau'])) for e in graph.edges]
+            edges = list(graph.edges)
+            fits = _ratefit.fit_all([numpy.asarray(properties[e]['tau']) for e in edges], workers=workers)
+            ebunch = [(e[0], e[1], _rate_record(f)) for e, f in zip(edges, fits)]
             self.graph.add_edges_from(ebunch)
         elif filename is not None:
             self.load(filename)
@@ -269,28 +271,7 @@ class HoppingGraph(object):
         (|0.5 - a| > 0.49) or has a negative rate."""
         if method != 'survivalfunction':
             raise NotImplementedError('Method "%s" is not implemented.' % method)
-        taus = numpy.asarray(taus)
-        dt = 1.0
-        tmax = numpy.max(taus) + 1.0 * dt
-        N = len(taus)
-        x = numpy.arange(0, tmax + 1, dt)
-        S = survivalfunction(taus, block_w=block_w)
-        Sx = S(x)
-        enough_data = (len(taus) > 10)
-        is_single_exp = False
-        if enough_data:
-            fit = fitExp2(x, Sx)
-            a, k1, k2 = fit.parameters
-            is_single_exp = abs(0.5 - a) > 0.49
-            all_k = numpy.array([k1, k2])
-            if numpy.any(all_k < 0):
-                is_single_exp = True
-            else:
-                k = all_k[all_k > 0].max()
-        if not enough_data or is_single_exp:
-            fit = fitExp(x, Sx)
-            k, = fit.parameters
-        return dict(k=k, N=N, fit=fit)
+        return _rate_record(_ratefit.fit_one(taus))
 
     def filename(self, filename=None, ext=None, set_default=False, use_my_ext=False):
         from .utilities import filename_function
@@ -317,32 +298,23 @@ class fit_func(object):
     """Fit a function f to data (x, y) by least squares (hop/graph.py:2354-2397); ``parameters``
     holds the fitted parameters."""
 
+    _kind = None
+
     def __init__(self, x, y):
-        import scipy.optimize
+        self.parameters, self.message = _ratefit.leastsq_fit(self._kind, x, y)
 
-        _x = numpy.asarray(x)
-        _y = numpy.asarray(y)
-        p0 = self.initial_values()
-        fitfunc = self.f_factory()
-
-        def errfunc(p, x, y):
-            return fitfunc(p, x) - y
-
-        p, msg = scipy.optimize.leastsq(errfunc, p0[:], args=(_x, _y))
-        try:
-            p[0]
-            self.parameters = p
-        except (TypeError, IndexError):
-            self.parameters = [p]
-        self.message = msg
+    @classmethod
+    def _from_fit(cls, parameters, message):
+        """An instance around parameters that were fitted elsewhere (a worker process)."""
+        self = cls.__new__(cls)
+        self.parameters, self.message = parameters, message
+        return self
 
     def f_factory(self):
-        def fitfunc(p, x):
-            raise NotImplementedError("base class must be extended for each fit function")
-        return fitfunc
+        return _ratefit.FUNCTIONS[self._kind]
 
     def initial_values(self):
-        raise NotImplementedError("base class must be extended for each fit function")
+        return list(_ratefit.INITIAL[self._kind])
 
     def fit(self, x):
         """Applies the fit to all x values"""
@@ -352,13 +324,7 @@ class fit_func(object):
 class fitExp(fit_func):
     """y = f(x) = exp(-p[0]*x)"""
 
-    def f_factory(self):
-        def fitfunc(p, x):
-            return numpy.exp(-p[0] * x)
-        return fitfunc
-
-    def initial_values(self):
-        return [1.0]
+    _kind = 'exp'
 
     def __repr__(self):
         return "<fitExp " + str(self.parameters) + ">"
@@ -367,13 +333,7 @@ class fitExp(fit_func):
 class fitExp2(fit_func):
     """y = f(x) = p[0]*exp(-p[1]*x) + (1-p[0])*exp(-p[2]*x)"""
 
-    def f_factory(self):
-        def fitfunc(p, x):
-            return p[0] * numpy.exp(-p[1] * x) + (1 - p[0]) * numpy.exp(-p[2] * x)
-        return fitfunc
-
-    def initial_values(self):
-        return [0.5, 0.1, 1e-4]
+    _kind = 'exp2'
 
     def __repr__(self):
         return "<fitExp2" + str(self.parameters) + ">"
@@ -382,16 +342,28 @@ class fitExp2(fit_func):
 class fitlin(fit_func):
     """y = f(x) = p[0]*x + p[1]"""
 
+    def __init__(self, x, y):
+        import scipy.optimize
+
+        p, self.message = scipy.optimize.leastsq(lambda p, x, y: p[0] * x + p[1] - y, [1.0, 0.0],
+                                                 args=(numpy.asarray(x), numpy.asarray(y)))
+        self.parameters = p
+
     def f_factory(self):
-        def fitfunc(p, x):
-            return p[0] * x + p[1]
-        return fitfunc
+        return lambda p, x: p[0] * x + p[1]
 
     def initial_values(self):
         return [1.0, 0.0]
 
     def __repr__(self):
         return "<fitlin" + str(self.parameters) + ">"
+
+
+def _rate_record(fitted):
+    """(kind, parameters, message, k, N) of _ratefit.fit_one -> the dict an edge carries."""
+    kind, p, msg, k, N = fitted
+    cls = fitExp2 if kind == 'exp2' else fitExp
+    return dict(k=k, N=N, fit=cls._from_fit(p, msg))
 
 
 def Unitstep(x, x0):
@@ -407,14 +379,10 @@ def survivalfunction(waitingtimes, block_w=200, block_t=1000):
     The reference sums one step function per waiting time for every t (O(N * T), blocked to save
     memory); here the waiting times are sorted once and S(t) = (#{t0 > t} + 0.5 #{t0 == t}) / N comes
     from two binary searches -- the same numbers (sums of 0, 0.5 and 1 are exact)."""
-    w = numpy.sort(numpy.asarray(waitingtimes, dtype=float))
-    n = len(w)
+    w = numpy.asarray(waitingtimes, dtype=float)
 
     def S(t):
-        _t = numpy.asarray(t, dtype=float)
-        right = numpy.searchsorted(w, _t, side='right')   # #{t0 <= t}
-        left = numpy.searchsorted(w, _t, side='left')     # #{t0 <  t}
-        return ((n - right) + 0.5 * (right - left)) / n
+        return _ratefit.survival_values(w, t)
 
     S.__doc__ = "Survival function S(t).  t can be a array."
     return S

@@ -207,3 +207,22 @@ def test_survivalfunction_and_rates_match_oracle():
     assert len(hg.waitingtime_fit((2, 4)).parameters) == 1
     assert isinstance(hg.waitingtime_fit((3, 2)), fitExp2)
     assert set(hg.rates(2)) == set(cases)
+
+
+def test_rate_fits_in_worker_processes_are_identical():
+    """The fits of a graph are spread over fresh worker interpreters (hop_b200/_ratefit.py); the results
+    must be the very same numbers as in-process fits, in the same order."""
+    import warnings
+
+    from hop_b200 import _ratefit
+
+    rng = np.random.default_rng(11)
+    taus = [np.round(rng.exponential(15, int(n))) + 1.0 for n in rng.integers(2, 120, 23)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        serial = _ratefit.fit_all(taus, workers=0)
+        pooled = _ratefit.fit_all(taus, workers=3)
+    assert len(serial) == len(pooled) == len(taus)
+    for a, b in zip(serial, pooled):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[3] == b[3] and a[4] == b[4]
+    assert _ratefit.default_workers(10) == 0
