@@ -185,6 +185,10 @@ class HopPipeline:
         cfg = self.cfg
         shape = self.grid.shape
         factor = density_conversion_factor("Angstrom^{-3}", cfg.density_unit)
+        busy = getattr(self, "_props_busy", None)
+        if busy is not None:     # the previous run's annotation still reads density / labels
+            torch.cuda.current_stream(self.device).wait_event(busy)
+            self._props_busy = None
         density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor,
                                         out=self._buf("density", shape, torch.float64))
         # two buffers, alternating: the finalisation of the previous run may still read its own
@@ -211,20 +215,33 @@ class HopPipeline:
         nb, words = K.brick_shape(shape)
         brick_buf = self._buf("brick", (nb * 64,), torch.int16)
         coarse_buf = self._buf("coarse", (words,), torch.int32)
-        props = None
-        if cfg.annotate:
-            # the per-site reductions are not needed by stage 3: they run beside the brick map
-            L = self.MAX_LABELS
-            out = (self._buf("p_count", (L,), torch.int64), self._buf("p_mean", (L,), torch.float64),
-                   self._buf("p_std", (L,), torch.float64), self._buf("p_center", (L, 3), torch.float64))
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                props = K.site_properties(self.grid, density, own, member, L, out=out)
-            self._props_done = torch.cuda.Event()
-            self._props_done.record(side)
+        # the per-site reductions are not needed by stage 3; annotate() queues them behind it
+        self._annotate_args = (density, own, member)
         fine_buf = self._buf("fine", (K.fine_map_bytes(shape),), torch.uint8)
         self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf, self._buf("cell2", (nb * 4,), torch.int32))
-        return density, own, member, map16, props
+        return density, own, member, map16, None
+
+    def annotate(self):
+        """site_properties of the site map just built (volume, occupancy, centre per site), on the side
+        stream.  Called after stage 3 has been launched: the hoptraj kernel needs whole SMs (1024
+        threads x 64 registers), so reductions already running there would hold it up, while queued behind
+        it they run beside the fix-up, the event ordering and the next run's histogram."""
+        self._props = None
+        if not self.cfg.annotate:
+            return
+        density, own, member = self._annotate_args
+        side = self._side_stream
+        ready = torch.cuda.Event()      # behind everything stage 3 has queued on the main stream
+        ready.record(torch.cuda.current_stream(self.device))
+        L = self.MAX_LABELS
+        out = (self._buf("p_count", (L,), torch.int64), self._buf("p_mean", (L,), torch.float64),
+               self._buf("p_std", (L,), torch.float64), self._buf("p_center", (L, 3), torch.float64))
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self._props = K.site_properties(self.grid, density, own, member, L, out=out)
+        self._props_done = torch.cuda.Event()
+        self._props_done.record(side)
+        self._props_busy = self._props_done
 
     def sync_scalars(self, events):
         """The one host synchronisation of a run: number of sites and number of events."""
@@ -332,10 +349,8 @@ class HopPipeline:
             # otherwise wait until the next run's histogram (tens of thousands of short-lived CTAs) drains
             s4 = self._s4_stream = torch.cuda.Stream(device=dev, priority=-1)
             self._fin_hosts = []      # pool of pinned 4-word result buffers; one per unresolved result
-        props_done = getattr(self, "_props_done", None)
+        props_done = getattr(self, "_props_done", None)   # the next run's stage 2 waits for it (site_map)
         self._props_done = None
-        if props_done is not None:
-            main.wait_event(props_done)   # the next run's stage 2 overwrites what the annotation reads
         w_cap = 256
         while w_cap < self._w_known + self._w_known // 4 + 8:
             w_cap *= 2
@@ -398,9 +413,10 @@ class HopPipeline:
         self._mark(marks, "start")
         res.counts = self.histogram(xyz)
         self._mark(marks, "S1_histogram")
-        res.density, res.own, res.member, res.map16, self._props = self.site_map(res.counts)
+        res.density, res.own, res.member, res.map16, _ = self.site_map(res.counts)
         self._mark(marks, "S2_sitemap")
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+        self.annotate()
         self._mark(marks, "S3S4_hoptraj")
         self._finalize(res, events, xyz, frame0)
         self._mark(marks, "S4_transitions", getattr(self, "_s4_stream", None) if res._pending is not None else None)
@@ -456,10 +472,11 @@ class HopPipeline:
         exchange.reduce_counts(counts)
         res = PipelineResult()
         res.counts = counts
-        res.density, res.own, res.member, res.map16, self._props = self.site_map(counts)
+        res.density, res.own, res.member, res.map16, _ = self.site_map(counts)
         if self._d2h_done is not None:
             main.wait_event(self._d2h_done)      # the previous run's planes are still being downloaded
         res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
+        self.annotate()
         free = torch.cuda.Event()
         free.record(main)
         self._xyz_free[par] = free

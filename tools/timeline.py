@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--atoms", type=int, default=30000)
     ap.add_argument("--frames", type=int, default=10000)
     ap.add_argument("--delta", type=float, default=0.5)
+    ap.add_argument("--dump-step", action="store_true", help="also list every kernel of the last step with its stream and start time")
     args = ap.parse_args()
     from hop_b200 import kernels as K
     from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
@@ -76,6 +77,14 @@ def main():
     print("|---|---:|---:|---:|")
     for k, (c, d) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %.1f | %.1f | %.1f |" % (k, c / n, d / n, d / c))
+    if args.dump_step:
+        hists = [e for e in ev if "hist_kernel" in e["name"]]
+        start = hists[-1]["ts"]
+        print("\nLast step, kernel by kernel (start us after the histogram kernel's start, duration, stream):\n")
+        for e in ev:
+            if e["ts"] >= start:
+                nm = re.split(r"[<(]", e["name"].replace("(anonymous namespace)::", "").replace("void ", ""))[0][:40]
+                print("%9.1f %8.1f  s%-3s %s" % (e["ts"] - start, e["dur"], e.get("args", {}).get("stream", "?"), nm))
     print("\nLargest idle gaps (us, kernel that follows):")
     for g, name in sorted(gaps, reverse=True)[:12]:
         print("* %.1f before %s" % (g, name))
