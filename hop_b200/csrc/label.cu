@@ -166,36 +166,41 @@ ccl_flatten_kernel(int* parent, const uint8_t* __restrict__ rowflag, int64_t n_r
 }
 
 // ---- 4. sizes ---------------------------------------------------------------------------------------
-// size[root] += cells of the row with that root; lanes with equal roots are merged first
-// (neighbouring z cells share a root), so a solid row costs one atomic per 32 cells.
+// size[root] += cells with that root.  Lanes with equal roots are merged first (neighbouring z cells
+// share a root) and lane 0 carries the running (root, count) of the first labelled cell of every chunk
+// across the chunks of a row AND across the rows of its warp: the one giant component of a bulk map then costs one atomic per warp instead of
+// one per row (40 000 atomics on a single address were most of this kernel's time).
 __global__ void __launch_bounds__(256)
 ccl_size_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ rowflag, int64_t n_rows, int nz,
                 int* __restrict__ size) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int run_root = -1, run_cnt = 0;
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     if (!rowflag[row]) continue;
     const int64_t base = row * nz;
-    int run_root = -1, run_cnt = 0;  // lane 0 carries the row's running (root, count) across chunks
     for (int z0 = 0; z0 < nz; z0 += 32) {
       const int z = z0 + lane;
       const int r = z < nz ? parent[base + z] : -1;
+      const unsigned valid = __ballot_sync(kFull, r >= 0);
+      if (valid == 0) continue;           // nothing but background here (e.g. the padding of the grid)
       const unsigned peers = __match_any_sync(kFull, r);
       const bool leader = (peers & ((1u << lane) - 1)) == 0;
-      const int r0 = __shfl_sync(kFull, r, 0);
-      const int n0 = __popc(__shfl_sync(kFull, peers, 0));
-      if (leader && r >= 0 && lane != 0) atomicAdd(size + r, __popc(peers));
+      const int f = __ffs(valid) - 1;     // the chunk's first labelled cell continues the running root
+      const int rf = __shfl_sync(kFull, r, f);
+      const int nf = __popc(__shfl_sync(kFull, peers, f));
+      if (leader && r >= 0 && lane != f) atomicAdd(size + r, __popc(peers));
       if (lane == 0) {
-        if (r0 == run_root) run_cnt += n0;
+        if (rf == run_root) run_cnt += nf;
         else {
           if (run_root >= 0) atomicAdd(size + run_root, run_cnt);
-          run_root = r0; run_cnt = n0;
+          run_root = rf; run_cnt = nf;
         }
       }
     }
-    if (lane == 0 && run_root >= 0) atomicAdd(size + run_root, run_cnt);
   }
+  if (lane == 0 && run_root >= 0) atomicAdd(size + run_root, run_cnt);
 }
 
 // roots with size >= minsite become sites; smaller components are dropped (label 0)
