@@ -342,6 +342,32 @@ def run_gpu(args):
                 "pipeline": {"bytes_per_atom_frame": 32, "GBps": value * 32 / 1e9 / n_gpus,
                              "frac": value * 32 / 1e9 / n_gpus / peak}}
 
+    # ---- two runs in flight (independent trajectories, e.g. BASELINE config 5): reported beside `value` ----
+    two_in_flight = None
+    if world == 1:
+        from hop_b200.pipeline import PipelinePool
+
+        pool = PipelinePool(edges, F_total, PipelineConfig(), n=2)
+        for _ in range(max(args.warmup, 2) * 2):
+            pool.run(xyz, frame0)
+        torch.cuda.synchronize()
+        t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a.record()
+        for _ in range(args.steps):
+            r_pool = pool.run(xyz, frame0)
+        for st in pool.streams:
+            torch.cuda.current_stream().wait_stream(st)
+        t_b.record()
+        torch.cuda.synchronize()
+        pool.synchronize()
+        ms2 = t_a.elapsed_time(t_b) / args.steps
+        two_in_flight = {"value": atom_frames_total / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+                         "same_result": bool(torch.equal(r_pool.hop_x, res.hop_x) and torch.equal(r_pool.events, res.events)),
+                         "note": "hop_b200.pipeline.PipelinePool(n=2): consecutive independent runs alternate between two "
+                                 "pipelines / streams; `value` above is one run after the other on one stream"}
+        del pool, r_pool
+        torch.cuda.empty_cache()
+
     # ---- invariants at full size (size-independent parity properties) ------------------------------
     checks = {}
     total_counts = res.counts.to(torch.int64).sum().item()
@@ -401,7 +427,7 @@ def run_gpu(args):
                 "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
                 "data": "synthetic", "config": {"workload": workload_name(n_gpus), "sites": int(res.n_labels),
                                                 "events_per_step_rank0": int(res.n_events_local)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clocks, "two_in_flight": two_in_flight, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "stage_ms": stage_ms, "checks": checks}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

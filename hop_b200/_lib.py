@@ -117,10 +117,34 @@ def lib():
     return _lib
 
 
+_lane_base = 0
+
+
+class lanes(object):
+    """Context manager: every handle requested inside uses lane `base` + its own lane number, i.e. a
+    set of handles (scratch memory) of its own.  Two pipelines whose work is in flight at the same time
+    on different streams each run under their own base."""
+
+    def __init__(self, base):
+        self.base = int(base)
+
+    def __enter__(self):
+        global _lane_base
+        self.saved, _lane_base = _lane_base, self.base
+        return self
+
+    def __exit__(self, *exc):
+        global _lane_base
+        _lane_base = self.saved
+        return False
+
+
 def handle(device_index=None, lane=0):
     """One hopb_handle per CUDA device (created on first use).  `lane` > 0 gives an additional
     handle with its own scratch memory, for work enqueued concurrently on a second stream."""
     import torch
+
+    lane = int(lane) + _lane_base
 
     if not torch.cuda.is_available():
         raise RuntimeError("hop_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")

@@ -581,3 +581,33 @@ def test_pipeline_async_results_are_lazy_and_correct(K, traj):
     r = small.run(b)
     assert r._pending is not None and same(snapshot(r), want["b"])
     assert small._events.capacity >= want["b"]["n_ev"]
+
+
+def test_pipeline_pool_two_runs_in_flight(K, traj):
+    """Independent runs on two pipelines / streams give what one pipeline gives, in any interleaving."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, PipelinePool, grid_edges_from_frame0
+
+    p, xyz = traj
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    inputs = [dev(np.ascontiguousarray(xyz)), dev(np.ascontiguousarray(xyz[::-1])), dev(np.ascontiguousarray(xyz[:, ::-1]))]
+    single = HopPipeline(edges, xyz.shape[0], PipelineConfig(async_results=False))
+    want = []
+    for x in inputs:
+        r = single.run(x)
+        want.append((r.hop_x.clone(), r.hop_y.clone(), r.events.clone(), r.count_matrix.clone(), r.n_labels))
+    pool = PipelinePool(edges, xyz.shape[0], PipelineConfig(), n=2)
+    order = [0, 1, 2, 1, 0, 2, 2, 0]
+    results = []
+    for i in order:
+        res = pool.run(inputs[i])
+        results.append((i, res))
+        if len(results) >= 2:           # look at a result while the next run is in flight, before its buffers are reused
+            j, old = results[-2]
+            hx, hy, ev, M, nl = want[j]
+            assert old.n_labels == nl and torch.equal(old.events, ev) and torch.equal(old.count_matrix, M)
+            assert torch.equal(old.hop_x, hx) and torch.equal(old.hop_y, hy)
+    pool.synchronize()
+    j, last = results[-1]
+    assert torch.equal(last.events, want[j][2]) and torch.equal(last.hop_x, want[j][0])
