@@ -109,13 +109,35 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
     if (err == cudaSuccess) err = cudaMalloc(&g->d_mid[d], n[d] * sizeof(double));
     if (err == cudaSuccess) err = cudaMemcpy(g->d_width[d], w.data(), n[d] * sizeof(double), cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(g->d_mid[d], m.data(), n[d] * sizeof(double), cudaMemcpyHostToDevice);
+    // width classes (exact comparison of the doubles)
+    std::vector<uint8_t> cls(n[d]);
+    int nc = 0;
+    for (int k = 0; k < n[d] && nc >= 0; ++k) {
+      int c = 0;
+      while (c < nc && g->cls_width[d][c] != w[k]) ++c;
+      if (c == nc) {
+        if (nc == HOPB_MAX_WIDTH_CLASSES) { nc = -1; break; }
+        g->cls_width[d][nc++] = w[k];
+      }
+      cls[k] = (uint8_t)c;
+    }
+    g->n_cls[d] = nc > 0 ? nc : 0;
+    if (err == cudaSuccess) err = cudaMalloc(&g->d_cls[d], n[d]);
+    if (err == cudaSuccess) err = cudaMemcpy(g->d_cls[d], cls.data(), n[d], cudaMemcpyHostToDevice);
   }
+  if (err == cudaSuccess) err = cudaMalloc(&g->d_cls_width, sizeof(g->cls_width));
+  if (err == cudaSuccess) err = cudaMemcpy(g->d_cls_width, g->cls_width, sizeof(g->cls_width), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     hopb_grid_destroy(g);
     return hopb_fail(h, HOPB_E_CUDA, "hopb_grid_create: %s", cudaGetErrorString(err));
   }
   *out = g;
   return HOPB_OK;
+}
+
+int hopb_grid_width_classes(const hopb_grid* g) {
+  if (!g || g->n_cls[0] == 0 || g->n_cls[1] == 0 || g->n_cls[2] == 0) return 0;
+  return g->n_cls[0] * g->n_cls[1] * g->n_cls[2];
 }
 
 void hopb_grid_destroy(hopb_grid* g) {
@@ -125,7 +147,9 @@ void hopb_grid_destroy(hopb_grid* g) {
   for (int d = 0; d < 3; ++d) {
     if (g->d_width[d]) cudaFree(g->d_width[d]);
     if (g->d_mid[d]) cudaFree(g->d_mid[d]);
+    if (g->d_cls[d]) cudaFree(g->d_cls[d]);
   }
+  if (g->d_cls_width) cudaFree(g->d_cls_width);
   delete g;
 }
 

@@ -406,13 +406,7 @@ density_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int 
     const uint32_t* src = counts + row * nz;
     double* dst = density + row * nz;
     for (int k = lane; k < nz; k += 32) {
-      double v = (double)src[k];
-      v = v / n_frames;   // DensityCollector.finish
-      v = v / dx;         // Grid.make_density, axis 0 then 1 then 2
-      v = v / dy;
-      v = v / wz[k];
-      if (apply_factor) v = v * factor;  // Grid.convert_density
-      dst[k] = v;
+      dst[k] = hopb_density_value(src[k], n_frames, dx, dy, wz[k], factor, apply_factor);
     }
   }
 }
@@ -520,15 +514,22 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
   return hopb_hist_accumulate_cells(h, stream, g, xyz, n_points, counts, nullptr);
 }
 
-int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
-                             int64_t n_frames, double factor, double* density) {
-  HOPB_REQUIRE(h, g && counts && density && n_frames > 0, "bad argument");
+int hopb_density_from_counts_ex(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                                int64_t n_frames, double factor, double* density, int ctas_per_sm) {
+  HOPB_REQUIRE(h, g && counts && density && n_frames > 0 && ctas_per_sm >= 0, "bad argument");
   const int64_t n_rows = (int64_t)g->n[0] * g->n[1];
-  HOPB_K(density_kernel)<<<hopb_grid_for(n_rows * 32, 256, h->num_sms, 16), 256, 0, (cudaStream_t)stream>>>(
+  unsigned grid = hopb_grid_for(n_rows * 32, 256, h->num_sms, 16);
+  if (ctas_per_sm > 0 && grid > (unsigned)(ctas_per_sm * h->num_sms)) grid = (unsigned)(ctas_per_sm * h->num_sms);
+  HOPB_K(density_kernel)<<<grid, 256, 0, (cudaStream_t)stream>>>(
       counts, n_rows, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
       factor != 1.0 ? 1 : 0, density);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
+}
+
+int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                             int64_t n_frames, double factor, double* density) {
+  return hopb_density_from_counts_ex(h, stream, g, counts, n_frames, factor, density, 0);
 }
 
 }  // extern "C"

@@ -32,7 +32,14 @@ struct hopb_grid {
   HopbPair* d_table2;  // packed pair tables (tab.table2_len entries)
   double* d_width[3];  // diff(edges[d]) in float64, n[d] entries
   double* d_mid[3];    // 0.5*(e[:-1]+e[1:]), n[d] entries
+  // bin widths by class: np.diff(np.linspace(...)) takes a handful of distinct values per axis.
+  // n_cls[d] = 0: more than HOPB_MAX_WIDTH_CLASSES distinct widths on some axis (feature off)
+  int n_cls[3];
+  uint8_t* d_cls[3];                               // class of every bin, n[d] entries
+  double cls_width[3][16];                         // width of every class
+  double* d_cls_width;                             // the same on the device, [3][16]
 };
+#define HOPB_MAX_WIDTH_CLASSES 16
 
 static inline int hopb_fail(hopb_handle* h, int code, const char* fmt, ...) {
   if (h) {
@@ -90,6 +97,20 @@ static inline unsigned hopb_grid_for(int64_t n, int block, int num_sms, int per_
   int64_t cap = (int64_t)num_sms * per_sm * scale;
   if (need < 1) need = 1;
   return (unsigned)(need < cap ? need : cap);
+}
+
+// The density of a cell with `c` counts, exactly as the reference computes it: DensityCollector.finish
+// (/ n_frames), Grid.make_density (/ dx, / dy, / dz in this order), Grid.convert_density (* factor).
+// IEEE double divisions: the results are bit-identical to numpy's.  Monotone non-decreasing in c.
+__device__ __forceinline__ double hopb_density_value(uint32_t c, double n_frames, double dx, double dy, double dz,
+                                                     double factor, int apply_factor) {
+  double v = (double)c;
+  v = v / n_frames;
+  v = v / dx;
+  v = v / dy;
+  v = v / dz;
+  if (apply_factor) v = v * factor;
+  return v;
 }
 
 // ---- bricked site map ---------------------------------------------------------------------------

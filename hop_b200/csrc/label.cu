@@ -27,19 +27,45 @@ constexpr unsigned kFull = 0xffffffffu;
 // hydration-site mask) are skipped after one byte read.
 
 // ---- 1. threshold + z-runs ----------------------------------------------------------------------
+// The mask comes either from the density (density >= threshold) or straight from the counts: the
+// density of a cell is a monotone function of its count for fixed bin widths, and the widths take
+// only a few distinct values per axis, so "density >= threshold" is "count >= cmin[width class]" with
+// cmin found by bisection over the very function that computes the density (count_threshold_kernel).
+// Labelling from the counts takes the density kernel (four double divisions per cell) off the
+// critical path of the pipeline.
+struct CountMask {
+  const uint32_t* counts;
+  const unsigned long long* cmin;   // [ncx][ncy][ncz]
+  const uint8_t* cls_x;
+  const uint8_t* cls_y;
+  const uint8_t* cls_z;
+  int ny, ncy, ncz;
+};
+
+template <bool FROM_COUNTS>
 __global__ void __launch_bounds__(256)
-ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_rows, int nz, int* __restrict__ parent,
-                uint8_t* __restrict__ rowflag) {
+ccl_rows_kernel(const double* __restrict__ density, double threshold, CountMask cm, int64_t n_rows, int nz,
+                int* __restrict__ parent, uint8_t* __restrict__ rowflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     const int64_t base = row * nz;
+    const unsigned long long* cmin_row = nullptr;
+    if (FROM_COUNTS) {
+      const int j = (int)(row % cm.ny);
+      const int i = (int)(row / cm.ny);
+      cmin_row = cm.cmin + ((int)cm.cls_x[i] * cm.ncy + (int)cm.cls_y[j]) * cm.ncz;
+    }
     int carry = -1;  // start (z) of the run that reaches the previous chunk's last cell, or -1
     unsigned any = 0;
     for (int z0 = 0; z0 < nz; z0 += 32) {
       const int z = z0 + lane;
-      const bool m = z < nz && density[base + z] >= threshold;
+      bool m = false;
+      if (z < nz) {
+        if (FROM_COUNTS) m = (unsigned long long)cm.counts[base + z] >= cmin_row[cm.cls_z[z]];
+        else m = density[base + z] >= threshold;
+      }
       const unsigned bits = __ballot_sync(kFull, m);
       any |= bits;
       const unsigned below = ~bits & ((1u << lane) - 1);  // non-mask cells below this lane
@@ -52,6 +78,27 @@ ccl_rows_kernel(const double* __restrict__ density, double threshold, int64_t n_
     }
     if (lane == 0) rowflag[row] = any ? 1 : 0;
   }
+}
+
+// smallest count whose density reaches the threshold, per width class; 2^32 = no count does
+__global__ void count_threshold_kernel(int n_classes, int ncy, int ncz, const double* __restrict__ wx,
+                                       const double* __restrict__ wy, const double* __restrict__ wz, double n_frames,
+                                       double factor, int apply_factor, double threshold,
+                                       unsigned long long* __restrict__ cmin) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_classes) return;
+  const double dz = wz[t % ncz], dy = wy[(t / ncz) % ncy], dx = wx[t / (ncz * ncy)];
+  auto reaches = [&](unsigned long long c) {
+    return hopb_density_value((uint32_t)c, n_frames, dx, dy, dz, factor, apply_factor) >= threshold;
+  };
+  unsigned long long lo = 0, hi = 1ull << 32;   // answer in [0, 2^32]; NaN threshold: never -> 2^32
+  if (!reaches(0xFFFFFFFFull)) { cmin[t] = hi; return; }
+  hi = 0xFFFFFFFFull;
+  while (lo < hi) {
+    const unsigned long long mid = lo + (hi - lo) / 2;
+    if (reaches(mid)) hi = mid; else lo = mid + 1;
+  }
+  cmin[t] = lo;
 }
 
 // ---- 2. merge -------------------------------------------------------------------------------------
@@ -453,9 +500,10 @@ __global__ void __launch_bounds__(256) copy_u32_to_i32_kernel(const uint32_t* __
 
 extern "C" {
 
-int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
-                           double threshold, int minsite, int32_t* labels, int32_t* n_sites_dev, int32_t* volumes) {
-  HOPB_REQUIRE(h, density && labels && n_sites_dev, "null argument");
+static int label_sites_impl(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density, double threshold,
+                            const hopb_grid* g, const uint32_t* counts, int64_t n_frames, double factor, int minsite,
+                            int32_t* labels, int32_t* n_sites_dev, int32_t* volumes) {
+  HOPB_REQUIRE(h, (density || counts) && labels && n_sites_dev, "null argument");
   HOPB_REQUIRE(h, nx > 0 && ny > 0 && nz > 0, "bad grid shape");
   HOPB_REQUIRE(h, minsite == 1 || minsite == 2, "MINsite must be 1 or 2 (hop/sitemap.py:453-456)");
   cudaStream_t s = (cudaStream_t)stream;
@@ -481,7 +529,25 @@ int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz,
   HOPB_CUDA(h, cudaMemsetAsync(size, 0, (size_t)n_cells * sizeof(int), s));
   HOPB_CUDA(h, cudaMemsetAsync(n_roots_dev, 0, sizeof(uint32_t), s));
   const unsigned grows = hopb_grid_for(n_rows * 32, 256, h->num_sms, 8);
-  HOPB_K(ccl_rows_kernel)<<<grows, 256, 0, s>>>(density, threshold, n_rows, nz, parent, rowflag);
+  CountMask cm;
+  memset(&cm, 0, sizeof(cm));
+  if (counts) {
+    const int n_classes = g->n_cls[0] * g->n_cls[1] * g->n_cls[2];
+    unsigned long long* cmin = nullptr;   // slot 9: the count thresholds
+    rc = hopb_scratch(h, 9, (size_t)n_classes * sizeof(unsigned long long), (void**)&cmin);
+    if (rc) return rc;
+    const double* w = g->d_cls_width;
+    HOPB_K(count_threshold_kernel)<<<(n_classes + 127) / 128, 128, 0, s>>>(n_classes, g->n_cls[1], g->n_cls[2], w, w + 16,
+                                                                          w + 32, (double)n_frames, factor,
+                                                                          factor != 1.0 ? 1 : 0, threshold, cmin);
+    cm.counts = counts; cm.cmin = cmin; cm.cls_x = g->d_cls[0]; cm.cls_y = g->d_cls[1]; cm.cls_z = g->d_cls[2];
+    cm.ny = ny; cm.ncy = g->n_cls[1]; cm.ncz = g->n_cls[2];
+    hopb_note_launch();
+    ccl_rows_kernel<true><<<grows, 256, 0, s>>>(nullptr, threshold, cm, n_rows, nz, parent, rowflag);
+  } else {
+    hopb_note_launch();
+    ccl_rows_kernel<false><<<grows, 256, 0, s>>>(density, threshold, cm, n_rows, nz, parent, rowflag);
+  }
   HOPB_K(ccl_merge_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, nx, ny, nz, 0);
   HOPB_K(ccl_flatten_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, n_rows, nz, 1);
   HOPB_K(ccl_merge_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, nx, ny, nz, 1);
@@ -494,6 +560,23 @@ int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz,
   HOPB_K(ccl_relabel_kernel)<<<grows, 256, 0, s>>>(parent, rowflag, size, n_rows, nz, labels);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
+}
+
+int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
+                           double threshold, int minsite, int32_t* labels, int32_t* n_sites_dev, int32_t* volumes) {
+  HOPB_REQUIRE(h, density != nullptr, "null argument");
+  return label_sites_impl(h, stream, nx, ny, nz, density, threshold, nullptr, nullptr, 0, 1.0, minsite, labels, n_sites_dev,
+                          volumes);
+}
+
+int hopb_label_sites_counts_async(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                                  int64_t n_frames, double factor, double threshold, int minsite, int32_t* labels,
+                                  int32_t* n_sites_dev, int32_t* volumes) {
+  HOPB_REQUIRE(h, g && counts && n_frames > 0, "bad argument");
+  HOPB_REQUIRE(h, g->n_cls[0] > 0 && g->n_cls[1] > 0 && g->n_cls[2] > 0,
+               "grid has too many distinct bin widths for count thresholds (use hopb_label_sites_async)");
+  return label_sites_impl(h, stream, g->n[0], g->n[1], g->n[2], nullptr, threshold, g, counts, n_frames, factor, minsite,
+                          labels, n_sites_dev, volumes);
 }
 
 int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density, double threshold,
@@ -544,7 +627,10 @@ int hopb_site_properties(hopb_handle* h, void* stream, const hopb_grid* g, const
   double* acc1 = acc + (size_t)n_labels * 5;
   double* mean = acc1 + (size_t)n_labels * 5;
   HOPB_CUDA(h, cudaMemsetAsync(acc, 0, (size_t)n_labels * 10 * sizeof(double), s));
-  const unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 4);
+  // two CTAs per SM: in the pipeline these reductions run on a side stream beside the labelling or the
+  // histogram of the next run and must leave room for those kernels' CTAs on every SM
+  unsigned gcells = hopb_grid_for(n_cells, 256, h->num_sms, 4);
+  if (gcells > 2u * (unsigned)h->num_sms) gcells = 2u * (unsigned)h->num_sms;
   HOPB_K(site_prop_kernel<0>)<<<gcells, 256, 0, s>>>(density, own, member, n_cells, g->n[1], g->n[2], g->d_mid[0], g->d_mid[1],
                                             g->d_mid[2], nullptr, acc);
   HOPB_K(site_prop_mean_kernel)<<<(n_labels + 255) / 256, 256, 0, s>>>(acc, n_labels, mean);

@@ -54,6 +54,8 @@ class GridTables:
                                          e[2].ctypes.data, self.shape[2], decs.ctypes.data, ctypes.byref(out))
         _lib.check(self._handle, rc)
         self._grid = out
+        # number of distinct (dx, dy, dz) bin-width triples; 0: irregular edges, no count thresholds
+        self.width_classes = int(_lib.lib().hopb_grid_width_classes(out))
 
     @property
     def ptr(self):
@@ -166,12 +168,16 @@ def brick_map(map16: torch.Tensor, brick=None, coarse=None, fine=None, cell2=Non
     return BrickMap(brick, coarse, fine, cell2)
 
 
-def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None):
+def density_from_counts(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float = 1.0, out=None,
+                        ctas_per_sm: int = 0):
+    """counts -> density, bit-identical to DensityCollector.finish + Grid.make_density + convert_density.
+    ctas_per_sm > 0 limits the grid (for running beside other kernels on another stream)."""
     _cuda(counts, torch.int32, "counts")
     if out is None:
         out = torch.empty(grid.shape, dtype=torch.float64, device=counts.device)
     h = _h(counts)
-    _lib.check(h, _lib.lib().hopb_density_from_counts(h, _stream(), grid.ptr, _p(counts), int(n_frames), float(factor), _p(out)))
+    _lib.check(h, _lib.lib().hopb_density_from_counts_ex(h, _stream(), grid.ptr, _p(counts), int(n_frames), float(factor),
+                                                         _p(out), int(ctas_per_sm)))
     return out
 
 
@@ -229,6 +235,21 @@ def labels_to_map16(labels: torch.Tensor, map16=None):
     h = _h(labels)
     _lib.check(h, _lib.lib().hopb_labels_to_map16(h, _stream(), labels.numel(), _p(labels), _p(map16)))
     return map16
+
+
+def label_sites_counts_async(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float, threshold: float,
+                             minsite: int, out: torch.Tensor, n_sites_dev: torch.Tensor, volumes=None, lane: int = 0):
+    """label_sites_async on density_from_counts(counts, n_frames, factor) without that density: the
+    threshold is translated into a count threshold per bin-width class on the device (identical labels).
+    Needs grid.width_classes > 0."""
+    _cuda(counts, torch.int32, "counts")
+    if tuple(counts.shape) != grid.shape:
+        raise ValueError("counts must have the shape of the grid")
+    h = _lib.handle(counts.device.index, lane)
+    rc = _lib.lib().hopb_label_sites_counts_async(h, _stream(), grid.ptr, _p(counts), int(n_frames), float(factor),
+                                                  float(threshold), int(minsite), _p(out), _p(n_sites_dev), _p(volumes))
+    _lib.check(h, rc)
+    return out
 
 
 def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, member, n_labels: int, out=None):

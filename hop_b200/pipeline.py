@@ -40,6 +40,7 @@ class PipelineConfig:
     coarse_map: bool = True          # block map in shared memory for stage 3 (False: always gather)
     block_map: str = "auto"          # "auto" (fine when it fits, else coarse), "fine", "coarse", "none"
     async_results: bool = True       # from the second run on: no host synchronisation inside run()
+    label_from_counts: bool = True   # threshold the counts instead of the density (identical labels)
 
 
 class PipelineResult(object):
@@ -192,33 +193,61 @@ class HopPipeline:
         cfg = self.cfg
         shape = self.grid.shape
         factor = density_conversion_factor("Angstrom^{-3}", cfg.density_unit)
-        busy = getattr(self, "_props_busy", None)
-        if busy is not None:     # the previous run's annotation still reads density / labels
+        # density / labels / membership alternate between two buffer sets: the annotation of a run is
+        # queued behind its stage 3 and may execute as late as the end of the next run's histogram, so it
+        # must not hold up the next run's stage 2; only the run after that reuses its inputs
+        par = "%d" % (self._run_index & 1)
+        busy = self.__dict__.setdefault("_props_busy", {}).pop(par, None)
+        if busy is not None:
             torch.cuda.current_stream(self.device).wait_event(busy)
-            self._props_busy = None
-        density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor,
-                                        out=self._buf("density", shape, torch.float64))
         # two buffers, alternating: the finalisation of the previous run may still read its own
         self.n_sites_dev = self._buf("n_sites_dev%d" % (self._run_index & 1), (2,), torch.int32)
         main = torch.cuda.current_stream(self.device)
         side = getattr(self, "_side_stream", None)
         if side is None:
             side = self._side_stream = torch.cuda.Stream(device=self.device)
-        own_buf = self._buf("own", shape, torch.int32)
+            self._density_stream = torch.cuda.Stream(device=self.device)
+        density_buf = self._buf("density" + par, shape, torch.float64)
+        from_counts = cfg.label_from_counts and self.grid.width_classes > 0
+        if from_counts:
+            # the labelling thresholds the counts directly (identical labels), so the density -- four
+            # double divisions per cell -- is computed beside it instead of in front of it
+            dstream = self._density_stream
+            dstream.wait_stream(main)
+            with torch.cuda.stream(dstream):
+                # two CTAs per SM: it trickles along on spare FP64 throughput instead of filling every SM
+                # in front of the labelling kernels
+                density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor, out=density_buf,
+                                                ctas_per_sm=2)
+                density_done = torch.cuda.Event()
+                density_done.record(dstream)
+            nf = self.n_frames_total
+
+            def label(thr, out, n_dev, lane=0):
+                return K.label_sites_counts_async(self.grid, counts, nf, factor, thr, cfg.minsite, out, n_dev, lane=lane)
+        else:
+            density = K.density_from_counts(self.grid, counts, self.n_frames_total, factor, out=density_buf)
+            density_done = None
+
+            def label(thr, out, n_dev, lane=0):
+                return K.label_sites_async(density, thr, cfg.minsite, out, n_dev, lane=lane)
+        own_buf = self._buf("own" + par, shape, torch.int32)
         if cfg.with_bulk:
             # the two labellings are independent: the (sparse, cheap) hydration-site map runs on a
             # side stream with its own scratch while the bulk map occupies the main stream
             bulk_buf = self._buf("bulk_labels", shape, torch.int32)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, own_buf, self.n_sites_dev[0:1], lane=1)
-            bulk_labels = K.label_sites_async(density, cfg.bulk_threshold, cfg.minsite, bulk_buf, self.n_sites_dev[1:2])
+                own = label(cfg.solvent_threshold, own_buf, self.n_sites_dev[0:1], lane=1)
+            bulk_labels = label(cfg.bulk_threshold, bulk_buf, self.n_sites_dev[1:2])
             main.wait_stream(side)
-            member, map16 = K.insert_bulk(own, bulk_labels, 1, self._buf("member", shape, torch.uint8),
+            member, map16 = K.insert_bulk(own, bulk_labels, 1, self._buf("member" + par, shape, torch.uint8),
                                           self._buf("map16", shape, torch.int16))
         else:
-            own = K.label_sites_async(density, cfg.solvent_threshold, cfg.minsite, own_buf, self.n_sites_dev[0:1])
+            own = label(cfg.solvent_threshold, own_buf, self.n_sites_dev[0:1])
             member, map16 = None, K.labels_to_map16(own, self._buf("map16", shape, torch.int16))
+        if density_done is not None:
+            main.wait_event(density_done)   # long finished; keeps res.density ordered on the main stream
         nb, words = K.brick_shape(shape)
         brick_buf = self._buf("brick", (nb * 64,), torch.int16)
         coarse_buf = self._buf("coarse", (words,), torch.int32)
@@ -248,7 +277,7 @@ class HopPipeline:
             self._props = K.site_properties(self.grid, density, own, member, L, out=out)
         self._props_done = torch.cuda.Event()
         self._props_done.record(side)
-        self._props_busy = self._props_done
+        self._props_busy["%d" % (self._run_index & 1)] = self._props_done
 
     def sync_scalars(self, events):
         """The one host synchronisation of a run: number of sites and number of events."""

@@ -116,6 +116,11 @@ int hopb_hist_bulk(hopb_handle* h, void* stream, const hopb_grid* g, const float
 int hopb_density_from_counts(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
                              int64_t n_frames, double factor, double* density);
 
+/* The same with the grid limited to ctas_per_sm CTAs per SM (0 = no limit): for running the density
+ * beside other kernels on another stream without crowding them out of the SMs. */
+int hopb_density_from_counts_ex(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                                int64_t n_frames, double factor, double* density, int ctas_per_sm);
+
 /* ---- stage 2: site map --------------------------------------------------------------------- */
 /* Density.map_sites (hop/sitemap.py:480-521): mask = density >= threshold; connected components
  * over the 7 forward offsets {0,1}^3 \ 0 and their negatives, no periodic wrap (_make_graph /
@@ -135,6 +140,21 @@ int hopb_label_sites(hopb_handle* h, void* stream, int nx, int ny, int nz, const
 int hopb_label_sites_async(hopb_handle* h, void* stream, int nx, int ny, int nz, const double* density,
                            double threshold, int minsite, int32_t* labels, int32_t* n_sites_dev,
                            int32_t* volumes);
+
+/* The same labelling straight from the histogram counts: "density >= threshold" is decided as
+ * "count >= cmin(bin-width class of the cell)", cmin found on the device by bisection over the very
+ * function hopb_density_from_counts evaluates (the density is monotone in the count, and the widths of
+ * a linspace grid take a handful of distinct values per axis), so the labels are identical to
+ * hopb_density_from_counts + hopb_label_sites_async while the density need not exist yet.
+ * factor: the unit factor of hopb_density_from_counts.  Fails with HOPB_E_INVALID when
+ * hopb_grid_width_classes(g) == 0. */
+int hopb_label_sites_counts_async(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                                  int64_t n_frames, double factor, double threshold, int minsite,
+                                  int32_t* labels, int32_t* n_sites_dev, int32_t* volumes);
+
+/* Number of distinct (dx, dy, dz) bin-width triples of the grid, or 0 when an axis has more than 16
+ * distinct widths (irregular edges): then only the density-based labelling is available. */
+int hopb_grid_width_classes(const hopb_grid* g);
 
 /* Density.site_insert_bulk (hop/sitemap.py:877-918) on label grids: the cells with
  * bulk_labels == bulklabel become site 1, every site of `labels` is shifted by +1 and overwrites

@@ -611,3 +611,52 @@ def test_pipeline_pool_two_runs_in_flight(K, traj):
     pool.synchronize()
     j, last = results[-1]
     assert torch.equal(last.events, want[j][2]) and torch.equal(last.hop_x, want[j][0])
+
+
+def test_label_from_counts_equals_label_from_density(K):
+    """Thresholding the counts (count >= cmin per bin-width class, cmin by bisection on the device) gives
+    exactly the labels of thresholding the density, also when the threshold equals a density value."""
+    import torch
+
+    rng = np.random.default_rng(12)
+
+    def check(edges, counts, n_frames, factor, thresholds):
+        g = K.GridTables(edges)
+        assert g.width_classes > 0
+        c = dev(counts.astype(np.int32))
+        dens = K.density_from_counts(g, c, n_frames, factor)
+        for thr in thresholds:
+            la = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+            lb = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+            na = torch.zeros(1, dtype=torch.int32, device="cuda")
+            nb = torch.zeros(1, dtype=torch.int32, device="cuda")
+            K.label_sites_async(dens, thr, 1, la, na)
+            K.label_sites_counts_async(g, c, n_frames, factor, thr, 1, lb, nb)
+            assert int(na.item()) == int(nb.item()), thr
+            assert torch.equal(la, lb), thr
+
+    # linspace edges as DensityCreator makes them: a few width classes from rounding
+    for n, lo, hi in [((24, 17, 31), -3.3, 21.7), ((40, 40, 40), 0.1, 20.1)]:
+        edges = [np.linspace(lo + d, hi + 1.7 * d, k + 1) for d, k in enumerate(n)]
+        counts = rng.poisson(6.0, n)
+        dens = O.make_density(counts, edges, 50, "water")
+        vals = np.unique(dens)
+        thresholds = [float(vals[len(vals) // 2]), float(vals[-2]), float(np.nextafter(vals[3], np.inf)), 0.0, -1.0,
+                      math.e, float("inf"), float("nan"), 1e-300]
+        check(edges, counts, 50, O.density_conversion_factor("Angstrom^{-3}", "water"), thresholds)
+        check(edges, counts, 50, 1.0, [float(np.median(counts) / 50 / np.prod([np.diff(e)[0] for e in edges])), 0.0])
+    # three clearly different widths per axis
+    w = np.array([0.5, 0.75, 1.0])
+    edges = [np.concatenate([[0.0], np.cumsum(w[rng.integers(0, 3, k)])]) for k in (19, 23, 35)]
+    counts = rng.poisson(3.0, (19, 23, 35))
+    dens = O.make_density(counts, edges, 7, "Angstrom^{-3}")
+    check(edges, counts, 7, 1.0, [float(v) for v in np.unique(dens)[[1, 5, 20]]] + [0.5])
+    # irregular edges: no classes, the count path refuses
+    edges = [np.concatenate([[0.0], np.cumsum(0.5 + rng.random(40))]) for _ in range(3)]
+    g = K.GridTables(edges)
+    assert g.width_classes == 0
+    from hop_b200._lib import HopbError
+
+    with pytest.raises((HopbError, ValueError, RuntimeError)):
+        K.label_sites_counts_async(g, torch.zeros(g.shape, dtype=torch.int32, device="cuda"), 5, 1.0, 1.0, 1,
+                                   torch.empty(g.shape, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
