@@ -90,6 +90,8 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
   HOPB_CUDA(h, cudaSetDevice(h->device));
   hopb_grid* g = new hopb_grid();
   memset(g, 0, sizeof(*g));
+  static uint64_t next_serial = 1;
+  g->serial = __atomic_fetch_add(&next_serial, 1, __ATOMIC_RELAXED);
   g->h = h;
   g->tab = tab;
   for (int d = 0; d < 3; ++d) g->n[d] = n[d];

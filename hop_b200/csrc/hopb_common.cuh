@@ -22,6 +22,8 @@ struct hopb_handle {
   void* scratch[HOPB_NUM_SCRATCH];
   size_t scratch_bytes[HOPB_NUM_SCRATCH];
   int64_t hist_l2_budget;  // bytes of the count grid that one histogram pass may reduce into
+  // count thresholds cached in scratch slot 9: valid for this (grid, n_frames, factor, threshold)
+  uint64_t cmin_grid; int64_t cmin_frames; double cmin_factor, cmin_threshold; void* cmin_ptr;
 };
 
 struct hopb_grid {
@@ -38,6 +40,7 @@ struct hopb_grid {
   uint8_t* d_cls[3];                               // class of every bin, n[d] entries
   double cls_width[3][16];                         // width of every class
   double* d_cls_width;                             // the same on the device, [3][16]
+  uint64_t serial;                                 // unique per created grid (cache keys)
 };
 #define HOPB_MAX_WIDTH_CLASSES 16
 

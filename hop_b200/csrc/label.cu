@@ -407,10 +407,13 @@ site_prop_kernel(const double* __restrict__ density, const int32_t* __restrict__
     const bool mb = member && member[c];
     if (o <= 0 && !mb) continue;
     const double rho = density[c];
-    const int k = (int)(c % nz);
-    const int64_t r = c / nz;
-    const int j = (int)(r % ny);
-    const int i = (int)(r / ny);
+    int i = 0, j = 0, k = 0;
+    if (PASS == 0) {   // 32-bit index arithmetic: the grid has fewer than 2^31 cells
+      const uint32_t cu = (uint32_t)c, r = cu / (uint32_t)nz;
+      k = (int)(cu - r * (uint32_t)nz);
+      i = (int)(r / (uint32_t)ny);
+      j = (int)(r - (uint32_t)i * (uint32_t)ny);
+    }
     if (o > 0) {
       if (o != cur) {
         prop_flush(acc, cur, a, NV);
@@ -536,10 +539,18 @@ static int label_sites_impl(hopb_handle* h, void* stream, int nx, int ny, int nz
     unsigned long long* cmin = nullptr;   // slot 9: the count thresholds
     rc = hopb_scratch(h, 9, (size_t)n_classes * sizeof(unsigned long long), (void**)&cmin);
     if (rc) return rc;
-    const double* w = g->d_cls_width;
-    HOPB_K(count_threshold_kernel)<<<(n_classes + 127) / 128, 128, 0, s>>>(n_classes, g->n_cls[1], g->n_cls[2], w, w + 16,
-                                                                          w + 32, (double)n_frames, factor,
-                                                                          factor != 1.0 ? 1 : 0, threshold, cmin);
+    // the thresholds depend on host-known constants only: computed once and reused while the handle
+    // keeps labelling the same grid at the same threshold (every step of a pipeline does).  Work on one
+    // handle is ordered (one stream at a time), so the cached table is complete when it is read.
+    const bool cached = h->cmin_ptr == (void*)cmin && h->cmin_grid == g->serial && h->cmin_frames == n_frames &&
+                        h->cmin_factor == factor && h->cmin_threshold == threshold;   // NaN threshold: never cached
+    if (!cached) {
+      const double* w = g->d_cls_width;
+      HOPB_K(count_threshold_kernel)<<<(n_classes + 127) / 128, 128, 0, s>>>(n_classes, g->n_cls[1], g->n_cls[2], w, w + 16,
+                                                                            w + 32, (double)n_frames, factor,
+                                                                            factor != 1.0 ? 1 : 0, threshold, cmin);
+      h->cmin_ptr = cmin; h->cmin_grid = g->serial; h->cmin_frames = n_frames; h->cmin_factor = factor; h->cmin_threshold = threshold;
+    }
     cm.counts = counts; cm.cmin = cmin; cm.cls_x = g->d_cls[0]; cm.cls_y = g->d_cls[1]; cm.cls_z = g->d_cls[2];
     cm.ny = ny; cm.ncy = g->n_cls[1]; cm.ncz = g->n_cls[2];
     hopb_note_launch();
