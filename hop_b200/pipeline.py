@@ -292,6 +292,8 @@ class HopPipeline:
         host[2:3].copy_(events.count, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         n_sites, n_bulk, n_ev = int(host[0]), int(host[1]), int(host[2])
+        if not self.cfg.with_bulk:
+            n_bulk = 0          # the second counter is only written by the bulk labelling
         if n_sites > K.HOPB_MAX_SITES or n_bulk > K.HOPB_MAX_SITES:
             from ._lib import TooManySitesError
 

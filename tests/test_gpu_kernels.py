@@ -660,3 +660,63 @@ def test_label_from_counts_equals_label_from_density(K):
     with pytest.raises((HopbError, ValueError, RuntimeError)):
         K.label_sites_counts_async(g, torch.zeros(g.shape, dtype=torch.int32, device="cuda"), 5, 1.0, 1.0, 1,
                                    torch.empty(g.shape, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_pipeline_random_small_cases(K, seed):
+    """Seeded random small trajectories -- odd atom / frame counts, tiny and flat grids, outliers, no bulk
+    site, MINsite 2, explicit chunk counts, synchronous and asynchronous results -- through HopPipeline
+    against the oracle, bit for bit."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+
+    rng = np.random.default_rng(1000 + seed)
+    n_atoms = int(rng.choice([1, 2, 31, 33, 97, 250, 601, 1000]))
+    n_frames = int(rng.choice([1, 2, 9, 17, 40, 121, 200, 333]))
+    delta = float(rng.choice([0.5, 1.0, 1.7]))
+    with_bulk = bool(rng.integers(0, 2))
+    minsite = int(rng.choice([1, 1, 2]))
+    p = SynthParams(n_atoms=n_atoms, n_frames=n_frames, seed=77 + seed, site_stride=int(rng.choice([3, 10, 50])))
+    xyz = generate(p)
+    if seed % 3 == 0 and n_frames > 1:       # outliers, never in frame 0 (it defines the grid)
+        m = rng.random(xyz.shape[:2]) < 0.05
+        m[0] = False
+        xyz[m] += np.float32(50.0)
+    if seed % 4 == 1:                        # a flat system: one axis of the grid only a few cells deep
+        xyz[:, :, 2] = xyz[:, :, 2] * np.float32(0.02) + np.float32(5.0)
+    thr = float(rng.choice([math.e, 1.0, 4.0]))
+    ref = O.pipeline(xyz, delta=delta, solvent_threshold=thr, minsite=minsite, with_bulk=with_bulk)
+    edges = grid_edges_from_frame0(xyz[0], delta=delta)
+    n_chunks = None if seed % 2 else int(rng.integers(1, max(2, n_frames // 2 + 1)))
+    block_map = ["auto", "fine", "coarse", "cell2", "none"][seed % 5]
+    planes = seed % 7 != 3                   # without the x / y planes: events and counts only
+    cfg = PipelineConfig(solvent_threshold=thr, minsite=minsite, with_bulk=with_bulk, n_chunks=n_chunks,
+                         label_from_counts=bool(seed % 2), cache_cells=bool((seed // 2) % 2), block_map=block_map,
+                         write_hoptraj=planes, annotate=bool(seed % 11 != 5))
+    pipe = HopPipeline(edges, n_frames, cfg)
+    x = dev(xyz)
+    for rep in range(2):                     # second run: asynchronous results
+        res = pipe.run(x)
+        assert np.array_equal(res.counts.cpu().numpy(), ref["counts"].astype(np.int32))
+        assert np.array_equal(res.density.cpu().numpy(), ref["grid"])
+        assert np.array_equal(res.map16.cpu().numpy(), ref["map"])
+        if planes:
+            assert np.array_equal(res.hop_x.cpu().numpy(), ref["hop"][:, :, 0])
+            assert np.array_equal(res.hop_y.cpu().numpy(), ref["hop"][:, :, 1])
+        else:
+            assert res.hop_x is None and res.hop_y is None
+        assert res.n_labels == len(ref["sites"])
+        ev = K.events_to_numpy(res.events)
+        ev_ref = ref["events"]
+        order = np.lexsort((ev_ref[:, 1], ev_ref[:, 0], ev_ref[:, 3], ev_ref[:, 2])) if len(ev_ref) else np.zeros(0, int)
+        got = np.stack([ev[k] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1).astype(np.int64)
+        assert np.array_equal(got, ev_ref[order].reshape(-1, 6))
+        pairs, cnts = O.events_to_counts(ev_ref)
+        assert np.array_equal(np.stack([res.edge_s0.cpu().numpy(), res.edge_s.cpu().numpy()], axis=1).reshape(-1, 2), pairs)
+        assert np.array_equal(res.edge_count.cpu().numpy(), cnts)
+        st = res.final_state.cpu().numpy()
+        ia = np.nonzero(st[0] != 0)[0]
+        nodes = np.stack([ia, st[0][ia], (n_frames - 1) - st[1][ia]], axis=1).reshape(-1, 3)
+        assert np.array_equal(nodes, ref["nodes"].reshape(-1, 3))
