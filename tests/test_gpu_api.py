@@ -393,3 +393,72 @@ def test_notwithin_selection_and_fused_densities(solvated):
     sites = O.site_insert_bulk(O.label_sites_ndimage(gs, math.e), O.label_sites_ndimage(gb, math.exp(-0.5)))
     assert np.array_equal(final.map, O.draw_map_from_sites(sites, gs.shape))
     assert final.has_bulk() and [list(s) for s in final.sites] == sites
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_workflow_random_systems(seed, tmp_path):
+    """The whole class workflow on seeded random solvated systems (different sizes, grid spacings,
+    cut-offs, solute sizes): DensityCreator(mode='all') -> DensityWithBulk -> HoppingTrajectory (file and
+    fused) -> TransportNetwork, every product against the oracle."""
+    import warnings
+
+    from hop_b200.density import DensityCreator
+    from hop_b200.graph import TransportNetwork
+    from hop_b200.trajectory import HoppingTrajectory
+    from hop_b200.universe import Universe
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    rng = np.random.default_rng(500 + seed)
+    n_w = int(rng.choice([150, 333, 700, 1025]))
+    n_f = int(rng.choice([3, 17, 40, 65]))
+    n_p = int(rng.choice([1, 7, 40, 120]))
+    delta = float(rng.choice([0.8, 1.0, 1.5]))
+    cutoff = float(rng.choice([2.0, 3.5, 5.0]))
+    p = SynthParams(n_atoms=n_w, n_frames=n_f, seed=900 + seed, site_stride=int(rng.choice([5, 20])))
+    water = generate(p)
+    c = p.box / 2
+    prot0 = (c + rng.normal(0, 2.5, size=(n_p, 3))).astype(np.float32)
+    prot = (prot0[None] + rng.normal(0, 0.3, size=(n_f, n_p, 3))).astype(np.float32)
+    xyz = np.concatenate([prot, water], axis=1)
+    u = Universe(coordinates=xyz, names=["CA"] * n_p + ["OH2"] * n_w, resnames=["ALA"] * n_p + ["TIP3"] * n_w, dt=1.5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        DC = DensityCreator(u, mode="all", delta=delta, atomselection="name OH2", cutoff=cutoff, soluteselection="protein")
+        dens = DC.create()
+        edges = dens["solvent"].edges
+        _, _, ref_edges = O.grid_geometry(water[0], delta=delta)
+        for a, b in zip(edges, ref_edges):
+            assert np.array_equal(a, b)
+        assert np.array_equal(dens["solvent"].grid, O.make_density(O.histogram_vectorised(water, edges), edges, n_f))
+        assert np.array_equal(dens["bulk"].grid, O.make_density(O.histogram_bulk(water, prot, edges, cutoff), edges, n_f))
+        final = DC.DensityWithBulk(density_unit="water", solvent_threshold=math.e, bulk_threshold=math.exp(-0.5))
+        gs = O.make_density(O.histogram_vectorised(water, edges), edges, n_f, "water")
+        gb = O.make_density(O.histogram_bulk(water, prot, edges, cutoff), edges, n_f, "water")
+        bulk_sites = O.label_sites_ndimage(gb, math.exp(-0.5))
+        if len(bulk_sites) > 1:
+            sites = O.site_insert_bulk(O.label_sites_ndimage(gs, math.e), bulk_sites)
+        else:
+            sites = list(O.label_sites_ndimage(gs, math.e))
+            sites.insert(1, [])
+        site_map = O.draw_map_from_sites(sites, gs.shape)
+        assert np.array_equal(final.map, site_map)
+        group = u.select_atoms("name OH2")
+        hop_ref = O.coord2hop_vectorised(water, edges, site_map)
+        h = HoppingTrajectory(u.trajectory, group, final)
+        h.write(str(tmp_path / "hoptraj"))
+        got = np.stack([ts._pos.copy() for ts in HoppingTrajectory(filename=str(tmp_path / "hoptraj")).hoptraj])
+        assert np.array_equal(got[:, :, 0], hop_ref[:, :, 0]) and np.array_equal(got[:, :, 1], hop_ref[:, :, 1])
+        assert not got[:, :, 2].any()
+        if n_f < 2 or len(sites) < 2:
+            return
+        props_ref, edges_ref, nodes_ref = O.analyze_hops_faithful(hop_ref[:, :, 0], dt=1.5)
+        tn = TransportNetwork(h, final)
+        tn.compute_residency_times()
+        gp = tn.graph_properties
+        assert set(gp.keys()) == set(props_ref.keys())
+        for k, d in props_ref.items():
+            for f in ("frame", "iatom"):
+                assert np.array_equal(gp[k][f], d[f]), (k, f)
+            np.testing.assert_allclose(gp[k]["tau"], d["tau"], rtol=1e-6)
+        assert tn.transition_counts() == {e: len(props_ref[e]["tau"]) for e in edges_ref}
