@@ -720,3 +720,27 @@ def test_pipeline_random_small_cases(K, seed):
         ia = np.nonzero(st[0] != 0)[0]
         nodes = np.stack([ia, st[0][ia], (n_frames - 1) - st[1][ia]], axis=1).reshape(-1, 3)
         assert np.array_equal(nodes, ref["nodes"].reshape(-1, 3))
+
+
+def test_pipeline_async_count_matrix_outgrown(K, traj):
+    """The asynchronous finalisation sizes the dense count matrix from the previous run; a run with many
+    more sites than that is noticed when its result is first used and finalised again."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    cfg = dict(solvent_threshold=1.6, with_bulk=False)           # noise peaks of the bulk: hundreds of small sites
+    lump = np.ascontiguousarray(np.broadcast_to(xyz[0, :1], xyz.shape)).copy()   # every atom in one cell: one site
+    want = HopPipeline(edges, xyz.shape[0], PipelineConfig(async_results=False, **cfg)).run(dev(xyz))
+    n_labels, M, ev = want.n_labels, want.count_matrix.clone(), want.events.clone()
+    assert n_labels > 300
+    pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig(**cfg))
+    first = pipe.run(dev(lump))
+    assert first.n_labels == 2 and pipe._w_known == 3
+    res = pipe.run(dev(xyz))
+    assert res._pending is not None
+    assert res.n_labels == n_labels and torch.equal(res.count_matrix, M) and torch.equal(res.events, ev)
+    again = pipe.run(dev(xyz))                                    # now sized for it
+    assert again._pending is not None and torch.equal(again.count_matrix, M)
