@@ -1,0 +1,188 @@
+"""Generates tests/golden/reference/*.npz by running the REFERENCE ITSELF (hop's own classes, loaded
+from /root/reference by tests/golden/reference_py3.py) on seeded synthetic trajectories.
+
+Run from the repo root, in the container that has /root/reference:
+
+    python tests/golden/make_reference_golden.py
+
+Every array in the files is an output of hop code: `DensityCreator(...).create()`
+(hop/density.py:188-304), `Density.convert_density` / `map_sites` / `site_insert_bulk`
+(hop/sitemap.py:236-264, 480-521, 877-918), `HoppingTrajectory.write` -> `map_dcd` -> `_coord2hop`
+(hop/trajectory.py:255-297, 379-468), `TransportNetwork.compute_residency_times` ->
+`_analyze_hops` + `HoppingGraph` (hop/graph.py:137-288, 1677-1748).  Nothing from oracle/ or hop_b200/
+takes part except `hop_b200.synth.generate`, which only makes the input coordinates (stored in the
+files).  The tests then hold the oracle (CPU, tests/test_reference_golden.py) and the CUDA path (GPU)
+to these files.
+"""
+import math
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import reference_py3 as R  # noqa: E402
+from hop_b200.synth import SynthParams, generate  # noqa: E402
+
+OUT = os.path.join(HERE, "reference")
+
+
+def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bulk_threshold,
+                  cutoff=3.5, dt=1.0, rates=True):
+    """The workflow of scripts/hop-generate-densities.py / -hoptraj.py / -hopgraph.py, through the
+    reference's classes.  xyz_all float32 [F][n_solvent + n_solute][3]."""
+    hop = R.load_reference()
+    n_total = xyz_all.shape[1]
+    sel = {"name OH2": np.arange(n_solvent), "protein": np.arange(n_solvent, n_total)}
+    u = R.FakeUniverse(xyz_all, selections=sel, dt=dt)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if n_total > n_solvent:
+            DC = hop.density.DensityCreator(u, mode="all", delta=delta, atomselection="name OH2",
+                                            soluteselection="protein", cutoff=cutoff, padding=2.0)
+            DC.create()
+            out["bulk_grid_hist"] = DC.densities["bulk"].grid.copy()      # Angstrom^-3, before conversion
+            density = DC.DensityWithBulk(density_unit=density_unit, solvent_threshold=solvent_threshold,
+                                         bulk_threshold=bulk_threshold)
+            out["bulk_map"] = DC.densities["bulk"].map.copy()
+        else:
+            DC = hop.density.DensityCreator(u, mode="solvent", delta=delta, atomselection="name OH2",
+                                            padding=2.0)
+            density = DC.create()["solvent"]
+            # no solute: the bulk density is the solvent histogram itself (what bench.py does)
+            bulk = hop.sitemap.Density(grid=density.grid.copy(), edges=[e.copy() for e in density.edges],
+                                       parameters={"isDensity": True},
+                                       unit={"length": "Angstrom", "density": "Angstrom^{-3}"})
+            density.convert_density(density_unit)
+            density.map_sites(solvent_threshold)
+            bulk.convert_density(density_unit)
+            bulk.map_sites(bulk_threshold)
+            density.site_insert_bulk(bulk)
+            out["bulk_map"] = bulk.map.copy()
+        out["edges"] = [np.asarray(e, dtype=np.float64) for e in density.edges]
+        out["grid"] = np.asarray(density.grid, dtype=np.float64)
+        out["map"] = np.asarray(density.map)
+        assert out["map"].dtype == np.int16
+        out["P"] = dict(density.P)
+        sp = density.site_properties
+        out["site_label"] = np.asarray(sp.label, dtype=np.int64)
+        out["site_volume"] = np.asarray(sp.volume, dtype=np.float64)
+        out["site_occupancy_avg"] = np.asarray(sp.occupancy_avg, dtype=np.float64)
+        out["site_occupancy_std"] = np.asarray(sp.occupancy_std, dtype=np.float64)
+        # the interstitial's centre is None (Python 2 / old numpy) or a scalar nan (numpy >= 1.x mean([]))
+        out["site_center"] = np.array([np.full(3, np.nan) if (c is None or np.ndim(c) == 0)
+                                       else np.asarray(c, dtype=np.float64) for c in sp.center])
+        out["site_ncells"] = np.array([len(s) for s in density.sites], dtype=np.int64)
+
+        group = u.select_atoms("name OH2")
+        u.trajectory.rewind()
+        ht = hop.trajectory.HoppingTrajectory(u.trajectory, group, density, verbosity=0)
+        with tempfile.TemporaryDirectory() as tmp:
+            base = os.path.join(tmp, "refhop")
+            ht.write(base)                       # map_dcd -> _coord2hop per frame -> (fake) DCD, reloaded
+            hopframes = R.FakeUniverse._files[base + ".dcd"].xyz
+            with open(base + ".psf") as fh:      # the PSF is written to disk by hop itself
+                out["psf_text"] = fh.read()
+        out["hop_cell"] = np.asarray(ht._ts.dimensions if ht._ts is not None else [], dtype=np.float64) \
+            if hasattr(ht, "_ts") else np.zeros(0)
+        out["hop"] = hopframes.copy()            # float32 [F][N][3]: x=site, y=orbit, z=0
+        tn = hop.graph.TransportNetwork(ht, density)
+        if rates:
+            tn.compute_residency_times(verbosity=0)       # _analyze_hops + HoppingGraph (rate fits)
+        else:
+            tn._analyze_hops()
+        gp = tn.graph_properties
+        ev, nodes = [], []
+        for key in sorted((k for k in gp if isinstance(k, tuple)), key=lambda k: (int(k[0]), int(k[1]))):
+            d = gp[key]
+            for j in range(len(d["tau"])):
+                ev.append((int(key[0]), int(key[1]), float(d["tau"][j]), float(d["tbarrier"][j]),
+                           int(d["frame"][j]), int(d["iatom"][j])))
+        for key in sorted(int(k) for k in gp if not isinstance(k, tuple)):
+            d = gp[key]
+            for j in range(len(d["tau"])):
+                nodes.append((key, float(d["tau"][j]), int(d["frame"][j]), int(d["iatom"][j])))
+        out["events"] = np.array(ev, dtype=np.float64).reshape(-1, 6)
+        out["nodes"] = np.array(nodes, dtype=np.float64).reshape(-1, 4)
+        out["graph_edges"] = np.array(sorted((int(a), int(b)) for a, b in tn.graph.edges()),
+                                      dtype=np.int64).reshape(-1, 2)
+        # graph_alltransitions (hop/graph.py:107-135)
+        tn2 = hop.graph.TransportNetwork(ht, density)
+        tn2.graph_alltransitions()
+        out["alltransitions"] = np.array(sorted((int(a), int(b)) for a, b in tn2.graph.edges()),
+                                         dtype=np.int64).reshape(-1, 2)
+        if rates:
+            hg = tn.hopgraph
+            rows = []
+            for (a, b) in sorted(hg.graph.edges()):
+                d = hg.graph[a][b]
+                k = d.get("k", np.nan)
+                rows.append((int(a), int(b), float(k), float(d.get("N", np.nan))))
+            out["rates"] = np.array(rows, dtype=np.float64).reshape(-1, 4)
+    return out
+
+
+def save(name, xyz_all, n_solvent, **kw):
+    res = run_reference(xyz_all, n_solvent, **kw)
+    P = res.pop("P")
+    edges = res.pop("edges")
+    os.makedirs(OUT, exist_ok=True)
+    hop = res.pop("hop")
+    assert np.array_equal(hop, np.round(hop)) and np.all(hop[:, :, 2] == 0)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), xyz=xyz_all, n_solvent=n_solvent,
+        delta=kw["delta"], density_unit=kw["density_unit"], solvent_threshold=kw["solvent_threshold"],
+        bulk_threshold=kw["bulk_threshold"], cutoff=kw.get("cutoff", 3.5), dt=kw.get("dt", 1.0),
+        edges_x=edges[0], edges_y=edges[1], edges_z=edges[2],
+        hop_x=hop[:, :, 0].astype(np.int16), hop_y=hop[:, :, 1].astype(np.int16),
+        P_threshold=P["threshold"], P_bulk_threshold=P["bulk_threshold"], P_bulk_site=P["bulk_site"],
+        numpy_version=np.__version__, **res)
+    print("%-16s grid %s sites %d events %d nodes %d outlier atom-frames %d rate edges %d" % (
+        name, res["grid"].shape, len(res["site_ncells"]) - 1, len(res["events"]), len(res["nodes"]),
+        int((hop[:, :, 0] == -1).sum()), len(res.get("rates", []))))
+
+
+def synth(n_atoms, n_frames, seed=None):
+    p = SynthParams(n_atoms=n_atoms, n_frames=n_frames) if seed is None else \
+        SynthParams(n_atoms=n_atoms, n_frames=n_frames, seed=seed)
+    return generate(p)
+
+
+def main():
+    water = 1.0 / (1e-24 * 6.02214179e+23 * 0.997 / 18.016)      # Angstrom^-3 -> 'water' units
+    # 1. clean box, thresholds in Angstrom^-3 (no unit table involved)
+    xyz = synth(300, 60)
+    save("ref_clean", xyz, 300, delta=1.0, density_unit="Angstrom^{-3}",
+         solvent_threshold=math.e / water, bulk_threshold=math.exp(-0.5) / water)
+    # 2. outliers (also in the first frame: the (-1, N) quirk), hop's default 'water' unit
+    xyz = synth(300, 60)
+    rng = np.random.default_rng(7)
+    m = rng.random(xyz.shape[:2]) < 0.03
+    m[0, :] = False
+    xyz[m] += np.float32(50.0)
+    xyz[0, 5:9] -= np.float32(60.0)
+    save("ref_outliers", xyz, 300, delta=1.0, density_unit="water",
+         solvent_threshold=math.e, bulk_threshold=math.exp(-0.5))
+    # 3. half-Angstrom grid, dt != 1
+    xyz = synth(400, 40)
+    save("ref_half", xyz, 400, delta=0.5, density_unit="water",
+         solvent_threshold=math.e, bulk_threshold=math.exp(-0.5), dt=2.5)
+    # 4. solute present: DensityCreator(mode='all') with the 'not within cutoff of solute' bulk selection
+    xyz = synth(300, 50, seed=20261023)
+    L = float(xyz[0].max())
+    rng = np.random.default_rng(11)
+    solute0 = (0.5 * L + rng.normal(0.0, 3.0, size=(24, 3))).astype(np.float32)
+    solute = solute0[None] + rng.normal(0.0, 0.2, size=(xyz.shape[0], 24, 3)).astype(np.float32)
+    save("ref_solute", np.concatenate([xyz, solute], axis=1), 300, delta=1.0, density_unit="water",
+         solvent_threshold=math.e, bulk_threshold=math.exp(-0.5), cutoff=3.5)
+
+
+if __name__ == "__main__":
+    main()

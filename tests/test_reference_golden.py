@@ -1,0 +1,280 @@
+"""Parity against outputs of the reference ITSELF.
+
+tests/golden/reference/*.npz were produced by hop's own classes (DensityCreator, Density.map_sites,
+site_insert_bulk, HoppingTrajectory.write, TransportNetwork.compute_residency_times, HoppingGraph)
+executed from /root/reference by tests/golden/reference_py3.py + make_reference_golden.py; see those
+files for how Python-2 hop is run under Python 3.  Here
+
+* the oracle is held to them on the CPU (this pins oracle/hop_oracle.py to the reference), and
+* the CUDA path is held to them through the drop-in classes (`-m gpu`).
+
+Integer products are compared bit-exactly.  The only normalisation is the numbering of hydration
+sites of EQUAL volume, which the reference leaves to set-iteration order (hop/sitemap.py:1560-1568);
+both sides are brought to the canonical order (volume descending, larger minimum C-order cell first)
+by `canonical_perm`.  Densities are compared bit-exactly, site properties and rates to 1e-6 relative
+(BASELINE.json north_star).
+"""
+import glob
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import hop_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "reference", "*.npz")))
+NAMES = [os.path.splitext(os.path.basename(f))[0] for f in FILES]
+
+
+def load(name):
+    return np.load(os.path.join(HERE, "golden", "reference", name + ".npz"), allow_pickle=False)
+
+
+def canonical_perm(site_map):
+    """perm[label] -> canonical label.  Labels <= 1 (outlier, interstitial, bulk) are fixed; hydration
+    sites are ordered by volume descending, then larger minimum C-order cell first."""
+    m = np.asarray(site_map).ravel().astype(np.int64)
+    S = int(m.max())
+    vol = np.bincount(m[m > 0], minlength=S + 1)
+    first = np.full(S + 1, -1, np.int64)
+    idx = np.nonzero(m > 0)[0]
+    order = np.argsort(m[idx], kind="stable")
+    ls, cs = m[idx][order], idx[order]
+    starts = np.r_[0, np.nonzero(np.diff(ls))[0] + 1]
+    first[ls[starts]] = cs[starts]
+    perm = np.arange(S + 1)
+    for new, old in enumerate(sorted(range(2, S + 1), key=lambda l: (-vol[l], -first[l])), start=2):
+        perm[old] = new
+    return perm
+
+
+def relabel(a, perm):
+    a = np.asarray(a).astype(np.int64)
+    out = a.copy()
+    pos = a > 0
+    out[pos] = perm[a[pos]]
+    return out
+
+
+def reference_products(g):
+    """The reference's outputs in canonical site numbering."""
+    perm = canonical_perm(g["map"])
+    inv = np.argsort(perm)                         # canonical label -> reference label
+    ev = g["events"].copy()
+    ev[:, 0], ev[:, 1] = relabel(ev[:, 0], perm), relabel(ev[:, 1], perm)
+    nodes = g["nodes"].copy()
+    nodes[:, 0] = relabel(nodes[:, 0], perm)
+    props = {}
+    for s0, s, tau, tb, frame, ia in ev:           # emission order inside an edge is the file order
+        d = props.setdefault((int(s0), int(s)), dict(tau=[], tbarrier=[], frame=[], iatom=[]))
+        d["tau"].append(tau), d["tbarrier"].append(tb), d["frame"].append(int(frame)), d["iatom"].append(int(ia))
+    nprops = {}
+    for s0, tau, frame, ia in nodes:
+        d = nprops.setdefault(int(s0), dict(tau=[], frame=[], iatom=[]))
+        d["tau"].append(tau), d["frame"].append(int(frame)), d["iatom"].append(int(ia))
+    for d in nprops.values():                      # node records are emitted in atom order
+        o = np.argsort(d["iatom"], kind="stable")
+        for k in d:
+            d[k] = list(np.asarray(d[k])[o])
+    allt = g["alltransitions"].copy()
+    allt = np.stack([relabel(allt[:, 0], perm), relabel(allt[:, 1], perm)], axis=1)
+    rates = g["rates"].copy()
+    rates[:, 0], rates[:, 1] = relabel(rates[:, 0], perm), relabel(rates[:, 1], perm)
+    return dict(perm=perm, map=relabel(g["map"], perm), hop_x=relabel(g["hop_x"], perm),
+                hop_y=relabel(g["hop_y"], perm), props=props, nprops=nprops,
+                alltransitions=set(map(tuple, allt.tolist())),
+                rates={(int(a), int(b)): (k, int(n)) for a, b, k, n in rates},
+                volume=g["site_volume"][inv], occ_avg=g["site_occupancy_avg"][inv],
+                occ_std=g["site_occupancy_std"][inv], center=g["site_center"][inv],
+                ncells=g["site_ncells"][inv])
+
+
+def check_transitions(gp, ref, dt):
+    """graph_properties (edge tuple or node int -> arrays) against the reference's records."""
+    edges = {k: v for k, v in gp.items() if isinstance(k, tuple)}
+    nodes = {k: v for k, v in gp.items() if not isinstance(k, tuple)}
+    assert set(edges) == set(ref["props"]) and set(nodes) == set(ref["nprops"])
+    for k, d in ref["props"].items():
+        assert np.array_equal(edges[k]["frame"], d["frame"]) and np.array_equal(edges[k]["iatom"], d["iatom"]), k
+        assert np.allclose(edges[k]["tau"], d["tau"], rtol=1e-12, atol=0) and \
+            np.allclose(edges[k]["tbarrier"], d["tbarrier"], rtol=1e-12, atol=0), k
+    for k, d in ref["nprops"].items():
+        assert np.array_equal(nodes[k]["iatom"], d["iatom"]) and np.array_equal(nodes[k]["frame"], d["frame"])
+        assert np.allclose(np.asarray(nodes[k]["tau"], dtype=float), d["tau"], rtol=1e-12, atol=0)
+        assert all(v is None for v in nodes[k]["tbarrier"])
+
+
+def check_site_properties(volume, occ_avg, occ_std, center, ref):
+    assert np.allclose(volume, ref["volume"], rtol=1e-9, atol=0)
+    assert np.allclose(occ_avg, ref["occ_avg"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(occ_std, ref["occ_std"], rtol=1e-6, atol=1e-9)
+    has = ref["ncells"] > 0
+    assert np.allclose(np.asarray(center)[has], ref["center"][has], rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: the oracle against the reference
+# ------------------------------------------------------------------------------------------------
+def test_reference_golden_files_exist():
+    assert set(NAMES) >= {"ref_clean", "ref_outliers", "ref_half", "ref_solute"}
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("faithful", [False, True])
+def test_oracle_matches_reference_run(name, faithful):
+    g = load(name)
+    if faithful and name == "ref_half":
+        pytest.skip("the loop restatement is exercised on the three 1.0 A cases")
+    n_solv = int(g["n_solvent"])
+    xyz, solute = g["xyz"][:, :n_solv], g["xyz"][:, n_solv:]
+    unit, dt = str(g["density_unit"]), float(g["dt"])
+    ref = reference_products(g)
+    F = xyz.shape[0]
+    bins, arange, edges = O.grid_geometry(xyz[0], float(g["delta"]), 2.0)
+    for d in range(3):
+        assert np.array_equal(edges[d], g["edges_" + "xyz"[d]])
+    counts = O.histogram_faithful(iter(xyz), bins, arange)[0] if faithful else O.histogram_vectorised(xyz, edges)
+    grid = O.make_density(counts, edges, F, unit)
+    assert np.array_equal(grid, g["grid"])                      # bit-exact density
+    if solute.shape[1]:
+        bulk_counts = O.histogram_bulk(xyz, solute, edges, float(g["cutoff"]))
+        bulk_grid = O.make_density(bulk_counts, edges, F, unit)
+        assert np.array_equal(O.make_density(bulk_counts, edges, F, "Angstrom^{-3}"), g["bulk_grid_hist"])
+    else:
+        bulk_grid = grid
+    label = O.label_sites_faithful if faithful else O.label_sites_ndimage
+    sites = label(grid, float(g["solvent_threshold"]), 1)
+    bulk_sites = label(bulk_grid, float(g["bulk_threshold"]), 1)
+    assert np.array_equal(O.draw_map_from_sites(bulk_sites, grid.shape) == 1, g["bulk_map"] == 1)
+    assert len(bulk_sites[1]) == int((g["bulk_map"] == 1).sum())
+    sites = O.site_insert_bulk(sites, bulk_sites)
+    site_map = O.draw_map_from_sites(sites, grid.shape)
+    assert site_map.dtype == np.int16
+    assert np.array_equal(site_map, ref["map"])                 # oracle ties are canonical already
+    hop = (O.coord2hop_faithful(iter(xyz), edges, site_map) if faithful
+           else O.coord2hop_vectorised(xyz, edges, site_map))
+    assert hop.dtype == np.float32 and np.all(hop[:, :, 2] == 0)
+    assert np.array_equal(hop[:, :, 0], ref["hop_x"]) and np.array_equal(hop[:, :, 1], ref["hop_y"])
+    props, e, n = O.analyze_hops_faithful(hop[:, :, 0], dt=dt)
+    check_transitions(props, ref, dt)
+    ev, _ = O.analyze_hops_vectorised(hop[:, :, 0])
+    pairs, cnt = O.events_to_counts(ev)
+    assert {tuple(p): c for p, c in zip(pairs.tolist(), cnt.tolist())} == \
+        {k: len(d["tau"]) for k, d in ref["props"].items()}
+    assert set(map(tuple, O.graph_alltransitions(hop[:, :, 0]).tolist())) == ref["alltransitions"]
+    sp = O.site_properties(sites, grid, edges, unit)
+    check_site_properties(sp["volume"], sp["occupancy_avg"], sp["occupancy_std"], sp["center"], ref)
+    if not faithful:                                            # rate constants of the busiest edges
+        busiest = sorted(ref["rates"], key=lambda k: -ref["rates"][k][1])[:12]
+        for k in busiest:
+            k_ref, n_ref = ref["rates"][k]
+            k_or, n_or, _ = O.rate_faithful(props[k]["tau"])
+            assert n_or == n_ref and abs(k_or - k_ref) <= 1e-6 * abs(k_ref), (k, k_or, k_ref)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/hop"), reason="reference sources not present")
+def test_reference_run_is_reproducible():
+    """Re-runs hop on the first case and compares with the committed file (only where /root/reference
+    exists, i.e. in the build container -- never on the GPU box)."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_reference_golden as M
+
+    g = load("ref_clean")
+    try:
+        res = _rerun(M, g)
+    finally:
+        M.R.unload_reference()              # do not leave the reference or the fakes importable
+    assert np.array_equal(res["grid"], g["grid"]) and np.array_equal(res["map"], g["map"])
+    assert np.array_equal(res["hop"][:, :, 0], g["hop_x"]) and np.array_equal(res["events"], g["events"])
+
+
+def _rerun(M, g):
+    return M.run_reference(g["xyz"], int(g["n_solvent"]), delta=float(g["delta"]),
+                          density_unit=str(g["density_unit"]), solvent_threshold=float(g["solvent_threshold"]),
+                          bulk_threshold=float(g["bulk_threshold"]), rates=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: the drop-in classes (CUDA path through the C ABI) against the reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_path_matches_reference_run(name, tmp_path):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hop_b200.density import DensityCreator
+    from hop_b200.graph import TransportNetwork
+    from hop_b200.sitemap import Density
+    from hop_b200.trajectory import HoppingTrajectory
+    from hop_b200.universe import Universe
+
+    g = load(name)
+    n_solv = int(g["n_solvent"])
+    n_total = g["xyz"].shape[1]
+    unit, dt = str(g["density_unit"]), float(g["dt"])
+    ref = reference_products(g)
+    names = ["OH2"] * n_solv + ["CA"] * (n_total - n_solv)
+    resn = ["TIP3"] * n_solv + ["ALA"] * (n_total - n_solv)
+    u = Universe(coordinates=g["xyz"], names=names, resnames=resn, dt=dt, filename="mem.psf")
+    if n_total > n_solv:
+        DC = DensityCreator(u, mode="all", delta=float(g["delta"]), atomselection="name OH2",
+                            soluteselection="protein", cutoff=float(g["cutoff"]), padding=2.0)
+        DC.create()
+        assert np.array_equal(DC.densities["bulk"].grid, g["bulk_grid_hist"])
+        dens = DC.DensityWithBulk(density_unit=unit, solvent_threshold=float(g["solvent_threshold"]),
+                                  bulk_threshold=float(g["bulk_threshold"]))
+        bulk = DC.densities["bulk"]
+    else:
+        DC = DensityCreator(u, mode="solvent", delta=float(g["delta"]), atomselection="name OH2", padding=2.0)
+        dens = DC.create()["solvent"]
+        bulk = Density(grid=np.array(dens.grid), edges=[np.array(e) for e in dens.edges],
+                       parameters={"isDensity": True}, unit={"length": "Angstrom", "density": "Angstrom^{-3}"})
+        dens.convert_density(unit)
+        dens.map_sites(float(g["solvent_threshold"]))
+        bulk.convert_density(unit)
+        bulk.map_sites(float(g["bulk_threshold"]))
+        dens.site_insert_bulk(bulk)
+    for d in range(3):
+        assert np.array_equal(dens.edges[d], g["edges_" + "xyz"[d]])
+    assert np.array_equal(dens.grid, g["grid"])                 # bit-exact density
+    assert np.array_equal(np.asarray(bulk.map) == 1, g["bulk_map"] == 1)
+    assert dens.map.dtype == np.int16 and np.array_equal(dens.map, ref["map"])
+    assert dens.P["threshold"] == float(g["P_threshold"]) and dens.P["bulk_threshold"] == float(g["P_bulk_threshold"])
+    assert dens.P["bulk_site"] == int(g["P_bulk_site"])
+    assert [len(s) for s in dens.sites] == ref["ncells"].tolist()
+    sp = dens.site_properties
+    assert np.array_equal(sp.label, np.arange(len(ref["ncells"])))
+    centers = np.array([np.full(3, np.nan) if c is None else np.asarray(c, dtype=float) for c in sp.center])
+    check_site_properties(sp.volume, sp.occupancy_avg, sp.occupancy_std, centers, ref)
+
+    group = u.select_atoms("name OH2")
+    h = HoppingTrajectory(u.trajectory, group, dens, verbosity=0)
+    fn = str(tmp_path / "hop")
+    h.write(fn)
+    assert open(fn + ".psf").read() == str(g["psf_text"])        # byte-identical PSF
+    frames = np.stack([ts._pos.copy() for ts in h])
+    assert frames.dtype == np.float32 and np.all(frames[:, :, 2] == 0)
+    assert np.array_equal(frames[:, :, 0], ref["hop_x"]) and np.array_equal(frames[:, :, 1], ref["hop_y"])
+    h2 = HoppingTrajectory(hopdcd=fn + ".dcd", hoppsf=fn + ".psf")
+    assert np.allclose(h2.ts.dimensions, g["hop_cell"])
+    for traj in (h, HoppingTrajectory(u.trajectory, group, dens, verbosity=0)):   # from the DCD, and fused
+        tn = TransportNetwork(traj, dens)
+        hg = tn.HoppingGraph()
+        assert abs(tn.dt - dt) < 1e-6
+        gp = {k: dict(v, tau=np.asarray(v["tau"]) * (dt / tn.dt)) for k, v in tn.graph_properties.items()}
+        for k, v in gp.items():
+            if isinstance(k, tuple):
+                v["tbarrier"] = np.asarray(v["tbarrier"]) * (dt / tn.dt)
+        check_transitions(gp, ref, dt)
+        assert tn.transition_counts() == {k: len(d["tau"]) for k, d in ref["props"].items()}
+        busiest = sorted(ref["rates"], key=lambda k: -ref["rates"][k][1])[:12]
+        for k in busiest:
+            k_ref, n_ref = ref["rates"][k]
+            assert hg.graph[k[0]][k[1]]["N"] == n_ref
+            assert abs(hg.graph[k[0]][k[1]]["k"] - k_ref) <= 2e-6 * abs(k_ref), (k, hg.graph[k[0]][k[1]]["k"], k_ref)
+    tn.graph_alltransitions()
+    assert set(tn.graph.edges()) == ref["alltransitions"]
