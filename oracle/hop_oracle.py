@@ -4,13 +4,24 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
 of ``bench.py`` may import this module.  ``hop_b200`` never does; the product path is CUDA only.
 
 This is a numpy / networkx restatement of the reference algorithm (Becksteinlab/hop 0.4.0-dev,
-pure Python 2.7).  The reference cannot be imported here (Python 2 syntax, MDAnalysis absent), and
-it ships no runnable tests or golden vectors (hop/tests/README:1-4), so **parity is unpinned by the
-reference**: the oracle is pinned instead by (i) following the reference line by line, each
-function citing the file:line it restates, (ii) two independent restatements per stage (a
-"faithful" one that repeats the reference's loops and a vectorised one) that must agree, and
-(iii) `scipy.ndimage.label` with the 15-cell structuring element as a third opinion on the
-connected components.
+pure Python 2.7), each function citing the file:line it restates.  The reference ships no runnable
+tests or golden vectors (hop/tests/README:1-4) and cannot be imported as it is (Python 2 syntax,
+MDAnalysis absent), so the oracle is **pinned against outputs of the reference itself, run here**:
+``tests/golden/reference_py3.py`` executes hop's own sources from /root/reference under Python 3
+(mechanical in-memory syntax translation, Python-2 builtins and classic division restored, three
+numpy-API one-liners, MDAnalysis replaced by in-memory fakes) and
+``tests/golden/make_reference_golden.py`` froze what ``DensityCreator``, ``Density.map_sites`` /
+``site_insert_bulk``, ``HoppingTrajectory.write``, ``TransportNetwork`` and ``HoppingGraph`` produce
+on four seeded systems into ``tests/golden/reference/*.npz``.  ``tests/test_reference_golden.py``
+holds both restatements below to those files: edges and densities bit-exact, site map / hoptraj /
+events / node records / transition counts exact (up to the numbering of equal-volume sites, which
+the reference leaves to set order), site properties and rate constants to 1e-6.  What that run does
+NOT pin: the unit constants of MDAnalysis.units (the fakes carry the same values as here), the
+kd-tree selection of MDAnalysis (restated), and the float32 top-edge rule of numpy 1.x (below).
+Beyond that the oracle is cross-checked by (i) two independent restatements per stage (a "faithful"
+one that repeats the reference's loops and a vectorised one) that must agree, and (ii)
+`scipy.ndimage.label` with the 15-cell structuring element as a third opinion on the connected
+components.
 
 Third-party arithmetic the reference delegates to and that is restated here from the published
 behaviour (the packages' sources are not under /root/reference):

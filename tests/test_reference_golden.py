@@ -261,6 +261,7 @@ def test_cuda_path_matches_reference_run(name, tmp_path):
     assert np.array_equal(frames[:, :, 0], ref["hop_x"]) and np.array_equal(frames[:, :, 1], ref["hop_y"])
     h2 = HoppingTrajectory(hopdcd=fn + ".dcd", hoppsf=fn + ".psf")
     assert np.allclose(h2.ts.dimensions, g["hop_cell"])
+    checked_rates = False
     for traj in (h, HoppingTrajectory(u.trajectory, group, dens, verbosity=0)):   # from the DCD, and fused
         tn = TransportNetwork(traj, dens)
         hg = tn.HoppingGraph()
@@ -275,6 +276,14 @@ def test_cuda_path_matches_reference_run(name, tmp_path):
         for k in busiest:
             k_ref, n_ref = ref["rates"][k]
             assert hg.graph[k[0]][k[1]]["N"] == n_ref
-            assert abs(hg.graph[k[0]][k[1]]["k"] - k_ref) <= 2e-6 * abs(k_ref), (k, hg.graph[k[0]][k[1]]["k"], k_ref)
+            # The survival function weighs a waiting time that EQUALS a mesh point by 1/2
+            # (hop/graph.py:2501-2518), so the fit depends on whether dt*frames lands exactly on the
+            # integer mesh.  The reference run had the exact dt (in-memory reader); through the DCD
+            # header dt makes a float32 AKMA round trip (as it does with MDAnalysis) and the fit is
+            # only comparable when it comes back exact.
+            if tn.dt == dt:
+                checked_rates = True
+                assert abs(hg.graph[k[0]][k[1]]["k"] - k_ref) <= 1e-6 * abs(k_ref), (k, hg.graph[k[0]][k[1]]["k"], k_ref)
+    assert checked_rates
     tn.graph_alltransitions()
     assert set(tn.graph.edges()) == ref["alltransitions"]
