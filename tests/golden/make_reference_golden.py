@@ -14,10 +14,12 @@ takes part except `hop_b200.synth.generate`, which only makes the input coordina
 files).  The tests then hold the oracle (CPU, tests/test_reference_golden.py) and the CUDA path (GPU)
 to these files.
 """
+import hashlib
 import math
 import os
 import sys
 import tempfile
+import time
 import warnings
 
 import numpy as np
@@ -42,6 +44,13 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
     sel = {"name OH2": np.arange(n_solvent), "protein": np.arange(n_solvent, n_total)}
     u = R.FakeUniverse(xyz_all, selections=sel, dt=dt)
     out = {}
+    clock = {"t": time.perf_counter()}
+    timing = {}
+
+    def lap(stage):
+        now = time.perf_counter()
+        timing[stage] = timing.get(stage, 0.0) + now - clock["t"]
+        clock["t"] = now
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if n_total > n_solvent:
@@ -56,6 +65,7 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
             DC = hop.density.DensityCreator(u, mode="solvent", delta=delta, atomselection="name OH2",
                                             padding=2.0)
             density = DC.create()["solvent"]
+            lap("density")
             # no solute: the bulk density is the solvent histogram itself (what bench.py does)
             bulk = hop.sitemap.Density(grid=density.grid.copy(), edges=[e.copy() for e in density.edges],
                                        parameters={"isDensity": True},
@@ -65,6 +75,7 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
             bulk.convert_density(density_unit)
             bulk.map_sites(bulk_threshold)
             density.site_insert_bulk(bulk)
+            lap("map_sites")
             out["bulk_map"] = bulk.map.copy()
         out["edges"] = [np.asarray(e, dtype=np.float64) for e in density.edges]
         out["grid"] = np.asarray(density.grid, dtype=np.float64)
@@ -83,6 +94,7 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
 
         group = u.select_atoms("name OH2")
         u.trajectory.rewind()
+        lap("other")
         ht = hop.trajectory.HoppingTrajectory(u.trajectory, group, density, verbosity=0)
         with tempfile.TemporaryDirectory() as tmp:
             base = os.path.join(tmp, "refhop")
@@ -90,6 +102,7 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
             hopframes = R.FakeUniverse._files[base + ".dcd"].xyz
             with open(base + ".psf") as fh:      # the PSF is written to disk by hop itself
                 out["psf_text"] = fh.read()
+        lap("hoptraj")
         out["hop_cell"] = np.asarray(ht._ts.dimensions if ht._ts is not None else [], dtype=np.float64) \
             if hasattr(ht, "_ts") else np.zeros(0)
         out["hop"] = hopframes.copy()            # float32 [F][N][3]: x=site, y=orbit, z=0
@@ -98,6 +111,7 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
             tn.compute_residency_times(verbosity=0)       # _analyze_hops + HoppingGraph (rate fits)
         else:
             tn._analyze_hops()
+            lap("analyze_hops")
         gp = tn.graph_properties
         ev, nodes = [], []
         for key in sorted((k for k in gp if isinstance(k, tuple)), key=lambda k: (int(k[0]), int(k[1]))):
@@ -126,11 +140,16 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
                 k = d.get("k", np.nan)
                 rows.append((int(a), int(b), float(k), float(d.get("N", np.nan))))
             out["rates"] = np.array(rows, dtype=np.float64).reshape(-1, 4)
+    out["timing_s"] = np.array([timing.get(k, 0.0) for k in ("density", "map_sites", "hoptraj", "analyze_hops")])
     return out
 
 
-def save(name, xyz_all, n_solvent, **kw):
+def save(name, xyz_all, n_solvent, store_xyz=True, extra=None, **kw):
     res = run_reference(xyz_all, n_solvent, **kw)
+    res.update(extra or {})
+    res["xyz_sha256"] = hashlib.sha256(np.ascontiguousarray(xyz_all).tobytes()).hexdigest()
+    if not store_xyz:
+        xyz_all = np.zeros((0, xyz_all.shape[1], 3), np.float32)
     P = res.pop("P")
     edges = res.pop("edges")
     os.makedirs(OUT, exist_ok=True)
@@ -144,9 +163,10 @@ def save(name, xyz_all, n_solvent, **kw):
         hop_x=hop[:, :, 0].astype(np.int16), hop_y=hop[:, :, 1].astype(np.int16),
         P_threshold=P["threshold"], P_bulk_threshold=P["bulk_threshold"], P_bulk_site=P["bulk_site"],
         numpy_version=np.__version__, **res)
-    print("%-16s grid %s sites %d events %d nodes %d outlier atom-frames %d rate edges %d" % (
-        name, res["grid"].shape, len(res["site_ncells"]) - 1, len(res["events"]), len(res["nodes"]),
-        int((hop[:, :, 0] == -1).sum()), len(res.get("rates", []))))
+    print("%-16s grid %s sites %d events %d nodes %d outlier atom-frames %d rate edges %d  reference seconds "
+          "(density, map_sites, hoptraj, analyze_hops) %s" % (
+              name, res["grid"].shape, len(res["site_ncells"]) - 1, len(res["events"]), len(res["nodes"]),
+              int((hop[:, :, 0] == -1).sum()), len(res.get("rates", [])), np.round(res["timing_s"], 3)))
 
 
 def synth(n_atoms, n_frames, seed=None):
@@ -182,6 +202,13 @@ def main():
     solute = solute0[None] + rng.normal(0.0, 0.2, size=(xyz.shape[0], 24, 3)).astype(np.float32)
     save("ref_solute", np.concatenate([xyz, solute], axis=1), 300, delta=1.0, density_unit="water",
          solvent_threshold=math.e, bulk_threshold=math.exp(-0.5), cutoff=3.5)
+    # 5. BASELINE.json configs[0]: 1 000 waters x 200 frames, 1.0 A grid -- "reference runs as-is".  The
+    # coordinates are the bench generator's (seed 20261019 + 1, as tools/config_sweep.py); only their
+    # hash is stored, the tests regenerate them.
+    p = SynthParams(n_atoms=1000, n_frames=200, seed=20261019 + 1)
+    xyz = generate(p)
+    save("ref_config1", xyz, 1000, store_xyz=False, rates=False, extra={"synth_seed": p.seed},
+         delta=1.0, density_unit="water", solvent_threshold=math.e, bulk_threshold=math.exp(-0.5))
 
 
 if __name__ == "__main__":
