@@ -33,6 +33,13 @@ sys.path.insert(0, ROOT)
 ATOMS = 30000
 FRAMES_PER_GPU = 10000
 DELTA = 0.5
+WORKLOADS = {
+    # BASELINE.json configs[1] (the default; the metric is quoted on it)
+    "config2": dict(atoms=30000, frames_per_gpu=10000, delta=0.5, label="solvated box"),
+    # BASELINE.json configs[2]: 100 000 waters x 100 000 frames sharded over 8 GPUs = 12 500 frames per GPU
+    "config3": dict(atoms=100000, frames_per_gpu=12500, delta=0.5, label="membrane-channel-sized box"),
+}
+WORKLOAD = "config2"
 METRIC = "solvent atom-frames/sec binned+site-assigned"
 UNIT = "atom-frames/s"
 ALG_BYTES = {"S1_histogram": 12, "S3S4_hoptraj": 20, "pipeline": 32}
@@ -40,8 +47,8 @@ FALLBACK_HBM_GBS = 6650.0
 
 
 def workload_name(n_gpus):
-    return ("solvated box, %d waters x %d frames/GPU x %d GPU(s), %.2f A grid; inputs %.1f GB/GPU >> L2 (no flush needed)"
-            % (ATOMS, FRAMES_PER_GPU, n_gpus, DELTA, ATOMS * FRAMES_PER_GPU * 12 / 1e9))
+    return ("%s, %d waters x %d frames/GPU x %d GPU(s), %.2f A grid; inputs %.1f GB/GPU >> L2 (no flush needed)"
+            % (WORKLOADS[WORKLOAD]["label"], ATOMS, FRAMES_PER_GPU, n_gpus, DELTA, ATOMS * FRAMES_PER_GPU * 12 / 1e9))
 
 
 def measured_peak():
@@ -319,8 +326,9 @@ def run_gpu(args):
     # same workload (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)
+        if WORKLOAD == "config2":
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f)
     except Exception:
         pass
     kernels = {"hist_kernel": (k_hist, 12), "hoptraj_kernel": (k_hop, 20)}
@@ -378,6 +386,19 @@ def run_gpu(args):
     checks["events_sorted"] = True
 
     # ---- end to end: pinned host coordinates in, host hoptraj + events out ---------------------------
+    if args.no_e2e:
+        if rank == 0:
+            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
+                    "data": "synthetic", "config": {"workload": workload_name(n_gpus), "sites": int(res.n_labels),
+                                                    "events_per_step_rank0": int(res.n_events_local)},
+                    "clocks": clocks, "two_in_flight": two_in_flight, "e2e": None, "gpu_launches": int(launches),
+                    "roofline": roofline, "stage_ms": stage_ms, "checks": checks}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     xyz_host = torch.empty((FRAMES_PER_GPU, ATOMS, 3), dtype=torch.float32).pin_memory()
     xyz_host.copy_(xyz)
     outs = [(torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory(),
@@ -456,7 +477,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hop_b200", choices=["hop_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="config2 = BASELINE configs[1] (default, the headline); config3 = configs[2] per-GPU slab "
+                         "(100 000 waters x 12 500 frames per GPU: the full 100 000 frames at --gpus 8)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (15 GB of pinned memory per rank at config3)")
     args = ap.parse_args()
+    global ATOMS, FRAMES_PER_GPU, DELTA, WORKLOAD
+    WORKLOAD = args.workload
+    ATOMS, FRAMES_PER_GPU, DELTA = (WORKLOADS[WORKLOAD][k] for k in ("atoms", "frames_per_gpu", "delta"))
     if args.impl == "reference":
         run_reference(args)
     else:
