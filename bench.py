@@ -219,7 +219,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": workload_name(args.gpus)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -395,7 +395,7 @@ def run_gpu(args):
                                                     "events_per_step_rank0": int(res.n_events_local)},
                     "clocks": clocks, "two_in_flight": two_in_flight, "e2e": None, "gpu_launches": int(launches),
                     "roofline": roofline, "stage_ms": stage_ms, "checks": checks}
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -452,7 +452,7 @@ def run_gpu(args):
                 "stage_ms": stage_ms, "checks": checks}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -470,6 +470,23 @@ def max_over_ranks_sum(x, world):
 T_START = time.perf_counter()
 
 
+_JSON_FD = 1
+
+
+def _stdout_to_stderr():
+    """Anything libraries print to fd 1 while the bench runs (NCCL's version banner, ...) goes to stderr, so
+    that stdout carries the one JSON line only (written by emit() to the saved descriptor)."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,6 +502,7 @@ def main():
     global ATOMS, FRAMES_PER_GPU, DELTA, WORKLOAD
     WORKLOAD = args.workload
     ATOMS, FRAMES_PER_GPU, DELTA = (WORKLOADS[WORKLOAD][k] for k in ("atoms", "frames_per_gpu", "delta"))
+    _stdout_to_stderr()
     if args.impl == "reference":
         run_reference(args)
     else:
