@@ -169,6 +169,65 @@ def save(name, xyz_all, n_solvent, store_xyz=True, extra=None, **kw):
               int((hop[:, :, 0] == -1).sum()), len(res.get("rates", [])), np.round(res["timing_s"], 3)))
 
 
+def sitemap_variants(name, xyz, delta, unit):
+    """Secondary behaviours of the site map, all from hop's Density (hop/sitemap.py): MINsite = 2
+    (:1526-1527), map_sites on a density that already carries a bulk site (:506-514),
+    site_insert_nobulk (:933-943), site_labels filters (:629-760), site_volume / site_occupancy
+    (:563-598), stats (:1301-1339)."""
+    hop = R.load_reference()
+    water = 1.0 / (1e-24 * 6.02214179e+23 * 0.997 / 18.016)
+    t_solvent = math.e if unit == "water" else math.e / water
+    t_bulk = math.exp(-0.5) if unit == "water" else math.exp(-0.5) / water
+    u = R.FakeUniverse(xyz, selections={"name OH2": np.arange(xyz.shape[1])})
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        def fresh(**parameters):
+            u.trajectory.rewind()                 # the grid is defined by the frame the universe is on
+            DC = hop.density.DensityCreator(u, mode="solvent", delta=delta, atomselection="name OH2", padding=2.0,
+                                            parameters=dict(parameters))
+            d = DC.create()["solvent"]
+            d.convert_density(unit)
+            return d
+        d2 = fresh(MINsite=2)
+        d2.map_sites(t_solvent)
+        out["minsite2_map"] = d2.map.copy()
+        out["minsite2_ncells"] = np.array([len(x) for x in d2.sites])
+        d1 = fresh()
+        d1.map_sites(t_solvent)
+        out["minsite1_map"] = d1.map.copy()
+        bulk = fresh()
+        bulk.map_sites(t_bulk)
+        d1.site_insert_bulk(bulk)
+        out["with_bulk_map"] = d1.map.copy()
+        for key, kw in (("default", {}), ("sites", dict(include="sites")), ("all_none", dict(include="all", exclude=None)),
+                        ("no_bulk", dict(exclude=["default", "bulk"])), ("explicit", dict(include=[2, 3, 5], exclude=None))):
+            out["labels_" + key] = np.asarray(d1.site_labels(**kw), dtype=np.int64)
+        labels, vol = d1.site_volume(include="sites")
+        out["site_volume_labels"], out["site_volume"] = np.asarray(labels), np.asarray(vol, dtype=np.float64)
+        labels, occ, occ_std = d1.site_occupancy(include="sites")
+        out["site_occupancy"] = np.asarray(occ, dtype=np.float64)
+        out["site_occupancy_std"] = np.asarray(occ_std, dtype=np.float64)
+        st = d1.stats()
+        out["stats_keys"] = np.array(sorted(st))
+        out["stats_values"] = np.array([float(st[k]) for k in sorted(st)])
+        # re-mapping at a higher threshold removes the bulk site first (and forgets it)
+        d1.map_sites(1.5 * t_solvent)
+        out["remap_map"] = d1.map.copy()
+        out["remap_has_bulk"] = bool(d1.has_bulk())
+        out["remap_P_keys"] = np.array(sorted(d1.P.keys()))
+        d1.site_insert_nobulk()
+        out["nobulk_map"] = d1.map.copy()
+        out["nobulk_ncells"] = np.array([len(x) for x in d1.sites])
+        out["nobulk_has_bulk"] = bool(d1.has_bulk())
+        out["nobulk_bulk_threshold_is_none"] = d1.P["bulk_threshold"] is None
+    os.makedirs(os.path.join(OUT, "variants"), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "variants", name + ".npz"), xyz=xyz, delta=delta, density_unit=unit,
+                        solvent_threshold=t_solvent, bulk_threshold=t_bulk, **out)
+    print("%-16s MINsite=1 sites %d, MINsite=2 sites %d, remapped sites %d" % (
+        name, out["minsite1_map"].max(), len(out["minsite2_ncells"]) - 1, len(out["nobulk_ncells"]) - 2))
+
+
 def synth(n_atoms, n_frames, seed=None):
     p = SynthParams(n_atoms=n_atoms, n_frames=n_frames) if seed is None else \
         SynthParams(n_atoms=n_atoms, n_frames=n_frames, seed=seed)
@@ -213,3 +272,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    sitemap_variants("variants_clean", synth(300, 60), 1.0, "water")

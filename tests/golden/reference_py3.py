@@ -210,6 +210,9 @@ class FakeReader(object):
     __next__ = next
 
     def __iter__(self):
+        # Stays on the last frame when the iteration ends: `_analyze_hops` reads `self.traj.ts.frame`
+        # after its loop as "the last frame" (hop/graph.py:259-264).  (Some MDAnalysis releases rewind
+        # here; the drivers rewind explicitly wherever hop's callers start from frame 0.)
         for i in range(self.n_frames):
             yield self._load(i)
 

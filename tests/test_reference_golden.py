@@ -222,3 +222,90 @@ def test_cuda_path_matches_reference_run(name, tmp_path):
     assert checked_rates or not ref["rates"]
     tn.graph_alltransitions()
     assert set(tn.graph.edges()) == ref["alltransitions"]
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary site-map behaviours (MINsite = 2, re-mapping, site_insert_nobulk, site_labels, stats)
+# ------------------------------------------------------------------------------------------------
+def load_variants():
+    return np.load(os.path.join(HERE, "golden", "reference", "variants", "variants_clean.npz"), allow_pickle=False)
+
+
+def canonical(site_map, first=1):
+    """Map with its sites of equal volume renumbered canonically; `first` = first label that may move."""
+    m = np.asarray(site_map).astype(np.int64)
+    shifted = np.where(m >= first, m + (2 - first), np.where(m > 0, 1, m))     # reuse canonical_perm (moves >= 2)
+    perm = canonical_perm(shifted)
+    out = relabel(shifted, perm)
+    return np.where(out >= 2, out - (2 - first), m)
+
+
+def test_oracle_matches_reference_sitemap_variants():
+    g = load_variants()
+    xyz, unit = g["xyz"], str(g["density_unit"])
+    bins, arange, edges = O.grid_geometry(xyz[0], float(g["delta"]), 2.0)
+    grid = O.make_density(O.histogram_vectorised(xyz, edges), edges, xyz.shape[0], unit)
+    for label in (O.label_sites_faithful, O.label_sites_ndimage):
+        s1 = label(grid, float(g["solvent_threshold"]), 1)
+        s2 = label(grid, float(g["solvent_threshold"]), 2)
+        assert np.array_equal(O.draw_map_from_sites(s1, grid.shape), canonical(g["minsite1_map"]))
+        assert np.array_equal(O.draw_map_from_sites(s2, grid.shape), canonical(g["minsite2_map"]))
+        assert [len(s) for s in s2] == g["minsite2_ncells"].tolist()
+        s3 = label(grid, 1.5 * float(g["solvent_threshold"]), 1)
+        assert np.array_equal(O.draw_map_from_sites(s3, grid.shape), canonical(g["remap_map"]))
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_reference_sitemap_variants():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import warnings
+
+    from hop_b200.density import DensityCreator
+    from hop_b200.universe import Universe
+
+    g = load_variants()
+    unit = str(g["density_unit"])
+    u = Universe(coordinates=g["xyz"], dt=1.0, filename="mem.psf")
+
+    def fresh(**parameters):
+        d = DensityCreator(u, mode="solvent", delta=float(g["delta"]), atomselection="name OH2", padding=2.0,
+                           parameters=dict(parameters)).create()["solvent"]
+        d.convert_density(unit)
+        return d
+
+    d2 = fresh(MINsite=2)
+    d2.map_sites(float(g["solvent_threshold"]))
+    assert np.array_equal(d2.map, canonical(g["minsite2_map"]))
+    assert [len(s) for s in d2.sites] == g["minsite2_ncells"].tolist()
+    d1 = fresh()
+    d1.map_sites(float(g["solvent_threshold"]))
+    assert np.array_equal(d1.map, canonical(g["minsite1_map"]))
+    bulk = fresh()
+    bulk.map_sites(float(g["bulk_threshold"]))
+    d1.site_insert_bulk(bulk)
+    assert np.array_equal(d1.map, canonical(g["with_bulk_map"], first=2))
+    for key, kw in (("default", {}), ("sites", dict(include="sites")), ("all_none", dict(include="all", exclude=None)),
+                    ("no_bulk", dict(exclude=["default", "bulk"])), ("explicit", dict(include=[2, 3, 5], exclude=None))):
+        assert np.array_equal(np.asarray(d1.site_labels(**kw)), g["labels_" + key]), key
+    labels, vol = d1.site_volume(include="sites")
+    assert np.array_equal(labels, g["site_volume_labels"]) and np.allclose(vol, g["site_volume"], rtol=1e-9)
+    # equal-volume sites may be numbered differently: compare occupancies as multisets per volume
+    labels, occ, occ_std = d1.site_occupancy(include="sites")
+    for v in np.unique(g["site_volume"]):
+        sel = g["site_volume"] == v
+        assert np.allclose(np.sort(np.asarray(occ)[sel]), np.sort(g["site_occupancy"][sel]), rtol=1e-6, atol=1e-12)
+        assert np.allclose(np.sort(np.asarray(occ_std)[sel]), np.sort(g["site_occupancy_std"][sel]), rtol=1e-6, atol=1e-9)
+    st = d1.stats()
+    assert sorted(st) == g["stats_keys"].tolist()
+    assert np.allclose([float(st[k]) for k in sorted(st)], g["stats_values"], rtol=1e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                      # "Removed bulk site in order to map sites ..."
+        d1.map_sites(1.5 * float(g["solvent_threshold"]))
+    assert np.array_equal(d1.map, canonical(g["remap_map"]))
+    assert d1.has_bulk() == bool(g["remap_has_bulk"]) and sorted(d1.P.keys()) == g["remap_P_keys"].tolist()
+    d1.site_insert_nobulk()
+    assert np.array_equal(d1.map, canonical(g["nobulk_map"], first=2))
+    assert [len(s) for s in d1.sites] == g["nobulk_ncells"].tolist()
+    assert d1.has_bulk() == bool(g["nobulk_has_bulk"]) and (d1.P["bulk_threshold"] is None) == bool(g["nobulk_bulk_threshold_is_none"])
