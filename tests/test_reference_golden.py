@@ -309,3 +309,44 @@ def test_cuda_path_matches_reference_sitemap_variants():
     assert np.array_equal(d1.map, canonical(g["nobulk_map"], first=2))
     assert [len(s) for s in d1.sites] == g["nobulk_ncells"].tolist()
     assert d1.has_bulk() == bool(g["nobulk_has_bulk"]) and (d1.P["bulk_threshold"] is None) == bool(g["nobulk_bulk_threshold_is_none"])
+
+
+# ------------------------------------------------------------------------------------------------
+# live: the reference against the oracle on random small systems (only where /root/reference exists)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isdir("/root/reference/hop"), reason="reference sources not present")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_vs_live_reference_random(seed):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_reference_golden as M
+    from hop_b200.synth import SynthParams, generate
+
+    rng = np.random.default_rng(1000 + seed)
+    n_atoms, n_frames = int(rng.integers(60, 160)), int(rng.integers(12, 40))
+    delta = float(rng.choice([1.0, 0.8, 0.6]))
+    xyz = generate(SynthParams(n_atoms=n_atoms, n_frames=n_frames, seed=77 + seed, site_stride=int(rng.integers(3, 9))))
+    if seed % 2:                                             # outliers, also in the first frame
+        m = rng.random(xyz.shape[:2]) < 0.05
+        xyz[m] += np.float32(rng.choice([-40.0, 35.0]))
+    unit = "water" if seed % 3 else "Angstrom^{-3}"
+    water = 1.0 / (1e-24 * 6.02214179e+23 * 0.997 / 18.016)
+    scale = 1.0 if unit == "water" else 1.0 / water
+    thr, bthr = float(rng.uniform(1.5, 3.0)) * scale, float(rng.uniform(0.3, 0.8)) * scale
+    try:
+        res = M.run_reference(xyz, n_atoms, delta=delta, density_unit=unit, solvent_threshold=thr,
+                              bulk_threshold=bthr, dt=float(rng.choice([1.0, 0.5])), rates=False)
+    except ValueError as exc:                                # hop itself refuses (e.g. fewer than 2 sites)
+        pytest.skip("reference raised: %s" % exc)
+    finally:
+        M.R.unload_reference()
+    g = dict(res, n_solvent=n_atoms, hop_x=res["hop"][:, :, 0], hop_y=res["hop"][:, :, 1], rates=np.zeros((0, 4)))
+    ref = reference_products(g)
+    out = O.pipeline(xyz, delta=delta, solvent_threshold=thr, bulk_threshold=bthr, density_unit=unit, faithful=False)
+    for a, b in zip(out["edges"], res["edges"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out["grid"], res["grid"])
+    assert np.array_equal(out["map"], ref["map"])
+    assert np.array_equal(out["hop"][:, :, 0], ref["hop_x"]) and np.array_equal(out["hop"][:, :, 1], ref["hop_y"])
+    props, _, _ = O.analyze_hops_faithful(out["hop"][:, :, 0], dt=1.0)
+    ev_ref = {k: (d["frame"], d["iatom"]) for k, d in ref["props"].items()}
+    assert {k: (list(v["frame"]), list(v["iatom"])) for k, v in props.items() if isinstance(k, tuple)} == ev_ref
