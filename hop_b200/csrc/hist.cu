@@ -411,6 +411,49 @@ density_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int 
   }
 }
 
+// The same values from a table.  For fixed bin widths the density of a cell is a function of its count
+// alone, and a linspace grid has a handful of distinct widths per axis (the width classes of
+// hopb_grid_create), so T[class triple][count] built by hopb_density_value itself holds every value a
+// cell with count < kDensityTableCounts can take -- bit-identical by construction.  The per-cell work
+// drops from four double divisions (~200 instructions of the FP64 pipe) to one 8-byte load from an
+// L1/L2-resident table; cells with larger counts take the division path.
+constexpr int kDensityTableCounts = 1024;
+
+__global__ void density_table_kernel(int n_classes, int ncy, int ncz, const double* __restrict__ wx,
+                                     const double* __restrict__ wy, const double* __restrict__ wz, double n_frames,
+                                     double factor, int apply_factor, double* __restrict__ table) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_classes * kDensityTableCounts) return;
+  const int cls = t / kDensityTableCounts, c = t - cls * kDensityTableCounts;
+  const double dz = wz[cls % ncz], dy = wy[(cls / ncz) % ncy], dx = wx[cls / (ncz * ncy)];
+  table[t] = hopb_density_value((uint32_t)c, n_frames, dx, dy, dz, factor, apply_factor);
+}
+
+__global__ void __launch_bounds__(256)
+density_lookup_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int nz, double n_frames,
+                      const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
+                      double factor, int apply_factor, const uint8_t* __restrict__ cls_x,
+                      const uint8_t* __restrict__ cls_y, const uint8_t* __restrict__ cls_z, int ncy, int ncz,
+                      const double* __restrict__ table, double* __restrict__ density) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp; row < n_rows; row += n_warps) {
+    const int j = (int)(row % ny);
+    const int i = (int)(row / ny);
+    const double* trow = table + (int64_t)((int)cls_x[i] * ncy + (int)cls_y[j]) * ncz * kDensityTableCounts;
+    const uint32_t* src = counts + row * nz;
+    double* dst = density + row * nz;
+    for (int k = lane; k < nz; k += 32) {
+      const uint32_t c = src[k];
+      double v;
+      if (c < (uint32_t)kDensityTableCounts) v = __ldg(trow + (int)cls_z[k] * kDensityTableCounts + (int)c);
+      else v = hopb_density_value(c, n_frames, wx[i], wy[j], wz[k], factor, apply_factor);
+      dst[k] = v;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -520,6 +563,22 @@ int hopb_density_from_counts_ex(hopb_handle* h, void* stream, const hopb_grid* g
   const int64_t n_rows = (int64_t)g->n[0] * g->n[1];
   unsigned grid = hopb_grid_for(n_rows * 32, 256, h->num_sms, 16);
   if (ctas_per_sm > 0 && grid > (unsigned)(ctas_per_sm * h->num_sms)) grid = (unsigned)(ctas_per_sm * h->num_sms);
+  const int n_classes = (g->n_cls[0] > 0 && g->n_cls[1] > 0 && g->n_cls[2] > 0) ? g->n_cls[0] * g->n_cls[1] * g->n_cls[2] : 0;
+  static const bool no_table = getenv("HOPB_DENSITY_TABLE") && atoi(getenv("HOPB_DENSITY_TABLE")) == 0;  // tuning hook
+  if (n_classes > 0 && n_classes <= 512 && !no_table && n_rows * g->n[2] >= (int64_t)n_classes * kDensityTableCounts) {
+    double* table = nullptr;
+    int rc = hopb_scratch(h, 10, (size_t)n_classes * kDensityTableCounts * sizeof(double), (void**)&table);
+    if (rc != HOPB_OK) return rc;
+    const double* w = g->d_cls_width;
+    const int n_entries = n_classes * kDensityTableCounts;
+    HOPB_K(density_table_kernel)<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        n_classes, g->n_cls[1], g->n_cls[2], w, w + 16, w + 32, (double)n_frames, factor, factor != 1.0 ? 1 : 0, table);
+    HOPB_K(density_lookup_kernel)<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        counts, n_rows, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
+        factor != 1.0 ? 1 : 0, g->d_cls[0], g->d_cls[1], g->d_cls[2], g->n_cls[1], g->n_cls[2], table, density);
+    HOPB_LAUNCH_CHECK(h);
+    return HOPB_OK;
+  }
   HOPB_K(density_kernel)<<<grid, 256, 0, (cudaStream_t)stream>>>(
       counts, n_rows, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,
       factor != 1.0 ? 1 : 0, density);

@@ -120,6 +120,26 @@ def test_density_normalisation_bit_exact(K, traj, unit):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape,lo,hi", [((40, 37, 45), 0.0, 20.3), ((64, 64, 64), -7.25, 24.75), ((9, 5, 130), 3.1, 68.2)])
+@pytest.mark.parametrize("unit", ["Angstrom^{-3}", "water", "Molar"])
+def test_density_table_path_bit_exact(K, shape, lo, hi, unit):
+    """density_lookup_kernel (values from the per-width-class table) against the reference's arithmetic,
+    with counts on both sides of the table limit (1024), zero counts and the largest uint32 counts."""
+    rng = np.random.default_rng(shape[0])
+    edges = [np.linspace(lo, hi + 0.37 * d, n + 1) for d, n in enumerate(shape)]
+    counts = rng.poisson(37, size=shape).astype(np.int64)
+    big = rng.random(shape) < 0.02
+    counts[big] = rng.integers(1000, 1050, size=int(big.sum()))
+    counts[rng.random(shape) < 0.01] = 0
+    counts[0, 0, :3] = [1023, 1024, 2**32 - 1]
+    n_frames = 977
+    ref = O.make_density(counts.astype(np.float64), edges, n_frames, unit)
+    g = K.GridTables(edges)
+    factor = O.density_conversion_factor("Angstrom^{-3}", unit)
+    got = K.density_from_counts(g, dev(counts.astype(np.uint32).view(np.int32)), n_frames, factor).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
 def _check_labels(K, grid, thr, minsite=1):
     sites, ref_map = O.map_sites(grid, thr, minsite)
     labels, n_sites, volumes = K.label_sites(dev(grid), thr, minsite)
