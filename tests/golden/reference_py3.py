@@ -53,6 +53,7 @@ NUMPY_PATCHES = [
     ("density", "range=self.arange, normed=False)", "range=self.arange)"),
     ("trajectory", "core = D*[slice(1,-1)]", "core = tuple(D*[slice(1,-1)])"),
     ("*", "numpy.float_", "numpy.float64"),          # alias removed in numpy 2.0
+    ("*", "numpy.rank(", "numpy.ndim("),              # removed in numpy 1.18 (same function)
 ]
 
 

@@ -350,3 +350,37 @@ def test_oracle_vs_live_reference_random(seed):
     props, _, _ = O.analyze_hops_faithful(out["hop"][:, :, 0], dt=1.0)
     ev_ref = {k: (d["frame"], d["iatom"]) for k, d in ref["props"].items()}
     assert {k: (list(v["frame"]), list(v["iatom"])) for k, v in props.items() if isinstance(k, tuple)} == ev_ref
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/hop"), reason="reference sources not present")
+def test_reference_equivalence_sites_cannot_run():
+    """Why `find_equivalence_sites_with` (hop/sitemap.py:1082-1279, the last part of SURVEY.md 8f rank 4)
+    is not built: with any numpy >= 1.3 (hop pins >= 1.12) `find_common_sites` (:1757-1790) gets a FLAT
+    array from `numpy.unique(list of tuples)` instead of the unique pairs the code was written for, and
+    the caller fails on it -- there is no reference behaviour to be in parity with."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_reference_golden as M
+
+    try:
+        hop = M.R.load_reference()
+        xyz = M.synth(300, 60)
+
+        def dens(frames):
+            u = M.R.FakeUniverse(xyz[frames], selections={"name OH2": np.arange(300)})
+            d = hop.density.DensityCreator(u, mode="solvent", delta=1.0, atomselection="name OH2",
+                                           padding=2.0).create()["solvent"]
+            d.convert_density("water")
+            d.map_sites(math.e)
+            return d
+
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a, b = dens(np.r_[0:60]), dens(np.r_[0, 30:60])          # same frame 0 -> same grid
+            m = hop.sitemap.find_common_sites(a, b)
+            assert np.ndim(m) == 1                                   # labels, not (label_a, label_b) pairs
+            with pytest.raises(ValueError):
+                a.find_equivalence_sites_with(b)
+    finally:
+        M.R.unload_reference()
