@@ -279,19 +279,27 @@ class HoppingGraph(object):
         return filename_function(self, filename, ext, set_default, use_my_ext)
 
     def save(self, filename=None):
-        """Save the graph, its properties, trjdata and site_properties as one pickle (hop/graph.py:760-767)."""
-        data = {'graph': self.graph, 'properties': self.properties, 'trjdata': self.trjdata,
-                'site_properties': self.site_properties}
+        """Save HoppingGraph as a pickled python object, like hop does (hop/graph.py:760-767): the
+        instance itself, so that hop's own load() -- which copies `graph`, `properties`, `trjdata`, ... from
+        the unpickled object and reads its `site_properties` -- accepts the file as well."""
         with open(self.filename(filename, 'pickle', set_default=True), 'wb') as fh:
-            pickle.dump(data, fh, pickle.HIGHEST_PROTOCOL)
+            pickle.dump(self, fh, pickle.HIGHEST_PROTOCOL)
 
     def load(self, filename=None):
+        """Reinstantiate from a pickled HoppingGraph (hop/graph.py:769-784): files written by save()
+        here, by hop's HoppingGraph.save(), or the attribute dictionary earlier versions of this class
+        wrote."""
+        from .utilities import load_pickle
+
         with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
-            data = pickle.load(fh)
-        self.graph = data['graph']
-        self.properties = data['properties']
-        self.trjdata = data.get('trjdata')
-        self.site_properties = data.get('site_properties')
+            h = load_pickle(fh)
+        data = h if isinstance(h, dict) else h.__dict__
+        for attr in ('graph', 'properties', 'filtered_graph', 'trjdata', 'node_properties', 'occupancy_avg',
+                     'occupancy_std'):
+            if attr in data:
+                self.__dict__[attr] = data[attr]
+        # hop keeps site_properties behind a property (name-mangled attribute)
+        self.site_properties = data.get('site_properties', data.get('_HoppingGraph__site_properties'))
 
 
 class fit_func(object):

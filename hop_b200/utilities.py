@@ -54,6 +54,22 @@ def filename_function(self, filename=None, ext=None, set_default=False, use_my_e
     return filename
 
 
+class _HopUnpickler(pickle.Unpickler):
+    """Reads pickles written by hop itself: classes of the package ``hop`` (hop.sitemap.Density,
+    hop.utilities.DefaultDict, hop.graph.HoppingGraph, hop.graph.fitExp2, ...) are resolved to their
+    counterparts here, so that the files load where hop is not installed."""
+
+    def find_class(self, module, name):
+        if module == 'hop' or module.startswith('hop.'):
+            module = 'hop_b200' + module[3:]
+        return super(_HopUnpickler, self).find_class(module, name)
+
+
+def load_pickle(fh):
+    """pickle.load that also accepts files saved by hop (Python-2 string encoding included)."""
+    return _HopUnpickler(fh, encoding='latin1').load()
+
+
 class DefaultDict(dict):
     """Dictionary based on defaults and updated with keys/values from user."""
 
@@ -111,7 +127,7 @@ class Saveable(object):
     def load(self, filename=None, merge=False):
         """Reinstantiate class from a pickled file (produced with save())."""
         with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
-            tmp = pickle.load(fh)
+            tmp = load_pickle(fh)
         try:
             # attributes may live behind properties (device mirrors): ask the object, not its __dict__
             data = tmp.__getstate__() if isinstance(tmp, Saveable) else tmp.__dict__

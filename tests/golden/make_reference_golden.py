@@ -36,7 +36,7 @@ OUT = os.path.join(HERE, "reference")
 
 
 def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bulk_threshold,
-                  cutoff=3.5, dt=1.0, rates=True):
+                  cutoff=3.5, dt=1.0, rates=True, pickles_to=None):
     """The workflow of scripts/hop-generate-densities.py / -hoptraj.py / -hopgraph.py, through the
     reference's classes.  xyz_all float32 [F][n_solvent + n_solute][3]."""
     hop = R.load_reference()
@@ -132,6 +132,12 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
         tn2.graph_alltransitions()
         out["alltransitions"] = np.array(sorted((int(a), int(b)) for a, b in tn2.graph.edges()),
                                          dtype=np.int64).reshape(-1, 2)
+        if rates and pickles_to:
+            # hop's own on-disk products: Saveable.save (hop/utilities.py:216-222), HoppingGraph.save
+            # (hop/graph.py:760-767) -- pickles of the instances, protocol 2
+            os.makedirs(pickles_to, exist_ok=True)
+            density.save(os.path.join(pickles_to, "density"))
+            tn.hopgraph.save(os.path.join(pickles_to, "hopgraph"))
         if rates:
             hg = tn.hopgraph
             rows = []
@@ -239,7 +245,8 @@ def main():
     # 1. clean box, thresholds in Angstrom^-3 (no unit table involved)
     xyz = synth(300, 60)
     save("ref_clean", xyz, 300, delta=1.0, density_unit="Angstrom^{-3}",
-         solvent_threshold=math.e / water, bulk_threshold=math.exp(-0.5) / water)
+         solvent_threshold=math.e / water, bulk_threshold=math.exp(-0.5) / water,
+         pickles_to=os.path.join(OUT, "pickles"))
     # 2. outliers (also in the first frame: the (-1, N) quirk), hop's default 'water' unit
     xyz = synth(300, 60)
     rng = np.random.default_rng(7)

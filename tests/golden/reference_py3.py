@@ -364,7 +364,9 @@ def install_fakes():
     module("gridData", OpenDX=types.SimpleNamespace())
     module("Bio.PDB")
     module("Bio", PDB=sys.modules["Bio.PDB"])
-    sys.modules.setdefault("cPickle", pickle)
+    # cPickle of Python 2: highest protocol 2
+    module("cPickle", dump=pickle.dump, dumps=pickle.dumps, load=pickle.load, loads=pickle.loads,
+           HIGHEST_PROTOCOL=2, PickleError=pickle.PickleError)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -384,3 +384,63 @@ def test_reference_equivalence_sites_cannot_run():
                 a.find_equivalence_sites_with(b)
     finally:
         M.R.unload_reference()
+
+
+# ------------------------------------------------------------------------------------------------
+# on-disk products written by hop itself (tests/golden/reference/pickles/*.pickle.gz: Saveable.save of the
+# Density and HoppingGraph.save of the ref_clean run) must load here, without hop installed
+# ------------------------------------------------------------------------------------------------
+def _gunzip_to(tmp_path, name):
+    import gzip
+
+    dst = tmp_path / name
+    with gzip.open(os.path.join(HERE, "golden", "reference", "pickles", name + ".gz"), "rb") as src:
+        dst.write_bytes(src.read())
+    return str(dst)
+
+
+def test_density_pickle_written_by_hop_loads(tmp_path):
+    from hop_b200.sitemap import Density
+
+    assert "hop" not in sys.modules or not getattr(sys.modules["hop"], "__reference_py3__", False)
+    g = load("ref_clean")
+    fn = _gunzip_to(tmp_path, "density.pickle")
+    d = Density(filename=fn)
+    assert np.array_equal(d.grid, g["grid"]) and np.array_equal(d.map, g["map"]) and d.map.dtype == np.int16
+    for a, k in zip(d.edges, ("edges_x", "edges_y", "edges_z")):
+        assert np.array_equal(a, g[k])
+    assert d.P["threshold"] == float(g["P_threshold"]) and d.P["bulk_threshold"] == float(g["P_bulk_threshold"])
+    assert d.P["bulk_site"] == 1 and d.P["isDensity"] and d.has_bulk()
+    assert d.unit["length"] == "Angstrom" and d.unit["density"] == "Angstrom^{-3}"
+    assert d.metadata["collector"] == "solvent" and d.metadata["n_frames"] == g["hop_x"].shape[0]
+    assert [len(s) for s in d.sites] == g["site_ncells"].tolist()
+    assert sorted(map(tuple, d.sites[1])) == sorted(map(tuple, np.argwhere(g["bulk_map"] == 1).tolist()))
+    sp = d.site_properties
+    assert np.allclose(sp.volume, g["site_volume"]) and np.allclose(sp.occupancy_avg, g["site_occupancy_avg"])
+    assert np.array_equal(np.asarray(d.site_labels("sites")), np.arange(2, len(g["site_ncells"])))
+    # and what is saved again loads again, with the same content
+    d.save(str(tmp_path / "again"))
+    d2 = Density(filename=str(tmp_path / "again"))
+    assert np.array_equal(d2.grid, d.grid) and np.array_equal(d2.map, d.map) and dict(d2.P) == dict(d.P)
+
+
+def test_hopgraph_pickle_written_by_hop_loads(tmp_path):
+    from hop_b200.graph import HoppingGraph
+
+    g = load("ref_clean")
+    fn = _gunzip_to(tmp_path, "hopgraph.pickle")
+    hg = HoppingGraph(filename=fn)
+    rates = {(int(a), int(b)): (k, int(n)) for a, b, k, n in g["rates"]}
+    assert set(hg.graph.edges()) == set(rates)
+    for (a, b), (k, n) in rates.items():
+        assert hg.graph[a][b]["N"] == n and hg.graph[a][b]["k"] == k
+        assert hg.number_of_hops(a, b) == n and len(hg.waitingtimes(a, b)) == n
+    e = max(rates, key=lambda e: rates[e][1])
+    fit = hg.waitingtime_fit(e)
+    assert type(fit).__module__ == "hop_b200.graph" and np.all(np.isfinite(fit.fit(np.arange(5.0))))
+    assert hg.trjdata["time_unit"] == "ps" and hg.trjdata["dt"] == float(g["dt"])
+    assert np.allclose(hg.site_properties.volume, g["site_volume"])
+    hg.save(str(tmp_path / "again"))
+    hg2 = HoppingGraph(filename=str(tmp_path / "again"))
+    assert set(hg2.graph.edges()) == set(hg.graph.edges()) and hg2.trjdata == hg.trjdata
+    assert all(np.array_equal(hg2.properties[k]["tau"], hg.properties[k]["tau"]) for k in hg.properties)
