@@ -35,6 +35,13 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
     "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "lts__t_sector_hit_rate.pct",
     "l1tex__t_sector_hit_rate.pct",
+    # the L2 side of the scattered reductions (binning): tag pipeline, atomic units, RED sectors by lookup result
+    "lts__t_tag_requests.avg.pct_of_peak_sustained_elapsed", "lts__t_tag_requests.max.pct_of_peak_sustained_elapsed",
+    "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum",
+    "lts__t_sectors.sum", "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed_op_global_red.sum",
 ]
 
 
