@@ -405,7 +405,7 @@ def run_gpu(args):
              torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory()) for _ in range(2)]
     del xyz
     pipe.run_host(xyz_host, frame0, *outs[0])   # warm-up (allocates the resident buffers)
-    e2e_steps = max(1, min(args.steps, 20))
+    e2e_steps = min(max(args.steps, 10), 20)   # at least 10: the first upload of the chain has nothing to overlap with
     barrier()
     t0 = time.perf_counter()
     # every step uploads its coordinates and downloads its hopping trajectory; the download of step
