@@ -137,6 +137,18 @@ def run_reference(xyz_all, n_solvent, delta, density_unit, solvent_threshold, bu
             # (hop/graph.py:760-767) -- pickles of the instances, protocol 2
             os.makedirs(pickles_to, exist_ok=True)
             density.save(os.path.join(pickles_to, "density"))
+            # host-side selections on that very density, for a CPU-only check of the drop-in's site_labels / stats
+            combos = {}
+            for i, (inc, exc) in enumerate(SITE_LABEL_COMBOS):
+                try:
+                    combos["labels_%02d" % i] = np.asarray(density.site_labels(include=inc, exclude=exc), dtype=np.int64)
+                except Exception as exc_:                      # noqa: BLE001 - record what hop raises
+                    combos["labels_%02d" % i] = np.array([-999])
+                    combos["error_%02d" % i] = np.array(type(exc_).__name__)
+            st = density.stats()
+            np.savez_compressed(os.path.join(pickles_to, "site_labels.npz"),
+                                stats_keys=np.array(sorted(st)), stats_values=np.array([float(st[k]) for k in sorted(st)]),
+                                **combos)
             tn.hopgraph.save(os.path.join(pickles_to, "hopgraph"))
         if rates:
             hg = tn.hopgraph
@@ -232,6 +244,15 @@ def sitemap_variants(name, xyz, delta, unit):
                         solvent_threshold=t_solvent, bulk_threshold=t_bulk, **out)
     print("%-16s MINsite=1 sites %d, MINsite=2 sites %d, remapped sites %d" % (
         name, out["minsite1_map"].max(), len(out["minsite2_ncells"]) - 1, len(out["nobulk_ncells"]) - 2))
+
+
+#: (include, exclude) arguments of Density.site_labels (hop/sitemap.py:629-760) frozen for the CPU-only test
+SITE_LABEL_COMBOS = [
+    ("default", "default"), ("all", "default"), ("all", None), ("sites", "default"), ("sites", None),
+    ("default", None), ("default", ["default", "bulk"]), ("default", "bulk"), ("default", "interstitial"),
+    (3, "default"), ([2, 5, 7], "default"), ([0, 1, 2], None), ([0, 1, 2], "default"), ([1, 4], "bulk"),
+    ("subsites", None), ("equivalencesites", None), (["sites", 1], None), ("all", ["bulk", "interstitial"]),
+]
 
 
 def synth(n_atoms, n_frames, seed=None):

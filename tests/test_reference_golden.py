@@ -444,3 +444,31 @@ def test_hopgraph_pickle_written_by_hop_loads(tmp_path):
     hg2 = HoppingGraph(filename=str(tmp_path / "again"))
     assert set(hg2.graph.edges()) == set(hg.graph.edges()) and hg2.trjdata == hg.trjdata
     assert all(np.array_equal(hg2.properties[k]["tau"], hg.properties[k]["tau"]) for k in hg.properties)
+
+
+def test_site_labels_and_stats_on_hop_density_match_hop(tmp_path):
+    """Host-side selections (Density.site_labels, hop/sitemap.py:629-760, and Density.stats, :1301-1339) on
+    the density hop itself saved, against what hop returned for the same arguments (CPU only)."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from hop_b200.sitemap import Density
+
+    combos_src = open(os.path.join(HERE, "golden", "make_reference_golden.py")).read()
+    ns = {}
+    exec(combos_src[combos_src.index("SITE_LABEL_COMBOS = ["):combos_src.index("def synth(")], ns)
+    g = np.load(os.path.join(HERE, "golden", "reference", "pickles", "site_labels.npz"), allow_pickle=False)
+    d = Density(filename=_gunzip_to(tmp_path, "density.pickle"))
+    for i, (inc, exc) in enumerate(ns["SITE_LABEL_COMBOS"]):
+        want = g["labels_%02d" % i]
+        if "error_%02d" % i in g.files:
+            with pytest.raises(Exception):
+                d.site_labels(include=inc, exclude=exc)
+            continue
+        got = np.asarray(d.site_labels(include=inc, exclude=exc), dtype=np.int64)
+        assert np.array_equal(got, want), (inc, exc, got[:8], want[:8])
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = d.stats()
+    assert sorted(st) == g["stats_keys"].tolist()
+    assert np.allclose([float(st[k]) for k in sorted(st)], g["stats_values"], rtol=1e-12)
