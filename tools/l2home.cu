@@ -67,6 +67,66 @@ __global__ void red_rate(uint32_t* buf, const uint32_t* __restrict__ list0, uint
   }
 }
 
+// 4. emulation of the histogram with die-local reductions.  `coords` stands for the 12 B / point coordinate
+// stream, cells_in holds the cell of every point (what the bin search would produce), cells_out is the 4 B
+// brick index stage 1 writes for stage 3.  home: 1 bit per 128-byte line of the grid (1 = homed with SM group 1).
+constexpr uint32_t kDone = 0x40000000u;
+
+__device__ __forceinline__ uint32_t home_of(const uint32_t* __restrict__ home, uint32_t cell) {
+  const uint32_t line = cell >> 5;
+  return (__ldg(home + (line >> 5)) >> (line & 31)) & 1u;
+}
+
+// mode 0: today's kernel (every point reduced where it is read); mode 1: phase A (only points homed on this SM's die)
+__global__ void __launch_bounds__(256)
+hist_emul(const float4* __restrict__ coords, const uint32_t* __restrict__ cells_in, uint32_t* __restrict__ cells_out,
+          uint32_t* grid, const uint32_t* __restrict__ home, const uint8_t* __restrict__ sm_group, int64_t n, int mode) {
+  const uint32_t g = sm_group[smid()];
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (int64_t q = i0; 4 * q + 3 < n; q += stride) {          // four points per thread and step: 48 B of coordinates
+    const float4 a = coords[3 * q], b = coords[3 * q + 1], c = coords[3 * q + 2];
+    acc += a.x + b.y + c.z;
+    const uint4 cc = reinterpret_cast<const uint4*>(cells_in)[q];
+    uint32_t v[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (mode == 0 || home_of(home, v[k]) == g) { atomicAdd(grid + v[k], 1u); v[k] |= kDone; }
+    }
+    reinterpret_cast<uint4*>(cells_out)[q] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  if (acc == 123.456f) grid[0] = 1;
+}
+
+// phase B: every die walks the whole index array (chunks handed out per die) and reduces what is left and its own
+__global__ void __launch_bounds__(256)
+hist_emul_b(const uint32_t* __restrict__ cells, uint32_t* grid, const uint32_t* __restrict__ home,
+            const uint8_t* __restrict__ sm_group, int64_t n, int* next_chunk /*[2]*/, int chunk) {
+  __shared__ int s_c;
+  const uint32_t g = sm_group[smid()];
+  const int64_t n_chunks = (n / 4 + chunk - 1) / chunk;
+  while (true) {
+    if (threadIdx.x == 0) s_c = atomicAdd(next_chunk + g, 1);
+    __syncthreads();
+    const int c = s_c;
+    __syncthreads();
+    if (c >= n_chunks) return;
+    const int64_t q0 = (int64_t)c * chunk, q1 = min(q0 + chunk, n / 4);
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      const uint4 cc = __ldg(reinterpret_cast<const uint4*>(cells) + q);
+      const uint32_t v[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!(v[k] & kDone) && home_of(home, v[k]) == g) atomicAdd(grid + v[k], 1u);
+    }
+  }
+}
+
+__global__ void fill_cells(uint32_t* cells, int64_t n, uint32_t n_cells) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    cells[i] = hash32((uint32_t)i * 2654435761u + 99u) % n_cells;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -171,5 +231,42 @@ int main(int argc, char** argv) {
       printf("3. %s: %.3f ms for %.3g REDs -> %.3g RED/s\n", names[mode], ms, (double)blocks * threads * per_thread,
              (double)blocks * threads * per_thread / (ms * 1e-3));
     }
+  // ---- 4. histogram emulation: one pass vs die-local two-phase ----------------------------------------
+  {
+    const int64_t n = 300000000;
+    const uint32_t n_cells = (uint32_t)(bytes / 4);
+    std::vector<uint32_t> home((n_lines + 31) / 32, 0u);
+    for (int64_t i = 0; i < n_lines; ++i) if (far_bits[0][i]) home[i >> 5] |= 1u << (i & 31);   // far from group 0 = homed with group 1
+    uint32_t *d_home, *d_cin, *d_cout; float4* d_xyz; int* d_next;
+    CK(cudaMalloc(&d_home, 4 * home.size()));
+    CK(cudaMemcpy(d_home, home.data(), 4 * home.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_cin, 4 * n)); CK(cudaMalloc(&d_cout, 4 * n)); CK(cudaMalloc(&d_xyz, 12 * n)); CK(cudaMalloc(&d_next, 8));
+    CK(cudaMemset(d_xyz, 0, 12 * n));
+    fill_cells<<<n_sm * 8, 256>>>(d_cin, n, n_cells);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    const int blocks = (int)((n / 4 + 256 * 4 - 1) / (256 * 4));     // ~4 steps per thread: many short-lived CTAs, like hist_kernel
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaMemset(buf, 0, bytes));
+      CK(cudaEventRecord(e0));
+      hist_emul<<<blocks, 256>>>(d_xyz, d_cin, d_cout, buf, d_home, d_group, n, 0);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float t0; CK(cudaEventElapsedTime(&t0, e0, e1));
+      uint32_t first_a; CK(cudaMemcpy(&first_a, buf + 12345, 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemset(buf, 0, bytes));
+      CK(cudaMemset(d_next, 0, 8));
+      CK(cudaEventRecord(e0));
+      hist_emul<<<blocks, 256>>>(d_xyz, d_cin, d_cout, buf, d_home, d_group, n, 1);
+      CK(cudaEventRecord(e1));
+      hist_emul_b<<<n_sm * 8, 256>>>(d_cout, buf, d_home, d_group, n, d_next, 2048);
+      CK(cudaEventRecord(e2));
+      CK(cudaDeviceSynchronize());
+      float ta, tb; CK(cudaEventElapsedTime(&ta, e0, e1)); CK(cudaEventElapsedTime(&tb, e1, e2));
+      uint32_t first_b; CK(cudaMemcpy(&first_b, buf + 12345, 4, cudaMemcpyDeviceToHost));
+      printf("4. %.3g points into the %zu MB grid: one pass %.3f ms; die-local phase A %.3f ms + phase B %.3f ms = %.3f ms (counts agree: %s)\n",
+             (double)n, bytes >> 20, t0, ta, tb, ta + tb, first_a == first_b ? "yes" : "NO");
+    }
+  }
   return 0;
 }
