@@ -348,7 +348,13 @@ def run_gpu(args):
                 "kernels": {k: {"ms": v[0], "GBps": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9,
                                 "frac": atom_frames_local * v[1] / (v[0] * 1e-3) / 1e9 / peak} for k, v in kernels.items()},
                 "pipeline": {"bytes_per_atom_frame": 32, "GBps": value * 32 / 1e9 / n_gpus,
-                             "frac": value * 32 / 1e9 / n_gpus / peak}}
+                             "frac": value * 32 / 1e9 / n_gpus / peak},
+                # the same two stages as they ran inside the timed region (CUDA events at the stage boundaries on
+                # the pipeline's stream; S1 includes zeroing the grid and, with N > 1, the all-reduce; S3S4 the
+                # slab-summary exchange and the fix-up)
+                "in_step": {k: {"ms": stage_ms[k], "GBps": atom_frames_local * b / (stage_ms[k] * 1e-3) / 1e9,
+                                "frac": atom_frames_local * b / (stage_ms[k] * 1e-3) / 1e9 / peak}
+                            for k, b in (("S1_histogram", 12), ("S3S4_hoptraj", 20)) if stage_ms.get(k)}}
 
     # ---- two runs in flight (independent trajectories, e.g. BASELINE config 5): reported beside `value` ----
     two_in_flight = None
