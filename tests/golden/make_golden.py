@@ -3,7 +3,6 @@
 so these pin the oracle itself: any later change to oracle/ or to the synthetic generator that
 alters a result shows up as a diff against the committed files."""
 import hashlib
-import math
 import os
 import sys
 

@@ -1,7 +1,6 @@
 """The oracle against the committed golden vectors, and its two restatements against each other."""
 import glob
 import hashlib
-import math
 import os
 
 import numpy as np

@@ -14,7 +14,6 @@ both sides are brought to the canonical order (volume descending, larger minimum
 by `canonical_perm`.  Densities are compared bit-exactly, site properties and rates to 1e-6 relative
 (BASELINE.json north_star).
 """
-import glob
 import math
 import os
 import sys

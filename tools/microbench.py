@@ -4,7 +4,6 @@ usage: python tools/microbench.py [--atoms N] [--frames F] [--delta D] [--reps R
 """
 import argparse
 import json
-import math
 import os
 import sys
 import time
