@@ -59,13 +59,13 @@ ccl_rows_kernel(const double* __restrict__ density, double threshold, CountMask 
     }
     int carry = -1;  // start (z) of the run that reaches the previous chunk's last cell, or -1
     unsigned any = 0;
-    for (int z0 = 0; z0 < nz; z0 += 32) {
+    auto in_mask = [&](int z) -> bool {
+      if (z >= nz) return false;
+      if (FROM_COUNTS) return (unsigned long long)cm.counts[base + z] >= cmin_row[cm.cls_z[z]];
+      return density[base + z] >= threshold;
+    };
+    auto chunk = [&](int z0, bool m) {
       const int z = z0 + lane;
-      bool m = false;
-      if (z < nz) {
-        if (FROM_COUNTS) m = (unsigned long long)cm.counts[base + z] >= cmin_row[cm.cls_z[z]];
-        else m = density[base + z] >= threshold;
-      }
       const unsigned bits = __ballot_sync(kFull, m);
       any |= bits;
       const unsigned below = ~bits & ((1u << lane) - 1);  // non-mask cells below this lane
@@ -75,6 +75,14 @@ ccl_rows_kernel(const double* __restrict__ density, double threshold, CountMask 
       if (z < nz) parent[base + z] = m ? (int)(base + start) : -1;
       const int s31 = __shfl_sync(kFull, start, 31);
       carry = (bits >> 31) ? s31 : -1;
+    };
+    // two chunks of 32 cells per step: both loads are in flight before either chunk is linked (a warp
+    // that walks its row with one 128-byte request at a time leaves the memory system idle)
+    for (int z0 = 0; z0 < nz; z0 += 64) {
+      const bool ma = in_mask(z0 + lane);
+      const bool mb = in_mask(z0 + 32 + lane);
+      chunk(z0, ma);
+      if (z0 + 32 < nz) chunk(z0 + 32, mb);
     }
     if (lane == 0) rowflag[row] = any ? 1 : 0;
   }
@@ -197,16 +205,24 @@ ccl_flatten_kernel(int* parent, const uint8_t* __restrict__ rowflag, int64_t n_r
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     if (!rowflag[row]) continue;
     const int64_t base = row * nz;
-    for (int z0 = 0; z0 < nz; z0 += 32) {
-      const int z = z0 + lane;
-      if (z >= nz) continue;
-      const int64_t c = base + z;
-      if (parent[c] < 0) continue;
-      const bool is_head = z == 0 || parent[c - 1] < 0;
+    // two chunks of 32 cells per step, all four loads issued before anything depends on them
+    for (int z0 = 0; z0 < nz; z0 += 64) {
+      const int za = z0 + lane, zb = za + 32;
+      const int pa = za < nz ? ld_parent(parent, (int)(base + za)) : -1;
+      const int pb = zb < nz ? ld_parent(parent, (int)(base + zb)) : -1;
+      const int qa = (za > 0 && za < nz) ? ld_parent(parent, (int)(base + za - 1)) : -1;   // the cell below in z
+      const int qb = zb < nz ? ld_parent(parent, (int)(base + zb - 1)) : -1;
+      const bool ha = pa >= 0 && qa < 0, hb = pb >= 0 && qb < 0;       // heads of z-runs (z == 0: qa = -1)
       if (heads) {
-        if (is_head) { const int r = uf_find(parent, (int)c); parent[c] = r; }
-      } else if (!is_head) {
-        parent[c] = ld_parent(parent, ld_parent(parent, (int)c));
+        if (ha) { const int r = uf_find(parent, (int)(base + za)); parent[base + za] = r; }
+        if (hb) { const int r = uf_find(parent, (int)(base + zb)); parent[base + zb] = r; }
+      } else {
+        // a non-head's parent is a head, flattened by the pass before: one more hop gives the root
+        const bool na = pa >= 0 && !ha, nb = pb >= 0 && !hb;
+        const int ra = na ? ld_parent(parent, pa) : 0;
+        const int rb = nb ? ld_parent(parent, pb) : 0;
+        if (na) parent[base + za] = ra;
+        if (nb) parent[base + zb] = rb;
       }
     }
   }
@@ -331,15 +347,14 @@ ccl_relabel_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ r
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     const int64_t base = row * nz;
     const bool any = rowflag[row] != 0;
-    for (int z0 = 0; z0 < nz; z0 += 32) {
-      const int z = z0 + lane;
-      if (z >= nz) continue;
-      int l = 0;
-      if (any) {
-        const int r = parent[base + z];
-        if (r >= 0) l = rootlabel[r];
-      }
-      labels[base + z] = l;
+    for (int z0 = 0; z0 < nz; z0 += 64) {            // two chunks per step: loads first, stores last
+      const int za = z0 + lane, zb = za + 32;
+      const int ra = (any && za < nz) ? parent[base + za] : -1;
+      const int rb = (any && zb < nz) ? parent[base + zb] : -1;
+      const int la = ra >= 0 ? rootlabel[ra] : 0;
+      const int lb = rb >= 0 ? rootlabel[rb] : 0;
+      if (za < nz) labels[base + za] = la;
+      if (zb < nz) labels[base + zb] = lb;
     }
   }
 }
