@@ -417,11 +417,30 @@ site_prop_kernel(const double* __restrict__ density, const int32_t* __restrict__
   double b[5] = {0, 0, 0, 0, 0};  // partial of the bulk membership (label 1)
   double a[5] = {0, 0, 0, 0, 0};  // partial of the run of `cur` labels
   int cur = 0;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-    const int o = own[c];
-    const bool mb = member && member[c];
+  // four cells per thread and step, their loads issued together (the kernel runs with few CTAs per SM beside
+  // other work: one dependent load chain per thread left it waiting on memory); the cells are then accumulated
+  // in the order c, c + stride, ... as before, so the floating-point sums are unchanged
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < n_cells; c0 += 4 * stride) {
+    int o4[4];
+    bool mb4[4];
+    double rho4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t cu = c0 + u * stride;
+      const bool valid = cu < n_cells;
+      o4[u] = valid ? own[cu] : 0;
+      mb4[u] = valid && member && member[cu];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rho4[u] = (o4[u] > 0 || mb4[u]) ? density[c0 + u * stride] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const int64_t c = c0 + u * stride;
+    const int o = o4[u];
+    const bool mb = mb4[u];
     if (o <= 0 && !mb) continue;
-    const double rho = density[c];
+    const double rho = rho4[u];
     int i = 0, j = 0, k = 0;
     if (PASS == 0) {   // 32-bit index arithmetic: the grid has fewer than 2^31 cells
       const uint32_t cu = (uint32_t)c, r = cu / (uint32_t)nz;
@@ -441,6 +460,7 @@ site_prop_kernel(const double* __restrict__ density, const int32_t* __restrict__
     if (mb) {
       if (PASS == 0) { b[0] += 1.0; b[1] += rho; b[2] += mx[i]; b[3] += my[j]; b[4] += mz[k]; }
       else { const double d = rho - mean[1]; b[0] += d * d; }
+    }
     }
   }
   // own-label partials: one block-level flush when the whole block ended on the same label
