@@ -444,12 +444,22 @@ density_lookup_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int n
     const double* trow = table + (int64_t)((int)cls_x[i] * ncy + (int)cls_y[j]) * ncz * kDensityTableCounts;
     const uint32_t* src = counts + row * nz;
     double* dst = density + row * nz;
-    for (int k = lane; k < nz; k += 32) {
-      const uint32_t c = src[k];
-      double v;
-      if (c < (uint32_t)kDensityTableCounts) v = __ldg(trow + (int)cls_z[k] * kDensityTableCounts + (int)c);
-      else v = hopb_density_value(c, n_frames, wx[i], wy[j], wz[k], factor, apply_factor);
-      dst[k] = v;
+    // four chunks of 32 cells per step: counts first, then the table look-ups, then the stores
+    for (int k0 = lane; k0 < nz; k0 += 128) {
+      uint32_t c[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c[u] = k0 + 32 * u < nz ? src[k0 + 32 * u] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        if (k >= nz) continue;
+        if (c[u] < (uint32_t)kDensityTableCounts) v[u] = __ldg(trow + (int)cls_z[k] * kDensityTableCounts + (int)c[u]);
+        else v[u] = hopb_density_value(c[u], n_frames, wx[i], wy[j], wz[k], factor, apply_factor);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k0 + 32 * u < nz) dst[k0 + 32 * u] = v[u];
     }
   }
 }
