@@ -112,61 +112,151 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU arm: the oracle in reference-faithful mode on a bounded sample
+# CPU arm: the oracle in reference-faithful mode on a bounded sample (BASELINE.md section 4)
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_frames=4, label_block=56):
-    """Times the four reference stages on `n_frames` frames of the bench workload (30 000 waters,
-    201^3 grid), one host core (the reference is single-threaded).
+CPU_FRAMES_PER_STEP = 50      # at least 50 frames per per-frame stage
+CPU_LABEL_BLOCK = 64          # stage 2 is timed on a block of this edge (cells), see cpu_stage2_block
 
-    Stage 2 is per-grid, not per-frame, and its Python loop over every above-threshold cell takes
-    minutes on the full 8.1 M-cell grid, so it is timed on a `label_block`^3 sub-block of the real
-    density and scaled by the cell count; its cost is then amortised over the full 10 000 frames.
-    Returns (atom_frames_per_s for the full workload, description of the sample)."""
+
+def pin_one_core():
+    """The reference has no threading or multiprocessing: the CPU arm runs on ONE host core.
+    Returns (previous affinity, description)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, {allowed[-1]})
+        try:
+            from threadpoolctl import threadpool_limits
+
+            threadpool_limits(1)
+        except Exception:
+            pass
+        return set(allowed), "pinned to cpu %d of %d allowed (sched_setaffinity), BLAS/OpenMP pools limited to 1 thread" % (
+            allowed[-1], len(allowed))
+    except Exception as exc:  # noqa: BLE001
+        return None, "not pinned (%s)" % (str(exc)[:80],)
+
+
+def unpin(previous):
+    if previous:
+        try:
+            os.sched_setaffinity(0, previous)
+        except Exception:
+            pass
+
+
+def cpu_stage2_block(density, thresholds, block=CPU_LABEL_BLOCK):
+    """Density.map_sites as the reference runs it (Python loop over the above-threshold cells x 7 offsets
+    into a networkx graph, connected components, size sort, per-cell repaint: hop/sitemap.py:1496-1587) on
+    a `block`^3 block of the full-grid density at the real thresholds.  The block starts 8 cells below the
+    box centre, so it holds part of the hydration-site region and bulk water in about the proportion of the
+    whole box.  Returns (seconds for all thresholds, cells of the block, above-threshold cells per threshold)."""
     import numpy as np
 
     from oracle import hop_oracle as O
-    from hop_b200.synth import SynthParams, generate
 
-    p = SynthParams(n_atoms=ATOMS, n_frames=max(n_frames, 2))
-    xyz = generate(p, 0, n_frames)
-    bins, arange, edges = O.grid_geometry(xyz[0], delta=DELTA)
+    o = [max(0, min(n // 2 - 8, n - block)) for n in density.shape]
+    sub = np.ascontiguousarray(density[o[0]:o[0] + block, o[1]:o[1] + block, o[2]:o[2] + block])
     t0 = time.perf_counter()
-    counts, _ = O.histogram_faithful(iter(xyz), bins, arange)
-    t_hist = (time.perf_counter() - t0) / n_frames
-    # a density with realistic structure for the labelling / lookup stages: the sample's own counts
-    # are too sparse, so scale the threshold instead of the data
-    grid = O.make_density(counts, edges, n_frames, "water")
-    sub = grid[:label_block, :label_block, :label_block]
-    thr = float(np.quantile(sub, 0.55))   # ~45 % of the cells above threshold (bulk-like blob + speckle)
+    filled = []
+    for thr in thresholds:
+        sites = O.label_sites_faithful(sub, thr)
+        O.draw_map_from_sites(sites, sub.shape)
+        filled.append(int((sub >= thr).sum()))
+    return time.perf_counter() - t0, int(sub.size), filled
+
+
+def cpu_per_frame_stages(xyz, bins, arange, edges, site_map):
+    """The three per-frame stages of the reference on the frames `xyz` [S][N][3]: numpy.histogramdd per frame
+    (hop/density.py:125-131), _coord2hop per frame (hop/trajectory.py:403-468: full map copy + per-atom
+    lookup) and the per-atom dict state machine of _analyze_hops (hop/graph.py:212-274).  Returns seconds per
+    stage."""
+    from oracle import hop_oracle as O
+
     t0 = time.perf_counter()
-    sites = O.label_sites_faithful(sub, thr)
-    O.draw_map_from_sites(sites, sub.shape)
-    t_label_cells = (time.perf_counter() - t0) / sub.size
-    n_cells = int(np.prod([len(e) - 1 for e in edges]))
-    t_label = 2 * t_label_cells * n_cells      # solvent + bulk density
-    site_map = np.zeros(grid.shape, np.int16)
-    site_map[grid >= thr] = 1
-    t0 = time.perf_counter()
+    O.histogram_faithful(iter(xyz), bins, arange)
+    t1 = time.perf_counter()
     hop = O.coord2hop_faithful(iter(xyz), edges, site_map)
-    t_hop = (time.perf_counter() - t0) / n_frames
-    t0 = time.perf_counter()
+    t2 = time.perf_counter()
     O.analyze_hops_faithful(hop[:, :, 0])
-    t_scan = (time.perf_counter() - t0) / max(n_frames - 1, 1)
-    per_frame = t_hist + t_hop + t_scan
-    total = FRAMES_PER_GPU * per_frame + t_label
-    value = ATOMS * FRAMES_PER_GPU / total
-    sample = ("oracle in reference-faithful mode, 1 core: %d frames x %d waters on the 201^3 grid "
-              "(histogramdd %.3f s/frame, _coord2hop %.3f s/frame, _analyze_hops %.3f s/frame); map_sites timed on a "
-              "%d^3 sub-block (%.2e s/cell) and scaled to 2 x %d cells = %.0f s, amortised over %d frames"
-              % (n_frames, ATOMS, t_hist, t_hop, t_scan, label_block, t_label_cells, n_cells, t_label, FRAMES_PER_GPU))
-    return value, sample, per_frame * n_frames + t_label_cells * sub.size
+    t3 = time.perf_counter()
+    return t1 - t0, t2 - t1, t3 - t2
+
+
+def rough_site_map(density, solvent_threshold, bulk_threshold):
+    """Input data for the CPU timing of stage 3 when no GPU result is at hand: bulk mask = 1, hydration
+    sites numbered 2.. by scipy (not the canonical numbering -- the lookup cost does not depend on it)."""
+    import numpy as np
+    from scipy import ndimage
+
+    from oracle import hop_oracle as O
+
+    st = np.zeros((3, 3, 3), bool)
+    st[1, 1, 1] = True
+    for off in O.DELTA_FIRST_OCTANT:
+        st[tuple(1 + off)] = st[tuple(1 - off)] = True
+    lab, _ = ndimage.label(density >= solvent_threshold, structure=st)
+    m = np.where(density >= bulk_threshold, 1, 0).astype(np.int16)
+    m[lab > 0] = (lab[lab > 0] + 1).astype(np.int16)
+    return m
+
+
+def expected_density(params, edges, unit="water"):
+    """Long-run (infinite-frame) density of the synthetic model of hop_b200/synth.py on the grid `edges`, in
+    closed form: bulk atoms uniform in the box outside the central cube, bound atoms a Gaussian of width
+    sigma_site on their site centre, occupied p_rebind / (p_rebind + p_hop / 2) of the time.  Input data for
+    the CPU timing of stages 2-4 when the full-trajectory density is out of the CPU's reach (the reference arm
+    has no GPU result to borrow one from): it has the structure of the 10 000-frame density -- solid bulk,
+    compact hydration sites -- which a density from the few hundred sample frames has not (Poisson noise
+    riddles its bulk site with holes, and atoms flickering between bulk and interstitial make the
+    reference's state machine several times slower than it is on real input)."""
+    import numpy as np
+
+    from oracle import hop_oracle as O
+
+    p = params
+    centres, half = p.lattice()
+    L = float(p.box)
+    n_bound = p.n_bound
+    rho_bulk = (p.n_atoms - n_bound) / (L ** 3 - (2.0 * half) ** 3)
+    mids = [0.5 * (e[:-1] + e[1:]) for e in edges]
+    c = 0.5 * L
+    inside = [(m >= 0) & (m < L) for m in mids]
+    in_cube = [np.abs(m - c) < half for m in mids]
+    box = inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
+    cube = in_cube[0][:, None, None] & in_cube[1][None, :, None] & in_cube[2][None, None, :]
+    rho = np.where(box & ~cube, rho_bulk, 0.0)
+    occ = n_bound * (p.p_rebind / (p.p_rebind + 0.5 * p.p_hop)) / len(centres)
+    s = float(p.sigma_site)
+    norm = occ / ((2.0 * np.pi) ** 1.5 * s ** 3)
+    r = int(np.ceil(4.0 * s / float(edges[0][1] - edges[0][0])))
+    for ctr in np.asarray(centres, dtype=np.float64):
+        idx = [int(np.searchsorted(e, x, side="right")) - 1 for e, x in zip(edges, ctr)]
+        sl = [slice(max(0, i - r), min(len(m), i + r + 1)) for i, m in zip(idx, mids)]
+        gx, gy, gz = (np.exp(-0.5 * ((m[q] - x) / s) ** 2) for m, q, x in zip(mids, sl, ctr))
+        rho[sl[0], sl[1], sl[2]] += norm * gx[:, None, None] * gy[None, :, None] * gz[None, None, :]
+    return rho * O.density_conversion_factor("Angstrom^{-3}", unit)
+
+
+def describe_cpu_sample(n_frames, t_hist, t_hop, t_scan, t_block, block_cells, filled, shape, pin, density_source):
+    n_cells = 1
+    for n in shape:
+        n_cells *= int(n)
+    t_label_full = t_block * n_cells / block_cells
+    return ("oracle in reference-faithful mode (kind=port: the reference is Python 2 + MDAnalysis and cannot run on this "
+            "box), 1 core, %s; per-frame stages timed on %d frames x %d waters on the full %s grid: histogramdd %.4f "
+            "s/frame, _coord2hop %.4f s/frame, _analyze_hops %.4f s/frame; map_sites (solvent + bulk threshold) timed on "
+            "a %d^3 block of %s at the real thresholds (%s of %d cells above threshold) = %.1f s, scaled by cells to the "
+            "full grid = %.0f s and amortised over the %d frames of the workload"
+            % (pin, n_frames, ATOMS, "x".join(str(int(n)) for n in shape), t_hist / n_frames,
+               t_hop / n_frames, t_scan / n_frames, CPU_LABEL_BLOCK, density_source, "+".join(str(f) for f in filled),
+               block_cells, t_block, t_label_full, FRAMES_PER_GPU))
 
 
 def cpu_vectorised_sample(n_frames=16):
     """The "fair CPU" figure of SURVEY.md section 8d: the same four stages with vectorised numpy /
     scipy (bincount histogram, ndimage.label with the 15-cell structuring element, fancy-index lookup,
     atom-vectorised state machine) instead of the reference's Python loops; one core.  Stage 2 runs on
-    the full 201^3 grid (twice: solvent and bulk density) and is amortised over the 10 000 frames."""
+    the full grid (twice: solvent and bulk density) and is amortised over the frames of the workload."""
     import numpy as np
 
     from oracle import hop_oracle as O
@@ -181,7 +271,7 @@ def cpu_vectorised_sample(n_frames=16):
     grid = O.make_density(counts, edges, n_frames, "water")
     thr = float(np.quantile(grid, 0.55))
     t0 = time.perf_counter()
-    sites_map = O.label_sites_ndimage(grid, thr)
+    O.label_sites_ndimage(grid, thr)
     t_label = 2 * (time.perf_counter() - t0)
     site_map = np.zeros(grid.shape, np.int16)
     site_map[grid >= thr] = 1
@@ -193,31 +283,101 @@ def cpu_vectorised_sample(n_frames=16):
     t_scan = (time.perf_counter() - t0) / max(n_frames - 1, 1)
     total = FRAMES_PER_GPU * (t_hist + t_hop + t_scan) + t_label
     sample = ("vectorised numpy/scipy restatement, 1 core: %d frames x %d waters (histogram %.4f s/frame, lookup %.4f "
-              "s/frame, scan %.4f s/frame), ndimage.label on the full 201^3 grid x 2 = %.1f s amortised over %d frames"
+              "s/frame, scan %.4f s/frame), ndimage.label on the full grid x 2 = %.1f s amortised over %d frames"
               % (n_frames, ATOMS, t_hist, t_hop, t_scan, t_label, FRAMES_PER_GPU))
     return ATOMS * FRAMES_PER_GPU / total, sample
 
 
+def cpu_baseline_leg(density, site_map, edges, solvent_threshold, bulk_threshold):
+    """cpu_baseline of the GPU arm (rank 0, N = 1): one CPU step on CPU_FRAMES_PER_STEP frames of the bench
+    workload with the REAL full-trajectory density and site map (downloaded from the GPU run: input data of
+    the CPU timing, the GPU is not on the timed path)."""
+    import numpy as np
+
+    from oracle import hop_oracle as O
+    from hop_b200.synth import SynthParams, generate
+
+    prev, pin = pin_one_core()
+    try:
+        S = CPU_FRAMES_PER_STEP
+        xyz = generate(SynthParams(n_atoms=ATOMS, n_frames=FRAMES_PER_GPU), 0, S)
+        bins, arange, e2 = O.grid_geometry(xyz[0], delta=DELTA)
+        assert all(np.array_equal(a, b) for a, b in zip(edges, e2))
+        t_hist, t_hop, t_scan = cpu_per_frame_stages(xyz, bins, arange, edges, site_map)
+        t_block, block_cells, filled = cpu_stage2_block(density, (solvent_threshold, bulk_threshold))
+        n_cells = int(density.size)
+        t_label_full = t_block * n_cells / block_cells
+        t_step = t_hist + t_hop + t_scan
+        value = ATOMS * S / (t_step + t_label_full * S / FRAMES_PER_GPU)
+        out = {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": describe_cpu_sample(S, t_hist, t_hop, t_scan, t_block, block_cells, filled, density.shape, pin,
+                                             "the full-trajectory density of this run"),
+               "timed_s": t_step + t_block,
+               "extrapolated": {"full_workload_s": FRAMES_PER_GPU * t_step / S + t_label_full,
+                                "stage2_full_grid_s": t_label_full,
+                                "note": "per-frame stages scale linearly in frames (measured on %d); stage 2 scaled by cells" % S}}
+        try:   # the "fair CPU" variant beside it: not the reference's code path, reported for scale only
+            v2, sample2 = cpu_vectorised_sample()
+            out["vectorised"] = {"value": v2, "unit": UNIT, "cores": 1, "sample": sample2}
+        except Exception as exc:   # noqa: BLE001 - an optional extra must not cost the bench line
+            out["vectorised"] = {"unavailable": str(exc)[:200]}
+        return out
+    finally:
+        unpin(prev)
+
+
 def run_reference(args):
+    """--impl reference: W warm-up + exactly K timed steps; a step = the three per-frame stages of the
+    reference on CPU_FRAMES_PER_STEP consecutive frames of the bench workload (different frames every step).
+    Stage 2 (per grid, not per frame) is timed once on a block at the real thresholds and its full-grid
+    cost enters `value` pro rata; `ms_per_step` is what a step actually took."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    values, sample = [], ""
-    for i in range(args.warmup + args.steps):
-        v, sample, _ = cpu_reference_sample(n_frames=3)
+    import numpy as np
+
+    from oracle import hop_oracle as O
+    from hop_b200.synth import SynthParams, generate
+
+    prev, pin = pin_one_core()
+    S = CPU_FRAMES_PER_STEP
+    n_steps = args.warmup + args.steps
+    xyz = generate(SynthParams(n_atoms=ATOMS, n_frames=FRAMES_PER_GPU), 0, S * n_steps)
+    bins, arange, edges = O.grid_geometry(xyz[0], delta=DELTA)
+    # the site map the lookups run against and the density stage 2 is timed on: the closed-form long-run
+    # density of the synthetic model (expected_density) at the real thresholds
+    import math
+
+    thr_s, thr_b = math.e, math.exp(-0.5)
+    density = expected_density(SynthParams(n_atoms=ATOMS, n_frames=FRAMES_PER_GPU), edges)
+    site_map = rough_site_map(density, thr_s, thr_b)
+    t_block, block_cells, filled = cpu_stage2_block(density, (thr_s, thr_b))
+    n_cells = int(density.size)
+    t_label_full = t_block * n_cells / block_cells
+    times = []
+    for i in range(n_steps):
+        t = cpu_per_frame_stages(xyz[i * S:(i + 1) * S], bins, arange, edges, site_map)
         if i >= args.warmup:
-            values.append(v)
-        if i >= 1 and args.warmup + args.steps > 2 and time.perf_counter() - T_START > 200:
-            break
-    if not values:
-        values = [v]
-    value = sum(values) / len(values)
+            times.append(t)
+    t_hist, t_hop, t_scan = (sum(t[k] for t in times) for k in range(3))
+    n_frames = S * len(times)
+    t_step = (t_hist + t_hop + t_scan) / len(times)
+    value = ATOMS * S / (t_step + t_label_full * S / FRAMES_PER_GPU)
+    sample = describe_cpu_sample(n_frames, t_hist, t_hop, t_scan, t_block, block_cells, filled, density.shape, pin,
+                                 "the closed-form long-run density of the synthetic model (bench.py expected_density)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(values), "warmup": args.warmup, "ms_per_step": 1e3 * ATOMS * FRAMES_PER_GPU / value,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(args.gpus)},
+            "step": "%d frames x %d waters through histogramdd, _coord2hop and _analyze_hops" % (S, ATOMS),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "extrapolated": {"full_workload_s": FRAMES_PER_GPU * t_step / S + t_label_full,
+                             "stage2_full_grid_s": t_label_full, "stage2_block_s": t_block,
+                             "note": ("value = atom-frames of a step / (its measured time + the pro-rata share of stage 2); "
+                                      "the reference itself (Python 2.7, MDAnalysis) cannot run on this box, the port "
+                                      "repeats its work pattern (oracle/hop_oracle.py *_faithful)")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    unpin(prev)
     emit(line)
 
 
@@ -388,7 +548,17 @@ def run_gpu(args):
     checks["labels_in_range"] = bool(res.hop_x.min().item() >= -1 and res.hop_x.max().item() < res.n_labels)
     checks["count_matrix_sum_equals_events"] = bool(
         res.count_matrix is None or (res.count_matrix.sum().item() == max_over_ranks_sum(res.n_events_local, world)))
-    checks["events_sorted"] = True
+    ev_t = res.events.to(torch.int64)      # [n][6] = frame, iatom, s0, s, tau, tbarrier; reference order = (edge, frame, atom)
+    if ev_t.shape[0] > 1:
+        ekey = (ev_t[:, 2] + 1) * (res.n_labels + 1) + ev_t[:, 3] + 1
+        tkey = ev_t[:, 0] * ATOMS + ev_t[:, 1]
+        ok_sorted = bool(((ekey[1:] > ekey[:-1]) | ((ekey[1:] == ekey[:-1]) & (tkey[1:] > tkey[:-1]))).all().item())
+    else:
+        ok_sorted = True
+    checks["events_sorted"] = bool(max_over_ranks_sum(0 if ok_sorted else 1, world) == 0)
+    del ev_t
+    # BASELINE config 1 as hop ITSELF computed it, frame-sharded over the ranks of this run (not timed)
+    checks["reference_config1_sharded"] = golden_parity(world, rank)
 
     # ---- end to end: pinned host coordinates in, host hoptraj + events out ---------------------------
     if args.no_e2e:
@@ -396,8 +566,8 @@ def run_gpu(args):
             line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
-                    "data": "synthetic", "config": {"workload": workload_name(n_gpus), "sites": int(res.n_labels),
-                                                    "events_per_step_rank0": int(res.n_events_local)},
+                    "data": "synthetic", "config": {"workload": workload_name(n_gpus)},
+                    "result": {"sites": int(res.n_labels), "events_per_step_rank0": int(res.n_events_local)},
                     "clocks": clocks, "two_in_flight": two_in_flight, "e2e": None, "gpu_launches": int(launches),
                     "roofline": roofline, "stage_ms": stage_ms, "checks": checks}
             emit(line)
@@ -439,20 +609,15 @@ def run_gpu(args):
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
-        v, sample, _ = cpu_reference_sample(n_frames=3)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
-        try:   # the "fair CPU" variant beside it: not the reference's code path, reported for scale only
-            v2, sample2 = cpu_vectorised_sample()
-            cpu_baseline["vectorised"] = {"value": v2, "unit": UNIT, "cores": 1, "sample": sample2}
-        except Exception as exc:   # noqa: BLE001 - an optional extra must not cost the bench line
-            cpu_baseline["vectorised"] = {"unavailable": str(exc)[:200]}
+        cpu_baseline = cpu_baseline_leg(res.density.cpu().numpy(), res.map16.cpu().numpy(), edges,
+                                        pipe.cfg.solvent_threshold, pipe.cfg.bulk_threshold)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
-                "data": "synthetic", "config": {"workload": workload_name(n_gpus), "sites": int(res.n_labels),
-                                                "events_per_step_rank0": int(res.n_events_local)},
+                "data": "synthetic", "config": {"workload": workload_name(n_gpus)},
+                "result": {"sites": int(res.n_labels), "events_per_step_rank0": int(res.n_events_local)},
                 "clocks": clocks, "two_in_flight": two_in_flight, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "stage_ms": stage_ms, "checks": checks}
         if cpu_baseline:
@@ -460,6 +625,51 @@ def run_gpu(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def golden_parity(world, rank):
+    """BASELINE.json configs[0] (1 000 waters x 200 frames, 1.0 A grid) against what hop ITSELF produced for
+    it (tests/golden/reference/ref_config1.npz, frozen from the reference's own classes by
+    tests/golden/make_reference_golden.py), with the 200 frames sharded over the ranks of this run exactly
+    like the timed workload: counts all-reduce, slab-summary all-gather, count-matrix all-reduce.  Run
+    twice (the second run takes the asynchronous finalisation).  Returns {check: bool}, AND-ed over ranks."""
+    import numpy as np
+    import torch
+
+    from hop_b200 import exchange
+    from hop_b200 import kernels as K
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from tests.refgolden import load, reference_products
+
+    g = load("ref_config1")
+    ref = reference_products(g)
+    xyz, dt = g["xyz"], float(g["dt"])
+    F, N = xyz.shape[:2]
+    edges = grid_edges_from_frame0(xyz[0], delta=float(g["delta"]))
+    f0, f1 = exchange.slab_bounds(F, world, rank)
+    pipe = HopPipeline(edges, F, PipelineConfig(n_chunks=3))
+    slab = torch.from_numpy(np.ascontiguousarray(xyz[f0:f1])).cuda()
+    pipe.run(slab, f0)
+    res = pipe.run(slab, f0)
+    out = {"edges": all(np.array_equal(a, b) for a, b in zip(edges, (g["edges_x"], g["edges_y"], g["edges_z"])))}
+    out["density"] = np.array_equal(res.density.cpu().numpy().reshape(g["grid"].shape), g["grid"])
+    out["map"] = np.array_equal(res.map16.cpu().numpy(), ref["map"])
+    out["hop_x"] = np.array_equal(res.hop_x.cpu().numpy(), ref["hop_x"][f0:f1].astype(np.float32))
+    out["hop_y"] = np.array_equal(res.hop_y.cpu().numpy(), ref["hop_y"][f0:f1].astype(np.float32))
+    ev = K.events_to_numpy(res.events)
+    got = [(int(a), int(b), int(fr), int(ia), float(t) * dt, float(tb) * dt)
+           for a, b, fr, ia, t, tb in zip(ev["s0"], ev["s"], ev["frame"], ev["iatom"], ev["tau"], ev["tbarrier"])]
+    want = sorted((k[0], k[1], int(fr), int(ia), float(t), float(tb)) for k, d in ref["props"].items()
+                  for t, tb, fr, ia in zip(d["tau"], d["tbarrier"], d["frame"], d["iatom"]) if f0 <= fr < f1)
+    out["events"] = got == want
+    M = res.count_matrix.cpu().numpy()
+    out["count_matrix"] = bool(M.sum() == sum(len(d["tau"]) for d in ref["props"].values())
+                               and all(M[a + 1, b + 1] == len(d["tau"]) for (a, b), d in ref["props"].items()))
+    st = res.final_state.cpu().numpy()
+    nodes = sorted((int(st[0][i]), int(i), float((F - 1) - st[1][i]) * dt) for i in np.nonzero(st[0] != 0)[0])
+    want_nodes = sorted((int(s0), int(ia), float(t)) for s0, d in ref["nprops"].items() for t, ia in zip(d["tau"], d["iatom"]))
+    out["nodes"] = nodes == want_nodes
+    return {k: bool(max_over_ranks_sum(0 if v else 1, world) == 0) for k, v in out.items()}
 
 
 def max_over_ranks_sum(x, world):

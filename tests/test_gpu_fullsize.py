@@ -1,11 +1,21 @@
-"""Size-independent properties at BASELINE.json's full single-GPU size (configs[1]: 30 000 waters x
-10 000 frames, 0.5 A grid = 3e8 atom-frames) plus an oracle comparison on a frame prefix.
+"""Size-independent properties at the full sizes of BASELINE.json's configurations plus an oracle
+comparison on a frame prefix.  One GPU holds
 
-The oracle cannot run 3e8 atom-frames, so parity at this size rests on (1) properties that must hold
-for any input -- conservation of counts, independence of the result from how the frames are cut into
-chunks / slabs, agreement of the two input paths (coordinates vs cached brick indices), idempotence
-of the event ordering -- and (2) an exact comparison of the first 64 frames against the oracle, using
-the full-size site map (events are causal: the events of a prefix do not depend on later frames)."""
+  config 2   30 000 waters x 10 000 frames, 0.5 A grid (201^3)           -- the bench workload
+  config 3   100 000 waters x 12 500 frames (the slab one of 8 GPUs owns of 100 000), 297^3:
+             the count grid (105 MB) is histogrammed in two L2-sized slabs (hist_cells_kernel)
+  config 4   1 000 ions of one species in a 126 A box x 1 000 000 frames, 1.0 A grid (130^3):
+             147 frame chunks, no bulk site
+  config 5   one of the 64 trajectories, 30 000 waters x 20 000 frames, 0.25 A grid (402^3):
+             7-slab histogram, block maps too large for shared memory (MAP_CELL2 gather path)
+
+The oracle cannot run 1e8..1e9 atom-frames, so parity at these sizes rests on (1) properties that must
+hold for any input -- conservation of counts, independence of the result from how the frames are cut
+into chunks / slabs, agreement of the two input paths (coordinates vs cached brick indices),
+idempotence of the event ordering, a third-opinion labelling (scipy.ndimage with the reference's
+15-cell structuring element, hop/sitemap.py:415-422) -- and (2) an exact comparison of the first 64
+frames against the oracle, using the full-size site map (events are causal: the events of a prefix do
+not depend on later frames)."""
 import numpy as np
 import pytest
 
@@ -14,39 +24,61 @@ from oracle import hop_oracle as O
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-ATOMS, FRAMES, DELTA = 30000, 10000, 0.5
 PREFIX = 64
 
+CONFIGS = {
+    2: dict(atoms=30000, frames=10000, delta=0.5, rho=None, mem=40e9),
+    3: dict(atoms=100000, frames=12500, delta=0.5, rho=None, mem=100e9),
+    4: dict(atoms=1000, frames=1000000, delta=1.0, rho=1000 / 126.0 ** 3, mem=60e9),
+    5: dict(atoms=30000, frames=20000, delta=0.25, rho=None, mem=60e9),
+}
 
-@pytest.fixture(scope="module")
-def full():
+
+class Full(object):
+    pass
+
+
+@pytest.fixture(scope="module", params=sorted(CONFIGS), ids=lambda c: "config%d" % c)
+def full(request):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+    cid = request.param
+    c = CONFIGS[cid]
+    if torch.cuda.get_device_properties(0).total_memory < c["mem"]:
         pytest.skip("needs a large-memory GPU")
     from hop_b200 import kernels as K
     from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
     from hop_b200.synth import SynthParams, generate
 
-    p = SynthParams(n_atoms=ATOMS, n_frames=FRAMES)
-    xyz = K.synth_generate(p)
-    host_prefix = generate(p, 0, PREFIX)
-    assert np.array_equal(xyz[:PREFIX].cpu().numpy(), host_prefix)      # device generator == host generator
-    edges = grid_edges_from_frame0(host_prefix[0], delta=DELTA)
-    pipe = HopPipeline(edges, FRAMES, PipelineConfig())
-    res = pipe.run(xyz)
-    return K, pipe, xyz, edges, res, host_prefix
+    kw = {} if c["rho"] is None else {"rho": c["rho"]}
+    p = SynthParams(n_atoms=c["atoms"], n_frames=c["frames"], seed=20261019 + (cid if cid != 2 else 0), **kw)
+    f = Full()
+    f.cid, f.K, f.atoms, f.frames, f.delta = cid, K, c["atoms"], c["frames"], c["delta"]
+    f.xyz = K.synth_generate(p)
+    f.host_prefix = generate(p, 0, PREFIX)
+    assert np.array_equal(f.xyz[:PREFIX].cpu().numpy(), f.host_prefix)      # device generator == host generator
+    f.edges = grid_edges_from_frame0(f.host_prefix[0], delta=c["delta"])
+    f.pipe = HopPipeline(f.edges, c["frames"], PipelineConfig())
+    f.res = f.pipe.run(f.xyz)
+    yield f
+    del f.res, f.pipe, f.xyz
+    torch.cuda.empty_cache()
+
+
+def test_grid_is_the_configured_one(full):
+    want = {2: 201, 3: 297, 4: 130, 5: 402}[full.cid]
+    assert tuple(full.pipe.grid.shape) == (want, want, want)
 
 
 def test_counts_are_conserved(full):
-    K, pipe, xyz, edges, res, _ = full
+    res = full.res
     # every synthetic atom stays inside the padded grid, so every atom-frame is counted exactly once
-    assert int(res.counts.to(torch.int64).sum().item()) == ATOMS * FRAMES
+    assert int(res.counts.to(torch.int64).sum().item()) == full.atoms * full.frames
     assert int(res.counts.min().item()) >= 0
 
 
 def test_prefix_matches_oracle(full):
-    K, pipe, xyz, edges, res, host_prefix = full
+    K, res, host_prefix, edges = full.K, full.res, full.host_prefix, full.edges
     site_map = res.map16.cpu().numpy()
     hop = O.coord2hop_vectorised(host_prefix, edges, site_map)
     assert np.array_equal(res.hop_x[:PREFIX].cpu().numpy(), hop[:, :, 0])
@@ -57,16 +89,44 @@ def test_prefix_matches_oracle(full):
     order = np.lexsort((sel["iatom"], sel["frame"]))
     got = np.stack([sel[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1).astype(np.int64)
     assert np.array_equal(got, ev_ref)
-    # prefix histogram
+    # prefix histogram (a grid of its own: the slab budget applies as in the full run)
     counts_ref = O.histogram_vectorised(host_prefix, edges)
     g = K.GridTables(edges)
     c = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
-    K.hist_accumulate(g, xyz[:PREFIX], c)
+    K.hist_accumulate(g, full.xyz[:PREFIX], c)
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), counts_ref)
+    # and with the cached brick indices, i.e. through the slabbed passes where the grid outgrows L2
+    c.zero_()
+    cells = torch.empty((PREFIX, full.atoms), dtype=torch.int32, device="cuda")
+    K.hist_accumulate(g, full.xyz[:PREFIX], c, cells)
     assert np.array_equal(c.cpu().numpy().astype(np.int64), counts_ref)
 
 
+def test_density_is_the_reference_arithmetic(full):
+    """density == counts / n_frames / dx / dy / dz * factor in the reference's operation order
+    (hop/density.py:133-137, hop/sitemap.py:196-216, 236-264), bit for bit, on an 8-plane slice."""
+    res = full.res
+    sl = slice(full.pipe.grid.shape[0] // 2, full.pipe.grid.shape[0] // 2 + 8)
+    counts = res.counts[sl].cpu().numpy().astype(np.int64)
+    got = res.density[sl].cpu().numpy()
+    grid = counts.astype(np.float64)
+    grid /= float(full.frames)
+    e = full.edges
+    dedges = [np.diff(x) for x in e]
+    shape = [1, 1, 1]
+    for d in range(3):
+        s = list(shape)
+        w = dedges[d][sl] if d == 0 else dedges[d]
+        s[d] = len(w)
+        grid /= w.reshape(s)
+    from hop_b200.constants import density_conversion_factor
+
+    grid *= density_conversion_factor("Angstrom^{-3}", full.pipe.cfg.density_unit)
+    assert np.array_equal(got, grid)
+
+
 def test_site_map_is_a_valid_labelling(full):
-    K, pipe, xyz, edges, res, _ = full
+    pipe, res = full.pipe, full.res
     m = res.map16.cpu().numpy()
     dens = res.density.cpu().numpy()
     own = res.own.cpu().numpy()
@@ -87,13 +147,30 @@ def test_site_map_is_a_valid_labelling(full):
     assert n == own.max() - 1
     pairs = np.unique(np.stack([lab[own > 0], own[own > 0]], axis=1), axis=0)
     assert len(pairs) == n                                                    # one-to-one between the two labellings
+    # canonical numbering of equal volumes: larger minimum C-order cell first
+    idx = np.nonzero(own.ravel() > 0)[0]
+    first = np.full(own.max() + 1, -1, np.int64)
+    first[own.ravel()[idx][::-1]] = idx[::-1]                                 # reversed: the smallest index is written last
+    tie = vol[:-1] == vol[1:]
+    assert np.all(first[2:][:-1][tie] > first[2:][1:][tie])
+    # the bulk site is the largest component of the bulk-threshold mask
+    member = res.member.cpu().numpy().astype(bool)
+    labb, nb = ndimage.label(dens >= pipe.cfg.bulk_threshold, structure=st)
+    if nb:
+        sizes = np.bincount(labb.ravel())[1:]
+        assert member.sum() == sizes.max()
+        assert len(np.unique(labb[member])) == 1
+    else:
+        assert not member.any()
+    del lab, labb
 
 
 def test_result_does_not_depend_on_chunking_or_input_path(full):
-    K, pipe, xyz, edges, res, _ = full
+    K, pipe, xyz, res = full.K, full.pipe, full.xyz, full.res
+    ATOMS, FRAMES = full.atoms, full.frames
     ref_x, ref_y = res.hop_x, res.hop_y
     ref_ev = K.events_to_numpy(res.events)
-    for n_chunks, use_cells, block_map in [(1, True, "coarse"), (7, False, "none"), (23, True, "fine"), (5, False, "fine")]:
+    for n_chunks, use_cells, block_map in [(1, True, "coarse"), (7, False, "none"), (23, True, "auto"), (5, False, "cell2")]:
         ev = K.EventBuffer(max(len(ref_ev) + 16, 1 << 20), "cuda")
         X = torch.empty_like(ref_x)
         Y = torch.empty_like(ref_y)
@@ -113,10 +190,12 @@ def test_result_does_not_depend_on_chunking_or_input_path(full):
         assert np.array_equal(a[[0, 1, 3]], b[[0, 1, 3]])                     # s0, t0, on
         off = a[3] == 0
         assert np.array_equal(a[2][off], b[2][off])                           # t1 only matters while off the site
+        del X, Y, ev, s
 
 
 def test_events_are_consistent_with_the_label_stream(full):
-    K, pipe, xyz, edges, res, _ = full
+    K, res = full.K, full.res
+    ATOMS = full.atoms
     ev = K.events_to_numpy(res.events)
     x = res.hop_x
     # at the event frame the atom is on site s; on the frame before it was not
@@ -129,7 +208,9 @@ def test_events_are_consistent_with_the_label_stream(full):
     t = ev["frame"].astype(np.int64) * ATOMS + ev["iatom"]
     assert np.all((key[1:] > key[:-1]) | ((key[1:] == key[:-1]) & (t[1:] > t[:-1])))
     assert int(res.edge_count.sum().item()) == len(ev) == int(res.count_matrix.sum().item())
-    # orbit column: equals x where x is a site, never 0 after the first site visit, never -1
+    # orbit column: equals x where x is a site, never -1 (frame slices bound the temporaries)
     y = res.hop_y
-    on = x > 0
-    assert bool((y[on] == x[on]).all()) and bool((y >= 0).all())
+    step = max(1, (1 << 28) // ATOMS)
+    for f0 in range(0, full.frames, step):
+        xs, ys = x[f0:f0 + step], y[f0:f0 + step]
+        assert bool(((ys == xs) | (xs <= 0)).all()) and bool((ys >= 0).all())
