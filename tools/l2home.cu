@@ -80,7 +80,8 @@ __device__ __forceinline__ uint32_t home_of(const uint32_t* __restrict__ home, u
 // mode 0: today's kernel (every point reduced where it is read); mode 1: phase A (only points homed on this SM's die)
 __global__ void __launch_bounds__(256)
 hist_emul(const float4* __restrict__ coords, const uint32_t* __restrict__ cells_in, uint32_t* __restrict__ cells_out,
-          uint32_t* grid, const uint32_t* __restrict__ home, const uint8_t* __restrict__ sm_group, int64_t n, int mode) {
+          uint32_t* grid, const uint32_t* __restrict__ home, const uint8_t* __restrict__ sm_group, int64_t n, int mode,
+          uint32_t n_cells_copy = 0, uint32_t pair_xor = 0) {
   const uint32_t g = sm_group[smid()];
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   float acc = 0.f;
@@ -91,7 +92,18 @@ hist_emul(const float4* __restrict__ coords, const uint32_t* __restrict__ cells_
     uint32_t v[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (mode == 0 || home_of(home, v[k]) == g) { atomicAdd(grid + v[k], 1u); v[k] |= kDone; }
+      if (mode == 2) {
+        // two copies of the grid (copy B starts n_cells_copy words further): reduce into a copy whose line is homed
+        // on this SM's die when there is one
+        const uint32_t hb = home_of(home, v[k] + n_cells_copy);
+        const uint32_t ha = home_of(home, v[k]);
+        atomicAdd(grid + v[k] + ((ha != g && hb == g) ? n_cells_copy : 0u), 1u);
+      } else if (mode == 3) {
+        // pairing inside a page: partner line = line ^ pair_mask (opposite home when the hash is linear)
+        const uint32_t w = ((v[k] / pair_xor) * (2u * pair_xor)) | (v[k] % pair_xor);   // a zero bit inserted at pair_xor
+        const uint32_t ha = home_of(home, w);
+        atomicAdd(grid + (w ^ (ha != g ? pair_xor : 0u)), 1u);
+      } else if (mode == 0 || home_of(home, v[k]) == g) { atomicAdd(grid + v[k], 1u); v[k] |= kDone; }
     }
     reinterpret_cast<uint4*>(cells_out)[q] = make_uint4(v[0], v[1], v[2], v[3]);
   }
@@ -267,6 +279,49 @@ int main(int argc, char** argv) {
       printf("4. %.3g points into the %zu MB grid: one pass %.3f ms; die-local phase A %.3f ms + phase B %.3f ms = %.3f ms (counts agree: %s)\n",
              (double)n, bytes >> 20, t0, ta, tb, ta + tb, first_a == first_b ? "yes" : "NO");
     }
+  }
+  // ---- 5. two copies of the grid, reductions into the copy that is homed on the reading SM's die ----------
+  if (argc > 2) {
+    FILE* f = fopen(argv[2], "wb");
+    if (f) {
+      fprintf(f, "%p %lld %d\n", (void*)buf, (long long)n_lines, n_sm);
+      fwrite(group.data(), 1, n_sm, f);
+      fwrite(far_bits[0].data(), 1, n_lines, f);
+      fclose(f);
+    }
+    const int64_t n = 300000000;
+    const uint32_t n_cells = (uint32_t)(bytes / 8);       // the logical grid is half the buffer
+    const uint32_t pair_xor = argc > 3 ? (uint32_t)strtoul(argv[3], 0, 0) : 32u;
+    std::vector<uint32_t> home((n_lines + 31) / 32, 0u);
+    int64_t near_any = 0;
+    for (int64_t i = 0; i < n_lines; ++i) if (far_bits[0][i]) home[i >> 5] |= 1u << (i & 31);
+    for (int64_t i = 0; i < n_lines / 2; ++i) near_any += far_bits[0][i] != far_bits[0][i + n_lines / 2];
+    int64_t pair_opp = 0;
+    for (int64_t i = 0; i < n_lines; ++i) pair_opp += far_bits[0][i] != far_bits[0][i ^ (pair_xor >> 5 ? pair_xor >> 5 : 1)];
+    printf("5. two copies: %.1f%% of the logical lines have opposite homes in copy A and B (both dies served near); "
+           "line ^ %u has the opposite home for %.1f%% of the lines\n", 100.0 * near_any / (n_lines / 2), pair_xor >> 5,
+           100.0 * pair_opp / n_lines);
+    uint32_t *d_home, *d_cin, *d_cout; float4* d_xyz;
+    CK(cudaMalloc(&d_home, 4 * home.size()));
+    CK(cudaMemcpy(d_home, home.data(), 4 * home.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_cin, 4 * n)); CK(cudaMalloc(&d_cout, 4 * n)); CK(cudaMalloc(&d_xyz, 12 * n));
+    CK(cudaMemset(d_xyz, 0, 12 * n));
+    fill_cells<<<n_sm * 8, 256>>>(d_cin, n, n_cells);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = (int)((n / 4 + 256 * 4 - 1) / (256 * 4));
+    for (int rep = 0; rep < 3; ++rep)
+      for (int mode = 0; mode <= 3; ++mode) {
+        if (mode == 1) continue;
+        CK(cudaMemset(buf, 0, bytes));
+        CK(cudaEventRecord(e0));
+        hist_emul<<<blocks, 256>>>(d_xyz, d_cin, d_cout, buf, d_home, d_group, n, mode, n_cells, pair_xor);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float t0; CK(cudaEventElapsedTime(&t0, e0, e1));
+        printf("5. %.3g points, logical grid %zu MB, %s: %.3f ms\n", (double)n, bytes >> 21,
+               mode == 0 ? "one copy" : mode == 2 ? "two copies, near one chosen per line" : "interleaved pair (line ^ xor)", t0);
+      }
   }
   return 0;
 }

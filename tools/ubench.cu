@@ -83,6 +83,88 @@ __global__ void stream_kernel(const float4* __restrict__ in, int64_t n4, float* 
   if (acc == 1234.5f) *out = acc;
 }
 
+// ---- shared-memory privatisation: what a spatially partitioned histogram would be made of -------------------
+// atomicAdd on shared memory at random addresses of a `tile`-counter tile (u32 counters; PACK = 2 / 4 packs u16 / u8
+// counters into the same words: the instruction is the same ATOMS.ADD, the tile holds 2x / 4x the cells)
+template <int PACK>
+__global__ void atoms_kernel(uint32_t* out, int tile_cells, int64_t n) {
+  extern __shared__ uint32_t s[];
+  const int words = tile_cells / PACK;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) s[i] = 0;
+  __syncthreads();
+  int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = i0; i < n; i += stride) {
+    const uint32_t c = hash32((uint32_t)i) % (uint32_t)tile_cells;
+    if (PACK == 1) atomicAdd(s + c, 1u);
+    else if (PACK == 2) atomicAdd(s + (c >> 1), 1u << (16 * (c & 1)));
+    else atomicAdd(s + (c >> 2), 1u << (8 * (c & 3)));
+  }
+  __syncthreads();
+  uint32_t acc = 0;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) acc += s[i];
+  if (acc == 0xdeadbeefu) out[0] = acc;
+}
+
+// the same into the shared memory of the CTAs of a cluster (DSMEM): the tile is spread over CL CTAs
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) dsmem_atoms_kernel(uint32_t* out, int tile_cells_per_cta, int64_t n) {
+  extern __shared__ uint32_t s[];
+  for (int i = threadIdx.x; i < tile_cells_per_cta; i += blockDim.x) s[i] = 0;
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(s);
+  int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = i0; i < n; i += stride) {
+    const uint32_t c = hash32((uint32_t)i) % (uint32_t)(tile_cells_per_cta * CL);
+    const uint32_t rank = c / (uint32_t)tile_cells_per_cta, off = c - rank * (uint32_t)tile_cells_per_cta;
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + 4u * off), "r"(rank));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"(1u) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  uint32_t acc = 0;
+  for (int i = threadIdx.x; i < tile_cells_per_cta; i += blockDim.x) acc += s[i];
+  if (acc == 0xdeadbeefu) out[0] = acc;
+}
+
+// the partition pass such a histogram needs first: 4-byte cell indices scattered into `NB` spatial buckets
+// (CTA-local counting in shared memory, one global reservation per bucket and CTA, then the scattered stores)
+template <int NB>
+__global__ void __launch_bounds__(1024) partition_kernel(const uint32_t* __restrict__ cells, int64_t n, uint32_t n_cells,
+                                                        uint32_t* __restrict__ bucket_fill, uint32_t* __restrict__ out,
+                                                        uint32_t bucket_cap) {
+  __shared__ uint32_t s_cnt[NB], s_base[NB];
+  constexpr int PER = 8;                                      // 8192 keys per CTA
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x * PER;
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) s_cnt[b] = 0;
+  __syncthreads();
+  uint32_t key[PER], slot[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+    key[u] = i < n ? cells[i] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int u = 0; u < PER; ++u)
+    if (key[u] != 0xFFFFFFFFu) slot[u] = atomicAdd(&s_cnt[(uint32_t)(((uint64_t)key[u] * NB) / n_cells)], 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) s_base[b] = atomicAdd(bucket_fill + b, s_cnt[b]);
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; ++u)
+    if (key[u] != 0xFFFFFFFFu) {
+      const uint32_t b = (uint32_t)(((uint64_t)key[u] * NB) / n_cells);
+      const uint32_t p = s_base[b] + slot[u];
+      if (p < bucket_cap) out[(size_t)b * bucket_cap + p] = key[u];
+    }
+}
+
+__global__ void fill_random_cells(uint32_t* cells, int64_t n, uint32_t n_cells) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    cells[i] = hash32((uint32_t)i * 2654435761u + 7u) % n_cells;
+}
+
 template <class F> float timeit(F f, int reps = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   f(); CK(cudaDeviceSynchronize());
@@ -144,6 +226,57 @@ int main() {
       printf("LDS 2-bit lookup words=%d  %.3f ms  %.3e lookup/s\n", w, ms, n / (ms * 1e-3));
     }
     CK(cudaFree(coarse));
+  }
+  {
+    // shared-memory atomics: the per-SM rate bounds any privatised histogram
+    uint32_t* o32 = (uint32_t*)out;
+    CK(cudaFuncSetAttribute(atoms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(atoms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(atoms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int64_t na = 4 * n;
+    for (int tile : {1024, 16384, 49152}) {
+      for (int threads : {256, 1024}) {
+        const int ctas = threads == 1024 ? 1 : 4;     // per SM, so that 4 x 48 K-counter tiles never have to fit
+        if (tile * 4 * ctas > 200 * 1024) continue;
+        float ms = timeit([&] { atoms_kernel<1><<<sms * ctas, threads, tile * 4>>>(o32, tile, na); });
+        printf("ATOMS.ADD u32 random in a %6d-counter tile, %d x %4d threads/SM  %.3f ms  %.3e atom/s\n", tile, ctas, threads, ms, na / (ms * 1e-3));
+      }
+    }
+    {
+      float ms = timeit([&] { atoms_kernel<2><<<sms, 1024, 49152 * 4>>>(o32, 49152 * 2, na); });
+      printf("ATOMS.ADD packed u16, 98304-counter tile (192 KB), 1 x 1024 threads/SM  %.3f ms  %.3e atom/s\n", ms, na / (ms * 1e-3));
+      ms = timeit([&] { atoms_kernel<4><<<sms, 1024, 49152 * 4>>>(o32, 49152 * 4, na); });
+      printf("ATOMS.ADD packed u8, 196608-counter tile (192 KB), 1 x 1024 threads/SM  %.3f ms  %.3e atom/s\n", ms, na / (ms * 1e-3));
+    }
+    {
+      CK(cudaFuncSetAttribute(dsmem_atoms_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      float ms = timeit([&] { dsmem_atoms_kernel<8><<<(sms / 8) * 8, 1024, 49152 * 4>>>(o32, 49152, na); });
+      printf("DSMEM red.shared::cluster.add.u32, 8-CTA cluster, 8 x 49152-counter tile  %.3f ms  %.3e atom/s\n", ms, na / (ms * 1e-3));
+      CK(cudaFuncSetAttribute(dsmem_atoms_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      CK(cudaFuncSetAttribute(dsmem_atoms_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      cudaError_t e = cudaSuccess;
+      ms = timeit([&] { dsmem_atoms_kernel<16><<<(sms / 16) * 16, 1024, 49152 * 4>>>(o32, 49152, na); e = cudaGetLastError(); });
+      if (e == cudaSuccess) printf("DSMEM red.shared::cluster.add.u32, 16-CTA cluster, 16 x 49152-counter tile  %.3f ms  %.3e atom/s\n", ms, na / (ms * 1e-3));
+      else printf("DSMEM 16-CTA cluster: %s\n", cudaGetErrorString(e));
+    }
+    // the partition pass: 3e8 4-byte cell indices into 64 / 256 spatial buckets
+    const int64_t np = 300000000;
+    const uint32_t n_cells = 8120601u;
+    uint32_t *cells, *fill, *pout;
+    CK(cudaMalloc(&cells, np * 4)); CK(cudaMalloc(&fill, 4096)); CK(cudaMalloc(&pout, np * 4 + (64 << 20)));
+    fill_random_cells<<<sms * 8, 256>>>(cells, np, n_cells);
+    const unsigned blocks = (unsigned)((np + 8191) / 8192);
+    {
+      const uint32_t cap = (uint32_t)(np / 64 + (1 << 16));
+      float ms = timeit([&] { cudaMemsetAsync(fill, 0, 4096); partition_kernel<64><<<blocks, 1024>>>(cells, np, n_cells, fill, pout, cap); });
+      printf("PARTITION 3e8 cell indices into  64 buckets  %.3f ms  %.3e keys/s (4 B in + 4 B out per key: %.0f GB/s)\n", ms, np / (ms * 1e-3), 8.0 * np / (ms * 1e-3) / 1e9);
+    }
+    {
+      const uint32_t cap = (uint32_t)(np / 256 + (1 << 16));
+      float ms = timeit([&] { cudaMemsetAsync(fill, 0, 4096); partition_kernel<256><<<blocks, 1024>>>(cells, np, n_cells, fill, pout, cap); });
+      printf("PARTITION 3e8 cell indices into 256 buckets  %.3f ms  %.3e keys/s (4 B in + 4 B out per key: %.0f GB/s)\n", ms, np / (ms * 1e-3), 8.0 * np / (ms * 1e-3) / 1e9);
+    }
+    CK(cudaFree(cells)); CK(cudaFree(fill)); CK(cudaFree(pout));
   }
   {
     const int64_t n4 = n * 3 / 4;  // 720 MB
