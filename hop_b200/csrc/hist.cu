@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "hopb_common.cuh"
+#include "hopb_tables.cuh"
 
 namespace {
 
@@ -411,23 +412,7 @@ density_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int 
   }
 }
 
-// The same values from a table.  For fixed bin widths the density of a cell is a function of its count
-// alone, and a linspace grid has a handful of distinct widths per axis (the width classes of
-// hopb_grid_create), so T[class triple][count] built by hopb_density_value itself holds every value a
-// cell with count < kDensityTableCounts can take -- bit-identical by construction.  The per-cell work
-// drops from four double divisions (~200 instructions of the FP64 pipe) to one 8-byte load from an
-// L1/L2-resident table; cells with larger counts take the division path.
-constexpr int kDensityTableCounts = 1024;
-
-__global__ void density_table_kernel(int n_classes, int ncy, int ncz, const double* __restrict__ wx,
-                                     const double* __restrict__ wy, const double* __restrict__ wz, double n_frames,
-                                     double factor, int apply_factor, double* __restrict__ table) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_classes * kDensityTableCounts) return;
-  const int cls = t / kDensityTableCounts, c = t - cls * kDensityTableCounts;
-  const double dz = wz[cls % ncz], dy = wy[(cls / ncz) % ncy], dx = wx[cls / (ncz * ncy)];
-  table[t] = hopb_density_value((uint32_t)c, n_frames, dx, dy, dz, factor, apply_factor);
-}
+using hopb_tables::kDensityTableCounts;
 
 __global__ void __launch_bounds__(256)
 density_lookup_kernel(const uint32_t* __restrict__ counts, int64_t n_rows, int ny, int nz, double n_frames,
@@ -581,7 +566,7 @@ int hopb_density_from_counts_ex(hopb_handle* h, void* stream, const hopb_grid* g
     if (rc != HOPB_OK) return rc;
     const double* w = g->d_cls_width;
     const int n_entries = n_classes * kDensityTableCounts;
-    HOPB_K(density_table_kernel)<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    HOPB_K(hopb_tables::density_table_kernel)<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         n_classes, g->n_cls[1], g->n_cls[2], w, w + 16, w + 32, (double)n_frames, factor, factor != 1.0 ? 1 : 0, table);
     HOPB_K(density_lookup_kernel)<<<grid, 256, 0, (cudaStream_t)stream>>>(
         counts, n_rows, g->n[1], g->n[2], (double)n_frames, g->d_width[0], g->d_width[1], g->d_width[2], factor,

@@ -13,7 +13,7 @@
 #include "hopb_binning.h"
 #include "hopb_machine.h"
 
-#define HOPB_NUM_SCRATCH 11
+#define HOPB_NUM_SCRATCH 16
 
 struct hopb_handle {
   int device;
@@ -24,6 +24,8 @@ struct hopb_handle {
   int64_t hist_l2_budget;  // bytes of the count grid that one histogram pass may reduce into
   // count thresholds cached in scratch slot 9: valid for this (grid, n_frames, factor, threshold)
   uint64_t cmin_grid; int64_t cmin_frames; double cmin_factor, cmin_threshold; void* cmin_ptr;
+  // tables of hopb_site_map_fused (scratch slots 11, 12): valid for fused_key = (grid, n_frames, factor, thresholds)
+  void* fused_cmin; void* fused_dtable; double fused_key[5];
 };
 
 struct hopb_grid {

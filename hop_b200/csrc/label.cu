@@ -17,10 +17,12 @@
 //      (size desc, root desc), labels 1..S, relabel.
 // All per-cell passes are HBM streams over G cells (8 B density + 4 B parent).
 #include "hopb_common.cuh"
+#include "hopb_ccl.cuh"
+#include "hopb_tables.cuh"
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
+using hopb_ccl::kFull;
 
 // Every per-cell pass below is "one warp per (x, y) row, lanes along z": accesses are contiguous,
 // no per-cell division is needed, and rows without a single above-threshold cell (most rows of a
@@ -88,182 +90,24 @@ ccl_rows_kernel(const double* __restrict__ density, double threshold, CountMask 
   }
 }
 
-// smallest count whose density reaches the threshold, per width class; 2^32 = no count does
-__global__ void count_threshold_kernel(int n_classes, int ncy, int ncz, const double* __restrict__ wx,
-                                       const double* __restrict__ wy, const double* __restrict__ wz, double n_frames,
-                                       double factor, int apply_factor, double threshold,
-                                       unsigned long long* __restrict__ cmin) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_classes) return;
-  const double dz = wz[t % ncz], dy = wy[(t / ncz) % ncy], dx = wx[t / (ncz * ncy)];
-  auto reaches = [&](unsigned long long c) {
-    return hopb_density_value((uint32_t)c, n_frames, dx, dy, dz, factor, apply_factor) >= threshold;
-  };
-  unsigned long long lo = 0, hi = 1ull << 32;   // answer in [0, 2^32]; NaN threshold: never -> 2^32
-  if (!reaches(0xFFFFFFFFull)) { cmin[t] = hi; return; }
-  hi = 0xFFFFFFFFull;
-  while (lo < hi) {
-    const unsigned long long mid = lo + (hi - lo) / 2;
-    if (reaches(mid)) hi = mid; else lo = mid + 1;
-  }
-  cmin[t] = lo;
-}
-
-// ---- 2. merge -------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_parent(const int* parent, int i) {
-  return *reinterpret_cast<const volatile int*>(parent + i);
-}
-
-// find with path halving.  Every value ever stored in parent[x] is a member of x's set with a smaller
-// index, and stores go through atomicMin, so parent[] only decreases: no cycles, and a union that
-// races with the compression still sees a valid (if stale) ancestor.
-__device__ __forceinline__ int uf_find(int* parent, int x) {
-  int p = ld_parent(parent, x);
-  while (p != x) {
-    const int gp = ld_parent(parent, p);
-    if (gp != p) atomicMin(parent + x, gp);
-    x = p;
-    p = gp;
-  }
-  return x;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { int t = a; a = b; b = t; }  // link the larger root under the smaller
-    const int old = atomicMin(parent + a, b);
-    if (old == a) return;
-    a = old;
-  }
-}
-
+// ---- 2.-4. merge, flatten, sizes: hopb_ccl.cuh -------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(int* parent, const uint8_t* __restrict__ rowflag, int nx, int ny, int nz, int phase) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n_rows = (int64_t)nx * ny;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t sy = nz, sx = (int64_t)ny * nz;
-  for (int64_t row = warp0; row < n_rows; row += nwarps) {
-    if (!rowflag[row]) continue;
-    const int y = (int)(row % ny);
-    const int x = (int)(row / ny);
-    const bool hx = x + 1 < nx, hy = y + 1 < ny, ly = y > 0;
-    // neighbour rows without any mask cell cannot contribute an edge
-    const bool ry = hy && rowflag[row + 1];
-    const bool rx = hx && rowflag[row + ny];
-    const bool rxy = hx && hy && rowflag[row + ny + 1];
-    if (!(ry | rx | rxy)) continue;
-    const int64_t base = row * nz;
-    for (int z0 = 0; z0 < nz; z0 += 32) {
-      const int z = z0 + lane;
-      if (z >= nz) continue;
-      const int64_t c = base + z;
-      if (parent[c] < 0) continue;
-      const bool hz = z + 1 < nz, lz = z > 0;
-      auto M = [&](int64_t idx) { return parent[idx] >= 0; };
-      const bool m_up = hz && M(c + 1);
-      const bool m_dn = lz && M(c - 1);
-      // phase 0: heads of z-runs only -- they tie the rows of a blob into one tree (the skeleton);
-      // phase 1 (after a flatten): every other cell; inside a blob both ends then already share a
-      // root one step away, so the many unions around isolated holes cost two loads each
-      if ((phase == 0) == m_dn) continue;
-      const bool m_y = ry && M(c + sy);              // (0,1,0)
-      const bool m_x = rx && M(c + sx);              // (1,0,0)
-      const bool m_xy = rxy && M(c + sx + sy);       // (1,1,0)
-      // An edge is skipped when its end points are already joined by edges that are themselves kept
-      // or skipped by a rule lower in the (y, z) order -- so the argument is well founded:
-      //   rule Z: (c, c+o), o_z = 0, follows from the same edge one cell down both z-runs;
-      //   rule Y: the x-edge follows from the x-edge one row down in y plus the two y-edges;
-      //   diagonals follow from any two-step path over in-plane / z edges.
-      if (m_y && !(m_dn && M(c + sy - 1))) uf_union(parent, (int)c, (int)(c + sy));
-      if (m_x && !(m_dn && M(c + sx - 1)) && !(ly && M(c - sy) && M(c + sx - sy))) uf_union(parent, (int)c, (int)(c + sx));
-      if (m_xy && !m_y && !m_x && !(m_dn && M(c + sx + sy - 1))) uf_union(parent, (int)c, (int)(c + sx + sy));
-      if (hz) {
-        // +z partners: (0,1,1), (1,0,1), (1,1,1)
-        if (ry && !m_y && !m_up && M(c + sy + 1)) uf_union(parent, (int)c, (int)(c + sy + 1));
-        if (rx && !m_x && !m_up && M(c + sx + 1)) uf_union(parent, (int)c, (int)(c + sx + 1));
-        // (1,1,1) is also reached through c+x then (0,1,1), or c+y then (1,0,1)
-        if (rxy && !m_xy && !m_up && !m_x && !m_y && M(c + sx + sy + 1)) uf_union(parent, (int)c, (int)(c + sx + sy + 1));
-      }
-    }
-  }
+  hopb_ccl::merge_rows(parent, rowflag, 1u, nx, ny, nz, phase, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                       ((int64_t)gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
 }
 
-// ---- 3. flatten -----------------------------------------------------------------------------------
-// Only heads of z-runs are ever parents (initial links, unions and path halving all point at
-// heads), so flattening is: heads find their root (few cells, possibly long walks), then every
-// other cell takes its head's root in one hop.
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(int* parent, const uint8_t* __restrict__ rowflag, int64_t n_rows, int nz, int heads) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp0; row < n_rows; row += nwarps) {
-    if (!rowflag[row]) continue;
-    const int64_t base = row * nz;
-    // two chunks of 32 cells per step, all four loads issued before anything depends on them
-    for (int z0 = 0; z0 < nz; z0 += 64) {
-      const int za = z0 + lane, zb = za + 32;
-      const int pa = za < nz ? ld_parent(parent, (int)(base + za)) : -1;
-      const int pb = zb < nz ? ld_parent(parent, (int)(base + zb)) : -1;
-      const int qa = (za > 0 && za < nz) ? ld_parent(parent, (int)(base + za - 1)) : -1;   // the cell below in z
-      const int qb = zb < nz ? ld_parent(parent, (int)(base + zb - 1)) : -1;
-      const bool ha = pa >= 0 && qa < 0, hb = pb >= 0 && qb < 0;       // heads of z-runs (z == 0: qa = -1)
-      if (heads) {
-        if (ha) { const int r = uf_find(parent, (int)(base + za)); parent[base + za] = r; }
-        if (hb) { const int r = uf_find(parent, (int)(base + zb)); parent[base + zb] = r; }
-      } else {
-        // a non-head's parent is a head, flattened by the pass before: one more hop gives the root
-        const bool na = pa >= 0 && !ha, nb = pb >= 0 && !hb;
-        const int ra = na ? ld_parent(parent, pa) : 0;
-        const int rb = nb ? ld_parent(parent, pb) : 0;
-        if (na) parent[base + za] = ra;
-        if (nb) parent[base + zb] = rb;
-      }
-    }
-  }
+  hopb_ccl::flatten_rows(parent, rowflag, 1u, n_rows, nz, heads, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                         ((int64_t)gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
 }
 
-// ---- 4. sizes ---------------------------------------------------------------------------------------
-// size[root] += cells with that root.  Lanes with equal roots are merged first (neighbouring z cells
-// share a root) and lane 0 carries the running (root, count) of the first labelled cell of every chunk
-// across the chunks of a row AND across the rows of its warp: the one giant component of a bulk map then costs one atomic per warp instead of
-// one per row (40 000 atomics on a single address were most of this kernel's time).
 __global__ void __launch_bounds__(256)
 ccl_size_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ rowflag, int64_t n_rows, int nz,
                 int* __restrict__ size) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int run_root = -1, run_cnt = 0;
-  for (int64_t row = warp0; row < n_rows; row += nwarps) {
-    if (!rowflag[row]) continue;
-    const int64_t base = row * nz;
-    for (int z0 = 0; z0 < nz; z0 += 32) {
-      const int z = z0 + lane;
-      const int r = z < nz ? parent[base + z] : -1;
-      const unsigned valid = __ballot_sync(kFull, r >= 0);
-      if (valid == 0) continue;           // nothing but background here (e.g. the padding of the grid)
-      const unsigned peers = __match_any_sync(kFull, r);
-      const bool leader = (peers & ((1u << lane) - 1)) == 0;
-      const int f = __ffs(valid) - 1;     // the chunk's first labelled cell continues the running root
-      const int rf = __shfl_sync(kFull, r, f);
-      const int nf = __popc(__shfl_sync(kFull, peers, f));
-      if (leader && r >= 0 && lane != f) atomicAdd(size + r, __popc(peers));
-      if (lane == 0) {
-        if (rf == run_root) run_cnt += nf;
-        else {
-          if (run_root >= 0) atomicAdd(size + run_root, run_cnt);
-          run_root = rf; run_cnt = nf;
-        }
-      }
-    }
-  }
-  if (lane == 0 && run_root >= 0) atomicAdd(size + run_root, run_cnt);
+  hopb_ccl::size_rows(parent, rowflag, 1u, n_rows, nz, size, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                      ((int64_t)gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
 }
 
 // roots with size >= minsite become sites; smaller components are dropped (label 0)
@@ -581,7 +425,7 @@ static int label_sites_impl(hopb_handle* h, void* stream, int nx, int ny, int nz
                         h->cmin_factor == factor && h->cmin_threshold == threshold;   // NaN threshold: never cached
     if (!cached) {
       const double* w = g->d_cls_width;
-      HOPB_K(count_threshold_kernel)<<<(n_classes + 127) / 128, 128, 0, s>>>(n_classes, g->n_cls[1], g->n_cls[2], w, w + 16,
+      HOPB_K(hopb_tables::count_threshold_kernel)<<<(n_classes + 127) / 128, 128, 0, s>>>(n_classes, g->n_cls[1], g->n_cls[2], w, w + 16,
                                                                             w + 32, (double)n_frames, factor,
                                                                             factor != 1.0 ? 1 : 0, threshold, cmin);
       h->cmin_ptr = cmin; h->cmin_grid = g->serial; h->cmin_frames = n_frames; h->cmin_factor = factor; h->cmin_threshold = threshold;

@@ -252,6 +252,39 @@ def label_sites_counts_async(grid: GridTables, counts: torch.Tensor, n_frames: i
     return out
 
 
+def site_map_fused_ok(grid: GridTables):
+    """Whether site_map_fused handles this grid (regular bin widths, z extent within its shared-memory tile)."""
+    return 0 < grid.width_classes <= 512 and grid.shape[2] <= 3072
+
+
+def site_map_fused(grid: GridTables, counts: torch.Tensor, n_frames: int, factor: float, solvent_threshold: float,
+                   bulk_threshold: float, with_bulk: bool, minsite: int, density, own, member, map16, brick: "BrickMap",
+                   n_sites_dev: torch.Tensor, props=None, volumes=None):
+    """Stage 2 in one launch (hopb_site_map_fused): counts -> density, hydration-site labels, bulk site,
+    int16 map, bricked map + block maps and (props = (count, mean, std, center) buffers) the annotation."""
+    _cuda(counts, torch.int32, "counts")
+    if tuple(counts.shape) != grid.shape:
+        raise ValueError("counts must have the shape of the grid")
+    _cuda(density, torch.float64, "density")
+    _cuda(own, torch.int32, "own")
+    _cuda(map16, torch.int16, "map16")
+    _cuda(n_sites_dev, torch.int32, "n_sites_dev")
+    if with_bulk:
+        _cuda(member, torch.uint8, "member")
+    n_cap, pc, pm, ps, pcen = 0, None, None, None, None
+    if props is not None:
+        pc, pm, ps, pcen = props
+        n_cap = int(pc.numel())
+    h = _h(counts)
+    rc = _lib.lib().hopb_site_map_fused(h, _stream(), grid.ptr, _p(counts), int(n_frames), float(factor),
+                                        float(solvent_threshold), float(bulk_threshold), 1 if with_bulk else 0, int(minsite),
+                                        _p(density), _p(own), _p(member if with_bulk else None), _p(map16), _p(brick.brick),
+                                        _p(brick.coarse), _p(brick.fine), _p(brick.cell2), _p(n_sites_dev), _p(volumes),
+                                        n_cap, _p(pc), _p(pm), _p(ps), _p(pcen))
+    _lib.check(h, rc)
+    return density, own, member, map16
+
+
 def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, member, n_labels: int, out=None):
     """(count int64[n], mean f64[n], std f64[n], center f64[n,3]) per site label.  `n_labels` may be
     an upper bound (rows past the real number of sites come back empty)."""

@@ -41,6 +41,7 @@ class PipelineConfig:
     block_map: str = "auto"          # "auto" (fine when it fits, else coarse), "fine", "coarse", "none"
     async_results: bool = True       # from the second run on: no host synchronisation inside run()
     label_from_counts: bool = True   # threshold the counts instead of the density (identical labels)
+    fused_site_map: bool = True      # stage 2 as one cooperative launch (hopb_site_map_fused) where the grid allows
 
 
 class PipelineResult(object):
@@ -193,6 +194,8 @@ class HopPipeline:
         cfg = self.cfg
         shape = self.grid.shape
         factor = density_conversion_factor("Angstrom^{-3}", cfg.density_unit)
+        if cfg.fused_site_map and cfg.label_from_counts and K.site_map_fused_ok(self.grid):
+            return self._site_map_fused(counts, factor)
         # density / labels / membership alternate between two buffer sets: the annotation of a run is
         # queued behind its stage 3 and may execute as late as the end of the next run's histogram, so it
         # must not hold up the next run's stage 2; only the run after that reuses its inputs
@@ -257,11 +260,39 @@ class HopPipeline:
         self.brick = K.brick_map(map16, brick_buf, coarse_buf, fine_buf, self._buf("cell2", (nb * 4,), torch.int32))
         return density, own, member, map16, None
 
+    def _site_map_fused(self, counts, factor):
+        """Stage 2 as one launch: density, both labellings, bulk insertion, painted and bricked map, block
+        maps and the annotation (csrc/sitemap_fused.cu)."""
+        cfg = self.cfg
+        shape = self.grid.shape
+        par = "%d" % (self._run_index & 1)     # results of a run stay intact while the next one is queued
+        self.n_sites_dev = self._buf("n_sites_dev" + par, (2,), torch.int32)
+        density = self._buf("density" + par, shape, torch.float64)
+        own = self._buf("own" + par, shape, torch.int32)
+        member = self._buf("member" + par, shape, torch.uint8) if cfg.with_bulk else None
+        map16 = self._buf("map16", shape, torch.int16)
+        nb, words = K.brick_shape(shape)
+        self.brick = K.BrickMap(self._buf("brick", (nb * 64,), torch.int16), self._buf("coarse", (words,), torch.int32),
+                                self._buf("fine", (K.fine_map_bytes(shape),), torch.uint8),
+                                self._buf("cell2", (nb * 4,), torch.int32))
+        props = None
+        if cfg.annotate:
+            L = self.MAX_LABELS
+            props = (self._buf("p_count" + par, (L,), torch.int64), self._buf("p_mean" + par, (L,), torch.float64),
+                     self._buf("p_std" + par, (L,), torch.float64), self._buf("p_center" + par, (L, 3), torch.float64))
+        K.site_map_fused(self.grid, counts, self.n_frames_total, factor, cfg.solvent_threshold, cfg.bulk_threshold,
+                         cfg.with_bulk, cfg.minsite, density, own, member, map16, self.brick, self.n_sites_dev, props=props)
+        self._annotate_args = None
+        self._props = props
+        return density, own, member, map16, None
+
     def annotate(self):
         """site_properties of the site map just built (volume, occupancy, centre per site), on the side
         stream.  Called after stage 3 has been launched: the hoptraj kernel needs whole SMs (1024
         threads x 64 registers), so reductions already running there would hold it up, while queued behind
         it they run beside the fix-up, the event ordering and the next run's histogram."""
+        if self._annotate_args is None:      # the one-launch site map has annotated already
+            return
         self._props = None
         if not self.cfg.annotate:
             return

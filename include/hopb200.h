@@ -179,6 +179,34 @@ int hopb_site_properties(hopb_handle* h, void* stream, const hopb_grid* g, const
                          const int32_t* own, const uint8_t* member, int n_labels, int64_t* out_count,
                          double* out_mean, double* out_std, double* out_center);
 
+/* The whole of stage 2 in one (cooperative) launch, for the common workflow in which the bulk density
+ * is the same histogram thresholded lower (no solute): what hop does with
+ *   density = DensityCollector.finish / Grid.make_density / convert_density  (hop/density.py:133-137,
+ *             hop/sitemap.py:196-216, 236-264)
+ *   density.map_sites(solvent_threshold); bulk.map_sites(bulk_threshold)     (hop/sitemap.py:480-521,
+ *             1496-1587)
+ *   density.site_insert_bulk(bulk)                                           (hop/sitemap.py:877-918)
+ *   _annotate_sites                                                          (hop/sitemap.py:1589-1612)
+ * plus the stage-3 view of the map (hopb_brick_map).  Same labels as hopb_label_sites_counts_async +
+ * hopb_insert_bulk; the annotation agrees with hopb_site_properties to rounding (one-pass shifted
+ * variance).  Needs 1 <= hopb_grid_width_classes(g) <= 512 and nz <= 3072; HOPB_E_INVALID otherwise
+ * (callers then use the stand-alone entry points).
+ *   counts   device uint32 [nx*ny*nz]; n_frames, factor as hopb_density_from_counts
+ *   with_bulk 0: plain map_sites (labels 1.., member untouched, may be NULL); 1: bulk site = label 1,
+ *            hydration sites 2..
+ *   density  device double [G] out; own device int32 [G] out; member device uint8 [G] out;
+ *   map16    device int16 [G] out; brick / coarse / fine / cell2 as hopb_brick_map (fine, cell2 may be NULL)
+ *   n_sites_dev device int32 [2] out: hydration sites, components of the bulk mask (a value above
+ *            HOPB_MAX_SITES means the int16 map cannot hold them; all labels are then 0)
+ *   volumes  device int32 [HOPB_MAX_SITES+1] or NULL: cells per hydration site, rank order
+ *   p_*      annotation as hopb_site_properties over n_labels_cap labels, or all NULL */
+int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const uint32_t* counts,
+                        int64_t n_frames, double factor, double solvent_threshold, double bulk_threshold,
+                        int with_bulk, int minsite, double* density, int32_t* own, uint8_t* member,
+                        int16_t* map16, int16_t* brick, uint32_t* coarse, uint8_t* fine, uint32_t* cell2,
+                        int32_t* n_sites_dev, int32_t* volumes, int n_labels_cap, int64_t* p_count,
+                        double* p_mean, double* p_std, double* p_center);
+
 /* Cell lists (Density.sites) in CSR form, cells ascending within a site.
  *   cells   device int32 [capacity]; offsets device int64 [n_labels+1]; n_cells host out.
  * Returns HOPB_E_CAPACITY (with *n_cells set) if capacity is too small.  Synchronises. */

@@ -579,7 +579,9 @@ def test_pipeline_async_results_are_lazy_and_correct(K, traj):
         return (x["n_labels"] == y["n_labels"] and x["n_ev"] == y["n_ev"] and torch.equal(x["events"], y["events"])
                 and torch.equal(x["e_s0"], y["e_s0"]) and torch.equal(x["e_s"], y["e_s"]) and torch.equal(x["e_count"], y["e_count"])
                 and torch.equal(x["e_start"], y["e_start"]) and torch.equal(x["M"], y["M"])
-                and all(torch.equal(s, t, ) or (torch.isnan(s) == torch.isnan(t)).all() for s, t in zip(x["props"], y["props"])))
+                # the annotation sums with floating-point atomics: equal up to summation order
+                and all(torch.allclose(s.double(), t.double(), rtol=1e-9, atol=1e-12, equal_nan=True)
+                        for s, t in zip(x["props"], y["props"])))
 
     want = {}
     for name, inp in (("a", a), ("b", b)):
@@ -680,6 +682,74 @@ def test_label_from_counts_equals_label_from_density(K):
     with pytest.raises((HopbError, ValueError, RuntimeError)):
         K.label_sites_counts_async(g, torch.zeros(g.shape, dtype=torch.int32, device="cuda"), 5, 1.0, 1.0, 1,
                                    torch.empty(g.shape, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
+
+
+@pytest.mark.parametrize("shape", [(24, 17, 31), (40, 40, 40), (9, 5, 130), (4, 4, 4), (3, 2, 1), (1, 1, 70), (33, 34, 35)])
+@pytest.mark.parametrize("with_bulk,minsite", [(True, 1), (False, 1), (True, 2)])
+def test_fused_site_map_equals_the_kernel_chain(K, shape, with_bulk, minsite):
+    """hopb_site_map_fused (stage 2 in one cooperative launch) against the stand-alone entry points it
+    replaces in the pipeline: density bit-identical, labels / membership / int16 map / bricked map /
+    block maps identical, annotation equal to rounding."""
+    import torch
+
+    rng = np.random.default_rng(sum(shape) + 7 * minsite + (100 if with_bulk else 0))
+    edges = [np.linspace(-1.3 + d, -1.3 + d + 0.5 * k, k + 1) for d, k in enumerate(shape)]
+    g = K.GridTables(edges)
+    assert K.site_map_fused_ok(g)
+    n_frames = 40
+    factor = O.density_conversion_factor("Angstrom^{-3}", "water")
+    # bulk-like counts with holes, plus a few dense blobs (hydration sites), and one with everything / nothing above
+    lam = 40 * 0.0334 * 0.125
+    base = rng.poisson(lam, shape)
+    blobs = (rng.random(shape) < 0.03) * rng.poisson(12 * lam, shape)
+    for counts, thr_s, thr_b in [(base + blobs, math.e, math.exp(-0.5)), (base, 0.0, 0.0), (base, 1e9, 1e8),
+                                 (base + blobs, 1.0, 2.0)]:
+        c = dev(counts.astype(np.int32))
+        # the chain
+        dens = K.density_from_counts(g, c, n_frames, factor)
+        own = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+        n_dev = torch.zeros(2, dtype=torch.int32, device="cuda")
+        K.label_sites_counts_async(g, c, n_frames, factor, thr_s, minsite, own, n_dev[0:1])
+        if with_bulk:
+            bl = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+            K.label_sites_counts_async(g, c, n_frames, factor, thr_b, minsite, bl, n_dev[1:2])
+            member, map16 = K.insert_bulk(own, bl, 1)
+        else:
+            member, map16 = None, K.labels_to_map16(own)
+        bm = K.brick_map(map16)
+        L = K.HOPB_MAX_SITES + 2
+        props = K.site_properties(g, dens, own, member, L)
+        # the one launch
+        nb, words = K.brick_shape(g.shape)
+        f_dens = torch.full(g.shape, -1.0, dtype=torch.float64, device="cuda")
+        f_own = torch.full(g.shape, -7, dtype=torch.int32, device="cuda")
+        f_member = torch.full(g.shape, 9, dtype=torch.uint8, device="cuda") if with_bulk else None
+        f_map = torch.full(g.shape, -7, dtype=torch.int16, device="cuda")
+        f_bm = K.BrickMap(torch.full((nb * 64,), -7, dtype=torch.int16, device="cuda"),
+                          torch.full((words,), -1, dtype=torch.int32, device="cuda"),
+                          torch.full((K.fine_map_bytes(g.shape),), 5, dtype=torch.uint8, device="cuda"),
+                          torch.full((nb * 4,), -1, dtype=torch.int32, device="cuda"))
+        f_n = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+        f_props = (torch.empty(L, dtype=torch.int64, device="cuda"), torch.empty(L, dtype=torch.float64, device="cuda"),
+                   torch.empty(L, dtype=torch.float64, device="cuda"), torch.empty((L, 3), dtype=torch.float64, device="cuda"))
+        for _ in range(2):      # twice: the second call takes the cached tables
+            K.site_map_fused(g, c, n_frames, factor, thr_s, thr_b, with_bulk, minsite, f_dens, f_own, f_member, f_map, f_bm, f_n,
+                             props=f_props)
+        assert torch.equal(f_dens, dens)
+        assert int(f_n[0].item()) == int(n_dev[0].item())
+        if with_bulk:
+            assert int(f_n[1].item()) == int(n_dev[1].item())
+            assert torch.equal(f_member, member)
+        assert torch.equal(f_own, own) and torch.equal(f_map, map16)
+        assert torch.equal(f_bm.brick, bm.brick) and torch.equal(f_bm.coarse, bm.coarse) and torch.equal(f_bm.cell2, bm.cell2)
+        nbp = (nb + 3) // 4 * 4
+        assert torch.equal(f_bm.fine[:nb], bm.fine[:nb]) and torch.equal(f_bm.fine[nbp:nbp + nb], bm.fine[nbp:nbp + nb])
+        assert torch.equal(f_bm.fine[2 * nbp:2 * nbp + 4], bm.fine[2 * nbp:2 * nbp + 4])
+        n_labels = int(n_dev[0].item()) + (2 if with_bulk else 1)
+        assert torch.equal(f_props[0][:n_labels], props[0][:n_labels])
+        for a_, b_ in zip(f_props[1:], props[1:]):
+            assert torch.allclose(a_[:n_labels], b_[:n_labels], rtol=1e-9, atol=1e-12)
+        assert int(f_props[0][n_labels:].abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("seed", range(32))
