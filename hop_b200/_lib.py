@@ -72,6 +72,7 @@ _SIGNATURES = {
     "hopb_label_sites_async": [_vp, _vp, _int, _int, _int, _vp, _dbl, _int, _vp, _vp, _vp],
     "hopb_label_sites_counts_async": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp, _vp, _vp],
     "hopb_grid_width_classes": [_vp],
+    "hopb_grid_set_periodic_box": [_vp, _vp, _vp],
     "hopb_insert_bulk": [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp],
     "hopb_labels_to_map16": [_vp, _vp, _i64, _vp, _vp],
     "hopb_site_properties": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],

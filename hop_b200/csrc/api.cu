@@ -137,6 +137,24 @@ int hopb_grid_create(hopb_handle* h, const double* ex, int nx, const double* ey,
   return HOPB_OK;
 }
 
+int hopb_grid_set_periodic_box(hopb_grid* g, const double* origin, const double* length) {
+  if (!g) return HOPB_E_INVALID;
+  if (!origin || !length) {   // off (the default): coordinates are binned as they are
+    g->tab.wrap = 0;
+    return HOPB_OK;
+  }
+  for (int d = 0; d < 3; ++d)
+    if (!(length[d] > 0.0) || !std::isfinite(length[d]) || !std::isfinite(origin[d]))
+      return hopb_fail(g->h, HOPB_E_INVALID, "hopb_grid_set_periodic_box: box lengths must be positive and finite");
+  for (int d = 0; d < 3; ++d) {
+    g->tab.box_o[d] = (float)origin[d];
+    g->tab.box_l[d] = (float)length[d];
+    g->tab.box_inv[d] = 1.0f / (float)length[d];
+  }
+  g->tab.wrap = 1;
+  return HOPB_OK;
+}
+
 int hopb_grid_width_classes(const hopb_grid* g) {
   if (!g || g->n_cls[0] == 0 || g->n_cls[1] == 0 || g->n_cls[2] == 0) return 0;
   return g->n_cls[0] * g->n_cls[1] * g->n_cls[2];

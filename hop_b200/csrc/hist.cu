@@ -96,6 +96,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
                                                const AxisReg& ay, const AxisReg& az, const float* s_tab,
                                                uint32_t* counts, const Slab& slab, uint32_t* counts_b = nullptr,
                                                bool to_b = false) {
+  hopb_wrap_point(x, y, z, tab);   // periodic image first, when the grid asks for it (default: off)
   int bx, by, bz;
   bool sure = false;
   if (FAST && tab.sure_eps > 0.0f) {

@@ -44,6 +44,12 @@ struct HopbGridTab {
   int32_t table2_len;  // total float2 entries in the packed pair table
   int32_t fast_ok;     // 1 if the one-step corrected guess is proven exact for these edges
   float sure_eps;      // > 0: hopb_bin_sure() with this margin is proven exact for these edges; 0: off
+  // optional periodic wrapping of the coordinates before they are binned (off by default: hop bins
+  // AtomGroup.positions as they are and expects pre-wrapped trajectories, hop/density.py:21-28)
+  int32_t wrap;        // 0: off
+  float box_o[3];      // box origin
+  float box_l[3];      // box lengths
+  float box_inv[3];    // float32(1 / length)
 };
 
 struct HopbPair { float lo, hi; };  // pair table entry b: (up32(e[b-1]) or -inf, up32(e[b]) or +inf)
@@ -121,6 +127,29 @@ HOPB_HD int hopb_bin_hist(float x, const HopbAxis& a, const float* eup) {
 #define HOPB_FMUL(a, b) ((a) * (b))
 #define HOPB_FDIV(a, b) ((a) / (b))
 #endif
+
+// Periodic image of x in [o, o + l): x - floor((x - o) * inv) * l, every step a separately rounded float32
+// operation (numpy: x - np.floor((x - o) * inv) * l on float32 arrays gives the same bits).
+HOPB_HD float hopb_wrap1(float x, float o, float l, float inv) {
+#if defined(__CUDA_ARCH__)
+  const float t = floorf(__fmul_rn(__fsub_rn(x, o), inv));
+  return __fsub_rn(x, __fmul_rn(t, l));
+#else
+  volatile float d = x - o;
+  volatile float q = d * inv;
+  volatile float t = floorf(q);
+  volatile float m = t * l;
+  return x - m;
+#endif
+}
+
+HOPB_HD void hopb_wrap_point(float& x, float& y, float& z, const HopbGridTab& tab) {
+  if (tab.wrap) {
+    x = hopb_wrap1(x, tab.box_o[0], tab.box_l[0], tab.box_inv[0]);
+    y = hopb_wrap1(y, tab.box_o[1], tab.box_l[1], tab.box_inv[1]);
+    z = hopb_wrap1(z, tab.box_o[2], tab.box_l[2], tab.box_inv[2]);
+  }
+}
 
 // numpy.around(float32, decimals): multiply, rint, divide in float32 (divide, rint, multiply for
 // negative decimals).

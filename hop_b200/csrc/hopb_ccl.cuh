@@ -165,53 +165,91 @@ __device__ __forceinline__ void size_rows(const int* parent, const uint8_t* rowf
 // heads in a compact list (a solid blob with holes has ~2 per row) one lane per head does the same unions:
 // forward from the head (= phase 0) and backward from the head to non-head sources (= phase 1).  Same union
 // set, hence the same components; roots are minimum indices either way.
-// `M(x, y, z)` tells whether a cell is in the mask (never asked outside the grid).
-template <class Mask>
-__device__ __forceinline__ void merge_head_forward(int* parent, int c, int nx, int ny, int nz, const Mask& M) {
+// `M(x, y, z)` tells whether a cell is in the mask and answers false outside the grid without branching, so that
+// the nine look-ups of a head are independent loads in flight together (one L2 latency instead of nine).
+template <class Mask, class Union>
+__device__ __forceinline__ void merge_head_forward(int* parent, int c, int nx, int ny, int nz, const Mask& M, const Union& uf_union) {
   const int z = c % nz;
   const int row = c / nz;
   const int y = row % ny, x = row / ny;
   const int64_t sy = nz, sx = (int64_t)ny * nz;
-  const bool hx = x + 1 < nx, hy = y + 1 < ny, ly = y > 0, hz = z + 1 < nz;
-  const bool m_up = hz && M(x, y, z + 1);
-  const bool m_y = hy && M(x, y + 1, z);
-  const bool m_x = hx && M(x + 1, y, z);
-  const bool m_xy = hx && hy && M(x + 1, y + 1, z);
+  const bool m_up = M(x, y, z + 1);
+  const bool m_y = M(x, y + 1, z);
+  const bool m_x = M(x + 1, y, z);
+  const bool m_xy = M(x + 1, y + 1, z);
+  const bool b_y = M(x, y - 1, z), b_xy = M(x + 1, y - 1, z);
+  const bool u_y = M(x, y + 1, z + 1), u_x = M(x + 1, y, z + 1), u_xy = M(x + 1, y + 1, z + 1);
   if (m_y) uf_union(parent, c, (int)(c + sy));
-  if (m_x && !(ly && M(x, y - 1, z) && M(x + 1, y - 1, z))) uf_union(parent, c, (int)(c + sx));
+  if (m_x && !(b_y && b_xy)) uf_union(parent, c, (int)(c + sx));
   if (m_xy && !m_y && !m_x) uf_union(parent, c, (int)(c + sx + sy));
-  if (hz) {
-    if (hy && !m_y && !m_up && M(x, y + 1, z + 1)) uf_union(parent, c, (int)(c + sy + 1));
-    if (hx && !m_x && !m_up && M(x + 1, y, z + 1)) uf_union(parent, c, (int)(c + sx + 1));
-    if (hx && hy && !m_xy && !m_up && !m_x && !m_y && M(x + 1, y + 1, z + 1)) uf_union(parent, c, (int)(c + sx + sy + 1));
+  if (!m_up) {
+    if (!m_y && u_y) uf_union(parent, c, (int)(c + sy + 1));
+    if (!m_x && u_x) uf_union(parent, c, (int)(c + sx + 1));
+    if (!m_xy && !m_x && !m_y && u_xy) uf_union(parent, c, (int)(c + sx + sy + 1));
   }
 }
 
-// t is a head; the sources c = t - o that merge_rows' phase 1 would join to it
-template <class Mask>
-__device__ __forceinline__ void merge_head_backward(int* parent, int t, int nx, int ny, int nz, const Mask& M) {
+// t is a head; the sources c = t - o that merge_rows' phase 1 would join to it.  In-plane offsets: the source
+// has the head's z and must itself not be a head (the cell below it is in the mask).  +z partners: the source
+// sits one cell lower; the cell below t is outside the mask because t is a head, which is the !m_y / !m_x /
+// !m_xy of the forward rules.
+template <class Mask, class Union>
+__device__ __forceinline__ void merge_head_backward(int* parent, int t, int nx, int ny, int nz, const Mask& M, const Union& uf_union) {
   const int z = t % nz;
   const int row = t / nz;
   const int y = row % ny, x = row / ny;
   const int64_t sy = nz, sx = (int64_t)ny * nz;
-  // in-plane offsets: the source has the head's z >= 1 and must itself not be a head (the cell below it is in the mask)
-  if (z >= 1) {
-    if (y >= 1 && M(x, y - 1, z) && M(x, y - 1, z - 1)) uf_union(parent, (int)(t - sy), t);                 // (0, 1, 0)
-    if (x >= 1 && M(x - 1, y, z) && M(x - 1, y, z - 1) &&                                                  // (1, 0, 0): not when
-        !(y >= 1 && M(x - 1, y - 1, z) && M(x, y - 1, z)))                                                 // the x-edge one row down in y exists
-      uf_union(parent, (int)(t - sx), t);
-    if (x >= 1 && y >= 1 && M(x - 1, y - 1, z) && M(x - 1, y - 1, z - 1) && !M(x - 1, y, z) && !M(x, y - 1, z))   // (1, 1, 0)
-      uf_union(parent, (int)(t - sx - sy), t);
-  }
-  // +z partners: the source has z - 1 >= 1 (a source at z = 0 is a head); the cell below t is outside the mask
-  // because t is a head, which is the !m_y / !m_x / !m_xy of the forward rules
-  if (z >= 2) {
-    if (y >= 1 && M(x, y - 1, z - 1) && M(x, y - 1, z - 2) && !M(x, y - 1, z)) uf_union(parent, (int)(t - sy - 1), t);          // (0, 1, 1)
-    if (x >= 1 && M(x - 1, y, z - 1) && M(x - 1, y, z - 2) && !M(x - 1, y, z)) uf_union(parent, (int)(t - sx - 1), t);          // (1, 0, 1)
-    if (x >= 1 && y >= 1 && M(x - 1, y - 1, z - 1) && M(x - 1, y - 1, z - 2) && !M(x - 1, y - 1, z) && !M(x, y - 1, z - 1) &&
-        !M(x - 1, y, z - 1))                                                                                                   // (1, 1, 1)
-      uf_union(parent, (int)(t - sx - sy - 1), t);
-  }
+  const bool y0 = M(x, y - 1, z), y1 = M(x, y - 1, z - 1), y2 = M(x, y - 1, z - 2);
+  const bool x0 = M(x - 1, y, z), x1 = M(x - 1, y, z - 1), x2 = M(x - 1, y, z - 2);
+  const bool d0 = M(x - 1, y - 1, z), d1 = M(x - 1, y - 1, z - 1), d2 = M(x - 1, y - 1, z - 2);
+  if (y0 && y1) uf_union(parent, (int)(t - sy), t);                                   // (0, 1, 0)
+  if (x0 && x1 && !(d0 && y0)) uf_union(parent, (int)(t - sx), t);                    // (1, 0, 0): not when the x-edge one row down in y exists
+  if (d0 && d1 && !x0 && !y0) uf_union(parent, (int)(t - sx - sy), t);                // (1, 1, 0)
+  if (y1 && y2 && !y0) uf_union(parent, (int)(t - sy - 1), t);                        // (0, 1, 1)
+  if (x1 && x2 && !x0) uf_union(parent, (int)(t - sx - 1), t);                        // (1, 0, 1)
+  if (d1 && d2 && !d0 && !y1 && !x1) uf_union(parent, (int)(t - sx - sy - 1), t);     // (1, 1, 1)
 }
+
+
+// ---- union-find with randomised linking ------------------------------------------------------------------------
+// Linking the larger INDEX under the smaller (uf_union) makes the root the canonical minimum cell for free, but on
+// the regular structures of a solvent box -- thousands of row heads joined along y, planes joined along x -- it
+// builds chains hundreds of links long that every later find has to walk (70 us of dependent L2 round trips at
+// 201^3, whatever the number of rows).  Linking by a hashed priority instead (the root with the larger hash goes
+// under the other; the hash is a bijection, so the order is total and there are no cycles) gives trees of
+// logarithmic expected height.  The minimum cell of a component is then collected separately (it is always a run
+// head).  Links and path halving go through compare-and-swap: a link only ever replaces parent[a] == a.
+__device__ __forceinline__ uint32_t uf_prio(int i) {
+  uint32_t x = (uint32_t)i;
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ int uf_find_h(int* parent, int x) {
+  int p = ld_parent(parent, x);
+  while (p != x) {
+    const int gp = ld_parent(parent, p);
+    if (gp != p) atomicCAS(parent + x, p, gp);   // path halving; losing the race is harmless
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+struct UnionHashed {
+  __device__ __forceinline__ void operator()(int* parent, int a, int b) const {
+    while (true) {
+      a = uf_find_h(parent, a);
+      b = uf_find_h(parent, b);
+      if (a == b) return;
+      if (uf_prio(a) < uf_prio(b)) { const int t = a; a = b; b = t; }   // a: the larger priority value, goes under b
+      if (atomicCAS(parent + a, a, b) == a) return;
+    }
+  }
+};
+
+struct UnionMinIndex {
+  __device__ __forceinline__ void operator()(int* parent, int a, int b) const { uf_union(parent, a, b); }
+};
 
 }  // namespace hopb_ccl

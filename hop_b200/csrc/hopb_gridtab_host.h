@@ -39,6 +39,8 @@ static inline int hopb_build_gridtab(const double* const edges[3], const int n[3
   table->clear();
   if (table2) table2->clear();
   tab->fast_ok = 1;
+  tab->wrap = 0;
+  for (int d = 0; d < 3; ++d) { tab->box_o[d] = 0.0f; tab->box_l[d] = 0.0f; tab->box_inv[d] = 0.0f; }
   for (int d = 0; d < 3; ++d) {
     const int nb = n[d];
     if (nb < 1 || nb + 1 > HOPB_MAX_EDGES) return -1;

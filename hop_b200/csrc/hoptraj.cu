@@ -76,6 +76,7 @@ __device__ __forceinline__ int hop_bin(float x, const AxisReg& a) {
 template <bool FAST>
 __device__ __forceinline__ uint32_t pack_cell(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                               const AxisReg& ay, const AxisReg& az, const float* s_tab, int cny, int cnz) {
+  hopb_wrap_point(x, y, z, tab);
   int bx, by, bz;
   if (FAST) {
     bx = hop_bin(x, ax); by = hop_bin(y, ay); bz = hop_bin(z, az);

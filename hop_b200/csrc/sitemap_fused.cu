@@ -61,8 +61,9 @@ struct FusedArgs {
   int* parent_s; int* parent_b; int* size_s; int* size_b;
   uint8_t* rowflag;
   uint64_t* keys; uint32_t* vals; uint32_t cap;
-  uint32_t* counters;                 // [0] hydration roots, [1] bulk roots, [2..3] best bulk key (u64), [4] / [5] run heads
+  uint32_t* counters;                 // [0] hydration roots, [1] bulk roots, [2..3] best bulk key (u64), [4] / [5] run heads, [6] root of the bulk site
   int* heads_s; int* heads_b;         // run heads of the two masks (cell indices)
+  int* minidx_s; int* minidx_b;       // at roots: the minimum cell of the component (the canonical tie-break key)
   uint32_t* mask_s; uint32_t* mask_b; // the masks as bits, [rows][wpr] words (bit z & 31 of word z >> 5)
   int wpr;
   double* acc; double* kshift; int n_labels_cap;
@@ -106,7 +107,8 @@ __device__ __forceinline__ void stage_flush(HeadStage& st, int lane) {
 struct RunState { int carry, pend; };   // z of the head of the run reaching the previous chunk's last cell (or -1), its length so far
 
 __device__ __forceinline__ void link_chunk(unsigned bits, int z0, int lane, int64_t base, int* __restrict__ parent,
-                                           int* __restrict__ size, uint32_t* __restrict__ mask_word, RunState& rs, HeadStage& st) {
+                                           int* __restrict__ size, int* __restrict__ minidx, uint32_t* __restrict__ mask_word,
+                                           RunState& rs, HeadStage& st) {
   if (lane == 0) *mask_word = bits;
   if (bits == 0u) {
     if (rs.carry >= 0) {
@@ -127,7 +129,8 @@ __device__ __forceinline__ void link_chunk(unsigned bits, int z0, int lane, int6
   if (below == 0) start = rs.carry >= 0 ? rs.carry : z0;
   else start = z0 + (32 - __clz(below));
   if (m) parent[base + z] = (int)(base + start);      // cells outside the mask have no parent entry: see the mask bits
-  const bool head = m && start == z;
+  bool head = m && start == z;
+  if (head) minidx[base + z] = (int)(base + z);
   const unsigned hbits = __ballot_sync(kFull, head);
   if (hbits) {
     const int nh = __popc(hbits);
@@ -161,9 +164,12 @@ __device__ __forceinline__ uint32_t zero_nibbles(uint32_t x) {
 
 struct MaskBits {
   const uint32_t* w;
-  int ny, wpr;
+  int nx, ny, nz, wpr;
+  // false outside the grid, without a branch (the address is clamped, the answer masked)
   __device__ __forceinline__ bool operator()(int x, int y, int z) const {
-    return (w[((int64_t)x * ny + y) * wpr + (z >> 5)] >> (z & 31)) & 1u;
+    const bool in = ((unsigned)x < (unsigned)nx) & ((unsigned)y < (unsigned)ny) & ((unsigned)z < (unsigned)nz);
+    const int xs = in ? x : 0, ys = in ? y : 0, zs = in ? z : 0;
+    return in & (bool)((w[((int64_t)xs * ny + ys) * wpr + (zs >> 5)] >> (zs & 31)) & 1u);
   }
 };
 
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
   for (int64_t i = tid; i < (int64_t)a.n_labels_cap * kAcc; i += nth) a.acc[i] = 0.0;
   for (int64_t i = tid; i < a.coarse_words; i += nth) a.coarse[i] = 0u;
   if (tid < 4) a.counters[tid] = 0u;
+  if (tid == 0) a.counters[6] = 0xFFFFFFFFu;
   if (tid == 0 && a.fine) *reinterpret_cast<uint32_t*>(a.fine + 2 * a.nb_pad) = 0u;
   for (int64_t row = warp0; row < n_rows; row += nwarps) {
     const int j = (int)(row % ny);
@@ -239,11 +246,11 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
         const bool ok = zc + lane < nz;
         const unsigned bs = __ballot_sync(kFull, ok && (unsigned long long)c[u] >= cs_row[cz[u]]);
         any_s |= bs;
-        link_chunk(bs, zc, lane, base, a.parent_s, a.size_s, mrow_s + (zc >> 5), rs_s, st_s);
+        link_chunk(bs, zc, lane, base, a.parent_s, a.size_s, a.minidx_s, mrow_s + (zc >> 5), rs_s, st_s);
         if (bulk) {
           const unsigned bb = __ballot_sync(kFull, ok && (unsigned long long)c[u] >= cb_row[cz[u]]);
           any_b |= bb;
-          link_chunk(bb, zc, lane, base, a.parent_b, a.size_b, mrow_b + (zc >> 5), rs_b, st_b);
+          link_chunk(bb, zc, lane, base, a.parent_b, a.size_b, a.minidx_b, mrow_b + (zc >> 5), rs_b, st_b);
         }
       }
     }
@@ -260,71 +267,86 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
 
   // ---- P1 - P4: union-find over the run heads --------------------------------------------------------------
   const int64_t nh_s = a.counters[4], nh_b = bulk ? a.counters[5] : 0;
-  const MaskBits Ms{a.mask_s, ny, a.wpr}, Mb{a.mask_b, ny, a.wpr};
-  for (int64_t i = tid; i < nh_s; i += nth) hopb_ccl::merge_head_forward(a.parent_s, a.heads_s[i], nx, ny, nz, Ms);
-  for (int64_t i = tid; i < nh_b; i += nth) hopb_ccl::merge_head_forward(a.parent_b, a.heads_b[i], nx, ny, nz, Mb);
+  const MaskBits Ms{a.mask_s, nx, ny, nz, a.wpr}, Mb{a.mask_b, nx, ny, nz, a.wpr};
+  const hopb_ccl::UnionHashed UF;
+  auto list_heads = [&](const int* list, int64_t nh, auto&& f) {
+    for (int64_t i = tid; i < nh; i += nth) f(list[i]);
+  };
+  list_heads(a.heads_s, nh_s, [&](int hd) { hopb_ccl::merge_head_forward(a.parent_s, hd, nx, ny, nz, Ms, UF); });
+  list_heads(a.heads_b, nh_b, [&](int hd) { hopb_ccl::merge_head_forward(a.parent_b, hd, nx, ny, nz, Mb, UF); });
   grid.sync();
   stamp(a, 2);
-  for (int64_t i = tid; i < nh_s; i += nth) { const int hd = a.heads_s[i]; a.parent_s[hd] = hopb_ccl::uf_find(a.parent_s, hd); }
-  for (int64_t i = tid; i < nh_b; i += nth) { const int hd = a.heads_b[i]; a.parent_b[hd] = hopb_ccl::uf_find(a.parent_b, hd); }
+  {
+    auto flat_s = [&](int hd) { a.parent_s[hd] = hopb_ccl::uf_find_h(a.parent_s, hd); };
+    auto flat_b = [&](int hd) { a.parent_b[hd] = hopb_ccl::uf_find_h(a.parent_b, hd); };
+    list_heads(a.heads_s, nh_s, flat_s);
+    if (bulk) { list_heads(a.heads_b, nh_b, flat_b); }
+  }
   grid.sync();
   stamp(a, 3);
-  for (int64_t i = tid; i < nh_s; i += nth) hopb_ccl::merge_head_backward(a.parent_s, a.heads_s[i], nx, ny, nz, Ms);
-  for (int64_t i = tid; i < nh_b; i += nth) hopb_ccl::merge_head_backward(a.parent_b, a.heads_b[i], nx, ny, nz, Mb);
+  {
+    auto back_s = [&](int hd) { hopb_ccl::merge_head_backward(a.parent_s, hd, nx, ny, nz, Ms, UF); };
+    auto back_b = [&](int hd) { hopb_ccl::merge_head_backward(a.parent_b, hd, nx, ny, nz, Mb, UF); };
+    list_heads(a.heads_s, nh_s, back_s);
+    if (bulk) { list_heads(a.heads_b, nh_b, back_b); }
+  }
   grid.sync();
   stamp(a, 4);
   // heads find their final roots; a head that is not a root hands its run length to the root (only roots
   // receive additions, and a root's own entry already holds its own run).  One giant component would make
   // that hundreds of thousands of atomics on one address, so every thread keeps a running (root, sum) and the
   // lanes of a warp that ended on the same root add once.
-  auto sizes = [&](int* parent, int* size, const int* heads, int64_t nh) {
-    int run_root = -1, run_sum = 0;
-    for (int64_t i = tid; i < nh; i += nth) {
-      const int hd = heads[i];
-      const int r = hopb_ccl::uf_find(parent, hd);
+  auto sizes = [&](int* parent, int* size, int* minidx, const int* heads, int64_t nh) {
+    int run_root = -1, run_sum = 0, run_min = 0x7fffffff;
+    auto one = [&](int hd) {
+      const int r = hopb_ccl::uf_find_h(parent, hd);
       parent[hd] = r;
-      if (r == hd) continue;
+      if (r == hd) return;
       const int len = size[hd];
-      if (r == run_root) run_sum += len;
+      if (r == run_root) { run_sum += len; run_min = hd < run_min ? hd : run_min; }
       else {
-        if (run_root >= 0) atomicAdd(size + run_root, run_sum);
-        run_root = r; run_sum = len;
+        if (run_root >= 0) { atomicAdd(size + run_root, run_sum); atomicMin(minidx + run_root, run_min); }
+        run_root = r; run_sum = len; run_min = hd;
       }
-    }
+    };
+    list_heads(heads, nh, one);
     const unsigned peers = __match_any_sync(kFull, run_root);
-    int tot = 0;
-    for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(peers, run_sum, __ffs(m) - 1);
-    if (run_root >= 0 && (peers & ((1u << lane) - 1)) == 0) atomicAdd(size + run_root, tot);
+    int tot = 0, mn = 0x7fffffff;
+    for (unsigned m = peers; m; m &= m - 1) {
+      tot += __shfl_sync(peers, run_sum, __ffs(m) - 1);
+      const int o = __shfl_sync(peers, run_min, __ffs(m) - 1);
+      mn = o < mn ? o : mn;
+    }
+    if (run_root >= 0 && (peers & ((1u << lane) - 1)) == 0) { atomicAdd(size + run_root, tot); atomicMin(minidx + run_root, mn); }
   };
-  sizes(a.parent_s, a.size_s, a.heads_s, nh_s);
-  if (bulk) sizes(a.parent_b, a.size_b, a.heads_b, nh_b);
+  sizes(a.parent_s, a.size_s, a.minidx_s, a.heads_s, nh_s);
+  if (bulk) sizes(a.parent_b, a.size_b, a.minidx_b, a.heads_b, nh_b);
   grid.sync();
   stamp(a, 5);
 
   // ---- P5: roots -----------------------------------------------------------------------------------------
   unsigned long long* best_bulk = reinterpret_cast<unsigned long long*>(a.counters + 2);
-  for (int64_t i = tid; i < nh_s; i += nth) {
-    const int c = a.heads_s[i];
-    if (a.parent_s[c] != c) continue;
-    const int sz = a.size_s[c];
-    if (sz < a.minsite) a.size_s[c] = 0;
-    else {
+  {
+    auto root_s = [&](int c) {
+      if (a.parent_s[c] != c) return;
+      const int sz = a.size_s[c];
+      if (sz < a.minsite) { a.size_s[c] = 0; return; }
       const uint32_t slot = atomicAdd(a.counters + 0, 1u);
       if (slot < a.cap) {
-        a.keys[slot] = ((uint64_t)(uint32_t)(n_cells - sz) << 32) | (uint32_t)(n_cells - 1 - c);
+        a.keys[slot] = ((uint64_t)(uint32_t)(n_cells - sz) << 32) | (uint32_t)(n_cells - 1 - a.minidx_s[c]);
         a.vals[slot] = (uint32_t)c;
       }
-    }
-  }
-  for (int64_t i = tid; i < nh_b; i += nth) {
-    const int c = a.heads_b[i];
-    if (a.parent_b[c] != c) continue;
-    const int sz = a.size_b[c];
-    if (sz >= a.minsite) {
+    };
+    auto root_b = [&](int c) {
+      if (a.parent_b[c] != c) return;
+      const int sz = a.size_b[c];
+      if (sz < a.minsite) return;
       atomicAdd(a.counters + 1, 1u);
-      // label 1 of the bulk map: the largest component, ties to the larger root index
-      atomicMax(best_bulk, ((unsigned long long)(uint32_t)sz << 32) | (uint32_t)c);
-    }
+      // label 1 of the bulk map: the largest component, ties to the larger minimum cell
+      atomicMax(best_bulk, ((unsigned long long)(uint32_t)sz << 32) | (uint32_t)a.minidx_b[c]);
+    };
+    list_heads(a.heads_s, nh_s, root_s);
+    if (bulk) { list_heads(a.heads_b, nh_b, root_b); }
   }
   grid.sync();
   stamp(a, 6);
@@ -349,20 +371,29 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
         if (a.p_count && rank + 1 + shift < a.n_labels_cap) a.kshift[rank + 1 + shift] = a.density[root];
       }
     }
+    if (bulk && *best_bulk) {     // which root is it: the one whose (size, minimum cell) won
+      const unsigned long long bb = *best_bulk;
+      auto match = [&](int c) {
+        if (a.parent_b[c] == c && (((unsigned long long)(uint32_t)a.size_b[c] << 32) | (uint32_t)a.minidx_b[c]) == bb) {
+          a.counters[6] = (uint32_t)c;
+          a.kshift[1] = a.density[c];
+        }
+      };
+      list_heads(a.heads_b, nh_b, match);
+    }
     if (tid == 0) {
       a.n_sites_dev[0] = (int32_t)n_all;
       a.n_sites_dev[1] = (int32_t)a.counters[1];
       if (a.volumes) a.volumes[0] = 0;
       a.kshift[0] = 0.0;
-      if (bulk) a.kshift[1] = *best_bulk ? a.density[(uint32_t)(*best_bulk & 0xFFFFFFFFull)] : 0.0;
+      if (!(bulk && *best_bulk)) a.kshift[1] = 0.0;
     }
   }
   grid.sync();
   stamp(a, 7);
 
   // ---- P7: paint -------------------------------------------------------------------------------------------
-  const unsigned long long bb = *best_bulk;
-  const int bulk_root = (bulk && bb) ? (int)(uint32_t)(bb & 0xFFFFFFFFull) : -1;
+  const int bulk_root = bulk ? (int)a.counters[6] : -1;      // 0xFFFFFFFF = -1: no bulk site
   const int cnx = (nx + 3) >> 2, cny = (ny + 3) >> 2, cnz = (nz + 3) >> 2;
   const int nzp = cnz * 4;
   int16_t* tile = reinterpret_cast<int16_t*>(smem_raw);          // [16][nzp]
@@ -571,7 +602,7 @@ int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const 
   // + the two run-head lists: a row holds at most ceil(nz / 2) runs
   const int64_t head_cap = n_rows * ((nz + 1) / 2);
   const int wpr = (nz + 31) / 32;
-  rc = hopb_scratch(h, 13, ((size_t)n_cells * 4 + (size_t)head_cap * 2 + (size_t)n_rows * wpr * 2) * sizeof(int) + (size_t)n_rows + 16,
+  rc = hopb_scratch(h, 13, ((size_t)n_cells * 6 + (size_t)head_cap * 2 + (size_t)n_rows * wpr * 2) * sizeof(int) + (size_t)n_rows + 16,
                     (void**)&parent_s);
   if (rc) return rc;
   const uint32_t cap = HOPB_MAX_SITES + 1;
@@ -591,7 +622,8 @@ int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const 
   a.n_frames = (double)n_frames; a.factor = factor; a.apply_factor = factor != 1.0 ? 1 : 0;
   a.minsite = minsite; a.with_bulk = with_bulk ? 1 : 0;
   a.parent_s = parent_s; a.parent_b = parent_s + n_cells; a.size_s = parent_s + 2 * n_cells; a.size_b = parent_s + 3 * n_cells;
-  a.heads_s = parent_s + 4 * n_cells; a.heads_b = a.heads_s + head_cap;
+  a.minidx_s = parent_s + 4 * n_cells; a.minidx_b = parent_s + 5 * n_cells;
+  a.heads_s = parent_s + 6 * n_cells; a.heads_b = a.heads_s + head_cap;
   a.mask_s = reinterpret_cast<uint32_t*>(a.heads_b + head_cap); a.mask_b = a.mask_s + n_rows * wpr; a.wpr = wpr;
   a.rowflag = reinterpret_cast<uint8_t*>(a.mask_b + n_rows * wpr);
   a.keys = reinterpret_cast<uint64_t*>(misc);

@@ -75,6 +75,8 @@ class TransportNetwork(object):
                 return int(n)
         except AttributeError:
             pass
+        if hx is None:        # the caller fetches the label plane and asks again
+            return None
         return int(hx.max().item()) + 1
 
     def graph_alltransitions(self):

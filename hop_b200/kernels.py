@@ -61,6 +61,19 @@ class GridTables:
     def ptr(self):
         return self._grid
 
+    def set_periodic_box(self, origin=None, length=None):
+        """Wrap every coordinate into [origin, origin + length) before it is binned (stages 1 and 3).  Off by
+        default -- hop never wraps (hop/density.py:21-28) -- and switched off again with no arguments."""
+        if origin is None or length is None:
+            rc = _lib.lib().hopb_grid_set_periodic_box(self._grid, None, None)
+            self.periodic_box = None
+        else:
+            o = np.ascontiguousarray(origin, dtype=np.float64).reshape(3)
+            l = np.ascontiguousarray(length, dtype=np.float64).reshape(3)
+            rc = _lib.lib().hopb_grid_set_periodic_box(self._grid, o.ctypes.data, l.ctypes.data)
+            self.periodic_box = (o, l)
+        _lib.check(self._handle, rc)
+
     def __del__(self):
         try:
             if getattr(self, "_grid", None):

@@ -42,6 +42,7 @@ class PipelineConfig:
     async_results: bool = True       # from the second run on: no host synchronisation inside run()
     label_from_counts: bool = True   # threshold the counts instead of the density (identical labels)
     fused_site_map: bool = True      # stage 2 as one cooperative launch (hopb_site_map_fused) where the grid allows
+    periodic_box: tuple | None = None  # (origin[3], length[3]): wrap coordinates before binning; None = hop's behaviour
 
 
 class PipelineResult(object):
@@ -143,6 +144,8 @@ class HopPipeline:
         self.cfg = config or PipelineConfig()
         self.lane_base = int(lane_base)   # handles (scratch memory) of its own: see PipelinePair
         self.grid = K.GridTables(edges, device=device)
+        if self.cfg.periodic_box is not None:
+            self.grid.set_periodic_box(*self.cfg.periodic_box)
         self.n_frames_total = int(n_frames_total)
         self.device = self.grid.device
         self._events = None

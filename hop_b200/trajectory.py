@@ -320,7 +320,9 @@ class HoppingTrajectory(object):
 
     def write(self, filename, start=None, step=None, delta=None, load=True):
         """Write hopping trajectory as standard dcd file, together with a minimal psf
-        (hop/trajectory.py:255-297)."""
+        (hop/trajectory.py:255-297).  start, step and delta are accepted and ignored exactly as in the
+        reference, whose docstring says so (hop/trajectory.py:264-266: "Ignore the other options and leave
+        them at the defaults. Currently, only the whole trajectory is written") and whose body never reads them."""
         psfname = self.filename(filename, 'psf')
         dcdname = self.filename(filename, 'dcd')
         x, y = self.hop_arrays()

@@ -94,22 +94,28 @@ class Saveable(object):
         if kwargs['filename'] is not None:
             self.load(kwargs['filename'], 'pickle')
 
+    # The pickle SCHEMA is the contract with hop (a dict of the attributes named in _saved_attributes, or of
+    # everything outside _excluded_attributes for 'all'; hop/utilities.py:154-261); files written by either
+    # package load in the other.
+
+    def _attribute_names(self, available):
+        """The attribute names that take part in save / load, given the names that exist."""
+        if self._saved_attributes == 'all':
+            return [name for name in available if name not in self._excluded_attributes]
+        return list(self._saved_attributes)
+
     def __getstate__(self):
         if not self._saved_attributes:
             warnings.warn("No data saved: the class declared empty '_saved_attributes'.")
             return False
-        data = {}
-        if self._saved_attributes == 'all':
-            saved_attributes = [x for x in self.__dict__.keys() if x not in self._excluded_attributes]
-        else:
-            saved_attributes = self._saved_attributes
-        for attr in saved_attributes:
+        state = {}
+        for name in self._attribute_names(self.__dict__.keys()):
             try:
-                data[attr] = self._get_saved_attribute(attr)
+                state[name] = self._get_saved_attribute(name)
             except (KeyError, AttributeError):
-                warnings.warn("Attribute '" + attr + "' has not been computed and will not be saved.",
+                warnings.warn("Attribute '%s' has not been computed and will not be saved." % name,
                               category=MissingDataWarning)
-        return data
+        return state
 
     def _get_saved_attribute(self, attr):
         return self.__dict__[attr]
@@ -121,42 +127,38 @@ class Saveable(object):
 
     def save(self, filename=None):
         """Save class to a pickled file."""
-        with open(self.filename(filename, 'pickle', set_default=True), 'wb') as fh:
+        target = self.filename(filename, 'pickle', set_default=True)
+        with open(target, 'wb') as fh:
             pickle.dump(self, fh, pickle.HIGHEST_PROTOCOL)
 
     def load(self, filename=None, merge=False):
         """Reinstantiate class from a pickled file (produced with save())."""
-        with open(self.filename(filename, 'pickle', set_default=True), 'rb') as fh:
-            tmp = load_pickle(fh)
-        try:
+        source = self.filename(filename, 'pickle', set_default=True)
+        with open(source, 'rb') as fh:
+            stored = load_pickle(fh)
+        if isinstance(stored, Saveable):
             # attributes may live behind properties (device mirrors): ask the object, not its __dict__
-            data = tmp.__getstate__() if isinstance(tmp, Saveable) else tmp.__dict__
-        except AttributeError:
+            data = stored.__getstate__()
+        elif hasattr(stored, '__dict__'):
+            data = stored.__dict__
+        else:
+            # a bare dict from the time before hop pickled instances; 'parameters' was renamed to 'P'
             warnings.warn("Loading an old-style save file.", category=DeprecationWarning)
-            data = tmp
-            try:
+            data = stored
+            if 'parameters' in data:
                 data['P'] = data['parameters']
-            except KeyError:
-                pass
-        del tmp
         if not self._saved_attributes:
             warnings.warn("No data loaded: the object declared empty '_saved_attributes'.",
                           category=MissingDataWarning)
             return False
-        if self._saved_attributes == 'all':
-            saved_attributes = [x for x in data.keys() if x not in self._excluded_attributes]
-        else:
-            saved_attributes = self._saved_attributes
-        for attr in saved_attributes:
-            try:
-                if merge and attr in self._merge_attributes:
-                    self.__dict__[attr].update(data[attr])
-                else:
-                    self._set_loaded_attribute(attr, data[attr])
-            except KeyError:
-                warnings.warn("Expected attribute '" + attr + "' was not found in saved file '" + str(filename) + "'.",
+        for name in self._attribute_names(data.keys()):
+            if name not in data:
+                warnings.warn("Expected attribute '%s' was not found in saved file '%s'." % (name, filename),
                               category=MissingDataWarning)
-        del data
+            elif merge and name in self._merge_attributes:
+                self.__dict__[name].update(data[name])       # dict-valued attributes only
+            else:
+                self._set_loaded_attribute(name, data[name])
         return True
 
     def _set_loaded_attribute(self, attr, value):

@@ -152,6 +152,15 @@ int hopb_label_sites_counts_async(hopb_handle* h, void* stream, const hopb_grid*
                                   int64_t n_frames, double factor, double threshold, int minsite,
                                   int32_t* labels, int32_t* n_sites_dev, int32_t* volumes);
 
+/* Optional periodic wrapping in front of every binning that uses this grid (stage 1 and stage 3): each
+ * coordinate is replaced by its image in [origin, origin + length) -- x - floor((x - o) * (1 / l)) * l in float32,
+ * every step rounded separately -- before the bin search.  OFF BY DEFAULT, and hop itself never wraps: it bins
+ * AtomGroup.positions as they are and asks for trajectories that were centred and wrapped beforehand
+ * (hop/density.py:21-28; no minimum image in the neighbour graph either, hop/sitemap.py:1521-1525), so a drop-in
+ * run leaves this off and the results are those of the reference bit for bit.  origin, length: host double[3];
+ * NULL for either switches wrapping off again. */
+int hopb_grid_set_periodic_box(hopb_grid* g, const double* origin, const double* length);
+
 /* Number of distinct (dx, dy, dz) bin-width triples of the grid, or 0 when an axis has more than 16
  * distinct widths (irregular edges): then only the density-based labelling is available. */
 int hopb_grid_width_classes(const hopb_grid* g);

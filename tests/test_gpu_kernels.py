@@ -684,6 +684,49 @@ def test_label_from_counts_equals_label_from_density(K):
                                    torch.empty(g.shape, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
 
 
+def test_periodic_wrap_is_off_by_default_and_exact_when_on(K, traj):
+    """The optional periodic wrapping (north_star kernel 1; hop itself never wraps, hop/density.py:21-28):
+    off -- the default, also after switching it on and off again -- the results are bit-identical to a grid
+    that never heard of it; on, atoms displaced by whole box vectors are binned (stage 1) and assigned
+    (stage 3) exactly like their images x - floor((x - o) / L) * L evaluated in float32 by numpy."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig
+
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=1.0)
+    rng = np.random.default_rng(5)
+    L = np.float32(p.box)
+    origin = np.zeros(3, np.float32)
+    shift = rng.integers(-3, 4, xyz.shape).astype(np.float32) * L
+    moved = (xyz + shift).astype(np.float32)
+    inv = np.float32(1.0) / L
+    image = (moved - np.floor((moved - origin) * inv) * L).astype(np.float32)      # float32 throughout, like the kernel
+
+    def run(coords, box):
+        pipe = HopPipeline(edges, coords.shape[0], PipelineConfig(periodic_box=box, async_results=False))
+        r = pipe.run(dev(coords))
+        return (r.counts.clone(), r.map16.clone(), r.hop_x.clone(), r.hop_y.clone(), r.events.clone()), pipe
+
+    plain, pipe = run(xyz, None)
+    # on and off again: still the plain result
+    pipe.grid.set_periodic_box(origin, [L, L, L])
+    pipe.grid.set_periodic_box()
+    again = pipe.run(dev(xyz))
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(plain, (again.counts, again.map16, again.hop_x, again.hop_y, again.events)))
+    # the displaced atoms without wrapping are mostly outliers ...
+    lost, _ = run(moved, None)
+    assert int(lost[0].sum().item()) < int(plain[0].sum().item())
+    # ... with wrapping they are their images, bit for bit, in both the cached-cell and the coordinate path of stage 3
+    want, _ = run(image, None)
+    got, wpipe = run(moved, ([0.0, 0.0, 0.0], [float(L)] * 3))
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(want, got))
+    assert np.array_equal(got[0].cpu().numpy().astype(np.int64), O.histogram_vectorised(image, edges))
+    wpipe.cfg.cache_cells = False
+    r = wpipe.run(dev(moved))
+    assert torch.equal(r.hop_x, want[2]) and torch.equal(r.hop_y, want[3]) and torch.equal(r.events, want[4])
+
+
 @pytest.mark.parametrize("shape", [(24, 17, 31), (40, 40, 40), (9, 5, 130), (4, 4, 4), (3, 2, 1), (1, 1, 70), (33, 34, 35)])
 @pytest.mark.parametrize("with_bulk,minsite", [(True, 1), (False, 1), (True, 2)])
 def test_fused_site_map_equals_the_kernel_chain(K, shape, with_bulk, minsite):
