@@ -317,6 +317,44 @@ def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, 
     return count, mean, std, center
 
 
+def site_occupancy(labels: torch.Tensor, n_labels: int, out=None):
+    """occ int32 [F][n_labels]: atoms per site and frame (hop/siteanalysis.py:837-841); labels = a hoptraj plane."""
+    _cuda(labels, torch.float32, "labels")
+    F, N = labels.shape
+    if out is None:
+        out = torch.empty((F, n_labels), dtype=torch.int32, device=labels.device)
+    h = _h(labels)
+    _lib.check(h, _lib.lib().hopb_site_occupancy(h, _stream(), _p(labels), int(F), int(N), int(n_labels), _p(out)))
+    return out
+
+
+def site_distance_hist(xyz: torch.Tensor, labels: torch.Tensor, centers: torch.Tensor, site2indx: torch.Tensor, edges: torch.Tensor,
+                       n_rows: int, hist: torch.Tensor, start=0, stop=None, step=1, atom_map=None):
+    """hist[row][bin] += per-frame (site, bin) hits of the atom-to-site-centre distance (hop/siteanalysis.py:753-776,
+    531-544); see hopb_site_distance_hist for the reference behaviours it keeps."""
+    _cuda(xyz, torch.float32, "xyz")
+    _cuda(labels, torch.float32, "labels")
+    _cuda(centers, torch.float64, "centers")
+    _cuda(site2indx, torch.int32, "site2indx")
+    _cuda(edges, torch.float64, "edges")
+    _cuda(hist, torch.int64, "hist")
+    F, N = int(xyz.shape[0]), int(xyz.shape[1])
+    if labels.shape[0] != F:
+        raise ValueError("Data trajectory and hopping trajectory differ in length: %d vs %d frames" % (F, labels.shape[0]))
+    if atom_map is not None:
+        _cuda(atom_map, torch.int32, "atom_map")
+    stop = F if stop is None else int(stop)
+    n_bins = int(edges.numel()) - 1
+    if tuple(hist.shape) != (int(n_rows), n_bins + 2):
+        raise ValueError("hist must have shape (n_rows, n_bins + 2)")
+    h = _h(xyz)
+    rc = _lib.lib().hopb_site_distance_hist(h, _stream(), _p(xyz), _p(labels), _p(atom_map), N, int(labels.shape[1]), int(start),
+                                            stop, int(step), _p(centers), _p(site2indx), int(centers.shape[0]), _p(edges),
+                                            n_bins, int(n_rows), _p(hist))
+    _lib.check(h, rc)
+    return hist
+
+
 def site_cells(own: torch.Tensor, member, n_labels: int):
     """CSR cell lists: (cells int32[M], offsets int64[n_labels+1])."""
     _cuda(own, torch.int32, "own")

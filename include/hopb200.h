@@ -223,6 +223,33 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
                     const uint8_t* member, int n_labels, int32_t* cells, int64_t capacity,
                     int64_t* offsets, int64_t* n_cells);
 
+/* ---- per-site observables (hop.siteanalysis) ------------------------------ */
+/* Atoms per site and frame: occ[f][l] = number of atoms whose label in frame f is l (outliers, -1, are not
+ * counted) -- the per-frame numpy.histogram of Occupancy._compute_occupancy (hop/siteanalysis.py:837-841),
+ * from the x plane of the hoptraj (occupancy) or its y plane (orbit occupancy, :860-861).
+ *   labels device float32 [F][N]; occ device int32 [F][n_labels] out */
+int hopb_site_occupancy(hopb_handle* h, void* stream, const float* labels, int64_t F, int64_t N, int n_labels,
+                        int32_t* occ);
+
+/* Distance of every selected atom from the centre of the site it is on, histogrammed per site: what
+ * Distance._compute_distance + SiteHistogramArray.add do per frame (hop/siteanalysis.py:753-776, 531-544),
+ * including that a (site, bin) pair hit by several atoms of one frame counts once for that frame, that the
+ * outlier label -1 reads the last site's centre and row (Python negative index), and that NaN distances
+ * (interstitial: centre NaN) fall into the upper outlier bin.
+ *   xyz        device float32 [n_frames_total][N][3], coordinates of the selected atoms
+ *   labels     device float32 [n_frames_total][N_hop], hoptraj x (Distance) or y (Orbit)
+ *   atom_map   device int32 [N] hoptraj column of every selected atom (idcd2ihop), or NULL for identity
+ *   frames     frame_start, frame_start + frame_step, ... < frame_stop
+ *   centers    device double [n_labels][3] (site_properties.center, NaN for the interstitial)
+ *   site2indx  device int32 [n_labels]: row of every label in hist; n_rows - 1 for sites not collected
+ *   edges      device double [n_bins + 1]; hist device uint64 [n_rows][n_bins + 2], += (column 0 / n_bins + 1:
+ *              below / above the range) */
+int hopb_site_distance_hist(hopb_handle* h, void* stream, const float* xyz, const float* labels,
+                            const int32_t* atom_map, int64_t N, int64_t N_hop, int64_t frame_start,
+                            int64_t frame_stop, int64_t frame_step, const double* centers,
+                            const int32_t* site2indx, int n_labels, const double* edges, int n_bins, int n_rows,
+                            uint64_t* hist);
+
 /* ---- stage 3 + 4: hopping trajectory and transition scan ------------------------------------ */
 /* HoppingTrajectory._coord2hop (hop/trajectory.py:403-468) fused with the per-atom state machine
  * of TransportNetwork._analyze_hops (hop/graph.py:212-254) over one slab of F frames.

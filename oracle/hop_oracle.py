@@ -623,3 +623,44 @@ def pipeline(xyz, delta=1.0, padding=2.0, solvent_threshold=math.e, bulk_thresho
         props = None
     return dict(edges=edges, counts=np.asarray(counts), grid=grid, sites=sites, map=site_map,
                 hop=hop, events=events, nodes=nodes, props=props)
+
+
+# -------------------------------------------------------------------------------------------------
+# Per-site observables (hop/siteanalysis.py) -- SURVEY.md 8f rank 3
+# -------------------------------------------------------------------------------------------------
+def site_histogram_edges(lo_bin, hi_bin, n_bins):
+    """SiteHistogramArray.__init__ (hop/siteanalysis.py:503-507): bins = linspace(lo, hi, Nbins, endpoint=False), one
+    more edge appended at the same spacing."""
+    bins = np.linspace(lo_bin, hi_bin, n_bins, endpoint=False)
+    return np.concatenate((bins, [2 * bins[-1] - bins[-2]]))
+
+
+def site_distance_histogram(xyz, labels, centers, site2indx, edges, start=0, stop=None, step=1):
+    """Distance._compute_distance + SiteHistogramArray.add, frame by frame as the reference does it
+    (hop/siteanalysis.py:753-776, 531-544).  xyz [F][N][3] float32, labels [F][N] (hoptraj x or y, integral),
+    centers [L][3] float64 with NaN for the interstitial, site2indx [L] -> row.  The label indexes the arrays
+    directly (so -1 reads the last entries), numpy.digitize sends NaN to the top, and the fancy-index `+= 1`
+    counts a (row, bin) pair once per frame.  Returns _histogram [max(site2indx) + 1][len(edges) + 1]."""
+    F = xyz.shape[0]
+    stop = F if stop is None else stop
+    centers = np.asarray(centers, dtype=np.float64)
+    site2indx = np.asarray(site2indx)
+    hist = np.zeros((int(site2indx.max()) + 1, len(edges) + 1), dtype=np.int64)
+    for f in range(start, stop, step):
+        sites = np.asarray(labels[f]).astype(int)
+        distvec = centers[sites] - xyz[f]
+        dist = np.sqrt(np.sum(distvec * distvec, axis=1))
+        bins = [np.digitize([x], edges)[0] for x in dist]
+        hist[site2indx[sites], bins] += 1
+    return hist
+
+
+def site_occupancy(labels, n_labels):
+    """Atoms per site and frame: numpy.histogram of the frame's labels with unit bins
+    (Occupancy._compute_occupancy, hop/siteanalysis.py:821-841); outliers (-1) fall outside."""
+    labels = np.asarray(labels).astype(np.int64)
+    occ = np.zeros((labels.shape[0], n_labels), dtype=np.int64)
+    for f in range(labels.shape[0]):
+        l = labels[f]
+        occ[f] = np.bincount(l[l >= 0], minlength=n_labels)[:n_labels]
+    return occ

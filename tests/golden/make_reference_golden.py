@@ -261,6 +261,66 @@ def synth(n_atoms, n_frames, seed=None):
     return generate(p)
 
 
+def siteanalysis_golden(name, xyz, delta=1.0):
+    """hop.siteanalysis.Collection with the Distance and Orbit observables (hop/siteanalysis.py:722-802, 866-1107)
+    on a trajectory with outliers.  compute() stops one frame short of the end: its frame iterator advances both
+    readers once more after the last frame and relies on the IOError old MDAnalysis readers raised there (:1173-1183).
+    Also records that the Occupancy observable cannot run (see tests/test_reference_golden.py)."""
+    hop = R.load_reference()
+    SA = R.load_siteanalysis()
+    n = xyz.shape[1]
+    u = R.FakeUniverse(xyz, selections={"name OH2": np.arange(n)})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        density = hop.density.DensityCreator(u, mode="solvent", delta=delta, atomselection="name OH2", padding=2.0).create()["solvent"]
+        bulk = hop.sitemap.Density(grid=density.grid.copy(), edges=[e.copy() for e in density.edges],
+                                   parameters={"isDensity": True}, unit={"length": "Angstrom", "density": "Angstrom^{-3}"})
+        density.convert_density("water")
+        density.map_sites(math.e)
+        bulk.convert_density("water")
+        bulk.map_sites(math.exp(-0.5))
+        density.site_insert_bulk(bulk)
+        group = u.select_atoms("name OH2")
+        u.trajectory.rewind()
+        ht = hop.trajectory.HoppingTrajectory(u.trajectory, group, density, verbosity=0)
+        with tempfile.TemporaryDirectory() as tmp:
+            ht.write(os.path.join(tmp, "refhop"))
+            hopframes = R.FakeUniverse._files[os.path.join(tmp, "refhop") + ".dcd"].xyz.copy()
+        ht.group = R.LegacySelection(ht.group)
+        u.trajectory.rewind()
+        out = {}
+        for tag, kw in (("default", {}), ("with_bulk", {"exclude_sites": ["default"]})):
+            C = SA.Collection(selection=R.LegacySelection(group), hoptraj=ht, density=density, **kw)
+            C.add_observable("distance", lo_bin=0, hi_bin=3)
+            C.add_observable("orbit", lo_bin=0, hi_bin=6, Nbins=24)
+            u.trajectory.rewind()
+            C.compute(stop=xyz.shape[0] - 1)
+            for obs in ("distance", "orbit"):
+                H = C.SiteHistograms[obs]
+                out["%s_%s_histogram" % (tag, obs)] = np.asarray(H._histogram, dtype=np.int64)
+                out["%s_%s_edges" % (tag, obs)] = np.asarray(H.edges, dtype=np.float64)
+                out["%s_%s_distribution" % (tag, obs)] = np.asarray(H.distribution, dtype=np.float64)
+                out["%s_%s_mean" % (tag, obs)] = np.asarray(H.mean(), dtype=np.float64)
+            out["%s_sites" % tag] = np.asarray(C.siteselection, dtype=np.int64)
+        C = SA.Collection(selection=R.LegacySelection(group), hoptraj=ht, density=density)
+        C.add_observable("occupancy", lo_bin=0, hi_bin=5)
+        try:
+            u.trajectory.rewind()
+            C.compute(stop=xyz.shape[0] - 1)
+            out["occupancy_error"] = np.array("")
+        except Exception as exc:                                   # noqa: BLE001 - record what hop raises
+            out["occupancy_error"] = np.array("%s: %s" % (type(exc).__name__, exc))
+    os.makedirs(os.path.join(OUT, "siteanalysis"), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "siteanalysis", name + ".npz"), xyz=xyz, delta=delta, stop=xyz.shape[0] - 1,
+                        map=np.asarray(density.map), hop_x=hopframes[:, :, 0].astype(np.int16),
+                        hop_y=hopframes[:, :, 1].astype(np.int16),
+                        site_center=np.array([np.full(3, np.nan) if (c is None or np.ndim(c) == 0) else np.asarray(c, float)
+                                              for c in density.site_properties.center]), **out)
+    print("%-16s sites %d  distance counts %d  orbit counts %d  occupancy: %s" % (
+        name, len(density.site_properties) - 1, int(out["default_distance_histogram"].sum()),
+        int(out["default_orbit_histogram"].sum()), str(out["occupancy_error"])[:70]))
+
+
 def main():
     water = 1.0 / (1e-24 * 6.02214179e+23 * 0.997 / 18.016)      # Angstrom^-3 -> 'water' units
     # 1. clean box, thresholds in Angstrom^-3 (no unit table involved)
@@ -301,3 +361,8 @@ def main():
 if __name__ == "__main__":
     main()
     sitemap_variants("variants_clean", synth(300, 60), 1.0, "water")
+    xyz = synth(300, 60)
+    m = np.random.default_rng(3).random(xyz.shape[:2]) < 0.02
+    m[0, :] = False
+    xyz[m] += np.float32(50.0)
+    siteanalysis_golden("siteanalysis", xyz)

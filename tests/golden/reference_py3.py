@@ -404,3 +404,50 @@ def load_reference():
         setattr(pkg, name, mod)
         exec(compile_module(name, mod.__file__), mod.__dict__)
     return pkg
+
+
+def load_siteanalysis():
+    """hop.siteanalysis of the reference, compiled like the other modules.  Two things it expects from its
+    surroundings are supplied here: `hop.MissingDataError` (the package __init__, which is not executed, exports
+    it) and `numpy.NaN` (removed in numpy 2; an alias of numpy.nan)."""
+    hop = load_reference()
+    if hasattr(hop, "siteanalysis"):
+        return hop.siteanalysis
+    hop.MissingDataError = hop.exceptions.MissingDataError
+    if not hasattr(numpy, "NaN"):
+        numpy.NaN = numpy.nan
+    name = "siteanalysis"
+    mod = types.ModuleType("hop." + name)
+    mod.__file__ = os.path.join(REFERENCE_ROOT, "hop", name + ".py")
+    mod.__package__ = "hop"
+    mod.__dict__.update(_py2_globals())
+    sys.modules["hop." + name] = mod
+    exec(compile_module(name, mod.__file__), mod.__dict__)
+    hop.siteanalysis = mod
+    return mod
+
+
+class LegacySelection(object):
+    """An AtomGroup as hop.siteanalysis.Collection.__init__ uses it (hop/siteanalysis.py:943-989): the MDAnalysis
+    API from before release 0.11 -- `selection.indices()` is a method, atoms carry `.segment.name` and
+    `.residue.id`, `selection.atoms[0].universe` is the Universe."""
+
+    def __init__(self, group):
+        self._group = group
+        self.universe = group.universe
+
+    atoms = property(lambda self: self)
+
+    def indices(self):
+        return numpy.asarray(self._group.index)
+
+    def __len__(self):
+        return len(self._group)
+
+    def __iter__(self):
+        for a in self._group:
+            yield types.SimpleNamespace(universe=self._group.universe, segment=types.SimpleNamespace(name=a.segid),
+                                        residue=types.SimpleNamespace(id=a.resid))
+
+    def __getitem__(self, i):
+        return list(self)[i]
