@@ -37,6 +37,9 @@ WORKLOADS = {
     "config2": dict(atoms=30000, frames_per_gpu=10000, delta=0.5, label="solvated box"),
     # BASELINE.json configs[2]: 100 000 waters x 100 000 frames sharded over 8 GPUs = 12 500 frames per GPU
     "config3": dict(atoms=100000, frames_per_gpu=12500, delta=0.5, label="membrane-channel-sized box"),
+    # BASELINE.json configs[2] in full on ONE GPU (north_star's target sentence): 100 000 waters x 100 000 frames = 1e10
+    # atom-frames, 120 GB of coordinates, streamed through HBM in frame chunks (HopPipeline.run_streamed)
+    "config3full": dict(atoms=100000, frames_per_gpu=100000, delta=0.5, label="membrane-channel-sized box, chunk-streamed"),
 }
 WORKLOAD = "config2"
 METRIC = "solvent atom-frames/sec binned+site-assigned"
@@ -382,6 +385,104 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------------
+# config 3 in full on one GPU: the trajectory does not fit into HBM and is streamed in frame chunks
+# -------------------------------------------------------------------------------------------------
+def run_streamed_workload(args, chunk_frames=2500):
+    import numpy as np
+    import torch
+
+    from hop_b200 import _lib
+    from hop_b200 import kernels as K
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+    from oracle import hop_oracle as O
+
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload config3full is the single-GPU run of configs[2]; use --workload config3 --gpus 8 for the sharded one")
+    torch.cuda.set_device(0)
+    F, N = FRAMES_PER_GPU, ATOMS
+    params = SynthParams(n_atoms=N, n_frames=F)
+    prefix = generate(params, 0, 64)
+    edges = grid_edges_from_frame0(prefix[0], delta=DELTA)
+    stream = K.SynthStream(params)
+    gen_events = []
+
+    def source(f0, f1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        x = stream(f0, f1)
+        b.record()
+        gen_events.append((a, b))
+        return x
+
+    keep = {}
+    sums = []
+
+    def sink(f0, hx, hy):
+        if f0 == 0 and "x" not in keep:
+            keep["x"], keep["y"] = hx[:64].clone(), hy[:64].clone()
+
+    pipe = HopPipeline(edges, F, PipelineConfig(async_results=False, event_capacity=64 << 20))
+    times, stage_ms, gen_ms_all = [], {}, []
+    sampler = ClockSampler(0)
+    launches = 0
+    for it in range(args.warmup + args.steps):
+        del gen_events[:]
+        if it == args.warmup:
+            sampler.start()
+            launches0 = _lib.lib().hopb_launch_count()
+        marks = []
+        torch.cuda.synchronize()
+        res = pipe.run_streamed(source, F, chunk_frames, sink=sink, marks=marks)
+        torch.cuda.synchronize()
+        gen_ms = sum(a.elapsed_time(b) for a, b in gen_events)
+        total_ms = marks[0][1].elapsed_time(marks[-1][1])
+        if it >= args.warmup:
+            times.append(total_ms - gen_ms)
+            gen_ms_all.append(gen_ms)
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
+    launches = (_lib.lib().hopb_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop()
+    ms_step = sum(times) / len(times)
+    gen_step = sum(gen_ms_all) / len(gen_ms_all)
+    stage_ms = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+    stage_ms["S1_histogram"] -= gen_step        # every chunk is generated inside pass 1 (pass 2 reads the cached brick indices)
+    value = N * F / (ms_step * 1e-3)
+    peak, peak_src = measured_peak()
+    checks = {"sum_counts_equals_atom_frames": bool(int(res.counts.to(torch.int64).sum().item()) == N * F)}
+    site_map = res.map16.cpu().numpy()
+    hop = O.coord2hop_vectorised(prefix, edges, site_map)
+    checks["prefix64_hop_x_equals_oracle"] = bool(np.array_equal(keep["x"].cpu().numpy(), hop[:, :, 0]))
+    checks["prefix64_hop_y_equals_oracle"] = bool(np.array_equal(keep["y"].cpu().numpy(), hop[:, :, 1]))
+    ev_ref, _ = O.analyze_hops_vectorised(hop[:, :, 0])
+    ev = K.events_to_numpy(res.events)
+    sel = ev[ev["frame"] < 64]
+    order = np.lexsort((sel["iatom"], sel["frame"]))
+    got = np.stack([sel[k][order] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1).astype(np.int64)
+    checks["prefix64_events_equal_oracle"] = bool(np.array_equal(got, ev_ref))
+    checks["count_matrix_sum_equals_events"] = bool(res.count_matrix is None or int(res.count_matrix.sum().item()) == len(ev))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+            "config": {"workload": "%s, %d waters x %d frames on ONE GPU, %.2f A grid; 120 GB of coordinates streamed through HBM in "
+                                   "%d-frame chunks (3 GB each >> L2), generated in HBM chunk by chunk" % (
+                                       WORKLOADS[WORKLOAD]["label"], N, F, DELTA, chunk_frames)},
+            "timing": ("CUDA events around HopPipeline.run_streamed minus the CUDA-event time of the chunk generator calls "
+                       "(the generator stands for the data source); generator %.1f ms per step on top" % gen_step),
+            "result": {"sites": int(res.n_labels), "events": int(len(ev))},
+            "clocks": clocks, "gpu_launches": int(launches), "stage_ms": stage_ms, "checks": checks,
+            "roofline": {"bound": "hbm", "kernel": "pipeline", "achieved": value * 32 / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": value * 32 / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_atom_frame": 32,
+                         "stages": {k: {"ms": stage_ms[k], "GBps": N * F * b / (stage_ms[k] * 1e-3) / 1e9,
+                                        "frac": N * F * b / (stage_ms[k] * 1e-3) / 1e9 / peak}
+                                    for k, b in (("S1_histogram", 12), ("S3S4_hoptraj", 20))}},
+            "e2e": None}
+    emit(line)
+
+
+# -------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -711,7 +812,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
                     help="config2 = BASELINE configs[1] (default, the headline); config3 = configs[2] per-GPU slab "
-                         "(100 000 waters x 12 500 frames per GPU: the full 100 000 frames at --gpus 8)")
+                         "(100 000 waters x 12 500 frames per GPU: the full 100 000 frames at --gpus 8); config3full = "
+                         "configs[2] in full on one GPU, chunk-streamed")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (15 GB of pinned memory per rank at config3)")
     args = ap.parse_args()
     global ATOMS, FRAMES_PER_GPU, DELTA, WORKLOAD
@@ -720,6 +822,8 @@ def main():
     _stdout_to_stderr()
     if args.impl == "reference":
         run_reference(args)
+    elif WORKLOAD == "config3full":
+        run_streamed_workload(args)
     else:
         run_gpu(args)
 

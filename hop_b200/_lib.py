@@ -93,6 +93,7 @@ _SIGNATURES = {
     "hopb_events_finalize_dev": [_vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "hopb_all_transitions": [_vp, _vp, _vp, _i64, _i64, _int, _vp],
     "hopb_synth_generate": [_vp, _vp, ctypes.POINTER(SynthParamsC), _vp, _i64, _i64, _vp],
+    "hopb_synth_generate_chunk": [_vp, _vp, ctypes.POINTER(SynthParamsC), _vp, _i64, _i64, _vp, _vp, _int],
 }
 _RESTYPES = {"hopb_launch_count": ctypes.c_uint64, "hopb_destroy": None, "hopb_grid_destroy": None, "hopb_last_error": ctypes.c_char_p}
 

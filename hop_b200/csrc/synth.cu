@@ -28,7 +28,8 @@ __device__ __forceinline__ float gauss3(uint64_t h) {
 }
 
 __global__ void __launch_bounds__(128)
-synth_kernel(hopb_synth_params p, const float* __restrict__ centres, int64_t frame_start, int64_t n_out, float* __restrict__ xyz) {
+synth_kernel(hopb_synth_params p, const float* __restrict__ centres, int64_t frame_start, int64_t n_out, float* __restrict__ xyz,
+             float4* __restrict__ walker, int resume) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t N = p.n_atoms;
   if (i >= N) return;
@@ -62,7 +63,16 @@ synth_kernel(hopb_synth_params p, const float* __restrict__ centres, int64_t fra
     float* o = xyz + i * 3;
     o[0] = pos[0]; o[1] = pos[1]; o[2] = pos[2];
   }
-  for (int64_t f = 1; f < f_stop; ++f) {
+  // a trajectory generated chunk by chunk continues from the walker the previous call left behind (position and
+  // site after frame frame_start - 1) instead of walking there from frame 0 again
+  int64_t f_first = 1;
+  if (resume && frame_start > 0) {
+    const float4 w = walker[i];
+    pos[0] = w.x; pos[1] = w.y; pos[2] = w.z;
+    site = (long long)__float_as_int(w.w);
+    f_first = frame_start;
+  }
+  for (int64_t f = f_first; f < f_stop; ++f) {
     const bool free_mover = site < 0;
     float nw[3];
     bool in_cube = true;
@@ -99,16 +109,25 @@ synth_kernel(hopb_synth_params p, const float* __restrict__ centres, int64_t fra
       o[0] = pos[0]; o[1] = pos[1]; o[2] = pos[2];
     }
   }
+  if (walker) walker[i] = make_float4(pos[0], pos[1], pos[2], __int_as_float((int)site));
 }
 
 }  // namespace
 
-extern "C" int hopb_synth_generate(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
-                                   int64_t frame_start, int64_t n_out, float* xyz) {
+extern "C" int hopb_synth_generate_chunk(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
+                                         int64_t frame_start, int64_t n_out, float* xyz, float* walker, int resume) {
   HOPB_REQUIRE(h, p && centres && xyz, "null argument");
   HOPB_REQUIRE(h, p->n_atoms > 0 && p->n_sites > 0 && p->site_stride > 0 && frame_start >= 0 && n_out >= 0, "bad parameters");
+  HOPB_REQUIRE(h, !resume || walker, "resume needs the walker buffer of the previous chunk");
+  HOPB_REQUIRE(h, ((uintptr_t)walker & 15) == 0, "walker must be 16-byte aligned");
   if (n_out == 0) return HOPB_OK;
-  HOPB_K(synth_kernel)<<<(unsigned)((p->n_atoms + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, centres, frame_start, n_out, xyz);
+  HOPB_K(synth_kernel)<<<(unsigned)((p->n_atoms + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      *p, centres, frame_start, n_out, xyz, reinterpret_cast<float4*>(walker), resume);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
+}
+
+extern "C" int hopb_synth_generate(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
+                                   int64_t frame_start, int64_t n_out, float* xyz) {
+  return hopb_synth_generate_chunk(h, stream, p, centres, frame_start, n_out, xyz, nullptr, 0);
 }

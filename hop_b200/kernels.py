@@ -566,6 +566,41 @@ def all_transitions(hop_x: torch.Tensor, n_labels: int):
     return np.stack([idx // W - 1, idx % W - 1], axis=1).astype(np.int64)
 
 
+class SynthStream(object):
+    """The synthetic trajectory chunk by chunk, each chunk continuing where the previous one stopped (a source for
+    HopPipeline.run_streamed).  chunk(f0, f1) must be called for consecutive ranges; a call with f0 == 0 restarts."""
+
+    def __init__(self, params, device=None):
+        self.params = params
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        centres, half = params.lattice()
+        self._c = _lib.SynthParamsC(seed=params.seed, n_atoms=params.n_atoms, n_frames=params.n_frames,
+                                    site_stride=params.site_stride, n_sites=len(centres), box=np.float32(params.box),
+                                    cube_half=np.float32(half), sigma_site=np.float32(params.sigma_site),
+                                    sigma_bulk=np.float32(params.sigma_bulk), p_hop=np.float32(params.p_hop),
+                                    p_rebind=np.float32(params.p_rebind))
+        self._centres = torch.from_numpy(np.ascontiguousarray(centres)).to(self.device)
+        self._walker = torch.zeros((params.n_atoms, 4), dtype=torch.float32, device=self.device)
+        self._next = 0
+        self._bufs = {}
+
+    def chunk(self, f0, f1):
+        if f0 != 0 and f0 != self._next:
+            raise ValueError("SynthStream: chunks must be consecutive (expected frame %d, got %d)" % (self._next, f0))
+        n = int(f1 - f0)
+        out = self._bufs.get(n)
+        if out is None:
+            out = self._bufs[n] = torch.empty((n, self.params.n_atoms, 3), dtype=torch.float32, device=self.device)
+        h = _lib.handle(self.device.index)
+        rc = _lib.lib().hopb_synth_generate_chunk(h, _stream(), ctypes.byref(self._c), _p(self._centres), int(f0), n, _p(out),
+                                                  _p(self._walker), 1 if f0 > 0 else 0)
+        _lib.check(h, rc)
+        self._next = int(f1)
+        return out
+
+    __call__ = chunk
+
+
 def synth_generate(params, frame_start=0, n_out=None, device=None, out=None):
     """Device twin of hop_b200.synth.generate: float32 [n_out][N][3] in HBM."""
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)

@@ -394,16 +394,19 @@ class HopPipeline:
             exchange.reduce_count_matrix(matrix)
         return ev, e_s0, e_s, e_start, e_count, matrix
 
-    def _finalize_sync(self, res, events, xyz, frame0):
+    def _finalize_sync(self, res, events, xyz, frame0, n_atoms=None):
         """Tail of a run with the host in the loop: wait for stage 3, read the counts, sort."""
         res.n_labels, n_ev = self.sync_scalars(events)
+        if n_ev > events.capacity and xyz is None:
+            self._event_buffer(n_ev + n_ev // 8)     # the next attempt fits
+            raise _capacity_error(n_ev, events.capacity)
         if n_ev > events.capacity:      # rare: more transitions than budgeted -- grow the buffer and redo stage 3
             self._event_buffer(n_ev + n_ev // 8)
             res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
             res.n_labels, n_ev = self.sync_scalars(events)
         res.n_events_local = n_ev
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
-         res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]), res.n_labels)
+         res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]) if n_atoms is None else n_atoms, res.n_labels)
         res.site_props = self._props
         res._pending = None
         self._w_known = res.n_labels + 1
@@ -498,6 +501,88 @@ class HopPipeline:
         self._mark(marks, "S3S4_hoptraj")
         self._finalize(res, events, xyz, frame0)
         self._mark(marks, "S4_transitions", getattr(self, "_s4_stream", None) if res._pending is not None else None)
+        return res
+
+    def run_streamed(self, source, n_frames, chunk_frames, sink=None, cache_cells=None, marks=None):
+        """The four stages over a trajectory that does not fit into HBM, in two passes over frame chunks
+        (hop reads the trajectory twice as well: DensityCreator.create, hop/density.py:292-304, then
+        HoppingTrajectory.map_dcd, hop/trajectory.py:379-394).
+
+        source(f0, f1) -> CUDA float32 [f1 - f0][N][3]: the coordinates of frames [f0, f1) (a reader, an upload
+        stage, a generator); called once per chunk and pass, unless the 4-byte brick indices of pass 1 fit into
+        HBM (`cache_cells`, default: when they take less than 40 % of the free memory), in which case pass 2
+        reads those instead of the coordinates.
+        sink(f0, hop_x, hop_y): receives every chunk of the hopping trajectory ([m][N] float32 views of a
+        buffer that is reused for the next chunk -- write it out or reduce it before returning).
+
+        Pass 1 accumulates the histogram chunk by chunk; stage 2 runs once; pass 2 carries the per-atom
+        machine state from chunk to chunk (`hop_fixup`), so tau / tbarrier / orbit are those of one run over
+        the whole trajectory.  Single rank.  Returns a PipelineResult without hop_x / hop_y."""
+        from . import _lib
+
+        with _lib.lanes(self.lane_base):
+            return self._run_streamed(source, int(n_frames), int(chunk_frames), sink, cache_cells, marks)
+
+    def _run_streamed(self, source, F, chunk, sink, cache_cells, marks):
+        if _dist() is not None:
+            raise RuntimeError("run_streamed is a single-rank path (shard the frames over ranks with run())")
+        if F != self.n_frames_total:
+            raise ValueError("n_frames must be the trajectory length the pipeline was created for")
+        cfg = self.cfg
+        dev = self.device
+        bounds = [(f0, min(F, f0 + chunk)) for f0 in range(0, F, chunk)]
+        self._mark(marks, "start")
+        counts = self._buf("counts", self.grid.shape, torch.int32)
+        counts.zero_()
+        first = source(*bounds[0])
+        N = int(first.shape[1])
+        if cache_cells is None:
+            free, _ = torch.cuda.mem_get_info(dev)
+            cache_cells = F * N * 4 < 0.4 * free
+        cells_all = self._buf("cells_all", (F, N), torch.int32) if cache_cells else None
+        # ---- pass 1: histogram -------------------------------------------------------------------------
+        for k, (f0, f1) in enumerate(bounds):
+            xyz = first if k == 0 else source(f0, f1)
+            K.hist_accumulate(self.grid, xyz, counts, None if cells_all is None else cells_all[f0:f1])
+            del xyz
+        del first
+        self._mark(marks, "S1_histogram")
+        res = PipelineResult()
+        res.counts = counts
+        res.density, res.own, res.member, res.map16, _ = self.site_map(counts)
+        self.annotate()
+        self._mark(marks, "S2_sitemap")
+        # ---- pass 2: hopping trajectory + transitions ----------------------------------------------------
+        m_max = max(f1 - f0 for f0, f1 in bounds)
+        hx_buf = self._buf("hop_x_chunk", (m_max, N), torch.float32)
+        hy_buf = self._buf("hop_y_chunk", (m_max, N), torch.float32)
+        cap = cfg.event_capacity or max(1 << 20, (F * N) // 64)
+        events = self._event_buffer(max(cap, self._events.capacity if self._events is not None else 0))
+        if self._s4_done is not None:
+            torch.cuda.current_stream(dev).wait_event(self._s4_done)
+            self._s4_done = None
+        events.reset()
+        state = self._buf("state", (K.STATE_INTS, N), torch.int32)
+        K.hop_advance(None, state, init=True)
+        for f0, f1 in bounds:
+            m = f1 - f0
+            n_chunks, chunk_len = K.plan_chunks(m, N, self.num_sms) if cfg.n_chunks is None else \
+                (-(-m // (-(-m // cfg.n_chunks))), -(-m // cfg.n_chunks))
+            xyz = None if cells_all is not None else source(f0, f1)
+            hx, hy = hx_buf[:m], hy_buf[:m]
+            summaries = self._buf("summaries_%d" % n_chunks, (n_chunks, K.SUMMARY_INTS, N), torch.int32)
+            K.hoptraj(self.grid, xyz, self.brick, f0, n_chunks, chunk_len, events, hx, hy, summaries,
+                      cells=None if cells_all is None else cells_all[f0:f1],
+                      block_map=cfg.block_map if cfg.coarse_map else "none")
+            K.hop_fixup(summaries, chunk_len, m, state, hy, events)
+            if sink is not None:
+                sink(f0, hx, hy)
+            del xyz
+        self._mark(marks, "S3S4_hoptraj")
+        res.state = res.final_state = state
+        self._finalize_sync(res, events, None, 0, n_atoms=N)
+        self._mark(marks, "S4_transitions")
+        self._run_index += 1
         return res
 
     def run_host(self, xyz_host, frame0=0, out_x=None, out_y=None, block_bytes=256 << 20):

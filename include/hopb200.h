@@ -374,6 +374,13 @@ typedef struct hopb_synth_params {
 int hopb_synth_generate(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
                         int64_t frame_start, int64_t n_out, float* xyz);
 
+/* The same for a trajectory produced chunk by chunk: `walker` (device float32 [n_atoms][4], 16-byte aligned)
+ * receives the state of every atom after the last frame written; with resume != 0 the call continues from the
+ * walker of the chunk that ended at frame_start - 1 instead of walking there from frame 0.  Same coordinates,
+ * bit for bit, as one call over the whole range. */
+int hopb_synth_generate_chunk(hopb_handle* h, void* stream, const hopb_synth_params* p, const float* centres,
+                              int64_t frame_start, int64_t n_out, float* xyz, float* walker, int resume);
+
 #ifdef __cplusplus
 }
 #endif

@@ -684,6 +684,54 @@ def test_label_from_counts_equals_label_from_density(K):
                                    torch.empty(g.shape, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
 
 
+@pytest.mark.parametrize("chunk,cache", [(200, True), (64, True), (37, False), (1, None)])
+def test_streamed_run_equals_resident_run(K, traj, chunk, cache):
+    """HopPipeline.run_streamed -- two passes over frame chunks for trajectories larger than HBM, the machine
+    state carried from chunk to chunk -- gives exactly what run() gives on the resident trajectory, whatever the
+    chunk length and whether pass 2 re-reads the coordinates or the cached brick indices."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    F, N = xyz.shape[:2]
+    if chunk == 1:
+        F = 23
+        xyz = xyz[:F]
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    full = dev(xyz)
+    want = HopPipeline(edges, F, PipelineConfig(async_results=False)).run(full)
+    calls = []
+
+    def source(f0, f1):
+        calls.append((f0, f1))
+        return full[f0:f1].clone()
+
+    X = torch.full((F, N), -9.0, device="cuda")
+    Y = torch.full((F, N), -9.0, device="cuda")
+
+    def sink(f0, hx, hy):
+        X[f0:f0 + hx.shape[0]].copy_(hx)
+        Y[f0:f0 + hy.shape[0]].copy_(hy)
+
+    pipe = HopPipeline(edges, F, PipelineConfig(async_results=False))
+    for _ in range(2):
+        del calls[:]
+        got = pipe.run_streamed(source, F, chunk, sink=sink, cache_cells=cache)
+        n_chunks = -(-F // chunk)
+        assert len(calls) == (n_chunks if cache in (True, None) else 2 * n_chunks)
+        assert torch.equal(got.counts, want.counts) and torch.equal(got.map16, want.map16) and torch.equal(got.density, want.density)
+        assert torch.equal(X, want.hop_x) and torch.equal(Y, want.hop_y)
+        assert got.n_labels == want.n_labels and torch.equal(got.events, want.events)
+        assert torch.equal(got.count_matrix, want.count_matrix) and torch.equal(got.edge_count, want.edge_count)
+        a, b = got.final_state.cpu().numpy(), want.final_state.cpu().numpy()
+        assert np.array_equal(a[[0, 1, 3]], b[[0, 1, 3]])
+        off = a[3] == 0
+        assert np.array_equal(a[2][off], b[2][off])
+    with pytest.raises(ValueError):
+        pipe.run_streamed(source, F + 1, chunk)
+
+
 def test_periodic_wrap_is_off_by_default_and_exact_when_on(K, traj):
     """The optional periodic wrapping (north_star kernel 1; hop itself never wraps, hop/density.py:21-28):
     off -- the default, also after switching it on and off again -- the results are bit-identical to a grid
