@@ -39,6 +39,10 @@ WORKLOADS = {
     "config3": dict(atoms=100000, frames_per_gpu=12500, delta=0.5, label="membrane-channel-sized box"),
     # BASELINE.json configs[2] in full on ONE GPU (north_star's target sentence): 100 000 waters x 100 000 frames = 1e10
     # atom-frames, 120 GB of coordinates, streamed through HBM in frame chunks (HopPipeline.run_streamed)
+    # BASELINE.json configs[3]: three ion species in a 200k-atom box (126 A), 10^6 frames, 1.0 A grids, one coordinate stream
+    "config4": dict(atoms=1200, frames_per_gpu=1000000, delta=1.0, label="ion hopping, 3 species x 400 ions in a 126 A box"),
+    # BASELINE.json configs[4]: 64 trajectories x 20 000 frames at 0.25 A (402^3 grid), 8 trajectories per GPU, no collective
+    "config5": dict(atoms=30000, frames_per_gpu=20000, delta=0.25, label="many-densities batch, 8 trajectories per GPU"),
     "config3full": dict(atoms=100000, frames_per_gpu=100000, delta=0.5, label="membrane-channel-sized box, chunk-streamed"),
 }
 WORKLOAD = "config2"
@@ -483,6 +487,202 @@ def run_streamed_workload(args, chunk_frames=2500):
 
 
 # -------------------------------------------------------------------------------------------------
+# config 4: several species from one coordinate stream (hop_b200.multispecies)
+# -------------------------------------------------------------------------------------------------
+def run_multispecies_workload(args, n_species=3):
+    import numpy as np
+    import torch
+
+    from hop_b200 import _lib
+    from hop_b200 import kernels as K
+    from hop_b200.multispecies import MultiSpeciesPipeline
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload config4 is a single-GPU workload (species are replicas: one box per GPU)")
+    torch.cuda.set_device(0)
+    F, N = FRAMES_PER_GPU, ATOMS
+    params = SynthParams(n_atoms=N, n_frames=F, rho=N / 126.0 ** 3)
+    frame0 = generate(params, 0, 1)[0]
+    per = N // n_species
+    columns = [(k * per, (k + 1) * per if k < n_species - 1 else N) for k in range(n_species)]
+    xyz = K.synth_generate(params)
+    cfg = PipelineConfig(event_capacity=max(1 << 22, F * per // 16))
+    multi = MultiSpeciesPipeline.from_frame0(frame0, columns, F, delta=DELTA, config=cfg)
+    for _ in range(args.warmup):
+        res = multi.run(xyz)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = _lib.lib().hopb_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        res = multi.run(xyz)
+    b.record()
+    torch.cuda.synchronize()
+    ms_step = a.elapsed_time(b) / args.steps
+    launches = (_lib.lib().hopb_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop()
+    value = N * F / (ms_step * 1e-3)
+    # the way hop does it: one run per species, each reading its own coordinates (parity + the cost of K reads)
+    checks, t_single = {}, 0.0
+    for k, (c0, c1) in enumerate(columns):
+        sub = xyz[:, c0:c1].contiguous()
+        pipe = HopPipeline(grid_edges_from_frame0(frame0[c0:c1], delta=DELTA), F, PipelineConfig(async_results=False, event_capacity=cfg.event_capacity))
+        pipe.run(sub)
+        torch.cuda.synchronize()
+        a.record()
+        r = pipe.run(sub)
+        b.record()
+        torch.cuda.synchronize()
+        t_single += a.elapsed_time(b)
+        checks["species%d_equals_single_species_run" % k] = bool(
+            torch.equal(r.counts, res[k].counts) and torch.equal(r.map16, res[k].map16) and torch.equal(r.hop_x, res[k].hop_x)
+            and torch.equal(r.hop_y, res[k].hop_y) and torch.equal(r.events, res[k].events) and r.n_labels == res[k].n_labels)
+        checks["species%d_counts_conserved" % k] = bool(int(res[k].counts.to(torch.int64).sum().item()) == (c1 - c0) * F)
+        del pipe, r, sub
+    peak, peak_src = measured_peak()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+            "config": {"workload": "%s x %d frames, %.1f A grids (one per species, %s); one coordinate stream of %.1f GB >> L2" % (
+                WORKLOADS[WORKLOAD]["label"], F, DELTA, " / ".join("x".join(str(n) for n in p.grid.shape) for p in multi.pipes),
+                N * F * 12 / 1e9)},
+            "step": "hop_b200.multispecies.MultiSpeciesPipeline.run: one histogram pass for all species, one site map and one "
+                    "hoptraj launch per species on the shared brick indices",
+            "result": {"sites": [int(r.n_labels) for r in res], "events": [int(r.n_events_local) for r in res]},
+            "one_run_per_species_ms": t_single, "clocks": clocks, "gpu_launches": int(launches), "checks": checks, "e2e": None,
+            "roofline": {"bound": "hbm", "kernel": "pipeline", "achieved": value * 32 / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": value * 32 / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_atom_frame": 32}}
+    emit(line)
+
+
+# -------------------------------------------------------------------------------------------------
+# config 5: a batch of independent trajectories, 8 per GPU (hop-generate-many-densities style); replicas only
+# -------------------------------------------------------------------------------------------------
+def run_batch_workload(args, per_gpu=8):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hop_b200 import _lib
+    from hop_b200 import kernels as K
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, PipelinePool, grid_edges_from_frame0
+    from hop_b200.synth import SynthParams, generate
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))   # barrier and max-over-ranks only
+    F, N = FRAMES_PER_GPU, ATOMS
+    seeds = [20261019 + 5 + 100 * (rank * per_gpu + k) for k in range(per_gpu)]
+    trajs = [K.synth_generate(SynthParams(n_atoms=N, n_frames=F, seed=sd)) for sd in seeds]
+    # frame 0 of the synthetic model spans the box for every seed (atoms 1 and 2 sit in its corners): one grid geometry
+    edges = grid_edges_from_frame0(generate(SynthParams(n_atoms=N, n_frames=2, seed=seeds[0]), 0, 1)[0], delta=DELTA)
+    for sd in seeds[1:2]:
+        e2 = grid_edges_from_frame0(generate(SynthParams(n_atoms=N, n_frames=2, seed=sd), 0, 1)[0], delta=DELTA)
+        assert all(np.array_equal(a, b) for a, b in zip(edges, e2))
+    cfg = PipelineConfig(event_capacity=max(1 << 22, F * N // 32))
+    pool = PipelinePool(edges, F, cfg, n=2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_batch(collect=None):
+        pending = []
+        for k, xyz in enumerate(trajs):
+            r = pool.run(xyz)
+            total = None
+            if collect is not None:
+                # the count grid is reused by the next run of the same pipeline: reduce it on that pipeline's stream now
+                with torch.cuda.stream(pool.streams[k % len(pool.streams)]):
+                    total = r.counts.sum(dtype=torch.int64)
+            pending.append((k, r, total))
+            if len(pending) > 2:                      # two runs in flight; look at a result before its buffers are reused
+                j, rj, tj = pending.pop(0)
+                if collect is not None:
+                    collect[j] = (int(rj.n_labels), int(rj.n_events_local), tj)
+                else:
+                    rj.wait()
+        for j, rj, tj in pending:
+            if collect is not None:
+                collect[j] = (int(rj.n_labels), int(rj.n_events_local), tj)
+            else:
+                rj.wait()
+        if collect is not None:
+            pool.synchronize()
+            for j in collect:
+                collect[j] = collect[j][:2] + (int(collect[j][2].item()),)
+
+    for _ in range(args.warmup):
+        one_batch()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().hopb_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        one_batch()
+    for st in pool.streams:
+        torch.cuda.current_stream().wait_stream(st)
+    b.record()
+    torch.cuda.synchronize()
+    pool.synchronize()
+    ms_local = a.elapsed_time(b) / args.steps
+    barrier()
+    launches = (_lib.lib().hopb_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    value = world * per_gpu * N * F / (ms_step * 1e-3)
+    # checks (not timed): conservation for every trajectory; trajectory 0 equals a stand-alone pipeline run
+    got = {}
+    one_batch(collect=got)
+    checks = {"sum_counts_equals_atom_frames": all(v[2] == N * F for v in got.values())}
+    single = HopPipeline(edges, F, PipelineConfig(async_results=False, event_capacity=cfg.event_capacity))
+    r0 = single.run(trajs[0])
+    checks["trajectory0_equals_single_pipeline"] = bool(got[0][0] == r0.n_labels and got[0][1] == r0.n_events_local)
+    rp = pool.run(trajs[0])
+    checks["trajectory0_hoptraj_equal"] = bool(torch.equal(rp.hop_x, r0.hop_x) and torch.equal(rp.hop_y, r0.hop_y)
+                                               and torch.equal(rp.events, r0.events))
+    ok = torch.tensor([0 if all(checks.values()) else 1], device="cuda")
+    if world > 1:
+        dist.all_reduce(ok)
+    checks["all_ranks"] = bool(int(ok.item()) == 0)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+                "config": {"workload": "%s: %d trajectories x %d waters x %d frames per GPU x %d GPU(s) = %d trajectories, %.2f A grid "
+                                       "(402^3, 260 MB of counts per trajectory > L2: slabbed histogram); inputs 7.2 GB per "
+                                       "trajectory >> L2; replicas only, no collective" % (
+                                           WORKLOADS[WORKLOAD]["label"], per_gpu, N, F, world, world * per_gpu, DELTA)},
+                "step": "one batch = %d independent trajectories per GPU through PipelinePool (two in flight)" % per_gpu,
+                "result": {"sites_by_trajectory": [v[0] for _, v in sorted(got.items())],
+                           "events_by_trajectory": [v[1] for _, v in sorted(got.items())]},
+                "clocks": clocks, "gpu_launches": int(launches), "checks": checks, "e2e": None,
+                "ms_per_trajectory": ms_step / per_gpu,
+                "roofline": {"bound": "hbm", "kernel": "pipeline", "achieved": value * 32 / 1e9 / world, "peak": peak, "unit": "GB/s",
+                             "frac": value * 32 / 1e9 / world / peak, "peak_source": peak_src, "traffic": None,
+                             "algorithmic_bytes_per_atom_frame": 32}}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -824,6 +1024,10 @@ def main():
         run_reference(args)
     elif WORKLOAD == "config3full":
         run_streamed_workload(args)
+    elif WORKLOAD == "config5":
+        run_batch_workload(args)
+    elif WORKLOAD == "config4":
+        run_multispecies_workload(args)
     else:
         run_gpu(args)
 

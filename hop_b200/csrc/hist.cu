@@ -391,6 +391,79 @@ hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ so
   }
 }
 
+// ---- several selections from one coordinate stream (BASELINE config 4: Na+ / K+ / Cl- in one box) -----------------
+// hop runs one DensityCreator per selection, i.e. reads the trajectory once per species
+// (scripts/hop-generate-many-densities.py:98-125; hop/density.py:271-304), each with a grid of its own (the extent
+// of THAT selection in frame 0).  Here every frame is read once: the species of an atom picks the grid tables, the
+// count grid and the brick numbering its point is binned with.  Species are few and small (10^2 .. 10^3 ions), so
+// the stream is latency- rather than reduction-bound: every thread takes four points per step, loads first.
+constexpr int kMaxSpecies = 8;
+struct MultiGrids {
+  HopbGridTab tab[kMaxSpecies];
+  const HopbPair* table2[kMaxSpecies];
+  uint32_t* counts[kMaxSpecies];
+  int n;
+};
+
+__global__ void __launch_bounds__(kHistThreads, 4)
+hist_multi_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, int64_t N, const uint8_t* __restrict__ species,
+                  const MultiGrids* __restrict__ mg, uint32_t* __restrict__ cells) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* stage = reinterpret_cast<float4*>(smem_raw);                           // [warps][96] float4, as hist_kernel
+  HopbPair* s_pairs = reinterpret_cast<HopbPair*>(stage + kWarpsPerBlock * 96);
+  __shared__ int s_off[kMaxSpecies];
+  __shared__ AxisReg s_ax[kMaxSpecies][3];
+  int off = 0;
+  for (int k = 0; k < mg->n; ++k) {
+    for (int i = threadIdx.x; i < mg->tab[k].table2_len; i += blockDim.x) s_pairs[off + i] = mg->table2[k][i];
+    if (threadIdx.x == 0) s_off[k] = off;
+    off += mg->tab[k].table2_len;
+  }
+  __syncthreads();
+  if (threadIdx.x < mg->n * 3) {
+    const int k = threadIdx.x / 3, d = threadIdx.x % 3;
+    s_ax[k][d] = load_axis(mg->tab[k].ax[d], s_pairs + s_off[k]);
+  }
+  __syncthreads();
+  const uint64_t pol = make_evict_first_policy();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* wbuf = stage + warp * 96;
+  const float* wf = reinterpret_cast<const float*>(wbuf);
+  const uint32_t Nu = (uint32_t)N;
+  auto point = [&](float x, float y, float z, uint32_t atom) -> uint32_t {
+    const int k = species[atom];
+    Slab slab; slab.x_lo = 0; slab.x_hi = mg->tab[k].ax[0].n; slab.done_flag = 0u;
+    return hist_point<true, true>(x, y, z, mg->tab[k], s_ax[k][0], s_ax[k][1], s_ax[k][2], nullptr, mg->counts[k], slab);
+  };
+  const int64_t nblk = (n_points - lead) / 128;
+  const float4* base = reinterpret_cast<const float4*>(xyz + 3 * lead);
+  const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + warp; b < nblk; b += total_warps) {
+    const float4* src = base + b * 96;
+    const float4 v0 = ld_stream(src + lane, pol);
+    const float4 v1 = ld_stream(src + 32 + lane, pol);
+    const float4 v2 = ld_stream(src + 64 + lane, pol);
+    wbuf[lane] = v0; wbuf[32 + lane] = v1; wbuf[64 + lane] = v2;
+    __syncwarp();
+    const int64_t p0 = lead + b * 128;
+    const uint32_t a0 = (uint32_t)(p0 % N);        // atom of the block's first point; the others follow modulo N
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = lane + 32 * j;
+      const uint32_t c = point(wf[3 * q], wf[3 * q + 1], wf[3 * q + 2], (a0 + (uint32_t)q) % Nu);
+      if (cells) cells[p0 + q] = c;
+    }
+    __syncwarp();
+  }
+  const int64_t tail0 = lead + nblk * 128;
+  const int64_t n_rem = lead + (n_points - tail0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rem; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i < lead ? i : tail0 + (i - lead);
+    const uint32_t c = point(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], (uint32_t)(p % N));
+    if (cells) cells[p] = c;
+  }
+}
+
 // One warp per (i, j) row of the grid: no per-cell index division, the two row divisors are loaded
 // once, loads and stores are contiguous.  The four divisions stay IEEE double divisions in the
 // reference's order (bit-identical densities); they are what the kernel spends its time on.
@@ -544,6 +617,46 @@ int hopb_hist_bulk(hopb_handle* h, void* stream, const hopb_grid* g, const float
   if (cells) { if (fast) HOPB_BULK_LAUNCH(true, true); else HOPB_BULK_LAUNCH(true, false); }
   else { if (fast) HOPB_BULK_LAUNCH(false, true); else HOPB_BULK_LAUNCH(false, false); }
 #undef HOPB_BULK_LAUNCH
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_hist_accumulate_multi(hopb_handle* h, void* stream, int n_species, const hopb_grid* const* grids,
+                               const uint8_t* species, const float* xyz, int64_t F, int64_t N, uint32_t* const* counts,
+                               uint32_t* cells) {
+  HOPB_REQUIRE(h, grids && species && xyz && counts && F >= 0 && N > 0, "bad argument");
+  HOPB_REQUIRE(h, n_species >= 1 && n_species <= kMaxSpecies, "1 to 8 species");
+  if (F == 0) return HOPB_OK;
+  MultiGrids mg;
+  memset(&mg, 0, sizeof(mg));
+  mg.n = n_species;
+  size_t smem = 0;
+  for (int k = 0; k < n_species; ++k) {
+    HOPB_REQUIRE(h, grids[k] && counts[k], "null grid or count array");
+    HOPB_REQUIRE(h, grids[k]->tab.fast_ok != 0, "hopb_hist_accumulate_multi needs regular (linspace) edges");
+    const int64_t nbk = (int64_t)((grids[k]->n[0] + 3) / 4) * ((grids[k]->n[1] + 3) / 4) * ((grids[k]->n[2] + 3) / 4);
+    HOPB_REQUIRE(h, nbk * 64 < ((int64_t)1 << 30), "grid too large for 30-bit brick indices");
+    mg.tab[k] = grids[k]->tab;
+    mg.table2[k] = grids[k]->d_table2;
+    mg.counts[k] = counts[k];
+    smem += (size_t)grids[k]->tab.table2_len * sizeof(HopbPair);
+  }
+  smem += kWarpsPerBlock * 96 * sizeof(float4);
+  HOPB_REQUIRE(h, smem <= 48 * 1024, "grids too large for the shared-memory tables of hopb_hist_accumulate_multi");
+  HOPB_REQUIRE(h, ((uintptr_t)xyz & 3) == 0 && N < ((int64_t)1 << 31), "bad coordinate array");
+  MultiGrids* d_mg = nullptr;
+  int rc = hopb_scratch(h, 17, sizeof(MultiGrids), (void**)&d_mg);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  HOPB_CUDA(h, cudaMemcpyAsync(d_mg, &mg, sizeof(mg), cudaMemcpyHostToDevice, s));
+  HOPB_CUDA(h, cudaStreamSynchronize(s));      // mg lives on this stack frame
+  const int64_t n_points = F * N;
+  int64_t lead = 0;
+  while (lead < n_points && (((uintptr_t)xyz + 12 * (uintptr_t)lead) & 15) != 0) ++lead;
+  const int64_t nblk = (n_points - lead) / 128;
+  int64_t blocks = (nblk + (int64_t)kWarpsPerBlock * 4 - 1) / ((int64_t)kWarpsPerBlock * 4);
+  if (blocks < 1) blocks = 1;
+  HOPB_K(hist_multi_kernel)<<<(unsigned)blocks, kHistThreads, smem, s>>>(xyz, n_points, lead, N, species, d_mg, cells);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

@@ -143,15 +143,18 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 // Work items are (warp of 32 consecutive atoms, chunk), numbered chunk-major and dealt to the warps
 // of the grid in order, so the CTA size (256 with a small block map, up to 1024 with a large one: one
 // copy of the map per CTA) does not change which items exist.
-template <int SRC, bool FAST, bool XY, int MAP, int DEEP = 8>
+template <int SRC, bool FAST, bool XY, int MAP, bool STRIDED = false, int DEEP = 8>
 __global__ void __launch_bounds__(1024, 1)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
-               int64_t F, int64_t N, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
+               int64_t F, int64_t N, int64_t ld_arg, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
                const uint32_t* __restrict__ blockmap, int map_words, int fine_value, uint32_t fine_auto_min,
                float* __restrict__ hop_x,
                float* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
                EventSink sink) {
+  // rows of the data arrays are N atoms apart, or ld_arg when the atoms are a column range of wider arrays (a
+  // variant of its own: the common case keeps one value less alive at the 64-register limit)
+  const int64_t ld = STRIDED ? ld_arg : N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
   float* s_tab = reinterpret_cast<float*>(s_pairs + (SRC == 0 ? tab.table2_len : 0));
@@ -193,26 +196,27 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
 
   // running pointers (one frame = N elements further)
-  float* px = hop_x ? hop_x + (int64_t)f_begin * N + atom : nullptr;
-  float* py = hop_y ? hop_y + (int64_t)f_begin * N + atom : nullptr;
+  // data rows are `ld` elements apart (ld = N unless the atoms are a column range of a wider array)
+  float* px = hop_x ? hop_x + (int64_t)f_begin * ld + atom : nullptr;
+  float* py = hop_y ? hop_y + (int64_t)f_begin * ld + atom : nullptr;
   auto store = [&](int l) {
     if (XY) {
-      *px = (float)l; px += N;
-      *py = (float)yorb; py += N;
+      *px = (float)l; px += ld;
+      *py = (float)yorb; py += ld;
     } else {
-      if (px) { *px = (float)l; px += N; }
-      if (py) { *py = (float)yorb; py += N; }
+      if (px) { *px = (float)l; px += ld; }
+      if (py) { *py = (float)yorb; py += ld; }
     }
   };
   // label of frame f, whatever the source
   auto label_at = [&](int64_t fr) -> int {
-    if (SRC == 1) return (int)__ldg(labels_in + fr * N + atom);
+    if (SRC == 1) return (int)__ldg(labels_in + fr * ld + atom);
     uint32_t c;
     if (SRC == 0) {
-      const float* p = xyz + (fr * N + atom) * 3;
+      const float* p = xyz + (fr * ld + atom) * 3;
       c = pack_cell<FAST>(__ldg(p), __ldg(p + 1), __ldg(p + 2), tab, ax, ay, az, s_tab, cny, cnz);
     } else {
-      c = __ldg(cells + fr * N + atom);
+      c = __ldg(cells + fr * ld + atom);
     }
     return label_of<MAP>(c, mv);
   };
@@ -258,7 +262,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       sp[1 * N] = T.z; sp[2 * N] = T.A1; sp[3 * N] = T.f1; sp[10 * N] = ypre;
     }
   };
-  const uint32_t Nu = (uint32_t)N;
+  const uint32_t Nu = (uint32_t)ld;
   // regime A, one block of K frames at global frame t; lab[] are its labels
   auto blockA = [&](const int* lab, auto kc, int, int t) {
     constexpr int K = decltype(kc)::value;
@@ -324,7 +328,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         float cx[kUnroll], cy[kUnroll], cz[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-          const float* p = xyz + ((int64_t)(f + u) * N + atom) * 3;
+          const float* p = xyz + ((int64_t)(f + u) * ld + atom) * 3;
           cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
         }
         int lab[kUnroll];
@@ -341,7 +345,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
       // gathers of block b+1 and loads of block b+2 in flight during block b -- was measured: slower.)
       constexpr int kDeep = DEEP;
       if (f + kDeep > f_end) return;
-      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + (int64_t)f * N + atom;
+      const uint32_t* src = (SRC == 2 ? cells : reinterpret_cast<const uint32_t*>(labels_in)) + (int64_t)f * ld + atom;
       uint32_t v[kDeep];
 #pragma unroll
       for (int u = 0; u < kDeep; ++u) v[u] = __ldg(src + (uint64_t)Nu * (uint32_t)u);
@@ -501,7 +505,7 @@ hop_advance_kernel(int64_t N, int n, const int32_t* __restrict__ summaries, int 
 }
 
 __global__ void __launch_bounds__(256)
-hop_fixup_kernel(int64_t N, int n_chunks, int64_t chunk_len, int64_t F, const int32_t* __restrict__ summaries,
+hop_fixup_kernel(int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t F, const int32_t* __restrict__ summaries,
                  int32_t* __restrict__ state, float* __restrict__ hop_y, EventSink sink) {
   const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (atom >= N) return;
@@ -515,7 +519,7 @@ hop_fixup_kernel(int64_t N, int n_chunks, int64_t chunk_len, int64_t F, const in
     if (hop_y && yin != 0 && T.ypre > 0) {
       const int64_t f0 = (int64_t)c * chunk_len;
       const float v = (float)yin;
-      for (int k = 0; k < T.ypre; ++k) hop_y[(f0 + k) * N + atom] = v;
+      for (int k = 0; k < T.ypre; ++k) hop_y[(f0 + k) * ld + atom] = v;
     }
     hopb_apply(S, T, emit);
   }
@@ -543,11 +547,12 @@ all_transitions_kernel(const float* __restrict__ hop_x, int64_t F, int64_t N, in
 extern "C" {
 
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
-                          const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t frame0,
+                          const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t ld, int64_t frame0,
                           const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value,
                           const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
                           int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   HOPB_REQUIRE(h, F > 0 && N > 0 && summaries && n_events, "bad argument");
+  HOPB_REQUIRE(h, ld >= N && ld < ((int64_t)1 << 31), "row stride must be >= the number of atoms");
   HOPB_REQUIRE(h, n_chunks >= 1 && chunk_len >= 1 && (int64_t)n_chunks * chunk_len >= F &&
                       (int64_t)(n_chunks - 1) * chunk_len < F, "chunks must tile the slab exactly");
   HOPB_REQUIRE(h, n_chunks <= 65535, "too many chunks");
@@ -563,10 +568,10 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     const unsigned grid = (unsigned)((items + kHopThreads / 32 - 1) / (kHopThreads / 32));
     hopb_note_launch();
     if (hop_x && hop_y)
-      hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
+      hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
           nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     else
-      hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, frame0, tab,
+      hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
           nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
@@ -596,14 +601,18 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   const size_t per_cta = smem + 1024;  // + the driver's reservation
   threads = per_cta * 4 <= 227 * 1024 ? 256 : (per_cta * 2 <= 227 * 1024 ? 512 : 1024);
   const unsigned grid = (unsigned)((items + threads / 32 - 1) / (threads / 32));
-#define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP)                                                                         \
+#define HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, ST)                                                                     \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST, XY, MAP><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, frame0, g->tab, g->d_table, \
+    hoptraj_kernel<SRC, FAST, XY, MAP, ST><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, ld, frame0, g->tab, g->d_table, \
         g->d_table2, map16, blockmap, map_words, fine_value, fine_auto_min, hop_x, hop_y, n_chunks, chunk_len,       \
         summaries, sink);                                                                                            \
+  } while (0)
+#define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP)                                                                         \
+  do {                                                                                                               \
+    if (ld != N) HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, true); else HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, false);       \
   } while (0)
 #define HOPB_HT_LAUNCH_XY(SRC, FAST, XY)                                                                             \
   do {                                                                                                               \
@@ -621,21 +630,30 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
 #undef HOPB_HT_LAUNCH
 #undef HOPB_HT_LAUNCH_XY
 #undef HOPB_HT_LAUNCH_M
+#undef HOPB_HT_LAUNCH_S
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
+}
+
+int hopb_hoptraj_strided(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
+                         int64_t N, int64_t ld, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
+                         int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
+                         int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
+  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, ld, frame0, map16, coarse, fine, fine_value,
+                        cell2, hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
                  int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
                  int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
                  int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
-  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, frame0, map16, coarse, fine, fine_value,
-                        cell2, hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
+  return hopb_hoptraj_strided(h, stream, g, xyz, cells, F, N, N, frame0, map16, coarse, fine, fine_value, cell2, hop_x, hop_y,
+                              n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N, int64_t frame0, int n_chunks,
                         int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
-  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, frame0, nullptr, nullptr, nullptr, 0, nullptr,
+  return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, N, frame0, nullptr, nullptr, nullptr, 0, nullptr,
                         nullptr, nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
@@ -672,11 +690,17 @@ int hopb_hop_advance(hopb_handle* h, void* stream, int64_t N, int n_summaries, c
 int hopb_hop_fixup(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_t chunk_len, int64_t F,
                    const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events, uint64_t* n_events,
                    uint64_t cap) {
-  HOPB_REQUIRE(h, N > 0 && n_chunks >= 1 && summaries && state && n_events, "bad argument");
+  return hopb_hop_fixup_strided(h, stream, N, N, n_chunks, chunk_len, F, summaries, state, hop_y, events, n_events, cap);
+}
+
+int hopb_hop_fixup_strided(hopb_handle* h, void* stream, int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t F,
+                           const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events, uint64_t* n_events,
+                           uint64_t cap) {
+  HOPB_REQUIRE(h, N > 0 && ld >= N && n_chunks >= 1 && summaries && state && n_events, "bad argument");
   HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
   (void)F;
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
-  HOPB_K(hop_fixup_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, n_chunks, chunk_len, F, summaries, state,
+  HOPB_K(hop_fixup_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, ld, n_chunks, chunk_len, F, summaries, state,
                                                                              hop_y, sink);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;

@@ -29,6 +29,17 @@ def _h(t=None):
     return _lib.handle(t.device.index if t is not None else None)
 
 
+def _rows(t, dtype, name):
+    """A 2-d CUDA tensor whose rows are contiguous (a column range of a wider contiguous array is fine)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.dim() == 2 and (t.shape[1] <= 1 or t.stride(1) == 1)):
+        raise TypeError("%s must be a CUDA tensor of dtype %s with contiguous rows" % (name, dtype))
+    return t
+
+
+def _ld(t):
+    return int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
+
+
 def _cuda(t, dtype, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
         raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
@@ -99,6 +110,31 @@ def hist_accumulate(grid: GridTables, xyz: torch.Tensor, counts: torch.Tensor, c
         return counts       # a frame with no selected atoms contributes nothing (hop/density.py:128)
     h = _h(xyz)
     _lib.check(h, _lib.lib().hopb_hist_accumulate_cells(h, _stream(), grid.ptr, _p(xyz), n_points, _p(counts), _p(cells)))
+    return counts
+
+
+def hist_accumulate_multi(grids, species: torch.Tensor, xyz: torch.Tensor, counts, cells=None):
+    """One pass over xyz (float32 [F][N][3]) for several selections: atom i belongs to selection species[i] (uint8) and is
+    binned on grids[species[i]] into counts[species[i]]; `cells` (int32 [F][N]) receives its brick index in that grid
+    (hopb_hist_accumulate_multi; hop reads the trajectory once per selection, scripts/hop-generate-many-densities.py:98-125)."""
+    _cuda(xyz, torch.float32, "xyz")
+    _cuda(species, torch.uint8, "species")
+    F, N = int(xyz.shape[0]), int(xyz.shape[1])
+    if species.numel() != N or len(grids) != len(counts):
+        raise ValueError("one species id per atom, one count array per grid")
+    for g, c in zip(grids, counts):
+        _cuda(c, torch.int32, "counts")
+        if c.numel() != g.n_cells:
+            raise ValueError("counts has the wrong size")
+    if cells is not None:
+        _cuda(cells, torch.int32, "cells")
+        if tuple(cells.shape) != (F, N):
+            raise ValueError("cells has the wrong shape")
+    K = len(grids)
+    gp = (ctypes.c_void_p * K)(*[g.ptr for g in grids])
+    cp = (ctypes.c_void_p * K)(*[c.data_ptr() for c in counts])
+    h = _h(xyz)
+    _lib.check(h, _lib.lib().hopb_hist_accumulate_multi(h, _stream(), K, gp, _p(species), _p(xyz), F, N, cp, _p(cells)))
     return counts
 
 
@@ -434,14 +470,25 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
         cell2 = bm.cell2 if block_map in ("auto", "cell2") else None
     _cuda(brick, torch.int16, "brick")
     map16 = brick
+    # Inputs and outputs may be column ranges of wider arrays (several selections binned in one pass,
+    # hist_accumulate_multi): rows `ld` atoms apart, atoms adjacent.
     if cells is not None:
-        _cuda(cells, torch.int32, "cells")
+        _rows(cells, torch.int32, "cells")
         F, N = cells.shape[0], cells.shape[1]
         dev = cells.device
+        ld = _ld(cells)
     else:
-        _cuda(xyz, torch.float32, "xyz")
+        if not (isinstance(xyz, torch.Tensor) and xyz.is_cuda and xyz.dtype == torch.float32 and xyz.dim() == 3
+                and xyz.stride(2) == 1 and xyz.stride(1) == 3 and xyz.stride(0) % 3 == 0):
+            raise TypeError("xyz must be a CUDA float32 [F][N][3] tensor (or a column range of one)")
         F, N = xyz.shape[0], xyz.shape[1]
         dev = xyz.device
+        ld = xyz.stride(0) // 3 if F > 1 else N
+    for name, t in (("hop_x", hop_x), ("hop_y", hop_y)):
+        if t is not None:
+            _rows(t, torch.float32, name)
+            if tuple(t.shape) != (F, N) or (F > 1 and _ld(t) != ld):
+                raise ValueError("%s must have the shape and row stride of the input" % name)
     nb = brick_shape(grid.shape)[0]
     if map16.numel() != nb * 64:
         raise ValueError("bricked map does not match the grid (use kernels.brick_map)")
@@ -458,10 +505,10 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
     h = _h(map16)
-    rc = _lib.lib().hopb_hoptraj(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N,
-                                 int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(cell2), _p(hop_x), _p(hop_y),
-                                 int(n_chunks), int(chunk_len), _p(summaries), _p(events.data), _p(events.count),
-                                 events.capacity)
+    rc = _lib.lib().hopb_hoptraj_strided(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N, int(ld),
+                                         int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(cell2), _p(hop_x),
+                                         _p(hop_y), int(n_chunks), int(chunk_len), _p(summaries), _p(events.data),
+                                         _p(events.count), events.capacity)
     _lib.check(h, rc)
     return summaries
 
@@ -497,8 +544,9 @@ def hop_advance(summaries, state: torch.Tensor, init: bool):
 def hop_fixup(summaries: torch.Tensor, chunk_len: int, n_frames: int, state: torch.Tensor, hop_y, events: EventBuffer):
     n_chunks, _, N = summaries.shape
     h = _h(summaries)
-    rc = _lib.lib().hopb_hop_fixup(h, _stream(), N, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(state),
-                                   _p(hop_y), _p(events.data), _p(events.count), events.capacity)
+    ld = N if hop_y is None else _ld(_rows(hop_y, torch.float32, "hop_y"))
+    rc = _lib.lib().hopb_hop_fixup_strided(h, _stream(), N, ld, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(state),
+                                           _p(hop_y), _p(events.data), _p(events.count), events.capacity)
     _lib.check(h, rc)
     return state
 

