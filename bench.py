@@ -877,8 +877,9 @@ def run_gpu(args):
         return
     xyz_host = torch.empty((FRAMES_PER_GPU, ATOMS, 3), dtype=torch.float32).pin_memory()
     xyz_host.copy_(xyz)
-    outs = [(torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory(),
-             torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.float32).pin_memory()) for _ in range(2)]
+    # the hoptraj planes come back as int16 (lossless; HostRun.planes_float32 restores the DCD's float32 on the host)
+    outs = [(torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.int16).pin_memory(),
+             torch.empty((FRAMES_PER_GPU, ATOMS), dtype=torch.int16).pin_memory()) for _ in range(2)]
     del xyz
     pipe.run_host(xyz_host, frame0, *outs[0])   # warm-up (allocates the resident buffers)
     e2e_steps = min(max(args.steps, 10), 20)   # at least 10: the first upload of the chain has nothing to overlap with
@@ -897,16 +898,16 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     barrier()
-    hx, hy = res.hop_x.cpu(), res.hop_y.cpu()
+    hx, hy = res.hop_x.cpu().to(torch.int16), res.hop_y.cpu().to(torch.int16)
     checks["e2e_matches_resident"] = bool(all(torch.equal(ox, hx) and torch.equal(oy, hy) for ox, oy in outs[:min(2, e2e_steps)]))
     del hx, hy
-    d2h = int(out_x.numel() * 4 + out_y.numel() * 4 + host["events"].numel() * 4 + host["edge_count"].numel() * 16
+    d2h = int(out_x.numel() * out_x.element_size() + out_y.numel() * out_y.element_size() + host["events"].numel() * 4 + host["edge_count"].numel() * 16
               + host["final_state"].numel() * 4)
     e2e = {"value": atom_frames_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(xyz_host.numel() * 4), "d2h_bytes_per_step": d2h,
            "steps": e2e_steps, "host_binding": numa,
-           "api": ("HopPipeline.run_host_begin/finish (pinned host float32 [F][N][3] in; host hop_x/hop_y, sorted events, "
-                   "COO counts out; download of step k overlaps upload of step k+1)")}
+           "api": ("HopPipeline.run_host_begin/finish (pinned host float32 [F][N][3] in; host hop_x/hop_y as int16 label planes, "
+                   "sorted events, COO counts out; download of step k overlaps upload of step k+1)")}
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:

@@ -526,6 +526,19 @@ hop_fixup_kernel(int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t
   store_state(state, N, atom, S);
 }
 
+// hoptraj planes as int16 for the trip to the host: labels are integers in [-1, 32767] (hop's site map is int16,
+// hop/sitemap.py:518-519), so the conversion is lossless and halves the download; the float32 of the DCD record is
+// restored on the host when a file is written.
+__global__ void __launch_bounds__(256)
+planes_to_int16_kernel(const float4* __restrict__ in, int64_t n4, const float* __restrict__ in_tail, int n_tail, short4* __restrict__ out,
+                       int16_t* __restrict__ out_tail) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    out[i] = make_short4((short)v.x, (short)v.y, (short)v.z, (short)v.w);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) out_tail[threadIdx.x] = (int16_t)in_tail[threadIdx.x];
+}
+
 // graph_alltransitions: set of (label[t-1], label[t]) pairs
 __global__ void __launch_bounds__(256)
 all_transitions_kernel(const float* __restrict__ hop_x, int64_t F, int64_t N, int n_labels, uint32_t* __restrict__ bitmap) {
@@ -702,6 +715,17 @@ int hopb_hop_fixup_strided(hopb_handle* h, void* stream, int64_t N, int64_t ld, 
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
   HOPB_K(hop_fixup_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, ld, n_chunks, chunk_len, F, summaries, state,
                                                                              hop_y, sink);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_labels_to_int16(hopb_handle* h, void* stream, const float* labels, int64_t n, int16_t* out) {
+  HOPB_REQUIRE(h, labels && out && n >= 0, "bad argument");
+  HOPB_REQUIRE(h, ((uintptr_t)labels & 15) == 0 && ((uintptr_t)out & 7) == 0, "labels must be 16-byte, out 8-byte aligned");
+  if (n == 0) return HOPB_OK;
+  const int64_t n4 = n / 4;
+  HOPB_K(planes_to_int16_kernel)<<<hopb_grid_for(n4 > 0 ? n4 : 1, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(labels), n4, labels + 4 * n4, (int)(n - 4 * n4), reinterpret_cast<short4*>(out), out + 4 * n4);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

@@ -600,6 +600,16 @@ def events_finalize_dev(events: EventBuffer, n_atoms: int, n_frames_total: int, 
     _lib.check(h, rc)
 
 
+def labels_to_int16(labels: torch.Tensor, out=None):
+    """float32 hoptraj plane -> int16 (lossless), for the download (hopb_labels_to_int16)."""
+    _cuda(labels, torch.float32, "labels")
+    if out is None:
+        out = torch.empty(labels.shape, dtype=torch.int16, device=labels.device)
+    h = _h(labels)
+    _lib.check(h, _lib.lib().hopb_labels_to_int16(h, _stream(), _p(labels), labels.numel(), _p(out)))
+    return out
+
+
 def all_transitions(hop_x: torch.Tensor, n_labels: int):
     """Sorted (K,2) int64 array of (label[t-1], label[t]) pairs (hop/graph.py:107-135)."""
     _cuda(hop_x, torch.float32, "hop_x")

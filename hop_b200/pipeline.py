@@ -94,6 +94,7 @@ class _PendingFinalize(object):
     def __init__(self, pipe, done, host, events, out, matrix, props, props_done, redo):
         self.pipe, self.done, self.host, self.events, self.out = pipe, done, host, events, out
         self.matrix, self.props, self.props_done, self.redo = matrix, props, props_done, redo
+        self.run_index = pipe._run_index
 
     def resolve(self, res):
         from . import _lib
@@ -102,6 +103,10 @@ class _PendingFinalize(object):
             self._resolve(res)
 
     def _resolve(self, res):
+        if self.pipe._run_index > self.run_index + 2:
+            # outputs alternate between two buffer sets: after two more runs this result's buffers hold another run's
+            raise RuntimeError("PipelineResult resolved too late: its buffers were reused by run %d (resolve a result, or "
+                               "call wait(), before queuing the run after next)" % (self.run_index + 2))
         self.done.synchronize()
         n_all, n_edges, n_labels, status = (int(v) for v in self.host.tolist())
         pipe = self.pipe
@@ -127,7 +132,8 @@ class _PendingFinalize(object):
         if self.props_done is not None:
             self.props_done.synchronize()
         res.site_props = self.props
-        pipe._w_known = W
+        if _dist() is None:       # with several ranks the matrix size must come from something all ranks share: the
+            pipe._w_known = W     # first (synchronous) run's site count, not from whichever rank looks at a result
 
 
 _dist = exchange.dist
@@ -397,13 +403,22 @@ class HopPipeline:
     def _finalize_sync(self, res, events, xyz, frame0, n_atoms=None):
         """Tail of a run with the host in the loop: wait for stage 3, read the counts, sort."""
         res.n_labels, n_ev = self.sync_scalars(events)
+        n_local = n_ev
+        d = _dist()
+        if d is not None:
+            # the redo below runs collectives (slab summaries, count matrix): every rank must take the same branch,
+            # so the decision is made on the largest event count of any rank
+            t = torch.tensor([n_ev, events.capacity], dtype=torch.int64, device=self.device)
+            d.all_reduce(t, op=d.ReduceOp.MAX)
+            n_ev = max(n_ev, int(t[0].item())) if int(t[0].item()) > events.capacity else n_ev
         if n_ev > events.capacity and xyz is None:
             self._event_buffer(n_ev + n_ev // 8)     # the next attempt fits
             raise _capacity_error(n_ev, events.capacity)
         if n_ev > events.capacity:      # rare: more transitions than budgeted -- grow the buffer and redo stage 3
             self._event_buffer(n_ev + n_ev // 8)
             res.hop_x, res.hop_y, events, res.state, res.final_state = self.hoptraj(xyz, res.map16, frame0)
-            res.n_labels, n_ev = self.sync_scalars(events)
+            res.n_labels, n_local = self.sync_scalars(events)
+        n_ev = n_local
         res.n_events_local = n_ev
         (res.events, res.edge_s0, res.edge_s, res.edge_start, res.edge_count,
          res.count_matrix) = self.transitions(events, n_ev, int(xyz.shape[1]) if n_atoms is None else n_atoms, res.n_labels)
@@ -444,6 +459,16 @@ class HopPipeline:
                                   2 if self.cfg.with_bulk else 1, out, matrix, result_dev)
             if matrix is not None:
                 exchange.reduce_count_matrix(matrix)
+            if _dist() is not None:
+                # every rank learns whether ANY rank ran out of event space: a rank-local recovery would issue
+                # collectives the other ranks never match
+                flags = self._buf("fin_flags" + par, (2,), torch.int64)
+                flags[0] = result_dev[3] & K.FIN_OVERFLOW
+                flags[1] = result_dev[0]
+                _dist().all_reduce(flags, op=_dist().ReduceOp.MAX)
+                result_dev[3] |= flags[0]
+                host_any = self._host_buf("fin_any" + par, (2,), torch.int64)
+                host_any.copy_(flags, non_blocking=True)
             host.copy_(result_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(s4)
@@ -451,7 +476,16 @@ class HopPipeline:
 
         run_index = self._run_index
 
+        distributed = _dist() is not None
+
         def redo(res_, n_needed):
+            if distributed and n_needed is not None:
+                # more transitions than budgeted on some rank (the flag is all-reduced, so every rank that looks at
+                # its result gets here): results are resolved lazily and not in lockstep, so the collective redo is
+                # left to the caller -- the buffers are grown for the next run
+                need = int(self._host_bufs["fin_any%d" % (run_index & 1)][1].item())
+                self._event_buffer(need + need // 8)
+                raise _capacity_error(need, events.capacity)
             if self._run_index != run_index + 1:
                 if n_needed is not None:
                     self._event_buffer(n_needed + n_needed // 8)   # at least the next runs will fit
@@ -601,6 +635,9 @@ class HopPipeline:
         """Start an end-to-end run and return a HostRun; HostRun.finish() waits for the hopping
         trajectory to be in host memory and returns (PipelineResult, host dict).
 
+        out_x / out_y: pinned host tensors [F_local][N], float32 (the DCD records) or int16 (the same labels, half the
+        download; HostRun.planes_float32 widens them).
+
         Coordinates go to HBM in blocks on an upload stream while the histogram kernel consumes the
         blocks already there; they stay resident for stage 3.  The hopping trajectory planes stream
         back into pinned host tensors (out_x / out_y, [F_local][N] float32) on a download stream; the
@@ -652,10 +689,17 @@ class HopPipeline:
         if out_x is None:
             out_x = torch.empty((F, N), dtype=torch.float32).pin_memory()
             out_y = torch.empty((F, N), dtype=torch.float32).pin_memory()
+        # int16 host planes (lossless: labels are int16 map values or -1) halve the download; the float32 of the DCD
+        # record is then restored on the host by whoever writes a file (HostRun.planes_float32)
+        if out_x.dtype == torch.int16:
+            src_x = K.labels_to_int16(res.hop_x, self._buf("hop_x16_%d" % par, (F, N), torch.int16))
+            src_y = K.labels_to_int16(res.hop_y, self._buf("hop_y16_%d" % par, (F, N), torch.int16))
+        else:
+            src_x, src_y = res.hop_x, res.hop_y
         d2h.wait_stream(main)
         with torch.cuda.stream(d2h):
-            out_x.copy_(res.hop_x, non_blocking=True)
-            out_y.copy_(res.hop_y, non_blocking=True)
+            out_x.copy_(src_x, non_blocking=True)
+            out_y.copy_(src_y, non_blocking=True)
             # fixed-size small result; the buffer is rewritten by the next run's stage 3
             state_host = self._host_buf("final_state%d" % par, tuple(res.final_state.shape), torch.int32)
             state_host.copy_(res.final_state, non_blocking=True)
@@ -679,6 +723,12 @@ class HostRun(object):
 
     def __init__(self, pipe, result, host, done):
         self.pipe, self.result, self.host, self._done = pipe, result, host, done
+
+    def planes_float32(self):
+        """hop_x / hop_y of the host result as float32 [F][N] (the X and Y records of the hoptraj DCD), whatever
+        dtype they were downloaded in."""
+        self._done.synchronize()
+        return self.host["hop_x"].to(torch.float32), self.host["hop_y"].to(torch.float32)
 
     def finish(self):
         res, host = self.result, self.host

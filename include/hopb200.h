@@ -380,6 +380,11 @@ int hopb_events_finalize_dev(hopb_handle* h, void* stream, const hopb_event* eve
                              hopb_event* events_sorted, int32_t* edge_s0, int32_t* edge_s, int64_t* edge_start,
                              int64_t* edge_count, int32_t* count_matrix, int matrix_stride, int64_t* result_dev);
 
+/* A plane of the hopping trajectory as int16 (lossless: the labels are the values of hop's int16 site map,
+ * hop/sitemap.py:518-519, or -1), for a half-size download; the float32 of the DCD record (hop/trajectory.py:456-463)
+ * is restored on the host.  labels: device float32 [n], 16-byte aligned; out: device int16 [n], 8-byte aligned. */
+int hopb_labels_to_int16(hopb_handle* h, void* stream, const float* labels, int64_t n, int16_t* out);
+
 /* TransportNetwork.graph_alltransitions (hop/graph.py:107-135): bit (a+1)*(n_labels+1)+(b+1) of
  * `bitmap` is set when some atom has label a in frame t-1 and b in frame t.
  * bitmap: device uint32 [ceil((n_labels+1)^2 / 32)], OR-ed into (not cleared). */

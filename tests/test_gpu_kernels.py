@@ -557,6 +557,13 @@ def test_run_host_overlapped_runs_match_resident_run(K, traj):
     r1, h1 = pipe.run_host(host_xyz)
     assert torch.equal(h1["hop_x"], ha["hop_x"]) and torch.equal(h1["hop_y"], ha["hop_y"])
     assert torch.equal(h1["events"], ha["events"])
+    # int16 host planes: the same labels in half the bytes; planes_float32 gives the DCD records back
+    o16 = (torch.empty(xyz.shape[:2], dtype=torch.int16).pin_memory(), torch.empty(xyz.shape[:2], dtype=torch.int16).pin_memory())
+    run = pipe.run_host_begin(host_xyz, 0, *o16)
+    r2, h2 = run.finish()
+    assert h2["hop_x"].dtype == torch.int16 and torch.equal(h2["hop_x"].to(torch.float32), ha["hop_x"])
+    fx, fy = run.planes_float32()
+    assert torch.equal(fx, ha["hop_x"]) and torch.equal(fy, ha["hop_y"]) and torch.equal(h2["events"], ha["events"])
 
 
 def test_pipeline_async_results_are_lazy_and_correct(K, traj):

@@ -71,6 +71,27 @@ def main():
                 rank, world, n_atoms, n_frames, f0, f1, "first run" if which == 0 else "third run (asynchronous)",
                 "OK" if not bad else "MISMATCH " + str(bad)), flush=True)
             ok &= not bad
+    # Event buffer too small on SOME ranks only (transition rates differ between slabs): the recovery re-runs stage 3,
+    # which all-gathers slab summaries, so the decision must be collective -- a rank-local one hangs here.
+    p = SynthParams(n_atoms=1000, n_frames=200)
+    xyz = generate(p)
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    ref = O.pipeline(xyz, delta=1.0)
+    f0, f1 = exchange.slab_bounds(200, world, rank)
+    er = ref["events"]
+    mine_ref = er[(er[:, 0] >= f0) & (er[:, 0] < f1)]
+    per_rank = torch.tensor([len(mine_ref)], device="cuda")
+    lo = per_rank.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    cap = int(lo.item()) + 1                      # the rank with the fewest events fits, the others do not
+    pipe = HopPipeline(edges, 200, PipelineConfig(n_chunks=3, event_capacity=cap))
+    res = pipe.run(torch.from_numpy(xyz[f0:f1]).cuda(), f0)
+    ev = K.events_to_numpy(res.events)
+    got = np.stack([ev[k] for k in ("frame", "iatom", "s0", "s", "tau", "tbarrier")], axis=1).astype(np.int64)
+    order = np.lexsort((mine_ref[:, 1], mine_ref[:, 0], mine_ref[:, 3], mine_ref[:, 2]))
+    good = np.array_equal(got, mine_ref[order]) and int(res.count_matrix.sum().item()) == len(er)
+    print("rank %d/%d  event buffer of %d for %d events: %s" % (rank, world, cap, len(mine_ref), "OK" if good else "MISMATCH"), flush=True)
+    ok &= good
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
