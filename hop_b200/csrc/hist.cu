@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kBulkThreads)
 hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ solute, int64_t Nw, int Np, float cutoff,
                  HopbGridTab tab, const float* __restrict__ table, const HopbPair* __restrict__ table2,
                  uint32_t* __restrict__ counts_solvent, uint32_t* __restrict__ counts_bulk, uint32_t* __restrict__ cells,
-                 uint8_t* __restrict__ within_out) {
+                 uint8_t* __restrict__ within_out, const uint8_t* __restrict__ within_in, int64_t solute_stride, int flags_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
   float* s_tab = reinterpret_cast<float*>(s_pairs + tab.table2_len);
@@ -279,7 +279,9 @@ hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ so
   __shared__ uint32_t s_warp[33];
 
   const int64_t frame = blockIdx.x;
-  const float* P = solute + frame * (int64_t)Np * 3;
+  // the solute may arrive in tiles (selections too large for the shared-memory cell list): P is this tile's part of the
+  // frame, within_in what the earlier tiles found; all tiles but the last only update the flags
+  const float* P = solute + frame * solute_stride * 3;
   const float* W = solvent + frame * Nw * 3;
   for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
   if (!FAST)
@@ -385,6 +387,8 @@ hist_bulk_kernel(const float* __restrict__ solvent, const float* __restrict__ so
           }
         }
     }
+    if (within_in) within = within || within_in[frame * Nw + i] != 0;
+    if (flags_only) { within_out[frame * Nw + i] = within ? 1 : 0; continue; }
     const uint32_t c = hist_point<CELLS, FAST>(x, y, z, tab, ax, ay, az, s_tab, counts_solvent, slab, counts_bulk, !within);
     if (CELLS) cells[frame * Nw + i] = c;
     if (within_out) within_out[frame * Nw + i] = within ? 1 : 0;
@@ -601,21 +605,43 @@ int hopb_hist_bulk(hopb_handle* h, void* stream, const hopb_grid* g, const float
   if (F == 0 || Nw == 0) return HOPB_OK;
   HOPB_REQUIRE(h, F < ((int64_t)1 << 31), "too many frames for one call");
   const bool fast = g->tab.fast_ok != 0;
-  const size_t smem = (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float)) +
-                      (size_t)(2 * kBulkMaxCells + 1) * sizeof(int) + (size_t)Np * 3 * sizeof(float) + 16;
-  HOPB_REQUIRE(h, smem <= 200 * 1024, "solute selection too large for the shared-memory cell list (max ~12000 atoms)");
+  const size_t smem_fixed = (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float)) +
+                            (size_t)(2 * kBulkMaxCells + 1) * sizeof(int) + 16;
+  // solute atoms per launch: what fits beside the tables in shared memory; larger selections go through in tiles, the
+  // "within" flag of every solvent atom carried from tile to tile (the kd-tree of the reference has no such limit)
+  const size_t kSmemBudget = 200 * 1024;
+  HOPB_REQUIRE(h, smem_fixed + 3 * sizeof(float) * 64 <= kSmemBudget, "grid tables too large for the bulk-selection kernel");
+  int64_t tile = (int64_t)((kSmemBudget - smem_fixed) / (3 * sizeof(float)));
+  if (const char* e = getenv("HOPB_BULK_TILE")) {          // testing hook: smaller tiles
+    const int64_t v = atoll(e);
+    if (v > 0 && v < tile) tile = v;
+  }
+  const int64_t n_tiles = Np > tile ? (Np + tile - 1) / tile : 1;
   cudaStream_t s = (cudaStream_t)stream;
-#define HOPB_BULK_LAUNCH(C, FA)                                                                                      \
+  uint8_t* flags = within;
+  if (n_tiles > 1 && !flags) {
+    int rc = hopb_scratch(h, 15, (size_t)F * Nw, (void**)&flags);
+    if (rc) return rc;
+  }
+#define HOPB_BULK_LAUNCH(C, FA, P0, NP, WIN, WOUT, ONLY)                                                             \
   do {                                                                                                               \
+    const size_t smem = smem_fixed + (size_t)(NP) * 3 * sizeof(float);                                               \
     if (smem > 48 * 1024)                                                                                            \
       HOPB_CUDA(h, cudaFuncSetAttribute(hist_bulk_kernel<C, FA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hist_bulk_kernel<C, FA><<<(unsigned)F, kBulkThreads, smem, s>>>(solvent, solute, Nw, (int)Np, (float)cutoff, g->tab, \
+    hist_bulk_kernel<C, FA><<<(unsigned)F, kBulkThreads, smem, s>>>(solvent, (P0), Nw, (int)(NP), (float)cutoff, g->tab, \
                                                                    g->d_table, g->d_table2, counts_solvent,          \
-                                                                   counts_bulk, cells, within);                      \
+                                                                   counts_bulk, cells, (WOUT), (WIN), Np, (ONLY));   \
   } while (0)
-  if (cells) { if (fast) HOPB_BULK_LAUNCH(true, true); else HOPB_BULK_LAUNCH(true, false); }
-  else { if (fast) HOPB_BULK_LAUNCH(false, true); else HOPB_BULK_LAUNCH(false, false); }
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    const float* p0 = solute ? solute + t * tile * 3 : nullptr;
+    const int64_t np = n_tiles == 1 ? Np : (t + 1 < n_tiles ? tile : Np - t * tile);
+    const uint8_t* win = t > 0 ? flags : nullptr;
+    const int only = t + 1 < n_tiles ? 1 : 0;
+    uint8_t* wout = only ? flags : within;
+    if (cells) { if (fast) HOPB_BULK_LAUNCH(true, true, p0, np, win, wout, only); else HOPB_BULK_LAUNCH(true, false, p0, np, win, wout, only); }
+    else { if (fast) HOPB_BULK_LAUNCH(false, true, p0, np, win, wout, only); else HOPB_BULK_LAUNCH(false, false, p0, np, win, wout, only); }
+  }
 #undef HOPB_BULK_LAUNCH
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;

@@ -381,6 +381,7 @@ def test_notwithin_selection_and_fused_densities(solvated):
     cb.finish(40)
     assert np.array_equal(cb.Density().grid, ref_bulk)
 
+
     # mode='bulk' alone
     only = DensityCreator(u, mode="bulk", delta=1.0, atomselection="name OH2", cutoff=cutoff,
                           soluteselection="protein and not name H*").create()["bulk"]
@@ -393,6 +394,49 @@ def test_notwithin_selection_and_fused_densities(solvated):
     sites = O.site_insert_bulk(O.label_sites_ndimage(gs, math.e), O.label_sites_ndimage(gb, math.exp(-0.5)))
     assert np.array_equal(final.map, O.draw_map_from_sites(sites, gs.shape))
     assert final.has_bulk() and [list(s) for s in final.sites] == sites
+
+
+def test_large_solute_goes_through_in_tiles(solvated, monkeypatch):
+    """A solute too large for the shared-memory cell list of hist_bulk_kernel is processed in tiles, the within
+    flags carried from tile to tile (the kd-tree selection of the reference has no size limit, hop/density.py:82-87).
+    The tile size is forced down so that the small test solute needs several tiles; also a really large one."""
+    import torch
+
+    from hop_b200 import kernels as K
+
+    u, xyz, water, heavy = solvated
+    cutoff = 3.5
+    _, _, edges = O.grid_geometry(water[0], delta=1.0)
+    g = K.GridTables(edges)
+    w, p = torch.from_numpy(water).cuda(), torch.from_numpy(np.ascontiguousarray(heavy)).cuda()
+
+    def run(with_flags):
+        cs = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+        cb = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+        cells = torch.empty(w.shape[:2], dtype=torch.int32, device="cuda")
+        flags = torch.full(w.shape[:2], 7, dtype=torch.uint8, device="cuda") if with_flags else None
+        K.hist_bulk(g, w, p, cutoff, cb, counts_solvent=cs, cells=cells, within=flags)
+        return cs, cb, cells, flags
+
+    want = run(True)
+    assert np.array_equal(want[1].cpu().numpy().astype(np.int64), O.histogram_bulk(water, heavy, edges, cutoff))
+    monkeypatch.setenv("HOPB_BULK_TILE", "5")
+    assert heavy.shape[1] > 10
+    for with_flags in (True, False):
+        got = run(with_flags)
+        assert all(torch.equal(a, b) for a, b in zip(want[:3], got[:3]))
+        if with_flags:
+            assert torch.equal(want[3], got[3])
+    monkeypatch.delenv("HOPB_BULK_TILE")
+    # 40 000 solute atoms (more than one launch can stage): compared with the brute-force oracle on two frames
+    rng = np.random.default_rng(2)
+    big = (rng.random((2, 40000, 3)) * (water[0].max() * 0.3) + water[0].max() * 0.35).astype(np.float32)
+    cb = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    flags = torch.empty((2, water.shape[1]), dtype=torch.uint8, device="cuda")
+    K.hist_bulk(g, w[:2].contiguous(), torch.from_numpy(big).cuda(), cutoff, cb, within=flags)
+    ref = np.stack([O.within_cutoff(water[f], big[f], cutoff) for f in range(2)])
+    assert np.array_equal(flags.cpu().numpy().astype(bool), ref) and 0 < ref.sum() < ref.size
+    assert np.array_equal(cb.cpu().numpy().astype(np.int64), O.histogram_bulk(water[:2], big, edges, cutoff))
 
 
 @pytest.mark.parametrize("seed", range(8))
