@@ -48,6 +48,51 @@ __device__ __forceinline__ void emit_event(const EventSink& sink, int iatom, int
   }
 }
 
+// Events are rare (~1e-3 per atom-frame) but every one used to pay a returning atomic on the one global counter --
+// a ~1 us round trip on the emitting thread's critical path, 2.3e5 of them serialised on one L2 address per launch.
+// Each warp now parks its events in a small shared-memory queue (a shared-memory atomic hands out the slot) and
+// reserves global space for the whole queue with one atomic when the warp next reaches a common point.
+constexpr int kEvQueue = 8;
+struct EvStage {
+  int* cnt;            // shared: events queued by this warp since the last flush (may exceed kEvQueue)
+  hopb_event* q;       // shared: [kEvQueue]
+};
+
+__device__ __forceinline__ void emit_staged(const EventSink& sink, const EvStage& st, int iatom, int s0, int s, int frame, int tau,
+                                            int tbar) {
+  const int slot = atomicAdd(st.cnt, 1);
+  if (slot < kEvQueue) {
+    hopb_event e;
+    e.frame = frame; e.iatom = iatom; e.s0 = s0; e.s = s; e.tau = tau; e.tbarrier = tbar;
+    st.q[slot] = e;
+  } else {
+    emit_event(sink, iatom, s0, s, frame, tau, tbar);     // queue full: straight to the global buffer
+  }
+}
+
+// all lanes of `lanes` call this together
+__device__ __forceinline__ void flush_staged(const EventSink& sink, const EvStage& st, unsigned lanes) {
+  __syncwarp(lanes);
+  int n = *reinterpret_cast<volatile int*>(st.cnt);
+  if (n == 0) return;
+  n = n < kEvQueue ? n : kEvQueue;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(lanes) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(sink.n_events, (unsigned long long)n);
+  base = __shfl_sync(lanes, base, leader);
+  // 6 ints per event: the active lanes copy the queue word by word
+  const int* src = reinterpret_cast<const int*>(st.q);
+  const int rank = __popc(lanes & ((1u << lane) - 1)), width = __popc(lanes);
+  for (int w = rank; w < n * 6; w += width) {
+    const unsigned long long ev = base + (unsigned long long)(w / 6);
+    if (ev < sink.cap) reinterpret_cast<int*>(sink.events + ev)[w % 6] = src[w];
+  }
+  __syncwarp(lanes);
+  if (lane == leader) *st.cnt = 0;
+  __syncwarp(lanes);
+}
+
 struct AxisReg {
   float lo, inv, nf, hop_lo, hop_hi;
   int n;
@@ -155,6 +200,9 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   // rows of the data arrays are N atoms apart, or ld_arg when the atoms are a column range of wider arrays (a
   // variant of its own: the common case keeps one value less alive at the 64-register limit)
   const int64_t ld = STRIDED ? ld_arg : N;
+  __shared__ int s_ev_cnt[32];
+  __shared__ hopb_event s_ev_q[32][kEvQueue];
+  if (threadIdx.x < 32) s_ev_cnt[threadIdx.x] = 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(smem_raw);
   float* s_tab = reinterpret_cast<float*>(s_pairs + (SRC == 0 ? tab.table2_len : 0));
@@ -171,7 +219,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   }
   if (SRC != 1 && (MAP == MAP_COARSE || MAP == MAP_FINE))
     for (int i = threadIdx.x; i < map_words; i += blockDim.x) s_map[i] = blockmap[i];
-  if (SRC != 1) __syncthreads();
+  __syncthreads();
   const AxisReg ax = load_axis(tab.ax[0], s_pairs);
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
   const AxisReg az = load_axis(tab.ax[2], s_pairs);
@@ -185,6 +233,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   const int chunk = (int)(item / atom_warps);
   const int64_t atom = (item - (int64_t)chunk * atom_warps) * 32 + (threadIdx.x & 31);
   if (chunk >= n_chunks || atom >= N) return;
+  const unsigned lanes = __activemask();
   // frame numbers inside the slab fit 32 bits (checked by the launcher)
   const int f_begin = (int)((int64_t)chunk * chunk_len);
   const int f_end = (int)((int64_t)f_begin + chunk_len > F ? F : (int64_t)f_begin + chunk_len);
@@ -193,7 +242,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   int ypre = 0, yorb = 0;
   bool yknown = false;
   const int iatom = (int)atom;
-  auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_event(sink, iatom, s0, s, frame, tau, tbar); };
+  const EvStage evs{&s_ev_cnt[threadIdx.x >> 5], s_ev_q[threadIdx.x >> 5]};
+  auto emit = [&](int s0, int s, int frame, int tau, int tbar) { emit_staged(sink, evs, iatom, s0, s, frame, tau, tbar); };
 
   // running pointers (one frame = N elements further)
   // data rows are `ld` elements apart (ld = N unless the atoms are a column range of a wider array)
@@ -336,6 +386,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         for (int u = 0; u < kUnroll; ++u) lab[u] = label_of<MAP>(pack_cell<FAST>(cx[u], cy[u], cz[u], tab, ax, ay, az, s_tab, cny, cnz), mv);
         body(lab, std::integral_constant<int, kUnroll>(), f, (int)(frame0 + f));
         f += kUnroll;
+        __syncwarp(lanes);
+        if (*reinterpret_cast<volatile int*>(evs.cnt) >= kEvQueue / 2) flush_staged(sink, evs, lanes);
         if (!more()) break;
       }
     } else {
@@ -361,6 +413,8 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         }
         body(lab, std::integral_constant<int, kDeep>(), f, (int)(frame0 + f));
         f += kDeep;
+        __syncwarp(lanes);
+        if (*reinterpret_cast<volatile int*>(evs.cnt) >= kEvQueue / 2) flush_staged(sink, evs, lanes);
         if (!more()) break;
       }
     }
@@ -368,11 +422,11 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   // Three loops, chosen per warp: no lane has seen a site yet; some have; all have.  (One loop that
   // serves both kinds of lanes needs more than the 64 registers there are, so the common all-A case
   // gets its own lean loop; per-lane loops instead would make a mixed warp walk its chunk twice.)
-  const unsigned lanes = __activemask();
   stream_blocks(blockB, [&]() { return !__any_sync(lanes, inA); });
   stream_blocks(blockU, [&]() { return !__all_sync(lanes, inA); });
   stream_blocks(blockA, [&]() { return true; });
   for (; f < f_end; ++f) generic(label_at(f), (int)(frame0 + f));
+  flush_staged(sink, evs, lanes);
   int32_t* sp = summaries + ((int64_t)chunk * HOPB_SUMMARY_FIELDS) * N + atom;
   if (inA) {
     if (T.kind == HOPB_FULL) T.s0 = cur;
