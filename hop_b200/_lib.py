@@ -78,6 +78,7 @@ _SIGNATURES = {
     "hopb_site_properties": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
     "hopb_site_map_fused": [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _int, _vp, _vp, _vp, _vp],
+    "hopb_rate_fit": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, ctypes.c_uint, _vp, _vp],
     "hopb_site_occupancy": [_vp, _vp, _vp, _i64, _i64, _int, _vp],
     "hopb_site_distance_hist": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _int, _int, _vp],
     "hopb_site_cells": [_vp, _vp, _i64, _vp, _vp, _int, _vp, _i64, _vp, ctypes.POINTER(_i64)],

@@ -202,7 +202,17 @@ class HoppingGraph(object):
     function of the waiting times; the survival function is evaluated by sorting instead of the
     reference's O(N * T) sum of step functions -- the values are identical."""
 
-    def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None, workers=None):
+    #: how the rate constants of a new graph are fitted: "gpu" -- every edge at once on the device (csrc/ratefit.cu:
+    #: the survival functions by histogram + suffix sum, MINPACK's lmdif restated with one warp per edge; it takes
+    #: the optimiser's path of the reference -- same nfev / info -- and agrees with it to ~1e-7, not always to 1e-6:
+    #: lmdif differentiates by forward differences, so rounding in exp() reaches the result); "minpack" -- scipy's
+    #: leastsq on the host, the very library call of the reference (hop/graph.py:2369), bit-compatible with it and
+    #: what `_rate` for a single edge always uses; "auto" -- "gpu", then the fits that a second, exp()-perturbed run
+    #: moves by more than 1e-8 (not determined by the data to the parity bar) once more with "minpack".
+    rate_method = "auto"
+
+    def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None, workers=None,
+                 rate_method=None):
         import networkx as NX
 
         self.trjdata = trjdata if isinstance(trjdata, dict) else None
@@ -213,7 +223,7 @@ class HoppingGraph(object):
             self.properties = properties
             self.graph.add_nodes_from(graph.nodes)
             edges = list(graph.edges)
-            fits = _ratefit.fit_all([numpy.asarray(properties[e]['tau']) for e in edges], workers=workers)
+            fits = _fit_edges([numpy.asarray(properties[e]['tau']) for e in edges], rate_method or self.rate_method, workers)
             ebunch = [(e[0], e[1], _rate_record(f)) for e, f in zip(edges, fits)]
             self.graph.add_edges_from(ebunch)
         elif filename is not None:
@@ -367,6 +377,44 @@ class fitlin(fit_func):
 
     def __repr__(self):
         return "<fitlin" + str(self.parameters) + ">"
+
+
+def _fit_edges(taus_list, method, workers=None):
+    """(kind, parameters, message, k, N) per edge, by the chosen method (HoppingGraph.rate_method)."""
+    if method == "minpack" or not taus_list:
+        return _ratefit.fit_all(taus_list, workers=workers)
+    if method not in ("gpu", "auto"):
+        raise ValueError("rate_method must be 'gpu', 'minpack' or 'auto'")
+    from . import kernels as K
+
+    out, _, _ = K.rate_fit(taus_list)
+    messages = {1: "Both actual and predicted relative reductions in the sum of squares are at most 0.000000",
+                2: "The relative error between two consecutive iterates is at most 0.000000",
+                3: "Both actual and predicted relative reductions in the sum of squares are at most 0.000000 and the "
+                   "relative error between two consecutive iterates is at most 0.000000",
+                4: "The cosine of the angle between func(x) and any column of the Jacobian is at most 0.000000 in "
+                   "absolute value",
+                5: "Number of calls to function has reached maxfev = %d."}
+
+    def record(o):
+        kind = 'exp2' if o[0] == 1.0 else 'exp'
+        p = numpy.array(o[1:4] if kind == 'exp2' else o[1:2], dtype=float)
+        info = int(o[5])
+        msg = messages.get(info, "info = %d" % info)
+        if info == 5:
+            msg = msg % (800 if kind == 'exp2' else 400)
+        return kind, p, msg, float(o[4]), int(o[7])
+
+    fits = [record(o) for o in out]
+    if method == "auto":
+        second, _, _ = K.rate_fit(taus_list, noise=1)
+        moved = (out[:, 0] != second[:, 0]) | (numpy.abs(out[:, 4] - second[:, 4]) > 1e-8 * numpy.abs(out[:, 4])) | (out[:, 5] >= 5)
+        idx = numpy.nonzero(moved)[0]
+        if len(idx):
+            redo = _ratefit.fit_all([taus_list[i] for i in idx], workers=workers)
+            for i, f in zip(idx, redo):
+                fits[i] = f
+    return fits
 
 
 def _rate_record(fitted):

@@ -353,6 +353,32 @@ def site_properties(grid: GridTables, density: torch.Tensor, own: torch.Tensor, 
     return count, mean, std, center
 
 
+def rate_fit(taus_list, device=None, perturb=0.0, noise=0):
+    """HoppingGraph._rate for many edges at once (hopb_rate_fit): taus_list = the waiting times of every edge.
+    Returns (out float64 [E][8] = kind, p0, p1, p2, k, info, nfev, N; S float64 concatenated; off_x int64 [E + 1])."""
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    E = len(taus_list)
+    lens = np.array([len(t) for t in taus_list], dtype=np.int64)
+    if E == 0 or lens.min() == 0:
+        if E == 0:
+            return np.zeros((0, 8)), np.zeros(0), np.zeros(1, np.int64)
+        raise ValueError("every edge needs at least one waiting time")
+    off_tau = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tau = np.concatenate([np.asarray(t, dtype=np.float64) for t in taus_list])
+    tmax = np.maximum.reduceat(tau, off_tau[:-1])
+    m = np.array([len(np.arange(0, t + 2.0, 1.0)) for t in tmax], dtype=np.int64)      # x = arange(0, tmax + 1, dt), tmax = max + dt
+    off_x = np.concatenate([[0], np.cumsum(m)]).astype(np.int64)
+    total = int(off_x[-1])
+    d_tau = torch.from_numpy(tau).to(dev)
+    d_ot = torch.from_numpy(off_tau).to(dev)
+    d_ox = torch.from_numpy(off_x).to(dev)
+    S = torch.empty(total, dtype=torch.float64, device=dev)
+    out = torch.empty((E, 8), dtype=torch.float64, device=dev)
+    h = _lib.handle(dev.index)
+    _lib.check(h, _lib.lib().hopb_rate_fit(h, _stream(), _p(d_tau), _p(d_ot), _p(d_ox), E, total, float(perturb), int(noise), _p(S), _p(out)))
+    return out.cpu().numpy(), S.cpu().numpy(), off_x
+
+
 def site_occupancy(labels: torch.Tensor, n_labels: int, out=None):
     """occ int32 [F][n_labels]: atoms per site and frame (hop/siteanalysis.py:837-841); labels = a hoptraj plane."""
     _cuda(labels, torch.float32, "labels")

@@ -234,6 +234,26 @@ int hopb_site_cells(hopb_handle* h, void* stream, int64_t n_grid_cells, const in
                     const uint8_t* member, int n_labels, int32_t* cells, int64_t capacity,
                     int64_t* offsets, int64_t* n_cells);
 
+/* ---- rate constants (hop.graph.HoppingGraph._rate) ------------------------------ */
+/* For every edge e: the survival function S(t) of its waiting times on the mesh t = 0, 1, ..., m_e - 1
+ * (hop/graph.py:2433-2518; m_e = len(numpy.arange(0, max(tau) + 2, 1.0))) and the least-squares fit of
+ * a exp(-k1 t) + (1 - a) exp(-k2 t) (more than 10 waiting times, start [0.5, 0.1, 1e-4]) or exp(-k t) (start
+ * [1.0]; also when the double exponential is degenerate: |0.5 - a| > 0.49 or a negative k) by MINPACK's lmdif
+ * with scipy.optimize.leastsq's defaults -- HoppingGraph._rate + fit_func (hop/graph.py:1677-1748, 2354-2419).
+ *   tau      device double [off_tau[n_edges]], the waiting times edge after edge (any order inside an edge)
+ *   off_tau  device int64 [n_edges + 1]; off_x device int64 [n_edges + 1], prefix sums of the mesh lengths
+ *   perturb  0 for the reference's start values; otherwise they are multiplied by 1 + perturb
+ *   noise    0 for the fit itself; != 0 nudges every exp() by +-1 ulp pseudo-randomly (seeded by `noise`) -- a second
+ *            opinion: lmdif differentiates by forward differences with h = 1.5e-8 |p|, so rounding in the model
+ *            function reaches the result at the 1e-8 .. 1e-6 level, more along flat directions.  A fit whose
+ *            result moves visibly between noise = 0 and noise != 0 is not determined to the 1e-6 of the parity
+ *            bar by ANY implementation other than the reference's own library call
+ *   S        device double [total_x] out
+ *   out      device double [n_edges][8] out: kind (0: exp, 1: double exp), the parameters p0, p1, p2, the rate
+ *            constant k, MINPACK's info, its nfev, the number of waiting times */
+int hopb_rate_fit(hopb_handle* h, void* stream, const double* tau, const int64_t* off_tau, const int64_t* off_x,
+                  int64_t n_edges, int64_t total_x, double perturb, unsigned noise, double* S, double* out);
+
 /* ---- per-site observables (hop.siteanalysis) ------------------------------ */
 /* Atoms per site and frame: occ[f][l] = number of atoms whose label in frame f is l (outliers, -1, are not
  * counted) -- the per-frame numpy.histogram of Occupancy._compute_occupancy (hop/siteanalysis.py:837-841),

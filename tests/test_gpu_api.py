@@ -506,3 +506,56 @@ def test_workflow_random_systems(seed, tmp_path):
                 assert np.array_equal(gp[k][f], d[f]), (k, f)
             np.testing.assert_allclose(gp[k]["tau"], d["tau"], rtol=1e-6)
         assert tn.transition_counts() == {e: len(props_ref[e]["tau"]) for e in edges_ref}
+
+
+def test_gpu_rate_fit_follows_minpack():
+    """hopb_rate_fit (survival functions + MINPACK's lmdif restated, one warp per edge) against scipy.optimize.leastsq,
+    the reference's own call (hop/graph.py:2354-2419, 1677-1748): the survival functions are identical; the fits take
+    the same optimiser path (nfev and info equal for the single exponentials, whose paths do not branch on rounding) and
+    agree to 1e-6 for the well-determined ones -- lmdif differentiates by forward differences (h = 1.5e-8 |p|), so the
+    last-bit differences of exp() reach any result at the 1e-8 .. 1e-6 level, and the parameters of a double
+    exponential whose fast component decays within one mesh step are not determined by the data at all.
+    HoppingGraph(rate_method='auto') therefore repeats the fits a perturbed second run moves with scipy itself."""
+    import warnings
+
+    import scipy.optimize
+
+    from hop_b200 import _ratefit
+    from hop_b200 import kernels as K
+    from hop_b200.graph import _fit_edges
+
+    rng = np.random.default_rng(0)
+    taus = []
+    for e in range(1200):
+        n = int(rng.choice([1, 2, 5, 10, 11, 12, 20, 50, 200]))
+        if rng.random() < 0.5:
+            t = rng.exponential(rng.choice([2.0, 10.0, 50.0, 300.0]), n)
+        else:
+            t = np.where(rng.random(n) < 0.6, rng.exponential(3.0, n), rng.exponential(120.0, n))
+        taus.append(np.floor(t) * float(rng.choice([1.0, 1.0, 2.5])))
+    out, S, off_x = K.rate_fit(taus)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = [_ratefit.fit_one(t) for t in taus]
+        single = [e for e, t in enumerate(taus) if len(t) <= 10]
+        for e in single[:200]:
+            x = np.arange(0, taus[e].max() + 2.0, 1.0)
+            y = _ratefit.survival_values(taus[e], x)
+            p, cov, info, msg, ier = scipy.optimize.leastsq(lambda p, x, y: np.exp(-p[0] * x) - y, [1.0], args=(x, y), full_output=True)
+            assert info["nfev"] == int(out[e][6]) and ier == int(out[e][5])
+    close = 0
+    for e, (r, o) in enumerate(zip(ref, out)):
+        x = np.arange(0, taus[e].max() + 2.0, 1.0)
+        assert np.array_equal(S[off_x[e]:off_x[e + 1]], _ratefit.survival_values(taus[e], x))
+        assert int(o[7]) == len(taus[e])
+        same = (r[0] == 'exp2') == (o[0] == 1.0) and abs(o[4] - r[3]) <= 1e-6 * abs(r[3])
+        close += same
+        if len(taus[e]) <= 10:
+            assert (o[0] == 0.0) and abs(o[4] - r[3]) <= 5e-6 * abs(r[3])
+    assert close >= 0.9 * len(taus)
+    # the default method of HoppingGraph: within 1e-6 of the reference's library call on (nearly) every edge
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        auto = _fit_edges(taus, "auto", workers=0)
+    ok = sum(1 for a_, r in zip(auto, ref) if a_[0] == r[0] and abs(a_[3] - r[3]) <= 1e-6 * abs(r[3]))
+    assert ok >= 0.995 * len(taus)
