@@ -95,7 +95,10 @@ template <bool CELLS, bool FAST>
 __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                                const AxisReg& ay, const AxisReg& az, const float* s_tab,
                                                uint32_t* counts, const Slab& slab, uint32_t* counts_b = nullptr,
-                                               bool to_b = false) {
+                                               bool to_b = false, uint32_t* lin_out = nullptr) {
+  // lin_out != NULL (partitioned histogram): the linear cell of an ordinary point is handed back instead of being
+  // reduced (0xFFFFFFFF: nothing to count, or counted here already -- the rare last-edge points)
+  if (lin_out) *lin_out = 0xFFFFFFFFu;
   hopb_wrap_point(x, y, z, tab);   // periodic image first, when the grid asks for it (default: off)
   int bx, by, bz;
   bool sure = false;
@@ -142,7 +145,8 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
   const bool ok = ((unsigned)(bx - 1) < (unsigned)ax.n) & ((unsigned)(by - 1) < (unsigned)ay.n) & ((unsigned)(bz - 1) < (unsigned)az.n);
   if (ok & (bx - 1 >= slab.x_lo) & (bx - 1 < slab.x_hi)) {
     const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)ay.n + (uint32_t)(by - 1)) * (uint32_t)az.n + (uint32_t)(bz - 1);
-    if (counts) atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
+    if (lin_out) *lin_out = cell;
+    else if (counts) atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
     if (to_b) atomicAdd(counts_b + cell, 1u);
   }
   if (!CELLS) return 0u;
@@ -249,6 +253,167 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
     const int64_t p = i < lead ? i : tail0 + (i - lead);
     const uint32_t c = hist_point<CELLS, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts, slab);
     if (CELLS) cells[p] = c;
+  }
+}
+
+// ---- spatially partitioned, shared-memory-privatised histogram (north_star kernel 2) ---------------------------------
+// Water at 0.5 A leaves 0.004 atoms per cell and frame: no tile of the coordinate stream sees a cell twice, so
+// privatisation only pays once the points are grouped by where they go.  Pass A is the streaming kernel above with
+// the reduction replaced by a CTA-local multisplit: the points of a tile (8192) are counted per bucket (= 16384
+// consecutive cells of the grid) in shared memory, every bucket's run is reserved in global memory with ONE atomic
+// per bucket and tile, the 14-bit bucket-local cell indices are staged in shared memory in bucket order and written
+// out in runs.  Pass B gives every bucket a CTA: ATOMS.ADD into a 64 KB shared tile (1.3e12 /s over the GPU against
+// 1.9e11 /s for scattered L2 reductions, profiles/r2_ubench_b200.txt), then counts[cell] += tile[cell], plain and
+// coalesced -- a bucket owns its cells.  Per point the L2 sees 2 B written and 2 B read in runs instead of one
+// scattered reduction.  Points a bucket has no room for (capacity = twice the mean) and the rare last-edge points
+// are reduced directly, so the result never depends on the distribution.  tools/histpart.cu is the stand-alone
+// prototype (1.55 vs 1.87 ms on the bench's shape).
+constexpr int kPartShift = 14;                  // 16384 cells per bucket: a 64 KB shared tile in pass B
+constexpr int kPartTile = 8192;                 // points per CTA and tile in pass A
+constexpr int kPartThreads = 512;
+constexpr int kPartMaxBuckets = 1024;
+
+template <bool FAST>
+__global__ void __launch_bounds__(kPartThreads, 2)
+hist_part_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbGridTab tab, const float* __restrict__ table,
+                 const HopbPair* __restrict__ table2, uint32_t* __restrict__ counts, uint32_t* __restrict__ cells, int n_buckets,
+                 uint32_t* __restrict__ gfill, uint16_t* __restrict__ buckets, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kWarps = kPartThreads / 32;
+  float4* stage = reinterpret_cast<float4*>(smem_raw);                             // [warps][96] float4
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(stage + kWarps * 96);               // [n_buckets] counts, then offsets
+  uint32_t* s_gbase = s_cnt + kPartMaxBuckets;                                      // [n_buckets]
+  uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_gbase + kPartMaxBuckets);       // [kPartTile] bucket-local cells in bucket order
+  uint16_t* s_bkt = s_stage + kPartTile;                                            // [kPartTile] their buckets
+  HopbPair* s_pairs = reinterpret_cast<HopbPair*>(s_bkt + kPartTile);
+  float* s_tab = reinterpret_cast<float*>(s_pairs + tab.table2_len);
+  __shared__ uint32_t s_warp[kWarps];
+  __shared__ uint32_t s_total;
+  for (int i = threadIdx.x; i < tab.table2_len; i += blockDim.x) s_pairs[i] = table2[i];
+  if (!FAST)
+    for (int i = threadIdx.x; i < tab.table_len; i += blockDim.x) s_tab[i] = table[i];
+  __syncthreads();
+  const AxisReg ax = load_axis(tab.ax[0], s_pairs);
+  const AxisReg ay = load_axis(tab.ax[1], s_pairs);
+  const AxisReg az = load_axis(tab.ax[2], s_pairs);
+  Slab slab; slab.x_lo = 0; slab.x_hi = tab.ax[0].n; slab.done_flag = 0u;
+  const uint64_t pol = make_evict_first_policy();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* wbuf = stage + warp * 96;
+  const float* wf = reinterpret_cast<const float*>(wbuf);
+  constexpr int kBlocksPerWarp = kPartTile / 128 / kWarps;      // 128-point groups per warp and tile (4)
+  const int64_t nblk = (n_points - lead) / 128;
+  const float4* base = reinterpret_cast<const float4*>(xyz + 3 * lead);
+  const int64_t n_tiles = (nblk + kPartTile / 128 - 1) / (kPartTile / 128);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int b = threadIdx.x; b < n_buckets; b += blockDim.x) s_cnt[b] = 0;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    uint32_t lin[kBlocksPerWarp * 4], slot[kBlocksPerWarp * 4];
+#pragma unroll
+    for (int g = 0; g < kBlocksPerWarp; ++g) {
+      const int64_t b = t * (kPartTile / 128) + (int64_t)g * kWarps + warp;
+      if (b < nblk) {
+        const float4* src = base + b * 96;
+        const float4 v0 = ld_stream(src + lane, pol);
+        const float4 v1 = ld_stream(src + 32 + lane, pol);
+        const float4 v2 = ld_stream(src + 64 + lane, pol);
+        wbuf[lane] = v0; wbuf[32 + lane] = v1; wbuf[64 + lane] = v2;
+        __syncwarp();
+        uint32_t* cout = cells + lead + b * 128 + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = 3 * (lane + 32 * j);
+          uint32_t l;
+          const uint32_t c = hist_point<true, FAST>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts, slab, nullptr, false, &l);
+          cout[32 * j] = c;
+          lin[4 * g + j] = l;
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lin[4 * g + j] = 0xFFFFFFFFu;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBlocksPerWarp * 4; ++u)
+      if (lin[u] != 0xFFFFFFFFu) slot[u] = atomicAdd(&s_cnt[lin[u] >> kPartShift], 1u);
+    __syncthreads();
+    // exclusive scan of the bucket counts (two buckets per thread), one global reservation per non-empty bucket
+    uint32_t c0 = 0, c1 = 0;
+    const int b0 = 2 * threadIdx.x, b1 = b0 + 1;
+    if (b0 < n_buckets) c0 = s_cnt[b0];
+    if (b1 < n_buckets) c1 = s_cnt[b1];
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < kWarps ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+      if (lane < kWarps) s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t ex = s_warp[warp] + incl - (c0 + c1);
+    if (b0 < n_buckets) { s_cnt[b0] = ex; s_gbase[b0] = c0 ? atomicAdd(gfill + b0, c0) : 0u; }
+    if (b1 < n_buckets) { s_cnt[b1] = ex + c0; s_gbase[b1] = c1 ? atomicAdd(gfill + b1, c1) : 0u; }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int u = 0; u < kBlocksPerWarp * 4; ++u)
+      if (lin[u] != 0xFFFFFFFFu) {
+        const uint32_t b = lin[u] >> kPartShift, p = s_cnt[b] + slot[u];
+        s_stage[p] = (uint16_t)(lin[u] & ((1u << kPartShift) - 1));
+        s_bkt[p] = (uint16_t)b;
+        ++total;
+      }
+    if (total) atomicAdd(&s_total, total);       // number of staged entries of the tile
+    __syncthreads();
+    const uint32_t n_st = s_total;
+    for (uint32_t i = threadIdx.x; i < n_st; i += blockDim.x) {
+      const uint32_t b = s_bkt[i];
+      const uint32_t pos = s_gbase[b] + (i - s_cnt[b]);
+      if (pos < cap) buckets[(size_t)b * cap + pos] = s_stage[i];
+      else atomicAdd(counts + ((b << kPartShift) | s_stage[i]), 1u);      // bucket full: an ordinary reduction
+    }
+    __syncthreads();
+  }
+  // scalar remainder: leading unaligned points and the tail, reduced directly
+  const int64_t tail0 = lead + nblk * 128;
+  const int64_t n_rem = lead + (n_points - tail0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rem; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i < lead ? i : tail0 + (i - lead);
+    cells[p] = hist_point<true, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts, slab);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+hist_tiles_kernel(const uint16_t* __restrict__ buckets, const uint32_t* __restrict__ gfill, uint32_t cap, int n_buckets,
+                  uint32_t* __restrict__ counts, uint32_t n_cells) {
+  extern __shared__ uint32_t s_tile[];
+  constexpr int kCells = 1 << kPartShift;
+  for (int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    for (int i = threadIdx.x; i < kCells; i += blockDim.x) s_tile[i] = 0;
+    __syncthreads();
+    uint32_t nb = gfill[b];
+    if (nb > cap) nb = cap;
+    const uint4* src = reinterpret_cast<const uint4*>(buckets + (size_t)b * cap);     // eight entries per load
+    for (uint32_t i = threadIdx.x; i < (nb + 7) / 8; i += blockDim.x) {
+      const uint4 v = src[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (8 * i + 2 * k < nb) atomicAdd(&s_tile[w[k] & 0xFFFFu], 1u);
+        if (8 * i + 2 * k + 1 < nb) atomicAdd(&s_tile[w[k] >> 16], 1u);
+      }
+    }
+    __syncthreads();
+    const uint32_t c0 = (uint32_t)b << kPartShift;
+    for (int i = threadIdx.x; i < kCells; i += blockDim.x)
+      if (c0 + i < n_cells && s_tile[i]) counts[c0 + i] += s_tile[i];
+    __syncthreads();
   }
 }
 
@@ -565,6 +730,45 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
   }
   // slabs are whole bricks (multiples of 4 cells) wide, so that the later passes can tell "in my slab"
   // from the brick index alone
+  // The partitioned, shared-memory-privatised histogram: one call with many points per cell of a grid that fits the
+  // bucket scheme (the pipeline's resident and streamed runs); small calls keep the direct reductions.
+  // OFF by default: measured on B200 at the bench shape the two passes take 2.13 + 0.21 ms against 1.75 ms for the
+  // direct reductions -- the multisplit costs ~170 thread instructions per point and pass A is issue-bound (67 % issue
+  // active, 1.6e9 warp instructions; profiles/r2_hist_partition.md).  HOPB_HIST_PART=1 enables it for large calls,
+  // =2 for every call (tests).
+  const char* part_env = getenv("HOPB_HIST_PART");
+  const int part_mode = part_env ? atoi(part_env) : 0;
+  const int64_t n_cells_all = (int64_t)g->n[0] * g->n[1] * g->n[2];
+  const int n_buckets = (int)((n_cells_all + (1 << kPartShift) - 1) >> kPartShift);
+  if (part_mode && cells && n_pass == 1 && n_buckets <= kPartMaxBuckets && (n_points >= 8 * n_cells_all || part_mode == 2)) {
+    const uint32_t cap = (uint32_t)((((2 * n_points) / n_buckets) + 65535) & ~(int64_t)7);     // twice the mean, 16-byte rows
+    unsigned char* scr = nullptr;
+    int rc = hopb_scratch(h, 18, (size_t)n_buckets * cap * sizeof(uint16_t) + (size_t)kPartMaxBuckets * sizeof(uint32_t) + 64, (void**)&scr);
+    if (rc) return rc;
+    uint32_t* gfill = reinterpret_cast<uint32_t*>(scr);
+    uint16_t* buckets = reinterpret_cast<uint16_t*>(scr + (size_t)kPartMaxBuckets * sizeof(uint32_t));
+    HOPB_CUDA(h, cudaMemsetAsync(gfill, 0, (size_t)n_buckets * sizeof(uint32_t), s));
+    const size_t smem_a = (size_t)(kPartThreads / 32) * 96 * sizeof(float4) + (size_t)kPartMaxBuckets * 8 + (size_t)kPartTile * 4 +
+                          (size_t)g->tab.table2_len * sizeof(HopbPair) + (fast ? 0 : (size_t)g->tab.table_len * sizeof(float));
+    const size_t smem_b = (size_t)4 << kPartShift;
+    const int64_t n_tiles = (nblk + kPartTile / 128 - 1) / (kPartTile / 128);
+    int64_t grid_a = (int64_t)h->num_sms * 2;
+    if (grid_a > n_tiles) grid_a = n_tiles < 1 ? 1 : n_tiles;
+    hopb_note_launch();
+    if (fast) {
+      HOPB_CUDA(h, cudaFuncSetAttribute(hist_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+      hist_part_kernel<true><<<(unsigned)grid_a, kPartThreads, smem_a, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells,
+                                                                            n_buckets, gfill, buckets, cap);
+    } else {
+      HOPB_CUDA(h, cudaFuncSetAttribute(hist_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+      hist_part_kernel<false><<<(unsigned)grid_a, kPartThreads, smem_a, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells,
+                                                                             n_buckets, gfill, buckets, cap);
+    }
+    HOPB_CUDA(h, cudaFuncSetAttribute(hist_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    HOPB_K(hist_tiles_kernel)<<<(unsigned)n_buckets, 1024, smem_b, s>>>(buckets + 0, gfill, cap, n_buckets, counts, (uint32_t)n_cells_all);
+    HOPB_LAUNCH_CHECK(h);
+    return HOPB_OK;
+  }
   int slab_w = (g->n[0] + n_pass - 1) / n_pass;
   if (n_pass > 1) slab_w = (slab_w + 3) / 4 * 4;
   Slab slab;

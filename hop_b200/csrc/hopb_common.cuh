@@ -13,7 +13,7 @@
 #include "hopb_binning.h"
 #include "hopb_machine.h"
 
-#define HOPB_NUM_SCRATCH 18
+#define HOPB_NUM_SCRATCH 20
 
 struct hopb_handle {
   int device;

@@ -92,6 +92,52 @@ def test_histogram_slabbed_passes(K, traj):
         K.set_hist_l2_budget(64 << 20)
 
 
+@pytest.mark.parametrize("delta", [1.0, 0.5])
+def test_partitioned_histogram_equals_direct_reductions(K, traj, delta, monkeypatch):
+    """The spatially partitioned, shared-memory-privatised histogram (hist_part_kernel + hist_tiles_kernel, taken for
+    large resident runs) gives the counts and brick indices of the one-reduction-per-point kernel: ordinary points
+    through the buckets, last-edge points, unaligned heads / tails and points a full bucket has no room for through
+    direct reductions."""
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=delta)
+    ref = O.histogram_vectorised(xyz, edges)
+    g = K.GridTables(edges)
+    flat = dev(xyz.reshape(-1, 3))
+
+    def run(points, mode):
+        monkeypatch.setenv("HOPB_HIST_PART", mode)
+        counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+        cells = torch.full((points.shape[0],), -5, dtype=torch.int32, device="cuda")
+        K.hist_accumulate(g, points, counts, cells)
+        return counts, cells
+
+    direct = run(flat, "0")
+    assert np.array_equal(direct[0].cpu().numpy().astype(np.int64), ref)
+    for pts in (flat, flat[1:], flat[3:100003], flat[:77]):
+        a, b = run(pts, "0"), run(pts, "2")
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # every point in the same few cells: far more than a bucket's capacity (twice the mean) -> the overflow path
+    lump = flat[:4096].repeat(60, 1).contiguous()
+    a, b = run(lump, "0"), run(lump, "2")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and int(a[0].sum().item()) == lump.shape[0]
+    # outliers, NaN, points on the last edges
+    odd = flat[:5000].clone()
+    odd[::7] += 1000.0
+    odd[3::11] = float("nan")
+    odd[5::13, 0] = float(edges[0][-1])
+    odd[6::17, 2] = float(edges[2][-1])
+    a, b = run(odd, "0"), run(odd, "2")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # accumulation over several calls adds up
+    monkeypatch.setenv("HOPB_HIST_PART", "2")
+    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    cells = torch.empty((flat.shape[0],), dtype=torch.int32, device="cuda")
+    cut = 1000 * 77 + 3
+    K.hist_accumulate(g, flat[:cut], counts, cells[:cut])
+    K.hist_accumulate(g, flat[cut:], counts, cells[cut:])
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref) and torch.equal(cells, direct[1])
+
+
 def test_histogram_edge_semantics(K):
     rng = np.random.default_rng(3)
     coords0 = (rng.random((300, 3)) * [17.3, 9.1, 23.7] - 1.9999).astype(np.float32)
