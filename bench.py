@@ -783,11 +783,11 @@ def run_gpu(args):
     k_hop = time_kernel(hop_once, max(args.steps, 3))
     peak, peak_src = measured_peak()
     # DRAM bytes per launch of the two kernels from the committed `ncu --set full` capture of this
-    # same workload (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)
+    # same workload (profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)
     traffic = {}
     try:
         if WORKLOAD == "config2":
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 traffic = json.load(f)
     except Exception:
         pass
