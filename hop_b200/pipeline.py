@@ -161,6 +161,22 @@ class HopPipeline:
         self._run_index = 0
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
+    def set_edges(self, edges):
+        """Another grid geometry for the next run (a batch of trajectories: every one spans its own grid in frame 0,
+        hop/density.py:271-278).  Keeps the buffers when the shape stays the same."""
+        if all(len(a) == len(b) and np.array_equal(a, b) for a, b in zip(edges, self.grid.edges)):
+            return
+        # grids seen before are kept: dropping one would free device tables that queued kernels may still read
+        cache = self.__dict__.setdefault("_grids", {})
+        key = b"".join(np.ascontiguousarray(e, dtype=np.float64).tobytes() for e in edges)
+        cache.setdefault(b"".join(e.tobytes() for e in self.grid.edges), self.grid)
+        grid = cache.get(key)
+        if grid is None:
+            grid = cache[key] = K.GridTables(edges, device=self.device)
+            if self.cfg.periodic_box is not None:
+                grid.set_periodic_box(*self.cfg.periodic_box)
+        self.grid = grid
+
     # -- buffers reused across runs (steady-state runs do not allocate) --------------------------
     def _buf(self, name, shape, dtype):
         t = self._bufs.get(name)
@@ -754,14 +770,17 @@ class PipelinePool(object):
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
         self._next = 0
 
-    def run(self, xyz, frame0=0, marks=None):
+    def run(self, xyz, frame0=0, marks=None, edges=None):
         """Queue one run on the next pipeline and return its PipelineResult without waiting; the
-        result's lazy fields, or synchronize(), wait for it."""
+        result's lazy fields, or synchronize(), wait for it.  `edges`: the grid of this trajectory when it differs
+        from the previous one's (same shape or not)."""
         i = self._next
         self._next = (i + 1) % len(self.pipes)
         stream = self.streams[i]
         stream.wait_stream(torch.cuda.current_stream(self.pipes[i].device))   # xyz was produced there
         with torch.cuda.stream(stream):
+            if edges is not None:
+                self.pipes[i].set_edges(edges)
             return self.pipes[i].run(xyz, frame0, marks)
 
     def synchronize(self):
