@@ -230,8 +230,14 @@ extern "C" int hopb_events_finalize_dev(hopb_handle* h, void* stream, const hopb
   int per_sm = 0;
   HOPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ev_finalize_kernel, kSortThreads, 0));
   HOPB_REQUIRE(h, per_sm >= 1, "cooperative launch not possible");
-  // one block per SM: the passes are barrier-latency bound at the event counts of this path
-  const int nblocks = h->num_sms < kMaxSortBlocks ? h->num_sms : kMaxSortBlocks;
+  // This variant runs on a side stream beside the next run's histogram.  Its CTAs spend most of their time spinning
+  // at grid barriers, and with one CTA on every SM that costs the histogram issue slots everywhere: measured on B200
+  // (bench shape, 2.3e5 events) 148 CTAs: S1 1.889 / S4 0.20 ms, step 3.133; 32 CTAs: S1 1.827 / S4 0.73 ms (still
+  // hidden behind S1), step 3.071; 16 CTAs: 1.796 / 1.58; 8 CTAs: S4 outlasts the histogram and stalls stage 3.
+  int nblocks = h->num_sms < kMaxSortBlocks ? h->num_sms : kMaxSortBlocks;
+  int want = 32;
+  if (const char* e = getenv("HOPB_EV_BLOCKS")) want = atoi(e);     // tuning hook
+  if (want >= 1 && want < nblocks) nblocks = want;
   unsigned char* buf = nullptr;
   const size_t per = 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
   const size_t bytes = (size_t)(cap + 2) * per + ((size_t)256 * nblocks + 256 + nblocks + 8) * sizeof(uint32_t) + 64;
