@@ -269,24 +269,16 @@ class DensityCreator(object):
             errmsg = "DensityCreator: mode must be one of %r, not %r" % (self.modes, self.mode)
             logger.fatal(errmsg)
             raise ValueError(errmsg)
-        modes = self.modes[1:] if self.mode == "all" else [self.mode]
         self.keep_coordinates = kwargs.pop("keep_coordinates", True)
-        self.collectors = []
-        min_coords = []
-        max_coords = []
-        for mode in modes:
-            modeargs = kwargs.copy()
-            if mode == "solvent":
-                modeargs['soluteselection'] = None
-                modeargs['cutoff'] = 0
-            c = DensityCollector(mode, self.universe, **modeargs)
-            self.collectors.append(c)
-            min_coords.append(c.min_coordinates())
-            max_coords.append(c.max_coordinates())
-        smin = numpy.sort(min_coords, axis=0)[0]
-        smax = numpy.sort(max_coords, axis=0)[-1]
+        wanted = list(self.modes[1:]) if self.mode == "all" else [self.mode]
+        # one collector per density; the plain solvent density ignores the solute (hop/density.py:259-270)
+        overrides = {"solvent": {'soluteselection': None, 'cutoff': 0}}
+        self.collectors = [DensityCollector(m, self.universe, **dict(kwargs, **overrides.get(m, {}))) for m in wanted]
+        # all densities of a run share ONE grid: the box around every collector's frame-0 extent (hop/density.py:271-278)
+        lower = numpy.min([c.min_coordinates() for c in self.collectors], axis=0)
+        upper = numpy.max([c.max_coordinates() for c in self.collectors], axis=0)
         for c in self.collectors:
-            c.init_histogram(smin=smin, smax=smax)
+            c.init_histogram(smin=lower, smax=upper)
         self.densities = {}
 
     def create(self):
@@ -379,21 +371,18 @@ class DensityCreator(object):
 
     def DensityWithBulk(self, density_unit='water', solvent_threshold=numpy.e, bulk_threshold=0.6):
         """Solvent density with the bulk site inserted (hop/density.py:306-356)."""
+        problem = None
         if len(self.densities) != 2:
-            errmsg = "DensityCreator.DensityWithBulk(): Need exactly two densities ('solvent' and 'bulk')."
-            logger.fatal(errmsg)
-            raise MissingDataError(errmsg)
-        try:
-            solvent = self.densities['solvent']
-            bulk = self.densities['bulk']
-        except KeyError:
-            errmsg = "Need a 'solvent' and a 'bulk' density in %s.densities" % self.__class__.__name__
-            logger.fatal(errmsg)
-            raise MissingDataError(errmsg)
-        solvent.convert_density(density_unit)
-        solvent.map_sites(solvent_threshold)
-        bulk.convert_density(density_unit)
-        bulk.map_sites(bulk_threshold)
+            problem = "DensityCreator.DensityWithBulk(): Need exactly two densities ('solvent' and 'bulk')."
+        elif not {'solvent', 'bulk'} <= set(self.densities):
+            problem = "Need a 'solvent' and a 'bulk' density in %s.densities" % self.__class__.__name__
+        if problem:
+            logger.fatal(problem)
+            raise MissingDataError(problem)
+        solvent, bulk = self.densities['solvent'], self.densities['bulk']
+        for dens, threshold in ((solvent, solvent_threshold), (bulk, bulk_threshold)):
+            dens.convert_density(density_unit)
+            dens.map_sites(threshold)
         solvent.site_insert_bulk(bulk)
         return solvent
 

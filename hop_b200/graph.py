@@ -15,6 +15,7 @@ reference, fed by the event arrays the GPU produced.
 from __future__ import annotations
 
 import logging
+import os
 import pickle
 
 import numpy
@@ -209,7 +210,7 @@ class HoppingGraph(object):
     #: leastsq on the host, the very library call of the reference (hop/graph.py:2369), bit-compatible with it and
     #: what `_rate` for a single edge always uses; "auto" -- "gpu", then the fits that a second, exp()-perturbed run
     #: moves by more than 1e-8 (not determined by the data to the parity bar) once more with "minpack".
-    rate_method = "auto"
+    rate_method = os.environ.get("HOPB_RATE_METHOD", "auto")
 
     def __init__(self, graph=None, properties=None, filename=None, trjdata=None, site_properties=None, workers=None,
                  rate_method=None):

@@ -172,7 +172,7 @@ class HopPipeline:
         cache.setdefault(b"".join(e.tobytes() for e in self.grid.edges), self.grid)
         grid = cache.get(key)
         if grid is None:
-            grid = cache[key] = K.GridTables(edges, device=self.device)
+            grid = cache[key] = K.GridTables(edges, device=self.device.index)
             if self.cfg.periodic_box is not None:
                 grid.set_periodic_box(*self.cfg.periodic_box)
         self.grid = grid

@@ -626,27 +626,26 @@ class Density(Grid):
         arrays site_volume, site_occupancy_rho_avg, site_occupancy_rho_std."""
         if self.site_properties is None:
             raise AttributeError('Stats require site_properties annotation.')
-        stats = dict()
         nodes = self.site_labels(exclude=['bulk', 'interstitial', 'subsites'])
-        try:
-            stats['rho_cut'] = self.P['threshold']
-            stats['rho_cut_bulk'] = self.P['bulk_threshold']
-        except KeyError:
-            warnings.warn("No bulk site defined", category=MissingDataWarning)
-        stats['N_sites'] = len(nodes)
-        stats['N_equivalence_sites'] = 0   # equivalence sites are not part of this package
-        stats['N_subsites'] = 0
         sp = self.site_properties.take(nodes)
-        stats['site_volume_avg'] = numpy.average(sp.volume)
-        stats['site_volume_std'] = numpy.std(sp.volume)
-        stats['site_occupancy_rho_avg'] = numpy.average(sp.occupancy_avg)
-        stats['site_occupancy_rho_std'] = numpy.std(sp.occupancy_avg)
-        try:
-            data['site_volume'] = sp.volume
-            data['site_occupancy_rho_avg'] = sp.occupancy_avg
-            data['site_occupancy_rho_std'] = sp.occupancy_std
-        except TypeError:
-            pass
+        stats = {}
+        if 'threshold' in self.P and 'bulk_threshold' in self.P:
+            stats['rho_cut'], stats['rho_cut_bulk'] = self.P['threshold'], self.P['bulk_threshold']
+        else:
+            if 'threshold' in self.P:        # the reference sets rho_cut before it trips over the missing bulk site
+                stats['rho_cut'] = self.P['threshold']
+            warnings.warn("No bulk site defined", category=MissingDataWarning)
+        # the key names are the contract (hop/sitemap.py:1318-1332); equivalence sites are not part of this package
+        stats.update(N_sites=len(nodes), N_equivalence_sites=0, N_subsites=0,
+                     site_volume_avg=numpy.average(sp.volume), site_volume_std=numpy.std(sp.volume),
+                     site_occupancy_rho_avg=numpy.average(sp.occupancy_avg),
+                     site_occupancy_rho_std=numpy.std(sp.occupancy_avg))
+        if data is not None:
+            try:
+                data.update(site_volume=sp.volume, site_occupancy_rho_avg=sp.occupancy_avg,
+                            site_occupancy_rho_std=sp.occupancy_std)
+            except (TypeError, AttributeError):
+                pass
         return stats
 
     def _draw_map_from_sites(self):

@@ -688,6 +688,34 @@ def test_pipeline_pool_two_runs_in_flight(K, traj):
     assert torch.equal(last.events, want[j][2]) and torch.equal(last.hop_x, want[j][0])
 
 
+def test_pipeline_pool_with_a_grid_per_trajectory(K, traj):
+    """A batch of trajectories (BASELINE config 5) where every trajectory spans its own grid in frame 0
+    (hop/density.py:271-278): PipelinePool.run(edges=...) switches the geometry per run, the results equal those of
+    pipelines built for each grid."""
+    import torch
+
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, PipelinePool, grid_edges_from_frame0
+
+    p, xyz = traj
+    shifted = (xyz + np.float32(0.37)).astype(np.float32)          # another extent: other edges, same shape
+    wide = xyz.copy()
+    wide[0, 5] += np.float32(3.0)                                  # one atom further out in frame 0: a larger grid
+    cases = [xyz, shifted, wide, xyz]
+    edges = [grid_edges_from_frame0(c[0], delta=1.0) for c in cases]
+    assert not np.array_equal(edges[0][0], edges[1][0]) and len(edges[2][0]) != len(edges[0][0])
+    want = []
+    for c, e in zip(cases, edges):
+        r = HopPipeline(e, c.shape[0], PipelineConfig(async_results=False)).run(dev(c))
+        want.append((r.counts.clone(), r.map16.clone(), r.hop_x.clone(), r.hop_y.clone(), r.events.clone()))
+    pool = PipelinePool(edges[0], xyz.shape[0], PipelineConfig(), n=2)
+    for rep in range(2):
+        for c, e, w in zip(cases, edges, want):
+            r = pool.run(dev(c), edges=e)
+            got = (r.counts, r.map16, r.hop_x, r.hop_y, r.events)
+            pool.synchronize()
+            assert all(torch.equal(a_, b_) for a_, b_ in zip(w, got))
+
+
 def test_label_from_counts_equals_label_from_density(K):
     """Thresholding the counts (count >= cmin per bin-width class, cmin by bisection on the device) gives
     exactly the labels of thresholding the density, also when the threshold equals a density value."""
