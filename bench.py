@@ -468,7 +468,7 @@ def run_streamed_workload(args, chunk_frames=2500):
     checks["count_matrix_sum_equals_events"] = bool(res.count_matrix is None or int(res.count_matrix.sum().item()) == len(ev))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels, i16 hoptraj planes", "data": "synthetic",
             "config": {"workload": "%s, %d waters x %d frames on ONE GPU, %.2f A grid; 120 GB of coordinates streamed through HBM in "
                                    "%d-frame chunks (3 GB each >> L2), generated in HBM chunk by chunk" % (
                                        WORKLOADS[WORKLOAD]["label"], N, F, DELTA, chunk_frames)},
@@ -546,7 +546,7 @@ def run_multispecies_workload(args, n_species=3):
     peak, peak_src = measured_peak()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+            "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels, i16 hoptraj planes", "data": "synthetic",
             "config": {"workload": "%s x %d frames, %.1f A grids (one per species, %s); one coordinate stream of %.1f GB >> L2" % (
                 WORKLOADS[WORKLOAD]["label"], F, DELTA, " / ".join("x".join(str(n) for n in p.grid.shape) for p in multi.pipes),
                 N * F * 12 / 1e9)},
@@ -662,7 +662,7 @@ def run_batch_workload(args, per_gpu=8):
         peak, peak_src = measured_peak()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels", "data": "synthetic",
+                "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels, i16 hoptraj planes", "data": "synthetic",
                 "config": {"workload": "%s: %d trajectories x %d waters x %d frames per GPU x %d GPU(s) = %d trajectories, %.2f A grid "
                                        "(402^3, 260 MB of counts per trajectory > L2: slabbed histogram); inputs 7.2 GB per "
                                        "trajectory >> L2; replicas only, no collective" % (
@@ -864,7 +864,7 @@ def run_gpu(args):
         if rank == 0:
             line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
+                    "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels, i16 hoptraj planes",
                     "data": "synthetic", "config": {"workload": workload_name(n_gpus)},
                     "result": {"sites": int(res.n_labels), "events_per_step_rank0": int(res.n_events_local)},
                     "clocks": clocks, "two_in_flight": two_in_flight, "e2e": None, "gpu_launches": int(launches),
@@ -896,7 +896,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     barrier()
-    hx, hy = res.hop_x.cpu().to(torch.int16), res.hop_y.cpu().to(torch.int16)
+    hx, hy = res.hop_x.cpu().to(torch.int16), res.hop_y.cpu().to(torch.int16)   # no-ops with the default int16 planes
     checks["e2e_matches_resident"] = bool(all(torch.equal(ox, hx) and torch.equal(oy, hy) for ox, oy in outs[:min(2, e2e_steps)]))
     del hx, hy
     d2h = int(out_x.numel() * out_x.element_size() + out_y.numel() * out_y.element_size() + host["events"].numel() * 4 + host["edge_count"].numel() * 16
@@ -915,7 +915,7 @@ def run_gpu(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels",
+                "vs_baseline": None, "dtype": "f32 coordinates, u32 counts, f64 density, i16/i32 labels, i16 hoptraj planes",
                 "data": "synthetic", "config": {"workload": workload_name(n_gpus)},
                 "result": {"sites": int(res.n_labels), "events_per_step_rank0": int(res.n_events_local)},
                 "clocks": clocks, "two_in_flight": two_in_flight, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

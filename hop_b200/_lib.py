@@ -87,6 +87,10 @@ _SIGNATURES = {
     "hopb_hoptraj_strided": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _i64, _vp, _vp,
                              _vp, _u64],
     "hopb_hop_fixup_strided": [_vp, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _u64],
+    "hopb_hoptraj_i16": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _i64, _vp, _vp,
+                         _vp, _u64],
+    "hopb_hop_fixup_i16": [_vp, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _u64],
+    "hopb_all_transitions_i16": [_vp, _vp, _vp, _i64, _i64, _int, _vp],
     "hopb_hist_accumulate_multi": [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _vp, _vp],
     "hopb_brick_map": [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp],
     "hopb_hopscan_labels": [_vp, _vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _u64],

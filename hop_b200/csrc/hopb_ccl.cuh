@@ -166,26 +166,26 @@ __device__ __forceinline__ void size_rows(const int* parent, const uint8_t* rowf
 // forward from the head (= phase 0) and backward from the head to non-head sources (= phase 1).  Same union
 // set, hence the same components; roots are minimum indices either way.
 // `M(x, y, z)` tells whether a cell is in the mask and answers false outside the grid without branching, so that
-// the nine look-ups of a head are independent loads in flight together (one L2 latency instead of nine).
+// the nine look-ups of a head are independent loads in flight together (one L2 latency instead of nine);
+// `M.head(x, y, z)` is the head of the z-run a mask cell belongs to -- only heads carry union-find state.
 template <class Mask, class Union>
 __device__ __forceinline__ void merge_head_forward(int* parent, int c, int nx, int ny, int nz, const Mask& M, const Union& uf_union) {
   const int z = c % nz;
   const int row = c / nz;
   const int y = row % ny, x = row / ny;
-  const int64_t sy = nz, sx = (int64_t)ny * nz;
   const bool m_up = M(x, y, z + 1);
   const bool m_y = M(x, y + 1, z);
   const bool m_x = M(x + 1, y, z);
   const bool m_xy = M(x + 1, y + 1, z);
   const bool b_y = M(x, y - 1, z), b_xy = M(x + 1, y - 1, z);
   const bool u_y = M(x, y + 1, z + 1), u_x = M(x + 1, y, z + 1), u_xy = M(x + 1, y + 1, z + 1);
-  if (m_y) uf_union(parent, c, (int)(c + sy));
-  if (m_x && !(b_y && b_xy)) uf_union(parent, c, (int)(c + sx));
-  if (m_xy && !m_y && !m_x) uf_union(parent, c, (int)(c + sx + sy));
+  if (m_y) uf_union(parent, c, M.head(x, y + 1, z));
+  if (m_x && !(b_y && b_xy)) uf_union(parent, c, M.head(x + 1, y, z));
+  if (m_xy && !m_y && !m_x) uf_union(parent, c, M.head(x + 1, y + 1, z));
   if (!m_up) {
-    if (!m_y && u_y) uf_union(parent, c, (int)(c + sy + 1));
-    if (!m_x && u_x) uf_union(parent, c, (int)(c + sx + 1));
-    if (!m_xy && !m_x && !m_y && u_xy) uf_union(parent, c, (int)(c + sx + sy + 1));
+    if (!m_y && u_y) uf_union(parent, c, M.head(x, y + 1, z + 1));
+    if (!m_x && u_x) uf_union(parent, c, M.head(x + 1, y, z + 1));
+    if (!m_xy && !m_x && !m_y && u_xy) uf_union(parent, c, M.head(x + 1, y + 1, z + 1));
   }
 }
 
@@ -198,16 +198,15 @@ __device__ __forceinline__ void merge_head_backward(int* parent, int t, int nx, 
   const int z = t % nz;
   const int row = t / nz;
   const int y = row % ny, x = row / ny;
-  const int64_t sy = nz, sx = (int64_t)ny * nz;
   const bool y0 = M(x, y - 1, z), y1 = M(x, y - 1, z - 1), y2 = M(x, y - 1, z - 2);
   const bool x0 = M(x - 1, y, z), x1 = M(x - 1, y, z - 1), x2 = M(x - 1, y, z - 2);
   const bool d0 = M(x - 1, y - 1, z), d1 = M(x - 1, y - 1, z - 1), d2 = M(x - 1, y - 1, z - 2);
-  if (y0 && y1) uf_union(parent, (int)(t - sy), t);                                   // (0, 1, 0)
-  if (x0 && x1 && !(d0 && y0)) uf_union(parent, (int)(t - sx), t);                    // (1, 0, 0): not when the x-edge one row down in y exists
-  if (d0 && d1 && !x0 && !y0) uf_union(parent, (int)(t - sx - sy), t);                // (1, 1, 0)
-  if (y1 && y2 && !y0) uf_union(parent, (int)(t - sy - 1), t);                        // (0, 1, 1)
-  if (x1 && x2 && !x0) uf_union(parent, (int)(t - sx - 1), t);                        // (1, 0, 1)
-  if (d1 && d2 && !d0 && !y1 && !x1) uf_union(parent, (int)(t - sx - sy - 1), t);     // (1, 1, 1)
+  if (y0 && y1) uf_union(parent, M.head(x, y - 1, z), t);                                   // (0, 1, 0)
+  if (x0 && x1 && !(d0 && y0)) uf_union(parent, M.head(x - 1, y, z), t);                    // (1, 0, 0): not when the x-edge one row down in y exists
+  if (d0 && d1 && !x0 && !y0) uf_union(parent, M.head(x - 1, y - 1, z), t);                // (1, 1, 0)
+  if (y1 && y2 && !y0) uf_union(parent, M.head(x, y - 1, z - 1), t);                        // (0, 1, 1)
+  if (x1 && x2 && !x0) uf_union(parent, M.head(x - 1, y, z - 1), t);                        // (1, 0, 1)
+  if (d1 && d2 && !d0 && !y1 && !x1) uf_union(parent, M.head(x - 1, y - 1, z - 1), t);     // (1, 1, 1)
 }
 
 

@@ -188,14 +188,16 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 // Work items are (warp of 32 consecutive atoms, chunk), numbered chunk-major and dealt to the warps
 // of the grid in order, so the CTA size (256 with a small block map, up to 1024 with a large one: one
 // copy of the map per CTA) does not change which items exist.
-template <int SRC, bool FAST, bool XY, int MAP, bool STRIDED = false, int DEEP = 8>
+// PT: element type of the two output planes -- float (the record type of the hoptraj DCD) or int16_t (the same labels
+// at a quarter of the kernel's DRAM traffic less: labels are int16 map values or -1; the pipeline's default).
+template <int SRC, bool FAST, bool XY, int MAP, bool STRIDED = false, int DEEP = 8, typename PT = float>
 __global__ void __launch_bounds__(1024, 1)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t ld_arg, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
                const HopbPair* __restrict__ table2, const int16_t* __restrict__ brick,
                const uint32_t* __restrict__ blockmap, int map_words, int fine_value, uint32_t fine_auto_min,
-               float* __restrict__ hop_x,
-               float* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
+               PT* __restrict__ hop_x,
+               PT* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
                EventSink sink) {
   // rows of the data arrays are N atoms apart, or ld_arg when the atoms are a column range of wider arrays (a
   // variant of its own: the common case keeps one value less alive at the 64-register limit)
@@ -247,15 +249,15 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
 
   // running pointers (one frame = N elements further)
   // data rows are `ld` elements apart (ld = N unless the atoms are a column range of a wider array)
-  float* px = hop_x ? hop_x + (int64_t)f_begin * ld + atom : nullptr;
-  float* py = hop_y ? hop_y + (int64_t)f_begin * ld + atom : nullptr;
+  PT* px = hop_x ? hop_x + (int64_t)f_begin * ld + atom : nullptr;
+  PT* py = hop_y ? hop_y + (int64_t)f_begin * ld + atom : nullptr;
   auto store = [&](int l) {
     if (XY) {
-      *px = (float)l; px += ld;
-      *py = (float)yorb; py += ld;
+      *px = (PT)l; px += ld;
+      *py = (PT)yorb; py += ld;
     } else {
-      if (px) { *px = (float)l; px += ld; }
-      if (py) { *py = (float)yorb; py += ld; }
+      if (px) { *px = (PT)l; px += ld; }
+      if (py) { *py = (PT)yorb; py += ld; }
     }
   };
   // label of frame f, whatever the source
@@ -320,14 +322,14 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
 #pragma unroll
     for (int u = 0; u < K; ++u) rare |= (lab[u] > 0) & (lab[u] != cur);
     if (!rare && XY) {
-      const float yf = (float)yorb;
+      const PT yf = (PT)yorb;
 #pragma unroll
       for (int u = 0; u < K; ++u) {
         const int l = lab[u];
         const bool same = l == cur, zero = l == 0;
         t1 = (zero && on) ? t + u : t1;
         on = same ? 1 : (zero ? 0 : on);
-        px[(uint64_t)Nu * (uint32_t)u] = (float)l;
+        px[(uint64_t)Nu * (uint32_t)u] = (PT)l;
         py[(uint64_t)Nu * (uint32_t)u] = yf;
       }
       px += (uint64_t)Nu * K;
@@ -346,14 +348,14 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
 #pragma unroll
     for (int u = 0; u < K; ++u) quiet &= lab[u] <= 0;
     if (quiet && XY) {
-      const float yf = (float)yorb;
+      const PT yf = (PT)yorb;
 #pragma unroll
       for (int u = 0; u < K; ++u) {
         const int l = lab[u];
         const bool first0 = (l == 0) & (T.kind == HOPB_EMPTY);
         T.z = first0 ? t + u : T.z;
         T.kind = first0 ? (int)HOPB_PRE : T.kind;
-        px[(uint64_t)Nu * (uint32_t)u] = (float)l;
+        px[(uint64_t)Nu * (uint32_t)u] = (PT)l;
         py[(uint64_t)Nu * (uint32_t)u] = yf;
       }
       ypre += K;
@@ -558,9 +560,10 @@ hop_advance_kernel(int64_t N, int n, const int32_t* __restrict__ summaries, int 
   store_state(state, N, atom, S);
 }
 
+template <typename PT>
 __global__ void __launch_bounds__(256)
 hop_fixup_kernel(int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t F, const int32_t* __restrict__ summaries,
-                 int32_t* __restrict__ state, float* __restrict__ hop_y, EventSink sink) {
+                 int32_t* __restrict__ state, PT* __restrict__ hop_y, EventSink sink) {
   const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (atom >= N) return;
   HopbState S = load_state(state, N, atom);
@@ -572,7 +575,7 @@ hop_fixup_kernel(int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t
     const int yin = S.s0 > 0 ? S.s0 : 0;
     if (hop_y && yin != 0 && T.ypre > 0) {
       const int64_t f0 = (int64_t)c * chunk_len;
-      const float v = (float)yin;
+      const PT v = (PT)yin;
       for (int k = 0; k < T.ypre; ++k) hop_y[(f0 + k) * ld + atom] = v;
     }
     hopb_apply(S, T, emit);
@@ -594,8 +597,9 @@ planes_to_int16_kernel(const float4* __restrict__ in, int64_t n4, const float* _
 }
 
 // graph_alltransitions: set of (label[t-1], label[t]) pairs
+template <typename PT>
 __global__ void __launch_bounds__(256)
-all_transitions_kernel(const float* __restrict__ hop_x, int64_t F, int64_t N, int n_labels, uint32_t* __restrict__ bitmap) {
+all_transitions_kernel(const PT* __restrict__ hop_x, int64_t F, int64_t N, int n_labels, uint32_t* __restrict__ bitmap) {
   const int64_t total = (F - 1) * N;
   const int64_t W = (int64_t)n_labels + 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -616,9 +620,10 @@ extern "C" {
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
                           const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t ld, int64_t frame0,
                           const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value,
-                          const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
-                          int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
+                          const uint32_t* cell2, void* hop_x, void* hop_y, int n_chunks, int64_t chunk_len,
+                          int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap, bool planes16 = false) {
   HOPB_REQUIRE(h, F > 0 && N > 0 && summaries && n_events, "bad argument");
+  HOPB_REQUIRE(h, !planes16 || (hop_x && hop_y && src != 1), "int16 planes: both hop_x and hop_y are needed");
   HOPB_REQUIRE(h, ld >= N && ld < ((int64_t)1 << 31), "row stride must be >= the number of atoms");
   HOPB_REQUIRE(h, n_chunks >= 1 && chunk_len >= 1 && (int64_t)n_chunks * chunk_len >= F &&
                       (int64_t)(n_chunks - 1) * chunk_len < F, "chunks must tile the slab exactly");
@@ -636,10 +641,10 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     hopb_note_launch();
     if (hop_x && hop_y)
       hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink);
     else
       hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, hop_x, hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
@@ -668,29 +673,31 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   const size_t per_cta = smem + 1024;  // + the driver's reservation
   threads = per_cta * 4 <= 227 * 1024 ? 256 : (per_cta * 2 <= 227 * 1024 ? 512 : 1024);
   const unsigned grid = (unsigned)((items + threads / 32 - 1) / (threads / 32));
-#define HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, ST)                                                                     \
+#define HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, ST, PT)                                                                 \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST, XY, MAP, ST><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, ld, frame0, g->tab, g->d_table, \
-        g->d_table2, map16, blockmap, map_words, fine_value, fine_auto_min, hop_x, hop_y, n_chunks, chunk_len,       \
+    hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, ld, frame0, g->tab, g->d_table, \
+        g->d_table2, map16, blockmap, map_words, fine_value, fine_auto_min, (PT*)hop_x, (PT*)hop_y, n_chunks, chunk_len, \
         summaries, sink);                                                                                            \
   } while (0)
-#define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP)                                                                         \
+#define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP, PT)                                                                     \
   do {                                                                                                               \
-    if (ld != N) HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, true); else HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, false);       \
+    if (ld != N) HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, true, PT); else HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, false, PT); \
   } while (0)
-#define HOPB_HT_LAUNCH_XY(SRC, FAST, XY)                                                                             \
+#define HOPB_HT_LAUNCH_XY(SRC, FAST, XY, PT)                                                                         \
   do {                                                                                                               \
-    if (mode == MAP_FINE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_FINE);                                                 \
-    else if (mode == MAP_COARSE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_COARSE);                                        \
-    else if (mode == MAP_CELL2) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_CELL2);                                          \
-    else HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_GATHER);                                                                \
+    if (mode == MAP_FINE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_FINE, PT);                                             \
+    else if (mode == MAP_COARSE) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_COARSE, PT);                                    \
+    else if (mode == MAP_CELL2) HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_CELL2, PT);                                      \
+    else HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP_GATHER, PT);                                                            \
   } while (0)
 #define HOPB_HT_LAUNCH(SRC, FAST)                                                                                    \
   do {                                                                                                               \
-    if (hop_x && hop_y) HOPB_HT_LAUNCH_XY(SRC, FAST, true); else HOPB_HT_LAUNCH_XY(SRC, FAST, false);                \
+    if (planes16) HOPB_HT_LAUNCH_XY(SRC, FAST, true, int16_t);                                                       \
+    else if (hop_x && hop_y) HOPB_HT_LAUNCH_XY(SRC, FAST, true, float);                                              \
+    else HOPB_HT_LAUNCH_XY(SRC, FAST, false, float);                                                                 \
   } while (0)
   if (src == 0) { if (fast) HOPB_HT_LAUNCH(0, true); else HOPB_HT_LAUNCH(0, false); }
   else HOPB_HT_LAUNCH(2, true);
@@ -710,6 +717,14 @@ int hopb_hoptraj_strided(hopb_handle* h, void* stream, const hopb_grid* g, const
                         cell2, hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
+int hopb_hoptraj_i16(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
+                     int64_t N, int64_t ld, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
+                     int fine_value, const uint32_t* cell2, int16_t* hop_x, int16_t* hop_y, int n_chunks, int64_t chunk_len,
+                     int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
+  return launch_hoptraj(h, stream, cells ? 2 : 0, g, xyz, nullptr, cells, F, N, ld, frame0, map16, coarse, fine, fine_value,
+                        cell2, hop_x, hop_y, n_chunks, chunk_len, summaries, events, n_events, cap, true);
+}
+
 int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells, int64_t F,
                  int64_t N, int64_t frame0, const int16_t* map16, const uint32_t* coarse, const uint8_t* fine,
                  int fine_value, const uint32_t* cell2, float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len,
@@ -721,7 +736,7 @@ int hopb_hoptraj(hopb_handle* h, void* stream, const hopb_grid* g, const float* 
 int hopb_hopscan_labels(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N, int64_t frame0, int n_chunks,
                         int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events, uint64_t cap) {
   return launch_hoptraj(h, stream, 1, nullptr, nullptr, hop_x, nullptr, F, N, N, frame0, nullptr, nullptr, nullptr, 0, nullptr,
-                        nullptr, nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
+                        (void*)nullptr, (void*)nullptr, n_chunks, chunk_len, summaries, events, n_events, cap);
 }
 
 int hopb_brick_map(hopb_handle* h, void* stream, int nx, int ny, int nz, const int16_t* map16, int16_t* brick,
@@ -767,8 +782,21 @@ int hopb_hop_fixup_strided(hopb_handle* h, void* stream, int64_t N, int64_t ld, 
   HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
   (void)F;
   EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
-  HOPB_K(hop_fixup_kernel)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, ld, n_chunks, chunk_len, F, summaries, state,
+  HOPB_K(hop_fixup_kernel<float>)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, ld, n_chunks, chunk_len, F, summaries, state,
                                                                              hop_y, sink);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_hop_fixup_i16(hopb_handle* h, void* stream, int64_t N, int64_t ld, int n_chunks, int64_t chunk_len, int64_t F,
+                       const int32_t* summaries, int32_t* state, int16_t* hop_y, hopb_event* events, uint64_t* n_events,
+                       uint64_t cap) {
+  HOPB_REQUIRE(h, N > 0 && ld >= N && n_chunks >= 1 && summaries && state && n_events, "bad argument");
+  HOPB_REQUIRE(h, cap == 0 || events, "events buffer missing");
+  (void)F;
+  EventSink sink{events, (unsigned long long*)n_events, (unsigned long long)cap};
+  HOPB_K(hop_fixup_kernel<int16_t>)<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, ld, n_chunks, chunk_len, F, summaries,
+                                                                                                 state, hop_y, sink);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }
@@ -788,7 +816,16 @@ int hopb_all_transitions(hopb_handle* h, void* stream, const float* hop_x, int64
                          uint32_t* bitmap) {
   HOPB_REQUIRE(h, hop_x && bitmap && F >= 1 && N > 0 && n_labels >= 1, "bad argument");
   if (F < 2) return HOPB_OK;
-  HOPB_K(all_transitions_kernel)<<<hopb_grid_for((F - 1) * N, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(hop_x, F, N, n_labels, bitmap);
+  HOPB_K(all_transitions_kernel<float>)<<<hopb_grid_for((F - 1) * N, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(hop_x, F, N, n_labels, bitmap);
+  HOPB_LAUNCH_CHECK(h);
+  return HOPB_OK;
+}
+
+int hopb_all_transitions_i16(hopb_handle* h, void* stream, const int16_t* hop_x, int64_t F, int64_t N, int n_labels,
+                             uint32_t* bitmap) {
+  HOPB_REQUIRE(h, hop_x && bitmap && F >= 1 && N > 0 && n_labels >= 1, "bad argument");
+  if (F < 2) return HOPB_OK;
+  HOPB_K(all_transitions_kernel<int16_t>)<<<hopb_grid_for((F - 1) * N, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(hop_x, F, N, n_labels, bitmap);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

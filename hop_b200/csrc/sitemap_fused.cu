@@ -118,8 +118,7 @@ __device__ __forceinline__ void link_chunk(unsigned bits, int z0, int lane, int6
     return;
   }
   const int z = z0 + lane;
-  if (bits == kFull && rs.carry >= 0) {
-    parent[base + z] = (int)(base + rs.carry);
+  if (bits == kFull && rs.carry >= 0) {        // the run goes on: nothing to record but its growing length
     rs.pend += 32;
     return;
   }
@@ -128,8 +127,8 @@ __device__ __forceinline__ void link_chunk(unsigned bits, int z0, int lane, int6
   int start;
   if (below == 0) start = rs.carry >= 0 ? rs.carry : z0;
   else start = z0 + (32 - __clz(below));
-  if (m) parent[base + z] = (int)(base + start);      // cells outside the mask have no parent entry: see the mask bits
   bool head = m && start == z;
+  if (head) parent[base + z] = (int)(base + z);       // only run heads carry union-find state (every other cell: mask bits -> its head)
   if (head) minidx[base + z] = (int)(base + z);
   const unsigned hbits = __ballot_sync(kFull, head);
   if (hbits) {
@@ -170,6 +169,16 @@ struct MaskBits {
     const bool in = ((unsigned)x < (unsigned)nx) & ((unsigned)y < (unsigned)ny) & ((unsigned)z < (unsigned)nz);
     const int xs = in ? x : 0, ys = in ? y : 0, zs = in ? z : 0;
     return in & (bool)((w[((int64_t)xs * ny + ys) * wpr + (zs >> 5)] >> (zs & 31)) & 1u);
+  }
+  // head of the z-run that the mask cell (x, y, z) belongs to: the cell after the nearest cell below it that is
+  // outside the mask (the row start if there is none); a solid 201-cell row is at most seven word loads, L1-resident
+  __device__ __forceinline__ int head(int x, int y, int z) const {
+    const uint32_t* row = w + ((int64_t)x * ny + y) * wpr;
+    int wi = z >> 5;
+    uint32_t inv = ~row[wi] & ((1u << (z & 31)) - 1u);
+    while (inv == 0u && wi > 0) inv = ~row[--wi];
+    const int hz = inv ? (wi << 5) + (32 - __clz(inv)) : 0;
+    return (int)(((int64_t)x * ny + y) * nz + hz);
   }
 };
 
@@ -415,24 +424,31 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
         const uint32_t* mrow_s = a.mask_s + row * a.wpr;
         const uint32_t* mrow_b = a.mask_b + row * a.wpr;
         constexpr int U = 4;   // chunks per step: every level of the dependent look-ups is issued for all of them at once
+        int carry_s = -1, carry_b = -1;
         for (int z0 = 0; z0 < nzp; z0 += 32 * U) {
-          // a cell's parent is a run head (initial link, unions and path halving all point at heads) and every
-          // head points at its root since P4, so root = parent[parent[cell]]; cells outside a mask have no entry
           int hs[U], hb[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int z = z0 + 32 * u + lane;
-            const bool ok = z < nz;
-            const bool in_s = ok && (fl & 1u) && ((mrow_s[z >> 5] >> (z & 31)) & 1u);
-            const bool in_b = ok && (fl & 2u) && ((mrow_b[z >> 5] >> (z & 31)) & 1u);
-            hs[u] = in_s ? a.parent_s[base + z] : -1;
-            hb[u] = in_b ? a.parent_b[base + z] : -1;
+            // the head of a cell's run from the mask word of its chunk (and the run carried in from the chunk below):
+            // no per-cell parent entry is read -- or was ever written
+            const int zc = z0 + 32 * u;
+            const uint32_t ws = (zc < nz && (fl & 1u)) ? mrow_s[zc >> 5] : 0u;
+            const uint32_t wb = (zc < nz && (fl & 2u)) ? mrow_b[zc >> 5] : 0u;
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t bs = ~ws & lt, bb = ~wb & lt;
+            const int st_s = bs ? zc + (32 - __clz(bs)) : (carry_s >= 0 ? carry_s : zc);
+            const int st_b = bb ? zc + (32 - __clz(bb)) : (carry_b >= 0 ? carry_b : zc);
+            hs[u] = ((ws >> lane) & 1u) ? (int)(base + st_s) : -1;
+            hb[u] = ((wb >> lane) & 1u) ? (int)(base + st_b) : -1;
+            const uint32_t b31s = ~ws & 0x7FFFFFFFu, b31b = ~wb & 0x7FFFFFFFu;      // the run that reaches the chunk's last cell
+            carry_s = (ws >> 31) ? (b31s ? zc + (32 - __clz(b31s)) : (carry_s >= 0 ? carry_s : zc)) : -1;
+            carry_b = (wb >> 31) ? (b31b ? zc + (32 - __clz(b31b)) : (carry_b >= 0 ? carry_b : zc)) : -1;
           }
           int ps[U], pb[U];
           double rho[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            ps[u] = hs[u] >= 0 ? a.parent_s[hs[u]] : -1;
+            ps[u] = hs[u] >= 0 ? a.parent_s[hs[u]] : -1;          // heads point at their roots since P4
             pb[u] = hb[u] >= 0 ? a.parent_b[hb[u]] : -1;
             // the density of every cell of a mask (a superset of the cells the annotation needs)
             rho[u] = (props && (hs[u] >= 0 || hb[u] >= 0)) ? a.density[base + z0 + 32 * u + lane] : 0.0;

@@ -510,9 +510,13 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
         F, N = xyz.shape[0], xyz.shape[1]
         dev = xyz.device
         ld = xyz.stride(0) // 3 if F > 1 else N
+    # planes: float32 (the DCD record type) or int16 (the same labels, half the bytes; both planes then)
+    planes16 = hop_x is not None and hop_x.dtype == torch.int16
+    if planes16 and (hop_y is None or hop_y.dtype != torch.int16):
+        raise TypeError("int16 planes: hop_x and hop_y must both be int16")
     for name, t in (("hop_x", hop_x), ("hop_y", hop_y)):
         if t is not None:
-            _rows(t, torch.float32, name)
+            _rows(t, torch.int16 if planes16 else torch.float32, name)
             if tuple(t.shape) != (F, N) or (F > 1 and _ld(t) != ld):
                 raise ValueError("%s must have the shape and row stride of the input" % name)
     nb = brick_shape(grid.shape)[0]
@@ -531,10 +535,11 @@ def hoptraj(grid: GridTables, xyz, brick, frame0: int, n_chunks: int, chunk_len:
     if summaries is None:
         summaries = torch.empty((n_chunks, SUMMARY_INTS, N), dtype=torch.int32, device=dev)
     h = _h(map16)
-    rc = _lib.lib().hopb_hoptraj_strided(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N, int(ld),
-                                         int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(cell2), _p(hop_x),
-                                         _p(hop_y), int(n_chunks), int(chunk_len), _p(summaries), _p(events.data),
-                                         _p(events.count), events.capacity)
+    fn = _lib.lib().hopb_hoptraj_i16 if planes16 else _lib.lib().hopb_hoptraj_strided
+    rc = fn(h, _stream(), grid.ptr, _p(None if cells is not None else xyz), _p(cells), F, N, int(ld),
+            int(frame0), _p(map16), _p(coarse), _p(fine), int(fine_value), _p(cell2), _p(hop_x),
+            _p(hop_y), int(n_chunks), int(chunk_len), _p(summaries), _p(events.data),
+            _p(events.count), events.capacity)
     _lib.check(h, rc)
     return summaries
 
@@ -570,9 +575,11 @@ def hop_advance(summaries, state: torch.Tensor, init: bool):
 def hop_fixup(summaries: torch.Tensor, chunk_len: int, n_frames: int, state: torch.Tensor, hop_y, events: EventBuffer):
     n_chunks, _, N = summaries.shape
     h = _h(summaries)
-    ld = N if hop_y is None else _ld(_rows(hop_y, torch.float32, "hop_y"))
-    rc = _lib.lib().hopb_hop_fixup_strided(h, _stream(), N, ld, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(state),
-                                           _p(hop_y), _p(events.data), _p(events.count), events.capacity)
+    y16 = hop_y is not None and hop_y.dtype == torch.int16
+    ld = N if hop_y is None else _ld(_rows(hop_y, torch.int16 if y16 else torch.float32, "hop_y"))
+    fn = _lib.lib().hopb_hop_fixup_i16 if y16 else _lib.lib().hopb_hop_fixup_strided
+    rc = fn(h, _stream(), N, ld, n_chunks, int(chunk_len), int(n_frames), _p(summaries), _p(state),
+            _p(hop_y), _p(events.data), _p(events.count), events.capacity)
     _lib.check(h, rc)
     return state
 
@@ -638,13 +645,15 @@ def labels_to_int16(labels: torch.Tensor, out=None):
 
 def all_transitions(hop_x: torch.Tensor, n_labels: int):
     """Sorted (K,2) int64 array of (label[t-1], label[t]) pairs (hop/graph.py:107-135)."""
-    _cuda(hop_x, torch.float32, "hop_x")
+    x16 = hop_x.dtype == torch.int16
+    _cuda(hop_x, torch.int16 if x16 else torch.float32, "hop_x")
     F, N = hop_x.shape
     W = n_labels + 1
     words = (W * W + 31) // 32
     bitmap = torch.zeros(words, dtype=torch.int32, device=hop_x.device)
     h = _h(hop_x)
-    _lib.check(h, _lib.lib().hopb_all_transitions(h, _stream(), _p(hop_x), F, N, int(n_labels), _p(bitmap)))
+    fn = _lib.lib().hopb_all_transitions_i16 if x16 else _lib.lib().hopb_all_transitions
+    _lib.check(h, fn(h, _stream(), _p(hop_x), F, N, int(n_labels), _p(bitmap)))
     bits = np.unpackbits(bitmap.cpu().numpy().view(np.uint8), bitorder="little")[: W * W]
     idx = np.nonzero(bits)[0]
     return np.stack([idx // W - 1, idx % W - 1], axis=1).astype(np.int64)

@@ -67,7 +67,7 @@ class MultiSpeciesPipeline(object):
 
     def run(self, xyz, frame0=0):
         """xyz: CUDA float32 [F][N][3], all species.  Returns one PipelineResult per species; hop_x / hop_y of a
-        species are column ranges of planes shared by all species ([F][N] float32, `self.hop_x`, `self.hop_y`)."""
+        species are column ranges of planes shared by all species ([F][N], PipelineConfig.plane_dtype, `self.hop_x`, `self.hop_y`)."""
         from . import _lib
 
         F, N = int(xyz.shape[0]), int(xyz.shape[1])
@@ -81,8 +81,9 @@ class MultiSpeciesPipeline(object):
             counts.append(c)
         cells = self._buf("cells", (F, N), torch.int32)
         K.hist_accumulate_multi([p.grid for p in self.pipes], self.species, xyz, counts, cells)
-        self.hop_x = self._buf("hop_x", (F, N), torch.float32)
-        self.hop_y = self._buf("hop_y", (F, N), torch.float32)
+        plane_dtype = self.pipes[0].cfg.plane_torch_dtype()
+        self.hop_x = self._buf("hop_x", (F, N), plane_dtype)
+        self.hop_y = self._buf("hop_y", (F, N), plane_dtype)
         results, pending = [], []
         for k, (p, (a, b)) in enumerate(zip(self.pipes, self.columns)):      # queue stages 2 and 3 of every species ...
             st = self.streams[k]

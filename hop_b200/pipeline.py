@@ -43,6 +43,14 @@ class PipelineConfig:
     label_from_counts: bool = True   # threshold the counts instead of the density (identical labels)
     fused_site_map: bool = True      # stage 2 as one cooperative launch (hopb_site_map_fused) where the grid allows
     periodic_box: tuple | None = None  # (origin[3], length[3]): wrap coordinates before binning; None = hop's behaviour
+    plane_dtype: str = "int16"       # element type of hop_x / hop_y in HBM: "int16" (lossless: labels are values of hop's
+                                     # int16 site map or -1; stage 3 writes 4 B per atom-frame) or "float32" (the DCD
+                                     # record type, 8 B per atom-frame); files and the class API always see float32
+
+    def plane_torch_dtype(self):
+        if self.plane_dtype not in ("int16", "float32"):
+            raise ValueError("plane_dtype must be 'int16' or 'float32'")
+        return torch.int16 if self.plane_dtype == "int16" else torch.float32
 
 
 class PipelineResult(object):
@@ -376,8 +384,8 @@ class HopPipeline:
         events.reset()
         hop_x = hop_y = None
         if cfg.write_hoptraj:
-            hop_x = self._buf("hop_x", (F, N), torch.float32)
-            hop_y = self._buf("hop_y", (F, N), torch.float32)
+            hop_x = self._buf("hop_x", (F, N), cfg.plane_torch_dtype())
+            hop_y = self._buf("hop_y", (F, N), cfg.plane_torch_dtype())
         summaries = self._buf("summaries", (n_chunks, K.SUMMARY_INTS, N), torch.int32)
         K.hoptraj(self.grid, xyz, self.brick, frame0, n_chunks, chunk_len, events, hop_x, hop_y, summaries,
                   cells=getattr(self, "cells", None), block_map=cfg.block_map if cfg.coarse_map else "none")
@@ -562,7 +570,7 @@ class HopPipeline:
         stage, a generator); called once per chunk and pass, unless the 4-byte brick indices of pass 1 fit into
         HBM (`cache_cells`, default: when they take less than 40 % of the free memory), in which case pass 2
         reads those instead of the coordinates.
-        sink(f0, hop_x, hop_y): receives every chunk of the hopping trajectory ([m][N] float32 views of a
+        sink(f0, hop_x, hop_y): receives every chunk of the hopping trajectory ([m][N] views (PipelineConfig.plane_dtype) of a
         buffer that is reused for the next chunk -- write it out or reduce it before returning).
 
         Pass 1 accumulates the histogram chunk by chunk; stage 2 runs once; pass 2 carries the per-atom
@@ -604,8 +612,8 @@ class HopPipeline:
         self._mark(marks, "S2_sitemap")
         # ---- pass 2: hopping trajectory + transitions ----------------------------------------------------
         m_max = max(f1 - f0 for f0, f1 in bounds)
-        hx_buf = self._buf("hop_x_chunk", (m_max, N), torch.float32)
-        hy_buf = self._buf("hop_y_chunk", (m_max, N), torch.float32)
+        hx_buf = self._buf("hop_x_chunk", (m_max, N), cfg.plane_torch_dtype())
+        hy_buf = self._buf("hop_y_chunk", (m_max, N), cfg.plane_torch_dtype())
         cap = cfg.event_capacity or max(1 << 20, (F * N) // 64)
         events = self._event_buffer(max(cap, self._events.capacity if self._events is not None else 0))
         if self._s4_done is not None:
@@ -707,11 +715,14 @@ class HopPipeline:
             out_y = torch.empty((F, N), dtype=torch.float32).pin_memory()
         # int16 host planes (lossless: labels are int16 map values or -1) halve the download; the float32 of the DCD
         # record is then restored on the host by whoever writes a file (HostRun.planes_float32)
-        if out_x.dtype == torch.int16:
+        if out_x.dtype == res.hop_x.dtype:
+            src_x, src_y = res.hop_x, res.hop_y        # int16 planes straight from stage 3 (the default), or float32 both ways
+        elif out_x.dtype == torch.int16:
             src_x = K.labels_to_int16(res.hop_x, self._buf("hop_x16_%d" % par, (F, N), torch.int16))
             src_y = K.labels_to_int16(res.hop_y, self._buf("hop_y16_%d" % par, (F, N), torch.int16))
         else:
-            src_x, src_y = res.hop_x, res.hop_y
+            src_x = self._buf("hop_x32_%d" % par, (F, N), torch.float32).copy_(res.hop_x)
+            src_y = self._buf("hop_y32_%d" % par, (F, N), torch.float32).copy_(res.hop_y)
         d2h.wait_stream(main)
         with torch.cuda.stream(d2h):
             out_x.copy_(src_x, non_blocking=True)

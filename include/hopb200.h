@@ -319,6 +319,16 @@ int hopb_hoptraj_strided(hopb_handle* h, void* stream, const hopb_grid* g, const
                          float* hop_x, float* hop_y, int n_chunks, int64_t chunk_len, int32_t* summaries,
                          hopb_event* events, uint64_t* n_events, uint64_t cap);
 
+/* hopb_hoptraj_strided with the two planes as int16 [F][ld] (both required): the labels _coord2hop writes are values
+ * of hop's int16 site map or -1 (hop/sitemap.py:518-519, hop/trajectory.py:456-463), so the conversion is lossless
+ * and the kernel writes 4 instead of 8 bytes per atom-frame; the float32 of the DCD record is restored where a file
+ * is written.  The whole-trajectory pipeline uses this form. */
+int hopb_hoptraj_i16(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz, const uint32_t* cells,
+                     int64_t F, int64_t N, int64_t ld, int64_t frame0, const int16_t* brick, const uint32_t* coarse,
+                     const uint8_t* fine, int fine_value, const uint32_t* cell2, int16_t* hop_x, int16_t* hop_y,
+                     int n_chunks, int64_t chunk_len, int32_t* summaries, hopb_event* events, uint64_t* n_events,
+                     uint64_t cap);
+
 /* Site map (device int16 [nx][ny][nz], Density.map) -> brick order + block maps.  A brick is a
  * 4x4x4 block of cells stored as 64 consecutive int16 (one 128-byte line), bricks in C order over
  * (ceil(nx/4), ceil(ny/4), ceil(nz/4)); inside a brick the cells are ordered by 2x2x2 sub-brick:
@@ -363,6 +373,11 @@ int hopb_hop_fixup(hopb_handle* h, void* stream, int64_t N, int n_chunks, int64_
 int hopb_hop_fixup_strided(hopb_handle* h, void* stream, int64_t N, int64_t ld, int n_chunks, int64_t chunk_len,
                            int64_t F, const int32_t* summaries, int32_t* state, float* hop_y, hopb_event* events,
                            uint64_t* n_events, uint64_t cap);
+
+/* hopb_hop_fixup_strided for an int16 hop_y plane (see hopb_hoptraj_i16). */
+int hopb_hop_fixup_i16(hopb_handle* h, void* stream, int64_t N, int64_t ld, int n_chunks, int64_t chunk_len,
+                       int64_t F, const int32_t* summaries, int32_t* state, int16_t* hop_y, hopb_event* events,
+                       uint64_t* n_events, uint64_t cap);
 
 /* Sort events into the reference's emission order and count transitions.
  * events_sorted is ordered by (s0, s) and within an edge by (frame, iatom) -- the order of the
@@ -410,6 +425,10 @@ int hopb_labels_to_int16(hopb_handle* h, void* stream, const float* labels, int6
  * bitmap: device uint32 [ceil((n_labels+1)^2 / 32)], OR-ed into (not cleared). */
 int hopb_all_transitions(hopb_handle* h, void* stream, const float* hop_x, int64_t F, int64_t N,
                          int n_labels, uint32_t* bitmap);
+
+/* The same on an int16 plane (see hopb_hoptraj_i16). */
+int hopb_all_transitions_i16(hopb_handle* h, void* stream, const int16_t* hop_x, int64_t F, int64_t N,
+                             int n_labels, uint32_t* bitmap);
 
 /* ---- synthetic input (bench / tests) ------------------------------------------- */
 typedef struct hopb_synth_params {

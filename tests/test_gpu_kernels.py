@@ -1044,3 +1044,35 @@ def test_pipeline_async_count_matrix_outgrown(K, traj):
     assert res.n_labels == n_labels and torch.equal(res.count_matrix, M) and torch.equal(res.events, ev)
     again = pipe.run(dev(xyz))                                    # now sized for it
     assert again._pending is not None and torch.equal(again.count_matrix, M)
+
+
+@pytest.mark.parametrize("n_chunks", [None, 3])
+def test_int16_planes_equal_float32_planes(K, traj, n_chunks):
+    """The pipeline keeps hop_x / hop_y as int16 in HBM (PipelineConfig.plane_dtype, the default): same labels, same
+    events and -- end to end -- the same host planes as the float32 record type of the hoptraj DCD."""
+    from hop_b200.pipeline import HopPipeline, PipelineConfig, grid_edges_from_frame0
+
+    p, xyz = traj
+    edges = grid_edges_from_frame0(xyz[0], delta=1.0)
+    out = {}
+    for dt in ("float32", "int16"):
+        pipe = HopPipeline(edges, xyz.shape[0], PipelineConfig(plane_dtype=dt, n_chunks=n_chunks))
+        res = pipe.run(dev(xyz))
+        assert res.hop_x.dtype == getattr(torch, dt) and res.hop_y.dtype == getattr(torch, dt)
+        ev = res.events.cpu().numpy().copy()
+        trans = K.all_transitions(res.hop_x, res.n_labels)
+        host = {}
+        for ht in (torch.float32, torch.int16):       # host planes of either type from device planes of either type
+            ox = torch.empty(xyz.shape[:2], dtype=ht).pin_memory()
+            oy = torch.empty(xyz.shape[:2], dtype=ht).pin_memory()
+            r2, h = pipe.run_host(torch.from_numpy(xyz).pin_memory(), 0, ox, oy)
+            host[ht] = (h["hop_x"].to(torch.float32).numpy().copy(), h["hop_y"].to(torch.float32).numpy().copy())
+        out[dt] = (res.hop_x.cpu().to(torch.float32).numpy(), res.hop_y.cpu().to(torch.float32).numpy(), ev, trans, host)
+    a, b = out["float32"], out["int16"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    for dt in out:
+        for ht in (torch.float32, torch.int16):
+            assert np.array_equal(out[dt][4][ht][0], a[0]) and np.array_equal(out[dt][4][ht][1], a[1])
+    with pytest.raises(ValueError):
+        PipelineConfig(plane_dtype="int8").plane_torch_dtype()
