@@ -19,9 +19,10 @@
 //   P4 flatten + sizes   heads find their roots and add their run length to the root's
 //   P5 roots     hydration sites -> key list; bulk mask -> its largest component (atomicMax)
 //   P6 rank      canonical numbering: volume descending, then larger minimum C-order cell first
-//   P7 paint     per 4 x 4 brick column: root = parent[parent[cell]] -> own / member / map16 rows, the bricked
-//                map, coarse / fine / 2-bit block maps, and the per-site sums of the annotation
+//   P7a paint    one warp per row: head from the mask bits, root = parent[head] -> own / member / map16 rows and
+//                the per-site sums of the annotation
 //   P8 annotate  count, mean, population std, centre per site
+//   P7b bricks   one warp per eight bricks: map16 (L2) -> bricked map, coarse / fine / 2-bit block maps
 // Only P0 and P7 walk the grid; everything between them works on the run heads (about two per row for a
 // bulk mask with thermal holes), which is what took the stand-alone chain from ~25 grid passes to two.
 // The labels are those of the stand-alone kernels (same union-find, same ranking key).  The
@@ -193,7 +194,6 @@ __device__ __forceinline__ void stamp(const FusedArgs& a, int k) {
 __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a) {
   cg::grid_group grid = cg::this_grid();
   stamp(a, 0);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarps + warp;
@@ -402,104 +402,155 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
   stamp(a, 7);
 
   // ---- P7: paint -------------------------------------------------------------------------------------------
+  // P7a: one warp per row, no block barriers (the earlier version staged a 4 x 4 brick column in shared memory
+  // between two __syncthreads; a third of the kernel's stall samples sat at those barriers, waiting for the slowest
+  // row of the column): own / member / map16 rows and the annotation sums.
+  // P7b (behind a grid barrier): one warp per 8 consecutive bricks of a column re-reads their 16 x 32 map16 cells
+  // from L2 and writes the bricked map and the block maps.
   const int bulk_root = bulk ? (int)a.counters[6] : -1;      // 0xFFFFFFFF = -1: no bulk site
   const int cnx = (nx + 3) >> 2, cny = (ny + 3) >> 2, cnz = (nz + 3) >> 2;
-  const int nzp = cnz * 4;
-  int16_t* tile = reinterpret_cast<int16_t*>(smem_raw);          // [16][nzp]
   // running sums of the bulk site (label 1), per lane
   double b_n = 0, b_d = 0, b_d2 = 0, b_mx = 0, b_my = 0, b_mz = 0;
   const bool props = a.p_count != nullptr;
   const double k_bulk = (bulk && props) ? a.kshift[1] : 0.0;
   uint32_t n_ones = 0;
-  for (int col = blockIdx.x; col < cnx * cny; col += gridDim.x) {
-    const int ci = col / cny, cj = col - ci * cny;
-    {
-      const int i = ci * 4 + (warp >> 2), j = cj * 4 + (warp & 3);
-      int16_t* trow = tile + warp * nzp;
-      if (i < nx && j < ny) {
-        const int64_t row = (int64_t)i * ny + j;
-        const int64_t base = row * nz;
-        const unsigned fl = a.rowflag[row];
-        const double mxi = props ? a.mx[i] : 0.0, myj = props ? a.my[j] : 0.0;
-        const uint32_t* mrow_s = a.mask_s + row * a.wpr;
-        const uint32_t* mrow_b = a.mask_b + row * a.wpr;
-        constexpr int U = 4;   // chunks per step: every level of the dependent look-ups is issued for all of them at once
-        int carry_s = -1, carry_b = -1;
-        for (int z0 = 0; z0 < nzp; z0 += 32 * U) {
-          int hs[U], hb[U];
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int j = (int)(row % ny);
+    const int i = (int)(row / ny);
+    const int64_t base = row * nz;
+    const unsigned fl = a.rowflag[row];
+    if (fl == 0u) {          // nothing of either mask in this row
+      for (int z = lane; z < nz; z += 32) {
+        a.own[base + z] = 0;
+        if (a.member) a.member[base + z] = 0;
+        a.map16[base + z] = 0;
+      }
+      continue;
+    }
+    const double mxi = props ? a.mx[i] : 0.0, myj = props ? a.my[j] : 0.0;
+    const uint32_t* mrow_s = a.mask_s + row * a.wpr;
+    const uint32_t* mrow_b = a.mask_b + row * a.wpr;
+    constexpr int U = 4;   // chunks per step: every level of the dependent look-ups is issued for all of them at once
+    int carry_s = -1, carry_b = -1;
+    for (int z0 = 0; z0 < nz; z0 += 32 * U) {
+      int hs[U], hb[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            // the head of a cell's run from the mask word of its chunk (and the run carried in from the chunk below):
-            // no per-cell parent entry is read -- or was ever written
-            const int zc = z0 + 32 * u;
-            const uint32_t ws = (zc < nz && (fl & 1u)) ? mrow_s[zc >> 5] : 0u;
-            const uint32_t wb = (zc < nz && (fl & 2u)) ? mrow_b[zc >> 5] : 0u;
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t bs = ~ws & lt, bb = ~wb & lt;
-            const int st_s = bs ? zc + (32 - __clz(bs)) : (carry_s >= 0 ? carry_s : zc);
-            const int st_b = bb ? zc + (32 - __clz(bb)) : (carry_b >= 0 ? carry_b : zc);
-            hs[u] = ((ws >> lane) & 1u) ? (int)(base + st_s) : -1;
-            hb[u] = ((wb >> lane) & 1u) ? (int)(base + st_b) : -1;
-            const uint32_t b31s = ~ws & 0x7FFFFFFFu, b31b = ~wb & 0x7FFFFFFFu;      // the run that reaches the chunk's last cell
-            carry_s = (ws >> 31) ? (b31s ? zc + (32 - __clz(b31s)) : (carry_s >= 0 ? carry_s : zc)) : -1;
-            carry_b = (wb >> 31) ? (b31b ? zc + (32 - __clz(b31b)) : (carry_b >= 0 ? carry_b : zc)) : -1;
+      for (int u = 0; u < U; ++u) {
+        // the head of a cell's run from the mask word of its chunk (and the run carried in from the chunk below):
+        // no per-cell parent entry is read -- or was ever written
+        const int zc = z0 + 32 * u;
+        const uint32_t ws = (zc < nz && (fl & 1u)) ? mrow_s[zc >> 5] : 0u;
+        const uint32_t wb = (zc < nz && (fl & 2u)) ? mrow_b[zc >> 5] : 0u;
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t bs = ~ws & lt, bb = ~wb & lt;
+        const int st_s = bs ? zc + (32 - __clz(bs)) : (carry_s >= 0 ? carry_s : zc);
+        const int st_b = bb ? zc + (32 - __clz(bb)) : (carry_b >= 0 ? carry_b : zc);
+        hs[u] = ((ws >> lane) & 1u) ? (int)(base + st_s) : -1;
+        hb[u] = ((wb >> lane) & 1u) ? (int)(base + st_b) : -1;
+        const uint32_t b31s = ~ws & 0x7FFFFFFFu, b31b = ~wb & 0x7FFFFFFFu;      // the run that reaches the chunk's last cell
+        carry_s = (ws >> 31) ? (b31s ? zc + (32 - __clz(b31s)) : (carry_s >= 0 ? carry_s : zc)) : -1;
+        carry_b = (wb >> 31) ? (b31b ? zc + (32 - __clz(b31b)) : (carry_b >= 0 ? carry_b : zc)) : -1;
+      }
+      int ps[U], pb[U];
+      double rho[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ps[u] = hs[u] >= 0 ? a.parent_s[hs[u]] : -1;          // heads point at their roots since P4
+        pb[u] = hb[u] >= 0 ? a.parent_b[hb[u]] : -1;
+        // the density of every cell of a mask (a superset of the cells the annotation needs)
+        rho[u] = (props && (hs[u] >= 0 || hb[u] >= 0)) ? a.density[base + z0 + 32 * u + lane] : 0.0;
+      }
+      int ls[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ls[u] = (ps[u] >= 0 && !too_many) ? a.size_s[ps[u]] : 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int z = z0 + 32 * u + lane;
+        if (z0 + 32 * u >= nz) break;
+        if (z >= nz) continue;
+        const int o = ls[u] > 0 ? ls[u] + shift : 0;
+        const bool mb = pb[u] >= 0 && pb[u] == bulk_root;
+        a.own[base + z] = o;
+        if (a.member) a.member[base + z] = mb ? 1 : 0;
+        a.map16[base + z] = (int16_t)(o > 0 ? o : (mb ? 1 : 0));
+        if (props && (o > 0 || mb)) {
+          const double mzk = a.mz[z];
+          if (o > 0 && o < a.n_labels_cap) {
+            const double d = rho[u] - a.kshift[o];
+            double* q = a.acc + (int64_t)o * kAcc;
+            atomicAdd(q + 0, 1.0); atomicAdd(q + 1, d); atomicAdd(q + 2, d * d);
+            atomicAdd(q + 3, mxi); atomicAdd(q + 4, myj); atomicAdd(q + 5, mzk);
           }
-          int ps[U], pb[U];
-          double rho[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            ps[u] = hs[u] >= 0 ? a.parent_s[hs[u]] : -1;          // heads point at their roots since P4
-            pb[u] = hb[u] >= 0 ? a.parent_b[hb[u]] : -1;
-            // the density of every cell of a mask (a superset of the cells the annotation needs)
-            rho[u] = (props && (hs[u] >= 0 || hb[u] >= 0)) ? a.density[base + z0 + 32 * u + lane] : 0.0;
-          }
-          int ls[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) ls[u] = (ps[u] >= 0 && !too_many) ? a.size_s[ps[u]] : 0;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int z = z0 + 32 * u + lane;
-            if (z0 + 32 * u >= nzp) break;
-            const bool ok = z < nz;
-            const int o = ls[u] > 0 ? ls[u] + shift : 0;
-            const bool mb = pb[u] >= 0 && pb[u] == bulk_root;
-            const int16_t m16 = (int16_t)(o > 0 ? o : (mb ? 1 : 0));
-            if (ok) {
-              a.own[base + z] = o;
-              if (a.member) a.member[base + z] = mb ? 1 : 0;
-              a.map16[base + z] = m16;
-            }
-            if (z < nzp) trow[z] = ok ? m16 : (int16_t)0;
-            if (props && (o > 0 || mb)) {
-              const double mzk = a.mz[z];
-              if (o > 0 && o < a.n_labels_cap) {
-                const double d = rho[u] - a.kshift[o];
-                double* q = a.acc + (int64_t)o * kAcc;
-                atomicAdd(q + 0, 1.0); atomicAdd(q + 1, d); atomicAdd(q + 2, d * d);
-                atomicAdd(q + 3, mxi); atomicAdd(q + 4, myj); atomicAdd(q + 5, mzk);
-              }
-              if (mb) {
-                const double d = rho[u] - k_bulk;
-                b_n += 1.0; b_d += d; b_d2 += d * d; b_mx += mxi; b_my += myj; b_mz += mzk;
-              }
-            }
+          if (mb) {
+            const double d = rho[u] - k_bulk;
+            b_n += 1.0; b_d += d; b_d2 += d * d; b_mx += mxi; b_my += myj; b_mz += mzk;
           }
         }
-      } else {
-        for (int z = lane; z < nzp; z += 32) trow[z] = 0;
       }
     }
-    __syncthreads();
-    // bricks of this column: one warp per brick, lane l holds the cells 2l, 2l + 1 of the brick order
-    {
-      const int i1 = (lane >> 4) & 1, j1 = (lane >> 3) & 1, k1 = (lane >> 2) & 1, i0 = (lane >> 1) & 1, j0 = lane & 1;
-      const int di = 2 * i1 + i0, dj = 2 * j1 + j0;
+  }
+  if (props && bulk) {
+    double sb[kAcc] = {b_n, b_d, b_d2, b_mx, b_my, b_mz};
+#pragma unroll
+    for (int q = 0; q < kAcc; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sb[q] += __shfl_xor_sync(kFull, sb[q], o);
+      if (lane == 0 && sb[0] != 0.0) atomicAdd(a.acc + 1 * kAcc + q, sb[q]);
+    }
+  }
+  grid.sync();
+  stamp(a, 8);
+
+  // ---- P8: annotation (the sums are complete; it runs in front of the bricks instead of behind another barrier) ----
+  for (int64_t l = tid; props && l < a.n_labels_cap; l += nth) {
+    const double* q = a.acc + l * kAcc;
+    const double n = q[0];
+    a.p_count[l] = (int64_t)n;
+    if (n > 0) {
+      const double md = q[1] / n;
+      double var = (q[2] - q[1] * md) / n;
+      if (!(var > 0.0)) var = 0.0;
+      a.p_mean[l] = a.kshift[l] + md;
+      a.p_std[l] = sqrt(var);
+      a.p_center[l * 3 + 0] = q[3] / n; a.p_center[l * 3 + 1] = q[4] / n; a.p_center[l * 3 + 2] = q[5] / n;
+    } else {
+      a.p_mean[l] = 0; a.p_std[l] = 0;
+      a.p_center[l * 3 + 0] = 0; a.p_center[l * 3 + 1] = 0; a.p_center[l * 3 + 2] = 0;
+    }
+  }
+
+  // P7b: bricks.  Lane l holds the cells 2l, 2l + 1 of the brick order; the 16 rows x 32 cells of eight bricks go
+  // through a per-warp tile (rows of a column are nz cells apart in map16: 64-byte row segments, read once).
+  {
+    __shared__ int16_t s_tile[kWarps][16 * 32];
+    int16_t* wt = s_tile[warp];
+    const int n_slabs = (cnz + 7) >> 3;
+    const int64_t n_tasks = (int64_t)cnx * cny * n_slabs;
+    const int i1 = (lane >> 4) & 1, j1 = (lane >> 3) & 1, k1 = (lane >> 2) & 1, i0 = (lane >> 1) & 1, j0 = lane & 1;
+    const int di = 2 * i1 + i0, dj = 2 * j1 + j0;
+    for (int64_t task = warp0; task < n_tasks; task += nwarps) {
+      const int sl = (int)(task % n_slabs);
+      const int col = (int)(task / n_slabs);
+      const int ci = col / cny, cj = col - ci * cny;
+      const int zl = sl * 32 + lane;
+      int16_t v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int i = ci * 4 + (r >> 2), j = cj * 4 + (r & 3);
+        v[r] = (i < nx && j < ny && zl < nz) ? a.map16[((int64_t)i * ny + j) * nz + zl] : (int16_t)0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) wt[r * 32 + lane] = v[r];
+      __syncwarp();
       const bool row_ok = (ci * 4 + di < nx) && (cj * 4 + dj < ny);
-      const int16_t* trow = tile + (di * 4 + dj) * nzp;
-      for (int ck = warp; ck < cnz; ck += kWarps) {
+      const int16_t* trow = wt + (di * 4 + dj) * 32;
+      for (int q = 0; q < 8; ++q) {
+        const int ck = sl * 8 + q;
+        if (ck >= cnz) break;
         const int64_t b = ((int64_t)ci * cny + cj) * cnz + ck;
         const int z = ck * 4 + 2 * k1;
-        const int v0 = trow[z], v1 = trow[z + 1];
+        const int v0 = trow[q * 4 + 2 * k1], v1 = trow[q * 4 + 2 * k1 + 1];
         const bool ok0 = row_ok && z < nz, ok1 = row_ok && z + 1 < nz;
         reinterpret_cast<short2*>(a.brick + b * 64)[lane] = make_short2((short)v0, (short)v1);
         const int ref = __shfl_sync(kFull, v0, 0);      // cell (0, 0, 0) of a brick is always inside the grid
@@ -526,42 +577,11 @@ __global__ void __launch_bounds__(kThreads, 2) sitemap_fused_kernel(FusedArgs a)
         }
       }
     }
-    __syncthreads();
   }
   if (a.fine) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_ones += __shfl_xor_sync(kFull, n_ones, o);
     if (lane == 0 && n_ones) atomicAdd(reinterpret_cast<uint32_t*>(a.fine + 2 * a.nb_pad), n_ones);
-  }
-  if (!props) return;
-  if (bulk) {
-    double s[kAcc] = {b_n, b_d, b_d2, b_mx, b_my, b_mz};
-#pragma unroll
-    for (int q = 0; q < kAcc; ++q) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(kFull, s[q], o);
-      if (lane == 0 && s[0] != 0.0) atomicAdd(a.acc + 1 * kAcc + q, s[q]);
-    }
-  }
-  grid.sync();
-  stamp(a, 8);
-
-  // ---- P8: annotation ---------------------------------------------------------------------------------------
-  for (int64_t l = tid; l < a.n_labels_cap; l += nth) {
-    const double* q = a.acc + l * kAcc;
-    const double n = q[0];
-    a.p_count[l] = (int64_t)n;
-    if (n > 0) {
-      const double md = q[1] / n;
-      double var = (q[2] - q[1] * md) / n;
-      if (!(var > 0.0)) var = 0.0;
-      a.p_mean[l] = a.kshift[l] + md;
-      a.p_std[l] = sqrt(var);
-      a.p_center[l * 3 + 0] = q[3] / n; a.p_center[l * 3 + 1] = q[4] / n; a.p_center[l * 3 + 2] = q[5] / n;
-    } else {
-      a.p_mean[l] = 0; a.p_std[l] = 0;
-      a.p_center[l * 3 + 0] = 0; a.p_center[l * 3 + 1] = 0; a.p_center[l * 3 + 2] = 0;
-    }
   }
   stamp(a, 9);
 }
@@ -588,8 +608,8 @@ int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const 
   const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
   const int64_t nb = (int64_t)cnx * cny * cnz;
   HOPB_REQUIRE(h, nb * 64 < ((int64_t)1 << 32) - 1, "grid too large for brick indices");
-  const size_t smem = (size_t)kWarps * cnz * 4 * sizeof(int16_t) > 8192 ? (size_t)kWarps * cnz * 4 * sizeof(int16_t) : 8192;
-  HOPB_REQUIRE(h, smem <= 96 * 1024, "grid too long in z for the one-launch site map");
+  const size_t smem = 0;      // static shared memory only (head staging, the per-warp brick tiles)
+  (void)cnz;
   if (!p_count) n_labels_cap = 2;
 
   // tables: count thresholds of both masks and the density of small counts, cached per handle
@@ -654,8 +674,6 @@ int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const 
   a.mx = g->d_mid[0]; a.my = g->d_mid[1]; a.mz = g->d_mid[2];
   a.p_count = p_count; a.p_mean = p_mean; a.p_std = p_std; a.p_center = p_center;
 
-  if (smem > 48 * 1024)
-    HOPB_CUDA(h, cudaFuncSetAttribute(sitemap_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   HOPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sitemap_fused_kernel, kThreads, smem));
   HOPB_REQUIRE(h, per_sm >= 1, "cooperative launch not possible");
@@ -680,7 +698,8 @@ int hopb_site_map_fused(hopb_handle* h, void* stream, const hopb_grid* g, const 
     HOPB_CUDA(h, cudaMemcpyAsync(t, d_trace, sizeof(t), cudaMemcpyDeviceToHost, s));
     HOPB_CUDA(h, cudaStreamSynchronize(s));
     fprintf(stderr, "sitemap_fused %dx%dx%d, %lld blocks: phases (us)", nx, ny, nz, (long long)nblocks);
-    for (int k = 1; k <= 9; ++k) fprintf(stderr, " P%d %.1f", k - 1, t[k] > t[k - 1] ? (t[k] - t[k - 1]) * 1e-3 : 0.0);
+    static const char* const names[] = {"", "P0", "P1", "P2", "P3", "P4", "P5", "P6", "P7a", "P8+P7b"};
+    for (int k = 1; k <= 9; ++k) fprintf(stderr, " %s %.1f", names[k], t[k] > t[k - 1] ? (t[k] - t[k - 1]) * 1e-3 : 0.0);
     fprintf(stderr, "\n");
   }
   return HOPB_OK;
