@@ -101,6 +101,9 @@ _SIGNATURES = {
     "hopb_events_finalize_ex": [_vp, _vp, _vp, _u64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64)],
     "hopb_events_finalize_dev": [_vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "hopb_labels_to_int16": [_vp, _vp, _vp, _i64, _vp],
+    "hopb_nvls_allreduce_u32": [_vp, _vp, _vp, _i64, _int, _int],
+    "hopb_p2p_allreduce_u32": [_vp, _vp, _vp, _vp, _i64, _int, _int],
+    "hopb_nvls_allgather": [_vp, _vp, _vp, _vp, _i64, _int, _int],
     "hopb_all_transitions": [_vp, _vp, _vp, _i64, _i64, _int, _vp],
     "hopb_synth_generate": [_vp, _vp, ctypes.POINTER(SynthParamsC), _vp, _i64, _i64, _vp],
     "hopb_synth_generate_chunk": [_vp, _vp, ctypes.POINTER(SynthParamsC), _vp, _i64, _i64, _vp, _vp, _int],

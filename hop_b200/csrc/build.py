@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libhopb200.so")
-SOURCES = ["api.cu", "hist.cu", "label.cu", "sitemap_fused.cu", "hoptraj.cu", "events.cu", "siteanalysis.cu", "ratefit.cu", "sort.cu", "synth.cu"]
+SOURCES = ["api.cu", "hist.cu", "label.cu", "sitemap_fused.cu", "hoptraj.cu", "events.cu", "exchange.cu", "siteanalysis.cu", "ratefit.cu", "sort.cu", "synth.cu"]
 HEADERS = ["hopb_common.cuh", "hopb_binning.h", "hopb_machine.h", "hopb_gridtab_host.h", "hopb_ccl.cuh", "hopb_tables.cuh",
            os.path.join(ROOT, "include", "hopb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -633,6 +633,36 @@ def events_finalize_dev(events: EventBuffer, n_atoms: int, n_frames_total: int, 
     _lib.check(h, rc)
 
 
+def nvls_allreduce_u32(t: torch.Tensor, mc_ptr: int, rank: int, world: int):
+    """In-place sum over the ranks of a 32-bit integer tensor in symmetric memory (csrc/exchange.cu); mc_ptr is the
+    multicast address of `t`.  The caller brackets it with cross-rank barriers (hop_b200/exchange.py)."""
+    if not (t.is_cuda and t.is_contiguous() and t.element_size() == 4):
+        raise TypeError("a contiguous CUDA tensor of 32-bit integers is needed")
+    h = _h(t)
+    _lib.check(h, _lib.lib().hopb_nvls_allreduce_u32(h, _stream(), ctypes.c_void_p(int(mc_ptr)), t.numel(), int(rank), int(world)))
+    return t
+
+
+def p2p_allreduce_u32(t: torch.Tensor, peer_ptrs, mc_ptr: int, rank: int, world: int):
+    """nvls_allreduce_u32 with the additions on the SM: peer_ptrs = the ranks' copies of `t` as mapped into this process."""
+    if not (t.is_cuda and t.is_contiguous() and t.element_size() == 4):
+        raise TypeError("a contiguous CUDA tensor of 32-bit integers is needed")
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    h = _h(t)
+    _lib.check(h, _lib.lib().hopb_p2p_allreduce_u32(h, _stream(), arr, ctypes.c_void_p(int(mc_ptr)), t.numel(), int(rank), int(world)))
+    return t
+
+
+def nvls_allgather(src: torch.Tensor, out: torch.Tensor, mc_out_ptr: int, rank: int, world: int):
+    """src -> slot `rank` of every rank's copy of out ([world] x src) through the switch (csrc/exchange.cu)."""
+    n_bytes = src.numel() * src.element_size()
+    if not (src.is_cuda and src.is_contiguous() and out.is_contiguous() and out.numel() * out.element_size() == world * n_bytes):
+        raise TypeError("out must be [world] x src, both contiguous CUDA tensors")
+    h = _h(src)
+    _lib.check(h, _lib.lib().hopb_nvls_allgather(h, _stream(), _p(src), ctypes.c_void_p(int(mc_out_ptr)), n_bytes, int(rank), int(world)))
+    return out
+
+
 def labels_to_int16(labels: torch.Tensor, out=None):
     """float32 hoptraj plane -> int16 (lossless), for the download (hopb_labels_to_int16)."""
     _cuda(labels, torch.float32, "labels")

@@ -186,11 +186,16 @@ class HopPipeline:
         self.grid = grid
 
     # -- buffers reused across runs (steady-state runs do not allocate) --------------------------
-    def _buf(self, name, shape, dtype):
+    def _buf(self, name, shape, dtype, symm=False):
+        """symm: a buffer of one of the three exchanges -- symmetric memory when several ranks run on an NVSwitch
+        box (allocation is then collective: all ranks reach it at the same point of the same run)."""
         t = self._bufs.get(name)
         shape = tuple(int(s) for s in shape)
         if t is None or tuple(t.shape) != shape or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            if symm and exchange.nvls_wanted():
+                t = exchange.symm_empty(shape, dtype, self.device)
+            else:
+                t = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[name] = t
         return t
 
@@ -210,7 +215,7 @@ class HopPipeline:
         return need < 0.5 * free
 
     def histogram(self, xyz):
-        counts = self._buf("counts", self.grid.shape, torch.int32)
+        counts = self._buf("counts", self.grid.shape, torch.int32, symm=True)
         counts.zero_()
         self.cells = None
         if self._use_cells(xyz):
@@ -399,7 +404,7 @@ class HopPipeline:
         else:
             rank, world = d.get_rank(), d.get_world_size()
             slab = K.hop_combine(summaries, chunk_len, F)
-            gathered = exchange.gather_slab_summaries(slab, self._buf("slabs", (world, K.SUMMARY_INTS, N), torch.int32))
+            gathered = exchange.gather_slab_summaries(slab, self._buf("slabs", (world, K.SUMMARY_INTS, N), torch.int32, symm=True))
             K.hop_advance(gathered[:rank] if rank > 0 else None, state, init=True)
             final_state = self._buf("final_state", (K.STATE_INTS, N), torch.int32)
             K.hop_advance(gathered, final_state, init=True)
@@ -470,7 +475,7 @@ class HopPipeline:
             w_cap *= 2
         # two sets of outputs, alternating: the results of a run stay intact while the next one is finalised
         par = "%d" % (self._run_index & 1)
-        matrix = self._buf("count_matrix_cap" + par, (w_cap, w_cap), torch.int32) if w_cap * w_cap <= (1 << 24) else None
+        matrix = self._buf("count_matrix_cap" + par, (w_cap, w_cap), torch.int32, symm=True) if w_cap * w_cap <= (1 << 24) else None
         cap = max(events.capacity, 1)
         out = (self._buf("ev_sorted" + par, (cap, 6), torch.int32), self._buf("e_s0" + par, (cap,), torch.int32),
                self._buf("e_s" + par, (cap,), torch.int32), self._buf("e_start" + par, (cap,), torch.int64),
@@ -675,7 +680,7 @@ class HopPipeline:
         dev = self.device
         par = self._run_index & 1
         xyz = self._buf("xyz_resident%d" % par, (F, N, 3), torch.float32)
-        counts = self._buf("counts", self.grid.shape, torch.int32)
+        counts = self._buf("counts", self.grid.shape, torch.int32, symm=True)
         counts.zero_()
         self.cells = self._buf("cells%d" % par, (F, N), torch.int32) if self._use_cells(xyz) else None
         if getattr(self, "_h2d_stream", None) is None:

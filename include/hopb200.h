@@ -430,6 +430,28 @@ int hopb_all_transitions(hopb_handle* h, void* stream, const float* hop_x, int64
 int hopb_all_transitions_i16(hopb_handle* h, void* stream, const int16_t* hop_x, int64_t F, int64_t N,
                              int n_labels, uint32_t* bitmap);
 
+/* ---- exchange steps of the frame-sharded path on NVSwitch multicast memory ------ */
+/* The reference is serial; sharding its frame loops (hop/density.py:125-131, hop/graph.py:212-254) over GPUs needs
+ * three small exchanges: the sum of the count grids, the gather of one slab summary per atom and rank, the sum of
+ * the transition-count matrices.  `mc` arguments are MULTICAST addresses of buffers in symmetric memory (the same
+ * allocation on every rank, e.g. torch.distributed._symmetric_memory), valid for multimem.* instructions only; the
+ * caller brackets every call with a cross-rank barrier before (all copies complete) and after (all slices
+ * delivered).
+ *
+ * In-place sum over the ranks of n_words 32-bit counters: rank r reduces slice r through the switch
+ * (multimem.ld_reduce.add) and writes it to every copy (multimem.st). */
+int hopb_nvls_allreduce_u32(hopb_handle* h, void* stream, uint32_t* mc, int64_t n_words, int rank, int world);
+
+/* The same sum with the additions on the SM: peer_ptrs = HOST array of `world` device pointers, the ranks' copies as
+ * mapped into this process (peer mappings; entry `rank` is the local copy); slice `rank` is read from every copy with
+ * 16-byte loads and the sum written to all copies with one multicast store. */
+int hopb_p2p_allreduce_u32(hopb_handle* h, void* stream, const void* const* peer_ptrs, uint32_t* mc, int64_t n_words,
+                           int rank, int world);
+
+/* src (device, n_bytes, a multiple of 16) -> slot `rank` of every rank's [world][n_bytes] buffer behind mc_out. */
+int hopb_nvls_allgather(hopb_handle* h, void* stream, const void* src, void* mc_out, int64_t n_bytes, int rank,
+                        int world);
+
 /* ---- synthetic input (bench / tests) ------------------------------------------- */
 typedef struct hopb_synth_params {
   uint64_t seed;
