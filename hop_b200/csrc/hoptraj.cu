@@ -19,6 +19,9 @@
 //
 // Roofline per atom-frame: 12 B read + 8 B written to HBM; the site-map gather (2 B out of a 32 B
 // sector) is served by L2 (map16 of 201^3 cells = 16 MB).
+#include <cuda.h>
+
+#include <cstdlib>
 #include <type_traits>
 
 #include "hopb_common.cuh"
@@ -98,6 +101,48 @@ struct AxisReg {
   int n;
   const HopbPair* pairs;
 };
+
+// ---- bulk-copy (TMA) staging of the brick-index stream ----------------------------------------------------------------
+// ncu put ~60 % of the kernel's stall samples on the first use of a loaded brick index and of a gathered label: with 64
+// registers per thread a block of 8 frames is all a thread can keep in flight.  The TMA variant moves the indices of
+// the next two blocks into shared memory with cp.async.bulk.tensor (one 32-atom x 8-frame box of the [frames][atoms]
+// array per block and warp, issued by one lane, completion on a per-warp mbarrier): they cost no registers while in
+// flight.  kTmaAhead additionally resolves the labels of block b+1 (its L2 gathers) before the state machine runs
+// block b.
+constexpr int kTmaStages = 2;
+#ifndef HOPB_K3_TMA_AHEAD
+#define HOPB_K3_TMA_AHEAD 0
+#endif
+constexpr bool kTmaAhead = HOPB_K3_TMA_AHEAD != 0;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" : : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// one box of the [frames][atoms] brick-index array (32 atoms x DEEP frames) -> shared memory; columns beyond the last
+// atom arrive as zeros and count towards the transaction bytes
+__device__ __forceinline__ void tma_box_g2s(void* dst_smem, const CUtensorMap* tmap, int c_atom, int c_frame, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               : : "r"(smem_u32(dst_smem)), "l"(tmap), "r"(c_atom), "r"(c_frame), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ AxisReg load_axis(const HopbAxis& a, const HopbPair* s_pairs) {
   AxisReg r;
@@ -190,7 +235,7 @@ __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
 // copy of the map per CTA) does not change which items exist.
 // PT: element type of the two output planes -- float (the record type of the hoptraj DCD) or int16_t (the same labels
 // at a quarter of the kernel's DRAM traffic less: labels are int16 map values or -1; the pipeline's default).
-template <int SRC, bool FAST, bool XY, int MAP, bool STRIDED = false, int DEEP = 8, typename PT = float>
+template <int SRC, bool FAST, bool XY, int MAP, bool STRIDED = false, int DEEP = 8, typename PT = float, bool TMA = false>
 __global__ void __launch_bounds__(1024, 1)
 hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_in, const uint32_t* __restrict__ cells,
                int64_t F, int64_t N, int64_t ld_arg, int64_t frame0, HopbGridTab tab, const float* __restrict__ table,
@@ -198,7 +243,7 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
                const uint32_t* __restrict__ blockmap, int map_words, int fine_value, uint32_t fine_auto_min,
                PT* __restrict__ hop_x,
                PT* __restrict__ hop_y, int n_chunks, int64_t chunk_len, int32_t* __restrict__ summaries,
-               EventSink sink) {
+               EventSink sink, const __grid_constant__ CUtensorMap cells_map) {
   // rows of the data arrays are N atoms apart, or ld_arg when the atoms are a column range of wider arrays (a
   // variant of its own: the common case keeps one value less alive at the 64-register limit)
   const int64_t ld = STRIDED ? ld_arg : N;
@@ -221,6 +266,21 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   }
   if (SRC != 1 && (MAP == MAP_COARSE || MAP == MAP_FINE))
     for (int i = threadIdx.x; i < map_words; i += blockDim.x) s_map[i] = blockmap[i];
+  // TMA staging: per warp kTmaStages x DEEP rows of 32 brick indices and one mbarrier per stage
+  uint32_t* w_stage = nullptr;
+  uint64_t* w_bar = nullptr;
+  if (TMA) {
+    const int words_before = (int)(reinterpret_cast<unsigned char*>(s_map + ((MAP == MAP_COARSE || MAP == MAP_FINE) ? map_words : 0)) - smem_raw);
+    unsigned char* st0 = smem_raw + ((words_before + 127) & ~127);
+    const int n_warps = blockDim.x >> 5;
+    w_stage = reinterpret_cast<uint32_t*>(st0) + (threadIdx.x >> 5) * (kTmaStages * DEEP * 32);
+    w_bar = reinterpret_cast<uint64_t*>(st0 + (size_t)n_warps * kTmaStages * DEEP * 128) + (threadIdx.x >> 5) * kTmaStages;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < kTmaStages; ++q) mbar_init(w_bar + q, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" : : : "memory");
+    }
+  }
   __syncthreads();
   const AxisReg ax = load_axis(tab.ax[0], s_pairs);
   const AxisReg ay = load_axis(tab.ax[1], s_pairs);
@@ -372,6 +432,33 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   };
 
   int f = f_begin;
+  // TMA pipeline state (see above): lab_cur = labels of the block at f; blocks are numbered from the chunk start
+  int lab_cur[DEEP];
+  int blk = 0;
+  const int n_blk = (f_end - f_begin) / DEEP;
+  const int lane_id = threadIdx.x & 31;
+  const int leader = __ffs(lanes) - 1;
+  const int64_t atom0 = atom - lane_id;
+  auto tma_issue = [&](int b) {      // box of block b -> stage b % kTmaStages
+    if (lane_id == leader) {
+      uint64_t* bar = w_bar + (b % kTmaStages);
+      mbar_expect_tx(bar, (uint32_t)(DEEP * 32 * 4));
+      tma_box_g2s(w_stage + (b % kTmaStages) * (DEEP * 32), &cells_map, (int)atom0, f_begin + b * DEEP, bar);
+    }
+  };
+  auto tma_consume = [&](int b, int* lab) {      // labels of block b (gathers in flight on return), its stage refilled
+    mbar_wait(w_bar + (b % kTmaStages), (uint32_t)((b / kTmaStages) & 1));
+    const uint32_t* st = w_stage + (b % kTmaStages) * (DEEP * 32) + lane_id;
+#pragma unroll
+    for (int u = 0; u < DEEP; ++u) lab[u] = label_of<MAP>(st[u * 32], mv);
+    __syncwarp(lanes);
+    if (b + kTmaStages < n_blk) tma_issue(b + kTmaStages);
+  };
+  if (TMA && SRC == 2 && n_blk > 0) {
+    tma_issue(0);
+    if (n_blk > 1) tma_issue(1);
+    if (kTmaAhead) tma_consume(0, lab_cur);
+  }
   // stream whole blocks of frames through `body` while `more()` (warp-uniform) holds and the chunk lasts
   auto stream_blocks = [&](auto&& body, auto&& more) {
     if (!more()) return;
@@ -391,6 +478,36 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
         __syncwarp(lanes);
         if (*reinterpret_cast<volatile int*>(evs.cnt) >= kEvQueue / 2) flush_staged(sink, evs, lanes);
         if (!more()) break;
+      }
+    } else if (TMA && SRC == 2) {
+      if (kTmaAhead) {
+        // labels of block b + 1 are resolved (their gathers issued) before the state machine runs block b
+        while (blk < n_blk) {
+          int lab_next[DEEP];
+          const bool nxt = blk + 1 < n_blk;
+          if (nxt) tma_consume(blk + 1, lab_next);
+          body(lab_cur, std::integral_constant<int, DEEP>(), f, (int)(frame0 + f));
+          f += DEEP;
+          ++blk;
+          if (nxt) {
+#pragma unroll
+            for (int u = 0; u < DEEP; ++u) lab_cur[u] = lab_next[u];
+          }
+          __syncwarp(lanes);
+          if (*reinterpret_cast<volatile int*>(evs.cnt) >= kEvQueue / 2) flush_staged(sink, evs, lanes);
+          if (!more()) break;
+        }
+      } else {
+        while (blk < n_blk) {
+          int lab[DEEP];
+          tma_consume(blk, lab);
+          body(lab, std::integral_constant<int, DEEP>(), f, (int)(frame0 + f));
+          f += DEEP;
+          ++blk;
+          __syncwarp(lanes);
+          if (*reinterpret_cast<volatile int*>(evs.cnt) >= kEvQueue / 2) flush_staged(sink, evs, lanes);
+          if (!more()) break;
+        }
       }
     } else {
       // 4-byte inputs (brick indices or labels) in blocks of kDeep frames: as soon as the labels of a
@@ -617,6 +734,29 @@ all_transitions_kernel(const PT* __restrict__ hop_x, int64_t F, int64_t N, int n
 
 extern "C" {
 
+// Tensor map of the brick-index array [F][N] (rows ld elements apart) with a box of 32 atoms x 8 frames; the driver
+// entry point is looked up once (no link against libcuda).  false: not available, the register-staged path runs.
+static bool encode_cells_map(CUtensorMap* map, const uint32_t* cells, int64_t F, int64_t N, int64_t ld) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = []() -> encode_fn {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<encode_fn>(fn);
+  }();
+  if (!encode) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)F};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, 8};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(cells), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid* g, const float* xyz,
                           const float* labels_in, const uint32_t* cells, int64_t F, int64_t N, int64_t ld, int64_t frame0,
                           const int16_t* map16, const uint32_t* coarse, const uint8_t* fine, int fine_value,
@@ -638,13 +778,15 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     HopbGridTab tab;
     memset(&tab, 0, sizeof(tab));
     const unsigned grid = (unsigned)((items + kHopThreads / 32 - 1) / (kHopThreads / 32));
+    CUtensorMap no_map;
+    memset(&no_map, 0, sizeof(no_map));
     hopb_note_launch();
     if (hop_x && hop_y)
       hoptraj_kernel<1, true, true, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink, no_map);
     else
       hoptraj_kernel<1, true, false, MAP_GATHER><<<grid, kHopThreads, 0, s>>>(nullptr, labels_in, nullptr, F, N, ld, frame0, tab,
-          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink);
+          nullptr, nullptr, nullptr, nullptr, 0, 0, 0u, (float*)hop_x, (float*)hop_y, n_chunks, chunk_len, summaries, sink, no_map);
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
@@ -670,17 +812,40 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
     mode = MAP_CELL2; blockmap = cell2;
   }
   const uint32_t fine_auto_min = (uint32_t)(((int64_t)g->n[0] * g->n[1] * g->n[2] + 7) / 8);
-  const size_t per_cta = smem + 1024;  // + the driver's reservation
-  threads = per_cta * 4 <= 227 * 1024 ? 256 : (per_cta * 2 <= 227 * 1024 ? 512 : 1024);
+  // Bulk-copy staging of the brick indices (see kTmaStages): rows must be 16-byte multiples apart at a 16-byte aligned
+  // address, both planes are written, and the staging area (2 KB + 16 B per warp) has to fit beside the block map.
+  static const bool tma_off = getenv("HOPB_K3_TMA") && atoi(getenv("HOPB_K3_TMA")) == 0;
+  bool tma = !tma_off && src == 2 && hop_x && hop_y && ld == N && (ld & 3) == 0 && ((uintptr_t)cells & 15) == 0 && F >= 8;
+  const size_t kStatic = 32 * 4 + 32 * kEvQueue * sizeof(hopb_event) + 1024;     // event queues + the driver's reservation
+  auto pick_threads = [&](bool with_tma, size_t& smem_out) -> int {
+    for (int t = 256; t <= 1024; t *= 2) {
+      const size_t stage = with_tma ? 128 + (size_t)(t / 32) * (kTmaStages * 8 * 128 + kTmaStages * 8) : 0;
+      const size_t per_cta = smem + stage + kStatic;
+      if (per_cta * (1024 / t) <= 227 * 1024 || (t == 1024 && !with_tma)) { smem_out = smem + stage; return t; }
+    }
+    return 0;
+  };
+  size_t smem_launch = smem;
+  CUtensorMap cells_map;
+  memset(&cells_map, 0, sizeof(cells_map));
+  if (tma) tma = encode_cells_map(&cells_map, cells, F, N, ld);
+  threads = tma ? pick_threads(true, smem_launch) : 0;
+  if (threads == 0) { tma = false; threads = pick_threads(false, smem_launch); }
+  smem = smem_launch;
   const unsigned grid = (unsigned)((items + threads / 32 - 1) / (threads / 32));
-#define HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, ST, PT)                                                                 \
+#define HOPB_HT_LAUNCH_T(SRC, FAST, XY, MAP, ST, PT, TM)                                                             \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      HOPB_CUDA(h, cudaFuncSetAttribute(hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     hopb_note_launch();                                                                                              \
-    hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, ld, frame0, g->tab, g->d_table, \
+    hoptraj_kernel<SRC, FAST, XY, MAP, ST, 8, PT, TM><<<grid, threads, smem, s>>>(xyz, nullptr, cells, F, N, ld, frame0, g->tab, g->d_table, \
         g->d_table2, map16, blockmap, map_words, fine_value, fine_auto_min, (PT*)hop_x, (PT*)hop_y, n_chunks, chunk_len, \
-        summaries, sink);                                                                                            \
+        summaries, sink, cells_map);                                                                                 \
+  } while (0)
+#define HOPB_HT_LAUNCH_S(SRC, FAST, XY, MAP, ST, PT)                                                                 \
+  do {                                                                                                               \
+    if (SRC == 2 && XY && !ST && tma) HOPB_HT_LAUNCH_T(SRC, FAST, XY, MAP, ST, PT, (SRC == 2 && XY && !ST));         \
+    else HOPB_HT_LAUNCH_T(SRC, FAST, XY, MAP, ST, PT, false);                                                        \
   } while (0)
 #define HOPB_HT_LAUNCH_M(SRC, FAST, XY, MAP, PT)                                                                     \
   do {                                                                                                               \
@@ -701,6 +866,7 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   } while (0)
   if (src == 0) { if (fast) HOPB_HT_LAUNCH(0, true); else HOPB_HT_LAUNCH(0, false); }
   else HOPB_HT_LAUNCH(2, true);
+#undef HOPB_HT_LAUNCH_T
 #undef HOPB_HT_LAUNCH
 #undef HOPB_HT_LAUNCH_XY
 #undef HOPB_HT_LAUNCH_M
