@@ -197,10 +197,12 @@ struct MapView {
 // of a 0.5 A water grid sit in a mixed 2x2x2 sub-brick, 20 % in a mixed 4x4x4 brick) is preferred
 // whenever it fits into shared memory.  Selects and one predicated load: no divergence, and the
 // load is the last thing that writes l so nothing waits for it before the label is used.
-template <int MAP>
+// PLAIN: the caller has checked that c is an ordinary brick index (no outlier, no bookkeeping bit) -- a warp vote per
+// block of frames in the TMA path, which takes four instructions per frame out of the look-up.
+template <int MAP, bool PLAIN = false>
 __device__ __forceinline__ int label_of(uint32_t c, const MapView& m) {
-  const bool out = c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
-  const uint32_t cc = out ? 0u : (c & 0x3FFFFFFFu);  // bit 30: bookkeeping of the slabbed histogram
+  const bool out = PLAIN ? false : c == 0xFFFFFFFFu;  // the -1 shell of buffered_map (trajectory.py:176-177)
+  const uint32_t cc = PLAIN ? c : (out ? 0u : (c & 0x3FFFFFFFu));  // bit 30: bookkeeping of the slabbed histogram
   int l;
   bool need;
   if (MAP == MAP_FINE) {
@@ -449,8 +451,17 @@ hoptraj_kernel(const float* __restrict__ xyz, const float* __restrict__ labels_i
   auto tma_consume = [&](int b, int* lab) {      // labels of block b (gathers in flight on return), its stage refilled
     mbar_wait(w_bar + (b % kTmaStages), (uint32_t)((b / kTmaStages) & 1));
     const uint32_t* st = w_stage + (b % kTmaStages) * (DEEP * 32) + lane_id;
+    uint32_t c[DEEP];
+    uint32_t any = 0u;
 #pragma unroll
-    for (int u = 0; u < DEEP; ++u) lab[u] = label_of<MAP>(st[u * 32], mv);
+    for (int u = 0; u < DEEP; ++u) { c[u] = st[u * 32]; any |= c[u]; }
+    if (!__any_sync(lanes, (any >> 30) != 0u)) {      // no outlier, no bookkeeping bit in this block of the warp
+#pragma unroll
+      for (int u = 0; u < DEEP; ++u) lab[u] = label_of<MAP, true>(c[u], mv);
+    } else {
+#pragma unroll
+      for (int u = 0; u < DEEP; ++u) lab[u] = label_of<MAP>(c[u], mv);
+    }
     __syncwarp(lanes);
     if (b + kTmaStages < n_blk) tma_issue(b + kTmaStages);
   };
