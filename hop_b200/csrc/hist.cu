@@ -20,6 +20,8 @@
 // j+64 (three fully coalesced 512 B requests), park them in a per-warp shared-memory slab, and read
 // the points back at a stride of 3 words (conflict-free) so that lane l handles points l, l+32,
 // l+64, l+96; the packed cells go out as four coalesced 128 B stores per warp.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "hopb_common.cuh"
@@ -91,11 +93,18 @@ struct Slab { int x_lo, x_hi; uint32_t done_flag; };  // reduce cells with x_lo 
 
 // counts: the selection's own histogram (may be NULL); counts_b: a second histogram that receives the
 // point only when `to_b` (the bulk density: solvent not within the cutoff of the solute)
-template <bool CELLS, bool FAST>
+// PACK16: the reduction goes into a grid of 16-bit counters, two cells per 32-bit word (red_packed) -- half the bytes
+// behind the scattered reductions, which is what bounds a pass once the grid outgrows L2 (see hist_flush16_kernel for
+// how a counter that wraps is found out); n_red counts the reductions this thread has made.
+__device__ __forceinline__ void red_packed(uint32_t* counts16, uint32_t cell) {
+  atomicAdd(counts16 + (cell >> 1), 1u << ((cell & 1u) << 4));   // result unused -> RED.E.ADD
+}
+
+template <bool CELLS, bool FAST, bool PACK16 = false>
 __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const HopbGridTab& tab, const AxisReg& ax,
                                                const AxisReg& ay, const AxisReg& az, const float* s_tab,
                                                uint32_t* counts, const Slab& slab, uint32_t* counts_b = nullptr,
-                                               bool to_b = false, uint32_t* lin_out = nullptr) {
+                                               bool to_b = false, uint32_t* lin_out = nullptr, uint32_t* n_red = nullptr) {
   // lin_out != NULL (partitioned histogram): the linear cell of an ordinary point is handed back instead of being
   // reduced (0xFFFFFFFF: nothing to count, or counted here already -- the rare last-edge points)
   if (lin_out) *lin_out = 0xFFFFFFFFu;
@@ -135,7 +144,8 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
     const bool okh = ((unsigned)(hx - 1) < (unsigned)ax.n) & ((unsigned)(hy - 1) < (unsigned)ay.n) & ((unsigned)(hz - 1) < (unsigned)az.n);
     if (okh) {  // counted now, whatever the slab; the later passes skip it (kCellDone)
       const uint32_t cell = ((uint32_t)(hx - 1) * (uint32_t)ay.n + (uint32_t)(hy - 1)) * (uint32_t)az.n + (uint32_t)(hz - 1);
-      if (counts) atomicAdd(counts + cell, 1u);
+      if (PACK16) { red_packed(counts, cell); ++*n_red; }
+      else if (counts) atomicAdd(counts + cell, 1u);
       if (to_b) atomicAdd(counts_b + cell, 1u);
     }
     if (!CELLS) return 0u;
@@ -146,6 +156,7 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
   if (ok & (bx - 1 >= slab.x_lo) & (bx - 1 < slab.x_hi)) {
     const uint32_t cell = ((uint32_t)(bx - 1) * (uint32_t)ay.n + (uint32_t)(by - 1)) * (uint32_t)az.n + (uint32_t)(bz - 1);
     if (lin_out) *lin_out = cell;
+    else if (PACK16) { red_packed(counts, cell); ++*n_red; }
     else if (counts) atomicAdd(counts + cell, 1u);  // result unused -> RED.E.ADD
     if (to_b) atomicAdd(counts_b + cell, 1u);
   }
@@ -158,8 +169,9 @@ __device__ __forceinline__ uint32_t hist_point(float x, float y, float z, const 
 // points that pass it (1 / n_pass of them) are decoded into a cell.
 struct CellSlab { uint32_t c_lo, c_hi; };  // brick-index range [c_lo, c_hi) of the slab
 
+template <bool PACK16>
 __device__ __forceinline__ void hist_cell(uint32_t c, const CellSlab& sl, uint32_t plane, int ny, int nz, int cnz,
-                                          uint32_t* __restrict__ counts) {
+                                          uint32_t* __restrict__ counts, uint32_t& n_red) {
   // outliers (0xFFFFFFFF) and already counted points (bit 30) are >= 2^30 > c_hi
   if (c < sl.c_lo || c >= sl.c_hi) return;
   const uint32_t cb = c >> 6;
@@ -170,12 +182,34 @@ __device__ __forceinline__ void hist_cell(uint32_t c, const CellSlab& sl, uint32
   const uint32_t cj = r / (uint32_t)cnz;
   const uint32_t ck = r - cj * (uint32_t)cnz;
   const uint32_t i = ci * 4 + (uint32_t)di, j = cj * 4 + (uint32_t)dj, k = ck * 4 + (uint32_t)dk;
-  atomicAdd(counts + (i * (uint32_t)ny + j) * (uint32_t)nz + k, 1u);
+  const uint32_t cell = (i * (uint32_t)ny + j) * (uint32_t)nz + k;
+  if (PACK16) { red_packed(counts, cell); ++n_red; }
+  else atomicAdd(counts + cell, 1u);
 }
 
+// sum of a per-thread count over the block, added to *total by one thread (PACK16 bookkeeping)
+__device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* total) {
+  __shared__ uint32_t s_part[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0 && w) atomicAdd(total, (unsigned long long)w);
+  }
+}
+
+// run_flag (may be NULL): the launch does nothing unless *run_flag != 0 -- the direct-reduction passes queued behind a
+// packed pass only run when the packed pass had to be thrown away (hist_flush16_kernel)
+template <bool PACK16>
 __global__ void __launch_bounds__(256)
 hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, int64_t lead, CellSlab sl, int ny, int nz, int cny,
-                  int cnz, uint32_t* __restrict__ counts) {
+                  int cnz, uint32_t* __restrict__ counts, unsigned long long* n_red_total, const uint32_t* run_flag) {
+  if (run_flag && *reinterpret_cast<const volatile uint32_t*>(run_flag) == 0u) return;
+  uint32_t n_red = 0;
   const uint64_t pol = make_evict_first_policy();
   const uint32_t plane = (uint32_t)(cny * cnz);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,24 +222,27 @@ hist_cells_kernel(const uint32_t* __restrict__ cells, int64_t n_points, int64_t 
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(c4 + q), "l"(pol));
-    hist_cell(v.x, sl, plane, ny, nz, cnz, counts);
-    hist_cell(v.y, sl, plane, ny, nz, cnz, counts);
-    hist_cell(v.z, sl, plane, ny, nz, cnz, counts);
-    hist_cell(v.w, sl, plane, ny, nz, cnz, counts);
+    hist_cell<PACK16>(v.x, sl, plane, ny, nz, cnz, counts, n_red);
+    hist_cell<PACK16>(v.y, sl, plane, ny, nz, cnz, counts, n_red);
+    hist_cell<PACK16>(v.z, sl, plane, ny, nz, cnz, counts, n_red);
+    hist_cell<PACK16>(v.w, sl, plane, ny, nz, cnz, counts, n_red);
   }
   const int64_t tail0 = lead + 4 * n4;
   const int64_t n_rem = lead + (n_points - tail0);
   for (int64_t i = tid; i < n_rem; i += nth) {
     const int64_t p = i < lead ? i : tail0 + (i - lead);
-    hist_cell(ld_stream_u32(cells + p, pol), sl, plane, ny, nz, cnz, counts);
+    hist_cell<PACK16>(ld_stream_u32(cells + p, pol), sl, plane, ny, nz, cnz, counts, n_red);
   }
+  if (PACK16) block_add_u64(n_red, n_red_total);
 }
 
-template <bool CELLS, bool FAST>
+template <bool CELLS, bool FAST, bool PACK16 = false>
 __global__ void __launch_bounds__(kHistThreads, 4)
 hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbGridTab tab,
             const float* __restrict__ table, const HopbPair* __restrict__ table2, uint32_t* __restrict__ counts,
-            uint32_t* __restrict__ cells, Slab slab) {
+            uint32_t* __restrict__ cells, Slab slab, unsigned long long* n_red_total = nullptr, const uint32_t* run_flag = nullptr) {
+  if (run_flag && *reinterpret_cast<const volatile uint32_t*>(run_flag) == 0u) return;
+  uint32_t n_red = 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* stage = reinterpret_cast<float4*>(smem_raw);                         // [warps][96] float4
   HopbPair* s_pairs = reinterpret_cast<HopbPair*>(stage + kWarpsPerBlock * 96);  // pair tables
@@ -241,7 +278,8 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = 3 * (lane + 32 * j);
-      const uint32_t c = hist_point<CELLS, FAST>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts, slab);
+      const uint32_t c = hist_point<CELLS, FAST, PACK16>(wf[p], wf[p + 1], wf[p + 2], tab, ax, ay, az, s_tab, counts, slab, nullptr, false,
+                                                         nullptr, &n_red);
       if (CELLS) cout[32 * j] = c;
     }
     __syncwarp();
@@ -251,9 +289,61 @@ hist_kernel(const float* __restrict__ xyz, int64_t n_points, int64_t lead, HopbG
   const int64_t n_rem = lead + (n_points - tail0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rem; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i < lead ? i : tail0 + (i - lead);
-    const uint32_t c = hist_point<CELLS, FAST>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts, slab);
+    const uint32_t c = hist_point<CELLS, FAST, PACK16>(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], tab, ax, ay, az, s_tab, counts, slab,
+                                                       nullptr, false, nullptr, &n_red);
     if (CELLS) cells[p] = c;
   }
+  if (PACK16) block_add_u64(n_red, n_red_total);
+}
+
+// ---- 16-bit packed count grid for grids larger than L2 ---------------------------------------------------------------
+// The scattered reductions run at the L2 rate only while their target stays well inside L2 (64 MiB budget: config 3's
+// 297^3 grid is 105 MB of u32, two x-slab passes; config 5's 402^3 is 260 MB, five).  With 16-bit counters the same
+// grids are 52 / 130 MB: one pass instead of two, three instead of five.  A launch covers a bounded number of frames, so a
+// 16-bit counter does not wrap for any physical input -- but the result must not depend on that: every wrap takes 65535 or
+// 65536 out of the sum of all counters (a carry out of a low half adds 1 to the high half; a high half's carry is lost)
+// and nothing ever adds to it, so "sum of the counters == number of reductions made" holds exactly when nothing wrapped.
+// This kernel (cooperative, two phases) checks that, then either adds the packed grid into the u32 grid or discards it
+// and raises *redo, on which the direct-reduction passes queued behind it run (they return at once otherwise).  The
+// packed grid is left zeroed either way.
+struct Flush16Ctl { unsigned long long n_red, total; uint32_t redo, pad; };
+
+__global__ void __launch_bounds__(512)
+hist_flush16_kernel(uint32_t* __restrict__ packed, int64_t n_words, uint32_t* __restrict__ counts, int64_t n_cells, Flush16Ctl* ctl) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  uint32_t part = 0;      // a thread sees at most 2^32 / 2^17 words: no overflow for grids below 2^40 cells
+  unsigned long long big = 0;
+  for (int64_t i = tid; i < n_words; i += nth) {
+    const uint32_t w = packed[i];
+    part += (w & 0xFFFFu) + (w >> 16);
+    if (part >= 0x80000000u) { big += part; part = 0; }
+  }
+  big += part;
+  __shared__ unsigned long long s_part[16];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) big += __shfl_xor_sync(0xffffffffu, big, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = big;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_part[k];
+    if (t) atomicAdd(&ctl->total, t);
+  }
+  grid.sync();
+  const bool ok = *reinterpret_cast<volatile unsigned long long*>(&ctl->total) == *reinterpret_cast<volatile unsigned long long*>(&ctl->n_red);
+  for (int64_t i = tid; i < n_words; i += nth) {
+    const uint32_t w = packed[i];
+    if (w == 0u) continue;
+    packed[i] = 0u;
+    if (ok) {
+      const int64_t c = 2 * i;
+      if (w & 0xFFFFu) counts[c] += w & 0xFFFFu;
+      if ((w >> 16) && c + 1 < n_cells) counts[c + 1] += w >> 16;
+    }
+  }
+  if (!ok && tid == 0) ctl->redo = 1u;
 }
 
 // ---- spatially partitioned, shared-memory-privatised histogram (north_star kernel 2) ---------------------------------
@@ -769,34 +859,83 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
     HOPB_LAUNCH_CHECK(h);
     return HOPB_OK;
   }
-  int slab_w = (g->n[0] + n_pass - 1) / n_pass;
-  if (n_pass > 1) slab_w = (slab_w + 3) / 4 * 4;
-  Slab slab;
-  slab.x_lo = 0; slab.x_hi = n_pass == 1 ? g->n[0] : slab_w; slab.done_flag = n_pass == 1 ? 0u : kCellDone;
-  hopb_note_launch();
-  if (cells) {
-    if (fast) hist_kernel<true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
-    else hist_kernel<true, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
-  } else {
-    if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
-    else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, counts, cells, slab);
-  }
-  if (n_pass > 1) {
-    const int cny = (g->n[1] + 3) / 4, cnz = (g->n[2] + 3) / 4;
-    const uint32_t plane64 = (uint32_t)(cny * cnz) * 64u;
-    int64_t lead4 = 0;  // points until the index stream is 16-byte aligned
-    while (lead4 < n_points && (((uintptr_t)cells + 4 * (uintptr_t)lead4) & 15) != 0) ++lead4;
-    for (int p = 1; p < n_pass; ++p) {
-      const int x_lo = p * slab_w;
-      const int x_hi = (p + 1) * slab_w < g->n[0] ? (p + 1) * slab_w : g->n[0];
-      if (x_lo >= x_hi) break;
-      CellSlab cs;
-      cs.c_lo = (uint32_t)(x_lo / 4) * plane64;
-      cs.c_hi = (uint32_t)((x_hi + 3) / 4) * plane64;
-      HOPB_K(hist_cells_kernel)<<<hopb_grid_for((n_points + 3) / 4, 256, h->num_sms, 8), 256, 0, s>>>(
-          cells, n_points, lead4, cs, g->n[1], g->n[2], cny, cnz, counts);
+  // all x-slab passes of one histogram: into the u32 grid, or (packed) into a grid of 16-bit counters
+  auto launch_passes = [&](bool packed, uint32_t* target, int passes, unsigned long long* n_red_total, const uint32_t* run_flag) {
+    int slab_w = (g->n[0] + passes - 1) / passes;
+    if (passes > 1) slab_w = (slab_w + 3) / 4 * 4;
+    Slab slab;
+    slab.x_lo = 0; slab.x_hi = passes == 1 ? g->n[0] : slab_w; slab.done_flag = passes == 1 ? 0u : kCellDone;
+    hopb_note_launch();
+    if (packed) {
+      hist_kernel<true, true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, target, cells, slab,
+                                                                    n_red_total, run_flag);
+    } else if (cells) {
+      if (fast) hist_kernel<true, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, target, cells, slab, nullptr, run_flag);
+      else hist_kernel<true, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, target, cells, slab, nullptr, run_flag);
+    } else {
+      if (fast) hist_kernel<false, true><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, target, cells, slab, nullptr, run_flag);
+      else hist_kernel<false, false><<<nb, kHistThreads, smem, s>>>(xyz, n_points, lead, g->tab, g->d_table, g->d_table2, target, cells, slab, nullptr, run_flag);
     }
+    if (passes > 1) {
+      const int cny = (g->n[1] + 3) / 4, cnz = (g->n[2] + 3) / 4;
+      const uint32_t plane64 = (uint32_t)(cny * cnz) * 64u;
+      int64_t lead4 = 0;  // points until the index stream is 16-byte aligned
+      while (lead4 < n_points && (((uintptr_t)cells + 4 * (uintptr_t)lead4) & 15) != 0) ++lead4;
+      for (int p = 1; p < passes; ++p) {
+        const int x_lo = p * slab_w;
+        const int x_hi = (p + 1) * slab_w < g->n[0] ? (p + 1) * slab_w : g->n[0];
+        if (x_lo >= x_hi) break;
+        CellSlab cs;
+        cs.c_lo = (uint32_t)(x_lo / 4) * plane64;
+        cs.c_hi = (uint32_t)((x_hi + 3) / 4) * plane64;
+        const unsigned gb = hopb_grid_for((n_points + 3) / 4, 256, h->num_sms, 8);
+        if (packed) HOPB_K(hist_cells_kernel<true>)<<<gb, 256, 0, s>>>(cells, n_points, lead4, cs, g->n[1], g->n[2], cny, cnz, target, n_red_total, run_flag);
+        else HOPB_K(hist_cells_kernel<false>)<<<gb, 256, 0, s>>>(cells, n_points, lead4, cs, g->n[1], g->n[2], cny, cnz, target, nullptr, run_flag);
+      }
+    }
+  };
+  // Grids that need more than one pass as u32 go through 16-bit packed counters first (hist_flush16_kernel): half the
+  // bytes behind the reductions, hence fewer passes.  HOPB_HIST_PACK16=0 switches it off, =2 forces it (tests).
+  const char* pack_env = getenv("HOPB_HIST_PACK16");
+  const int pack_mode = pack_env ? atoi(pack_env) : 1;
+  if (cells && fast && pack_mode && (n_pass > 1 || pack_mode == 2) && n_cells_all < ((int64_t)1 << 32)) {
+    const int64_t n_words = (n_cells_all + 1) / 2;
+    int64_t budget16 = h->hist_l2_budget;
+    if (const char* e = getenv("HOPB_HIST_PACK16_BUDGET_MB")) {      // tuning hook
+      if (atoll(e) > 0) budget16 = atoll(e) << 20;
+    }
+    int passes16 = (int)((row_bytes / 2 * g->n[0] + budget16 - 1) / budget16);
+    if (passes16 < 1) passes16 = 1;
+    if (passes16 > g->n[0]) passes16 = g->n[0];
+    unsigned char* scr = nullptr;
+    const size_t had = h->scratch_bytes[19];
+    int rc = hopb_scratch(h, 19, (size_t)n_words * 4 + sizeof(Flush16Ctl) + 64, (void**)&scr);
+    if (rc) return rc;
+    uint32_t* packed = reinterpret_cast<uint32_t*>(scr + 64);
+    Flush16Ctl* ctl = reinterpret_cast<Flush16Ctl*>(scr);
+    if (had != h->scratch_bytes[19])      // fresh memory: the packed grid starts zeroed (every flush leaves it zeroed)
+      HOPB_CUDA(h, cudaMemsetAsync(scr, 0, h->scratch_bytes[19], s));
+    HOPB_CUDA(h, cudaMemsetAsync(ctl, 0, sizeof(Flush16Ctl), s));
+    launch_passes(true, packed, passes16, &ctl->n_red, nullptr);
+    {
+      int per_sm = 0;
+      HOPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist_flush16_kernel, 512, 0));
+      HOPB_REQUIRE(h, per_sm >= 1, "cooperative launch not possible");
+      if (per_sm > 2) per_sm = 2;
+      int64_t nblocks = (int64_t)per_sm * h->num_sms;
+      const int64_t useful = (n_words + 511) / 512;
+      if (nblocks > useful) nblocks = useful;
+      uint32_t* counts_arg = counts;
+      int64_t n_words_arg = n_words, n_cells_arg = n_cells_all;
+      void* kargs[] = {(void*)&packed, (void*)&n_words_arg, (void*)&counts_arg, (void*)&n_cells_arg, (void*)&ctl};
+      hopb_note_launch();
+      HOPB_CUDA(h, cudaLaunchCooperativeKernel((void*)hist_flush16_kernel, dim3((unsigned)nblocks), dim3(512), kargs, 0, s));
+    }
+    launch_passes(false, counts, n_pass, nullptr, &ctl->redo);     // only does anything when the packed grid was discarded
+    HOPB_LAUNCH_CHECK(h);
+    return HOPB_OK;
   }
+  launch_passes(false, counts, n_pass, nullptr, nullptr);
   HOPB_LAUNCH_CHECK(h);
   return HOPB_OK;
 }

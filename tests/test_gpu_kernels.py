@@ -58,8 +58,11 @@ def test_histogram_counts(K, traj, delta):
     assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
 
 
-def test_histogram_slabbed_passes(K, traj):
-    """Grids beyond the L2 budget are reduced slab by slab from the cached cell indices."""
+@pytest.mark.parametrize("pack16", ["0", "1"])
+def test_histogram_slabbed_passes(K, traj, pack16, monkeypatch):
+    """Grids beyond the L2 budget are reduced slab by slab from the cached cell indices -- straight into the u32 grid
+    (HOPB_HIST_PACK16=0) or through the 16-bit packed grid first (the default for such grids)."""
+    monkeypatch.setenv("HOPB_HIST_PACK16", pack16)
     p, xyz = traj
     xyz = xyz[:50].copy()
     _, _, edges = O.grid_geometry(xyz[0], delta=0.5)
@@ -90,6 +93,44 @@ def test_histogram_slabbed_passes(K, traj):
             assert np.array_equal(X.cpu().numpy(), res["hop"][:, :, 0]) and np.array_equal(Y.cpu().numpy(), res["hop"][:, :, 1])
     finally:
         K.set_hist_l2_budget(64 << 20)
+
+
+def test_packed16_histogram_is_exact_even_when_a_counter_wraps(K, traj, monkeypatch):
+    """The 16-bit packed count grid (hist_flush16_kernel): equal to the direct reductions on ordinary input, in one and
+    in several x-slab passes, accumulating over calls -- and equal as well when a 16-bit counter wraps inside one call
+    (70 000 points in one cell, its neighbour in the same word occupied too): the sum check finds the wrap out, the
+    packed grid is discarded and the direct-reduction passes queued behind it run."""
+    p, xyz = traj
+    _, _, edges = O.grid_geometry(xyz[0], delta=1.0)
+    g = K.GridTables(edges)
+    mids = [0.5 * (e[:-1] + e[1:]) for e in edges]
+    hot = np.array([mids[0][5], mids[1][6], mids[2][8]], np.float32)          # cell (5, 6, 8) and its z neighbour (5, 6, 9)
+    hot2 = np.array([mids[0][5], mids[1][6], mids[2][9]], np.float32)
+    crowd = xyz[:80].copy()                                                       # 80 frames x 1000 atoms
+    crowd[:70, :, :] = hot                                                        # 70 000 points in one cell
+    crowd[70:75, :500, :] = hot2
+    cases = {"ordinary": xyz, "wrap": crowd}
+    out = {}
+    try:
+        for mode in ("0", "2"):
+            monkeypatch.setenv("HOPB_HIST_PACK16", mode)
+            for name, data in cases.items():
+                for budget in (64 << 20, 1 << 14):
+                    K.set_hist_l2_budget(budget)
+                    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+                    cells = torch.empty(data.shape[:2], dtype=torch.int32, device="cuda")
+                    K.hist_accumulate(g, dev(data), counts, cells)
+                    K.hist_accumulate(g, dev(data[:7]), counts, cells[:7])        # a second call adds to the same grid
+                    out[(mode, name, budget)] = (counts.cpu().numpy().copy(), cells.cpu().numpy().copy())
+    finally:
+        K.set_hist_l2_budget(64 << 20)
+    for name, data in cases.items():
+        ref = O.histogram_vectorised(data, edges) + O.histogram_vectorised(data[:7], edges)
+        for budget in (64 << 20, 1 << 14):
+            a, b = out[("0", name, budget)], out[("2", name, budget)]
+            assert np.array_equal(a[0].astype(np.int64), ref), (name, budget)
+            assert np.array_equal(b[0], a[0]) and np.array_equal(b[1], a[1]), (name, budget)
+    assert out[("2", "wrap", 64 << 20)][0][5, 6, 8] >= 70000 + 7000
 
 
 @pytest.mark.parametrize("delta", [1.0, 0.5])
