@@ -841,7 +841,8 @@ static int launch_hoptraj(hopb_handle* h, void* stream, int src, const hopb_grid
   const uint32_t fine_auto_min = (uint32_t)(((int64_t)g->n[0] * g->n[1] * g->n[2] + 7) / 8);
   // Bulk-copy staging of the brick indices (see kTmaStages): rows must be 16-byte multiples apart at a 16-byte aligned
   // address, both planes are written, and the staging area (2 KB + 16 B per warp) has to fit beside the block map.
-  static const bool tma_off = getenv("HOPB_K3_TMA") && atoi(getenv("HOPB_K3_TMA")) == 0;
+  const char* tma_env = getenv("HOPB_K3_TMA");      // HOPB_K3_TMA=0: register-staged input (tests compare the two)
+  const bool tma_off = tma_env && atoi(tma_env) == 0;
   bool tma = !tma_off && src == 2 && hop_x && hop_y && ld == N && (ld & 3) == 0 && ((uintptr_t)cells & 15) == 0 && F >= 8;
   const size_t kStatic = 32 * 4 + 32 * kEvQueue * sizeof(hopb_event) + 1024;     // event queues + the driver's reservation
   auto pick_threads = [&](bool with_tma, size_t& smem_out) -> int {

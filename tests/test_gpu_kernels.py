@@ -1117,3 +1117,38 @@ def test_int16_planes_equal_float32_planes(K, traj, n_chunks):
             assert np.array_equal(out[dt][4][ht][0], a[0]) and np.array_equal(out[dt][4][ht][1], a[1])
     with pytest.raises(ValueError):
         PipelineConfig(plane_dtype="int8").plane_torch_dtype()
+
+
+@pytest.mark.parametrize("n_atoms", [1000, 996, 64])
+def test_tma_staged_hoptraj_equals_register_staged(K, n_atoms, monkeypatch):
+    """Stage 3 reads the cached brick indices through TMA boxes of 32 atoms x 8 frames (full and partial last warp, chunks
+    that are not multiples of 8 frames) or, with HOPB_K3_TMA=0 / a row stride that is no multiple of 16 bytes, through
+    registers: same planes, same summaries, same events."""
+    p = SynthParams(n_atoms=n_atoms, n_frames=203)
+    xyz = generate(p)
+    ref = O.pipeline(xyz, delta=1.0)
+    g = K.GridTables(ref["edges"])
+    counts = torch.zeros(g.shape, dtype=torch.int32, device="cuda")
+    cells = torch.empty(xyz.shape[:2], dtype=torch.int32, device="cuda")
+    K.hist_accumulate(g, dev(xyz), counts, cells)
+    brick = K.brick_map(dev(ref["map"]))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HOPB_K3_TMA", mode)
+        for dt in (torch.int16, torch.float32):
+            for n_chunks, chunk_len in ((1, 203), (4, 51), (7, 29)):
+                ev = K.EventBuffer(xyz.shape[0] * xyz.shape[1], "cuda")
+                X = torch.empty(xyz.shape[:2], dtype=dt, device="cuda")
+                Y = torch.empty(xyz.shape[:2], dtype=dt, device="cuda")
+                s = K.hoptraj(g, None, brick, 0, n_chunks, chunk_len, ev, X, Y, cells=cells)
+                st = K.new_state(xyz.shape[1], "cuda")
+                K.hop_advance(None, st, init=True)
+                K.hop_fixup(s, chunk_len, 203, st, Y, ev)
+                e = ev.data[: ev.n()].cpu().numpy()
+                e = e[np.lexsort((e[:, 1], e[:, 0]))]
+                out[(mode, dt, n_chunks)] = (X.cpu().numpy().astype(np.float32), Y.cpu().numpy().astype(np.float32), s.cpu().numpy(), e)
+                assert np.array_equal(out[(mode, dt, n_chunks)][0], ref["hop"][:, :, 0])
+                assert np.array_equal(out[(mode, dt, n_chunks)][1], ref["hop"][:, :, 1])
+    for key, val in out.items():
+        other = out[("0",) + key[1:]]
+        assert all(np.array_equal(a, b) for a, b in zip(val, other)), key
