@@ -898,7 +898,9 @@ int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g,
   // bytes behind the reductions, hence fewer passes.  HOPB_HIST_PACK16=0 switches it off, =2 forces it (tests).
   const char* pack_env = getenv("HOPB_HIST_PACK16");
   const int pack_mode = pack_env ? atoi(pack_env) : 1;
-  if (cells && fast && pack_mode && (n_pass > 1 || pack_mode == 2) && n_cells_all < ((int64_t)1 << 32)) {
+  // (only for calls with at least a point per cell: the flush walks the whole grid, which a call of a few frames would
+  // not earn back)
+  if (cells && fast && pack_mode && ((n_pass > 1 && n_points >= n_cells_all) || pack_mode == 2) && n_cells_all < ((int64_t)1 << 32)) {
     const int64_t n_words = (n_cells_all + 1) / 2;
     int64_t budget16 = h->hist_l2_budget;
     if (const char* e = getenv("HOPB_HIST_PACK16_BUDGET_MB")) {      // tuning hook

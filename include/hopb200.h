@@ -89,7 +89,7 @@ int hopb_hist_accumulate(hopb_handle* h, void* stream, const hopb_grid* g, const
  * hopb_hoptraj need not read the coordinates again.
  * cells: device uint32 [n_points] (NULL = off).
  * Grids larger than the handle's L2 budget (hopb_set_hist_l2_budget, 64 MiB by default) are reduced in x-slab passes
- * over the cached brick indices, by default through a grid of 16-bit counters packed two per word (half the bytes,
+ * over the cached brick indices, for calls with at least one point per cell through a grid of 16-bit counters packed two per word (half the bytes,
  * hence fewer passes) that is added into `counts` once a sum check has shown that no 16-bit counter wrapped; if one
  * did, the same call falls back to reductions straight into `counts`.  The result is exact either way. */
 int hopb_hist_accumulate_cells(hopb_handle* h, void* stream, const hopb_grid* g, const float* xyz,

@@ -58,10 +58,11 @@ def test_histogram_counts(K, traj, delta):
     assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref)
 
 
-@pytest.mark.parametrize("pack16", ["0", "1"])
+@pytest.mark.parametrize("pack16", ["0", "2"])
 def test_histogram_slabbed_passes(K, traj, pack16, monkeypatch):
     """Grids beyond the L2 budget are reduced slab by slab from the cached cell indices -- straight into the u32 grid
-    (HOPB_HIST_PACK16=0) or through the 16-bit packed grid first (the default for such grids)."""
+    (HOPB_HIST_PACK16=0) or through the 16-bit packed grid first (=2; the default for such grids when the call brings
+    at least a point per cell)."""
     monkeypatch.setenv("HOPB_HIST_PACK16", pack16)
     p, xyz = traj
     xyz = xyz[:50].copy()
