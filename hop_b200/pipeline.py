@@ -214,9 +214,33 @@ class HopPipeline:
         free, _ = torch.cuda.mem_get_info(self.device)
         return need < 0.5 * free
 
+    def _zeroed_counts(self):
+        """The count grid of this run, already zeroed: two grids alternate, and the one of the NEXT run is cleared on a
+        side stream while this run's histogram is busy (a 32 MB memset otherwise sits in front of every histogram).
+        The counts of a result stay valid until the next run starts, as before."""
+        par = self._run_index & 1
+        main = torch.cuda.current_stream(self.device)
+        zs = getattr(self, "_zero_stream", None)
+        if zs is None:
+            zs = self._zero_stream = torch.cuda.Stream(device=self.device)
+            self._zeroed = {}
+        counts = self._buf("counts%d" % par, self.grid.shape, torch.int32, symm=True)
+        ready = self._zeroed.pop(par, None)
+        if ready is not None and ready[0] is counts:
+            main.wait_event(ready[1])
+        else:
+            counts.zero_()
+        other = self._buf("counts%d" % (1 - par), self.grid.shape, torch.int32, symm=True)
+        zs.wait_stream(main)                  # everything queued so far that reads the other grid (the previous run) is done
+        with torch.cuda.stream(zs):
+            other.zero_()
+            ev = torch.cuda.Event()
+            ev.record(zs)
+        self._zeroed[1 - par] = (other, ev)
+        return counts
+
     def histogram(self, xyz):
-        counts = self._buf("counts", self.grid.shape, torch.int32, symm=True)
-        counts.zero_()
+        counts = self._zeroed_counts()
         self.cells = None
         if self._use_cells(xyz):
             self.cells = self._buf("cells", (xyz.shape[0], xyz.shape[1]), torch.int32)
