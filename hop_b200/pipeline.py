@@ -410,7 +410,10 @@ class HopPipeline:
         if self._s4_done is not None:     # the previous run's finalisation reads the event buffer
             torch.cuda.current_stream(self.device).wait_event(self._s4_done)
             self._s4_done = None
-        events.reset()
+        if getattr(self, "_events_clean", None) is events:
+            self._events_clean = None     # the previous run's finalisation left the counter at zero (on its own stream)
+        else:
+            events.reset()
         hop_x = hop_y = None
         if cfg.write_hoptraj:
             hop_x = self._buf("hop_x", (F, N), cfg.plane_torch_dtype())
@@ -523,9 +526,11 @@ class HopPipeline:
                 host_any = self._host_buf("fin_any" + par, (2,), torch.int64)
                 host_any.copy_(flags, non_blocking=True)
             host.copy_(result_dev, non_blocking=True)
+            events.reset()        # for the next run's stage 3, which waits for `done` anyway: one launch less in front of it
             done = torch.cuda.Event()
             done.record(s4)
         self._s4_done = done
+        self._events_clean = events
 
         run_index = self._run_index
 
@@ -648,6 +653,7 @@ class HopPipeline:
         if self._s4_done is not None:
             torch.cuda.current_stream(dev).wait_event(self._s4_done)
             self._s4_done = None
+        self._events_clean = None
         events.reset()
         state = self._buf("state", (K.STATE_INTS, N), torch.int32)
         K.hop_advance(None, state, init=True)
