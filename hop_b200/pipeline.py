@@ -128,7 +128,7 @@ class _PendingFinalize(object):
             # rare: more transitions than budgeted, or more sites than the count matrix was sized for
             # -- redo the tail of the run synchronously with what is known now
             pipe._w_known = n_labels + 1
-            self.redo(res, n_all if status & K.FIN_OVERFLOW else None)
+            self.redo(res, n_all if status & K.FIN_OVERFLOW else None, n_all)
             return
         sorted_ev, e_s0, e_s, e_start, e_count = self.out
         res.events = sorted_ev[:n_all]
@@ -536,7 +536,7 @@ class HopPipeline:
 
         distributed = _dist() is not None
 
-        def redo(res_, n_needed):
+        def redo(res_, n_needed, n_all=0):
             if distributed and n_needed is not None:
                 # more transitions than budgeted on some rank (the flag is all-reduced, so every rank that looks at
                 # its result gets here): results are resolved lazily and not in lockstep, so the collective redo is
@@ -554,6 +554,8 @@ class HopPipeline:
                 res_.hop_x, res_.hop_y, ev2, res_.state, res_.final_state = self.hoptraj(xyz, res_.map16, frame0)
             else:
                 ev2 = events
+                events.count.fill_(n_all)     # the finalisation left the counter at zero for the next run; the records are intact
+                self._events_clean = None
             self._finalize_sync(res_, ev2, xyz, frame0)
 
         res._pending = _PendingFinalize(self, done, host, events, out, matrix, self._props, props_done, redo)
