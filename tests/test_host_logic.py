@@ -230,3 +230,22 @@ def test_rate_fits_in_worker_processes_are_identical():
     for a, b in zip(serial, pooled):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[3] == b[3] and a[4] == b[4]
     assert _ratefit.default_workers(10) == 0
+
+
+def test_pipeline_config_plane_dtype_and_exchange_fallbacks():
+    """Host-side switches of the later part of round 2: the plane type of the pipeline is int16 by default and checked;
+    without a process group nothing asks for symmetric memory and the exchanges are no-ops on one rank."""
+    torch = pytest.importorskip("torch")
+    from hop_b200 import exchange
+    from hop_b200.pipeline import PipelineConfig
+
+    assert PipelineConfig().plane_torch_dtype() == torch.int16
+    assert PipelineConfig(plane_dtype="float32").plane_torch_dtype() == torch.float32
+    with pytest.raises(ValueError):
+        PipelineConfig(plane_dtype="int8").plane_torch_dtype()
+    assert exchange.dist() is None and not exchange.nvls_wanted()
+    assert exchange.symm_entry(None) is None and exchange.symm_entry(torch.zeros(4)) is None
+    t = torch.arange(6, dtype=torch.int32)
+    assert exchange.reduce_counts(t) is t and exchange.reduce_count_matrix(t) is t
+    assert tuple(exchange.gather_slab_summaries(t.view(2, 3)).shape) == (1, 2, 3)
+    assert exchange.slab_bounds(10, 4, 0) == (0, 3) and exchange.slab_bounds(10, 4, 3) == (8, 10)
