@@ -20,6 +20,11 @@
 // j+64 (three fully coalesced 512 B requests), park them in a per-warp shared-memory slab, and read
 // the points back at a stride of 3 words (conflict-free) so that lane l handles points l, l+32,
 // l+64, l+96; the packed cells go out as four coalesced 128 B stores per warp.
+//
+// Grids beyond the L2 budget (the reduction rate falls once the target outgrows ~half of L2) are reduced in x-slab
+// passes over the cached brick indices (hist_cells_kernel) -- for large calls through a grid of 16-bit counters packed
+// two per word, which halves the bytes behind the reductions and with them the number of passes; a sum check makes
+// that exact whatever the input (hist_flush16_kernel).
 #include <cooperative_groups.h>
 
 #include <cstdlib>

@@ -17,8 +17,11 @@
 // (L2 evict-first hints on the streamed loads / stores were measured and made this kernel 5-25 %
 // slower on B200; plain ld.global.nc / st.global it is.)
 //
-// Roofline per atom-frame: 12 B read + 8 B written to HBM; the site-map gather (2 B out of a 32 B
-// sector) is served by L2 (map16 of 201^3 cells = 16 MB).
+// Roofline per atom-frame: 12 B read + 8 B written to HBM.  The pipeline moves less: stage 1 leaves a
+// 4-byte brick index per atom-frame which is read here instead of the coordinates (through TMA boxes, see
+// kTmaStages), and the planes are written as int16 (hopb_hoptraj_i16: labels are int16 map values or -1) -- 4 + 4
+// bytes; the site-map gather (2 B out of a 32 B sector) is served by shared-memory block maps and L2 (map16 of
+// 201^3 cells = 16 MB).  Measured: profiles/r2_k3_decomposition.md.
 #include <cuda.h>
 
 #include <cstdlib>

@@ -4,8 +4,9 @@ This is the hot path the classes in density.py / sitemap.py / trajectory.py / gr
 stage at a time, put together for whole-trajectory runs (bench.py, smoke, multi-GPU).  Each rank
 holds one frame slab [frame0, frame0 + F_local) of the same atoms.
 
-Exchange steps, all through torch.distributed (NCCL on GPUs, gloo in CPU tests of
-the host logic):
+Exchange steps (hop_b200/exchange.py: kernels of the library on NVSwitch multicast
+memory where the box has it, else torch.distributed -- NCCL on GPUs, gloo in the CPU tests of the
+host logic):
   * counts: all-reduce(sum) of the uint32 histogram -> every rank labels the identical grid;
   * slab summaries: all-gather of one 44-byte summary per atom and rank; every rank replays the
     slabs before its own to obtain the exact state its slab starts from;
