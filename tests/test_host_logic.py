@@ -249,3 +249,26 @@ def test_pipeline_config_plane_dtype_and_exchange_fallbacks():
     assert exchange.reduce_counts(t) is t and exchange.reduce_count_matrix(t) is t
     assert tuple(exchange.gather_slab_summaries(t.view(2, 3)).shape) == (1, 2, 3)
     assert exchange.slab_bounds(10, 4, 0) == (0, 3) and exchange.slab_bounds(10, 4, 3) == (8, 10)
+
+
+def test_packed16_sum_check_detects_every_wrap():
+    """The invariant behind hist_flush16_kernel (csrc/hist.cu), replayed with numpy's wrapping uint32 arithmetic: adding
+    1 << 16 * (cell & 1) into word cell >> 1 per hit, the sum of all decoded 16-bit counters equals the number of hits
+    exactly when no counter passed 65535 -- every wrap takes 65535 (low half: the carry lands in the high half) or 65536
+    (high half: the carry is lost) out of it."""
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n_cells = int(rng.integers(2, 40))
+        hits = rng.integers(0, 3000, n_cells).astype(np.int64)
+        if trial % 2:                                     # make some counters wrap, in low and in high halves
+            for c in rng.choice(n_cells, size=int(rng.integers(1, 4)), replace=False):
+                hits[c] = int(rng.integers(65536, 200000))
+        words = np.zeros((n_cells + 1) // 2, np.uint32)
+        for c, h in enumerate(hits):
+            words[c >> 1] += np.uint32((int(h) << (16 * (c & 1))) & 0xFFFFFFFF)      # h reductions of 1 << shift, mod 2^32
+        decoded_sum = int((words & 0xFFFF).astype(np.int64).sum() + (words >> 16).astype(np.int64).sum())
+        wrapped = bool((hits > 65535).any())
+        assert (decoded_sum == int(hits.sum())) == (not wrapped), (trial, hits)
+        if not wrapped:
+            dec = np.stack([words & 0xFFFF, words >> 16], axis=1).ravel()[:n_cells]
+            assert np.array_equal(dec.astype(np.int64), hits)
